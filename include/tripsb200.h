@@ -1,0 +1,125 @@
+/* libtripsb200 - C ABI of the B200 (sm_100a) Krylov hot path for TRIPs-Py.
+ *
+ * This is the drop-in boundary: plain C, device pointers + sizes + a cudaStream_t (passed as void*), no
+ * torch / numpy / C++ types.  The reference (mpasha3/trips-py) is pure Python; the "FFI" a maintainer binds is
+ * ctypes.  Each entry point names the reference call site(s) it replaces; paths are
+ * relative to the reference repository root.
+ *
+ * Conventions
+ *   - return value: 0 = ok; 1..999 = cudaError_t; >= 1000 = TB200_E*; message via tb200_last_error().
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in _host.
+ *   - all launches are asynchronous on `stream`; the library allocates nothing, keeps no pointer after the
+ *     call returns and never frees caller memory.  Workspaces are caller-owned (tb200_*_workspace_len()).
+ *   - a "basis" is kmax columns, column j contiguous at V + j*ld (ld >= column length).
+ *   - scalars that may live on the device come as a (x_host, x_dev) pair: x_dev wins when it is not NULL.
+ *   - norm outputs are two doubles: out[0] = sum of squares, out[1] = its square root.
+ *   - reductions are two-stage fixed-order trees (no atomics): results are bitwise reproducible run to run.
+ */
+#ifndef TRIPSB200_H
+#define TRIPSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB200_EINVAL 1001
+#define TB200_ENOTSM100 1002
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+const char* tb200_last_error(void);
+int tb200_version(void);
+int tb200_device_info(int* sm_count, int64_t* l2_bytes, int64_t* mem_bytes, int* cc);
+int tb200_require_sm100(void);
+
+/* ---- CSR SpMV: y = A x - coef * z, optional fused ||y||^2 ---------------------------------------------
+ * Replaces `A @ v` and (on the explicitly stored transpose) `A.T @ u`:
+ *   trips/utilities/decompositions.py:177,181 (golub_kahan), :235-240 (golub_kahan_update), :212 (arnoldi_update)
+ *   trips/solvers/CGLS.py:45-46,60,68; GKS.py:37,82,92; MMGKS.py:43-44,56,115,124
+ * i.e. scipy sparsetools csr_matvec / csc_matvec behind scipy.sparse `__matmul__`.
+ * The epilogue `- coef*z` is the three-term recurrence of decompositions.py:237,240 (z = NULL: plain product).
+ * rowptr: int64[m+1]; colidx: int32[nnz] (16-byte aligned); vals: fp64 (or fp32 for _f32s; 32-byte aligned).
+ * norm_out (nullable): 2 doubles; ws: tb200_spmv_workspace_len(m) doubles, required iff norm_out != NULL. */
+int64_t tb200_spmv_workspace_len(int64_t m);
+int tb200_spmv_launches(int with_norm);
+int tb200_spmv_csr_f64(int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx,
+                       const double* vals, const double* x, double* y, double coef_host, const double* coef_dev,
+                       const double* z, double* norm_out, double* ws, void* stream);
+/* fp32-storage / fp64-accumulate variant (reported separately from the fp64 parity build). */
+int tb200_spmv_csr_f32s(int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx,
+                        const float* vals, const double* x, double* y, double coef_host, const double* coef_dev,
+                        const double* z, double* norm_out, double* ws, void* stream);
+int tb200_reduce_finalize(const double* partials, int64_t n, double* out, void* stream);
+
+/* ---- BLAS-1 between operator applies -------------------------------------------------------------------
+ * v/alpha, u/beta: decompositions.py:238-242 ; x+beta*p, r-beta*w, t+c*p, norms: CGLS.py:49-76 ;
+ * smoothed Holder weights: weights.py:66-68, MMGKS.py:57,93 ; wf*(AVy-b), wr*(LVy): MMGKS.py:111-113 ;
+ * la.norm(x - x_true): Hybrid_LSQR.py:110, GKS.py:101.  Element-wise ops round like NumPy (no FMA contraction). */
+int64_t tb200_reduce_workspace_len(void);
+int tb200_vec_div(int64_t n, const double* x, double d_host, const double* d_dev, double* out, void* stream);
+int tb200_vec_axpy(int64_t n, double a_host, const double* a_dev, double sign, const double* x, const double* y,
+                   double* out, double* norm_out, double* ws, void* stream); /* out = y + sign*(a*x), sign = +-1 */
+int tb200_vec_norm2(int64_t n, const double* x, double* out, double* ws, void* stream);
+int tb200_vec_dot(int64_t n, const double* x, const double* y, double* out, double* ws, void* stream);
+int tb200_vec_diffnorm2(int64_t n, const double* x, const double* y, double* out, double* ws, void* stream);
+/* mode 0: out = x*y ; 1: out = x-y ; 2: out = w*(x-y) ; 3: out = x+y */
+int tb200_vec_binary(int mode, int64_t n, const double* x, const double* y, const double* w, double* out, void* stream);
+int tb200_irls_weights(int64_t n, const double* v, double eps, double expo, double* out, void* stream);
+
+/* ---- tall-skinny basis kernels ---------------------------------------------------------------------------
+ * h = V^T w and w -= V h: MMGKS.py:119-120 (CGS2), GKS.py:86-88 (x3), decompositions.py:216-218 (MGS columns);
+ * lifts x = V y, AV y, LV y: Hybrid_LSQR.py:105, Hybrid_GMRES.py:77, GKS.py:76-83, MMGKS.py:107-116;
+ * U^T b: reg_param/discrepancy_principle.py:34. */
+int64_t tb200_basis_workspace_len(int64_t k);
+int tb200_basis_dots(int64_t n, int64_t k, const double* V, int64_t ld, const double* w, double* h, double* ws,
+                     void* stream);
+/* out = w + sign * V h (w NULL => out = sign * V h); optional fused norm of out */
+int tb200_basis_combine(int64_t n, int64_t k, const double* V, int64_t ld, const double* h, const double* w, double sign,
+                        double* out, double* norm_out, double* ws, void* stream);
+
+/* ---- weighted Gram + k x k factorisation (replaces the per-iteration host QRs) ----------------------------
+ * la.qr(AV*wf), la.qr(LV*wr), Q_A.T@b: MMGKS.py:57-59,94-106 ; la.qr(AV), la.qr(LV): GKS.py:54-58.
+ * Double-double accumulation; tb200_gram_factor_dd runs on the HOST (all pointers host). */
+int64_t tb200_gram_workspace_len(int64_t K);
+int tb200_weighted_gram(int64_t m, int64_t k, const double* B, int64_t ld, const double* w, int n_extra,
+                        const double* const* extras_host, const int* extra_weighted_host, double* Ghi, double* Glo,
+                        double* ws, void* stream);
+int tb200_gram_factor_dd(int k, int ne, const double* Ghi_host, const double* Glo_host, double* R_host, double* C_host,
+                         double* resid2_host);
+
+/* ---- parallel-beam CT system matrix (A in CSR, A^T in CSR) -----------------------------------------------
+ * Stands where ASTRA does in the reference (trips/test_problems/Tomography.py:49-88, utilities/io.py:392-400,
+ * utilities/cil_io.py:271-275): theta = linspace(0, pi, views, endpoint=False), n_det = int(sqrt(2)*nx),
+ * unit detector spacing, entry = chord length of the ray through the unit pixel.
+ * Row of A = angle*n_det + det over the n_ang angles given by the cos/sin tables; column = iy*nx + ix. */
+int tb200_ct_count_rows(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
+                        void* stream);
+int tb200_ct_fill_rows(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
+                       const int64_t* rowptr, int32_t* colidx, double* vals, void* stream);
+int tb200_ct_count_cols(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
+                        void* stream);
+int tb200_ct_fill_cols(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
+                       const int64_t* rowptr, int32_t* colidx, double* vals, void* stream);
+
+/* ---- stencils ---------------------------------------------------------------------------------------------
+ * PSF blur and its reference "adjoint": trips/test_problems/Deblurring2D.py:66-73 (scipy.ndimage.convolve,
+ * mode='reflect'); zero-padded variant for gen_data :121-133 (mode 1).  Bit-identical to ndimage (tap order and
+ * rounding).  Pass W = flipped PSF for A, W = PSF for A^T; ch/cw = ph/2, pw/2 minus one for even sizes. */
+int tb200_correlate2d_f64(int nrow, int ncol, const double* x, const double* W, int ph, int pw, int ch, int cw, int mode,
+                          double* out, void* stream);
+/* Forward-difference regularisation operators: trips/utilities/operators.py:24-28 (1-D), :30-36 (2-D, nt = 1),
+ * :39-45 (space-time).  Fused IRLS weights wout = (u^2+eps^2)^expo: MMGKS.py:60,93; weighted adjoint
+ * L^T (w . r): MMGKS.py:113-117.  x_next / rt_prev / wt_prev: one-frame halos for frame-sharded dynamic CT. */
+int64_t tb200_fd_rows(int nt, int nrow, int ncol, int has_next);
+int tb200_fd_apply(int nt, int nrow, int ncol, const double* x, const double* x_next, double* u, double* wout, double eps,
+                   double expo, void* stream);
+int tb200_fd_adjoint(int nt, int nrow, int ncol, int has_next, const double* r, const double* w, const double* rt_prev,
+                     const double* wt_prev, double* out, void* stream);
+int tb200_fd1d_apply(int64_t n, const double* x, double* u, void* stream);
+int tb200_fd1d_adjoint(int64_t n, const double* r, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIPSB200_H */

@@ -1,0 +1,619 @@
+"""TEST INFRASTRUCTURE - CPU oracle for the Krylov hot path of TRIPs-Py (mpasha3/trips-py).
+
+A NumPy/SciPy restatement of the reference's algorithms, written so that every floating-point operation happens
+in the same order as in the reference: on identical inputs it reproduces the reference BIT FOR BIT (pinned by
+tests/test_oracle_pinned.py against the real reference in the build container, and by the golden vectors under
+tests/golden/ everywhere else).  It exists because /root/reference cannot travel to the GPU box and because
+the reference needs pylops/astra/matplotlib to import.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this file.
+Nothing under trips-py_b200/ does: the product has no CPU path.
+
+Each function cites the reference lines it follows (paths relative to the reference root).  Operators passed as
+A / L are anything supporting `@` and `.T` (scipy.sparse matrices, ndarrays, FunctionOp below).
+"""
+import numpy as np
+import scipy.linalg as la
+import scipy.optimize as op
+import scipy.sparse as sp
+from scipy.ndimage import convolve
+
+
+# ======================================================================================================
+# Krylov cores                                                   trips/utilities/decompositions.py
+# ======================================================================================================
+
+def golub_kahan_update(A, U, S, V):
+    """decompositions.py:230-255."""
+    k = S.shape[0]
+    u_last = U[:, -1]
+    if k == 1:
+        v = A.T @ u_last
+    else:
+        v = A.T @ u_last - S[k - 1, k - 2] * V[:, k - 2]
+    alpha = np.linalg.norm(v)
+    v = v / alpha
+    u = A @ v - alpha * u_last
+    beta = np.linalg.norm(u)
+    u = u / beta
+    U = np.hstack((U, u.reshape((-1, 1))))
+    V = v.reshape((-1, 1)) if k == 1 else np.hstack((V, v.reshape((-1, 1))))
+    if k == 1:
+        S = np.array([[alpha], [beta]])
+    else:
+        col = np.zeros(k)
+        col[-1] = alpha
+        row = np.zeros(k)
+        row[-1] = beta
+        S = np.vstack((np.hstack((S, col.reshape((-1, 1)))), row.reshape((1, -1))))
+    return (U, S, V)
+
+
+def golub_kahan(A, b, n_iter):
+    """decompositions.py:118-205 with dp_stop=False."""
+    rows, cols = A.shape
+    betas = np.zeros(1)
+    alphas = np.zeros(1)
+    U = np.zeros((rows, 2))
+    V = np.zeros((cols, 1))
+    U[:, 0] = (b / np.linalg.norm(b)).flatten()
+    for it in range(n_iter):
+        if it != 0:
+            U = np.pad(U, ((0, 0), (0, 1)))
+            V = np.pad(V, ((0, 0), (0, 1)))
+            betas = np.pad(betas, ((0, 1)))
+            alphas = np.pad(alphas, ((0, 1)))
+        V[:, it] = A.T @ U[:, it] - betas[it - 1] * V[:, it - 1]
+        alphas[it] = np.linalg.norm(V[:, it])
+        V[:, it] = V[:, it] / alphas[it]
+        U[:, it + 1] = A @ V[:, it] - alphas[it] * U[:, it]
+        betas[it] = np.linalg.norm(U[:, it + 1])
+        U[:, it + 1] = U[:, it + 1] / betas[it]
+    k = alphas.shape[0]
+    S = np.zeros((k + 1, k))
+    S[range(0, k), range(0, k)] = alphas
+    S[range(1, k + 1), range(0, k)] = betas
+    return (U, S, V)
+
+
+def arnoldi_update(A, V, H):
+    """decompositions.py:207-228 (modified Gram-Schmidt, single pass)."""
+    k = H.shape[0]
+    w = A @ V[:, -1]
+    h = np.zeros((k, 1))
+    for j in range(k):
+        h[j] = np.dot(V[:, j], w)
+        w = w - h[j] * V[:, j]
+    H = h if k == 1 else np.hstack((H, h))
+    last = np.zeros((1, k))
+    last[:, -1] = np.linalg.norm(w)
+    H = np.vstack((H, last))
+    V = np.hstack((V, w.reshape((-1, 1)) / H[-1, -1]))
+    return (V, H)
+
+
+def arnoldi_update_cgs2(A, V, H):
+    """The north-star variant (NOT reference behaviour): classical Gram-Schmidt applied twice."""
+    k = H.shape[0]
+    w = A @ V[:, -1]
+    h1 = V.T @ w
+    w = w - V @ h1
+    h2 = V.T @ w
+    w = w - V @ h2
+    h = (h1 + h2).reshape(-1, 1)
+    H = h if k == 1 else np.hstack((H, h))
+    last = np.zeros((1, k))
+    last[:, -1] = np.linalg.norm(w)
+    H = np.vstack((H, last))
+    V = np.hstack((V, w.reshape((-1, 1)) / H[-1, -1]))
+    return (V, H)
+
+
+# ======================================================================================================
+# parameter-choice rules                                          trips/utilities/reg_param/
+# ======================================================================================================
+
+def _todense(M):
+    return M.todense() if hasattr(M, "todense") and not isinstance(M, np.ndarray) else M
+
+
+def gcv_numerator(lam, Q_A, R_A, R_L, b):
+    """gcv.py:25-49, 'standard' variant (the reference never forwards kwargs to it: gcv.py:94)."""
+    RA2 = _todense(R_A.T @ R_A)
+    RL2 = _todense(R_L.T @ R_L)
+    inv = la.solve((RA2 + lam * RL2), (R_A.T @ Q_A.T @ b))
+    return (np.linalg.norm(R_A @ inv - Q_A.T @ b)) ** 2
+
+
+def gcv_denominator(lam, R_A, R_L, b, **kwargs):
+    """gcv.py:51-78."""
+    variant = kwargs["variant"] if ("variant" in kwargs) else "standard"
+    RA2 = _todense(R_A.T @ R_A)
+    RL2 = _todense(R_L.T @ R_L)
+    inv = la.solve((RA2 + lam * RL2), R_A.T)
+    if variant == "modified":
+        trace_term = kwargs["fullsize"] - np.trace(R_A @ inv)
+    else:
+        trace_term = R_A.shape[0] - np.trace(R_A @ inv)
+    return trace_term ** 2
+
+
+def generalized_crossvalidation(Q_A, R_A, R_L, b, **kwargs):
+    """gcv.py:80-95, gcvtype='tikhonov'."""
+    f = lambda lam: gcv_numerator(lam, Q_A, R_A, R_L, b) / gcv_denominator(lam, R_A, R_L, b, **kwargs)  # noqa: E731
+    return op.fminbound(func=f, x1=1e-09, x2=1e2, args=(), xtol=1e-12, maxfun=1000, full_output=0, disp=0)
+
+
+class IdentityOp:
+    """Stand-in for pylops.Identity where the reference passes one as L / R_L (Hybrid_LSQR.py:76, Hybrid_GMRES.py:56)."""
+
+    def __init__(self, n):
+        self.shape = (n, n)
+
+    @property
+    def T(self):
+        return self
+
+    def __matmul__(self, x):
+        return self if isinstance(x, IdentityOp) else x
+
+    def todense(self):
+        return np.eye(self.shape[0])
+
+
+def is_identity(L):
+    """trips/utilities/utils.py:47-62."""
+    if isinstance(L, IdentityOp):
+        return True
+    if isinstance(L, np.ndarray) and (L.shape[0] == L.shape[1]) and np.allclose(L, np.eye(L.shape[0])):
+        return True
+    if sp.issparse(L) and (L.shape[0] == L.shape[1]) and (L - sp.eye(L.shape[0])).sum() < 10 ** (-6):
+        return True
+    return False
+
+
+def discrepancy_principle(Q, A, L, b, delta=None, eta=1.01, **kwargs):
+    """discrepancy_principle.py:19-99, dptype='tikhonov'."""
+    if not (isinstance(delta, float) or isinstance(delta, int)):
+        raise Exception("A value for the noise level delta was not provided and the discrepancy principle cannot be applied.")
+    explicitProj = kwargs["explicitProj"] if ("explicitProj" in kwargs) else False
+    bfull = b
+    b = Q.T @ b
+    if is_identity(L):
+        Anew, bnew = A, b
+    else:
+        UL, SL, VL = la.svd(L)
+        if L.shape[0] >= L.shape[1] and SL[-1] != 0:
+            Anew = A @ (VL.T @ np.diag((SL) ** (-1)))
+            bnew = b
+        else:
+            if L.shape[0] >= L.shape[1]:
+                W = VL[np.where(SL == 0), :].reshape((-1, 1))
+            else:
+                W = VL[L.shape[0] - L.shape[1]:, :].T
+            AW = A @ W
+            Q_AW, R_AW = np.linalg.qr(AW, mode="reduced")
+            Q_LT, R_LT = np.linalg.qr(L.T, mode="reduced")
+            LAwpinv = (np.eye(L.shape[1]) - (W @ np.linalg.inv(R_AW) @ Q_AW.T @ A)) @ Q_LT @ np.linalg.inv(R_LT.T)
+            Anew = A @ LAwpinv
+            xnull = W @ np.linalg.inv(R_AW) @ Q_AW.T @ b
+            bnew = b - A @ xnull
+    U, S, V = la.svd(Anew)
+    sv = S ** 2
+    bhat = U.T @ bnew
+    if Anew.shape[0] > Anew.shape[1]:
+        sv = np.append(sv.reshape((-1, 1)), np.zeros((Anew.shape[0] - Anew.shape[1], 1)))
+        if explicitProj:
+            testzero = la.norm(bhat[Anew.shape[1] - Anew.shape[0]:, :]) ** 2 + la.norm(bfull - Q @ b) ** 2 - (eta * delta) ** 2
+        else:
+            testzero = la.norm(bhat[Anew.shape[1] - Anew.shape[0]:, :]) ** 2 - (eta * delta) ** 2
+    else:
+        testzero = la.norm(bfull - Q @ b) ** 2 - (eta * delta) ** 2
+    sv.shape = (sv.shape[0], 1)
+    beta = 1e-8
+    iterations = 0
+    if testzero < 0:
+        while (iterations < 30) or ((iterations <= 100) and (np.abs(alpha) < 10 ** (-16))):
+            zbeta = (((sv * beta + 1) ** (-1)) * bhat.reshape((-1, 1))).reshape((-1, 1))
+            if explicitProj:
+                f = la.norm(zbeta) ** 2 + la.norm(bfull - Q @ b) ** 2 - (eta * delta) ** 2
+            else:
+                f = la.norm(zbeta) ** 2 - (eta * delta) ** 2
+            wbeta = (((sv * beta + 1) ** (-1)) * zbeta).reshape((-1, 1))
+            f_prime = 2 / beta * zbeta.T @ (wbeta - zbeta)
+            beta_new = beta - f / f_prime
+            if abs(beta_new - beta) < 10 ** (-12) * beta:
+                break
+            beta = beta_new
+            alpha = 1 / beta_new[0, 0]
+            iterations += 1
+    else:
+        alpha = 0
+    return alpha
+
+
+# ======================================================================================================
+# solvers                                                                   trips/solvers/
+# ======================================================================================================
+
+def _stack_solve(B, L, rhs_top, lam):
+    return np.linalg.lstsq(np.vstack((B, np.sqrt(lam) * L)),
+                           np.vstack((rhs_top.reshape((-1, 1)), np.zeros((B.shape[1], 1)))), rcond=None)[0]
+
+
+def CGLS(A, b, x0, max_iter, tol, x_true=None):
+    """CGLS.py:42-86 (with np.eps -> machine epsilon, never reached on the test problems)."""
+    b = b.reshape((-1, 1))
+    x = x0
+    r = b - A @ x
+    t = A.T @ r
+    p = t
+    x_history, rel_residual, rel_error = [], [], []
+    norms_t0 = np.linalg.norm(t)
+    gamma, xmax = norms_t0 ** 2, np.linalg.norm(x)
+    k, check = 0, 0
+    while (k < max_iter) and (check == 0):
+        x_old = x
+        k += 1
+        w = A @ p
+        delta = np.linalg.norm(w) ** 2
+        if delta == 0:
+            delta = np.finfo(float).eps
+        beta = gamma / delta
+        x = x + beta * p
+        x_history.append(x)
+        r = r - beta * w
+        t = A.T @ r
+        gamma_old = gamma
+        norm_t = np.linalg.norm(t)
+        gamma = norm_t ** 2
+        p = t + (gamma / gamma_old) * p
+        norm_x = np.linalg.norm(x)
+        xmax = max(xmax, norm_x)
+        check = (norm_t <= norms_t0 * tol) or (norm_x * tol >= 1)
+        rel_residual.append(np.linalg.norm(x - x_old) / np.linalg.norm(x))
+        if x_true is not None:
+            rel_error.append(np.linalg.norm(x - x_true) / np.linalg.norm(x))
+    info = {"xHistory": x_history, "regParam": [], "relResidual": rel_residual, "its": k}
+    if x_true is not None:
+        info["relError"] = rel_error
+    return (x, info)
+
+
+def Hybrid_LSQR(A, b, n_iter=100, regparam="gcv", x_true=None, **kwargs):
+    """Hybrid_LSQR.py:55-114 (dp_stop=False)."""
+    n = A.shape[1]
+    beta = np.linalg.norm(b)
+    U = b.reshape((-1, 1)) / beta
+    B = np.empty(1)
+    V = np.empty((n, 1))
+    x_history, lambda_history = [], []
+    bhat = np.zeros(1)
+    bhat[0] = beta
+    for ii in range(n_iter):
+        (U, B, V) = golub_kahan_update(A, U, B, V)
+        bhat = np.append(bhat, 0)
+        k = B.shape[1]
+        if ii == 0:
+            lambdah = 0
+            continue
+        if regparam == "gcv":
+            Q_A, s, _ = la.svd(B, full_matrices=False)
+            lambdah = generalized_crossvalidation(Q_A, np.diag(s), np.eye(k), bhat, variant="modified",
+                                                  fullsize=A.shape[0], **kwargs)
+        elif regparam == "dp":
+            lambdah = discrepancy_principle(U, B, IdentityOp(k), b, **kwargs)
+        else:
+            lambdah = regparam
+        lambda_history.append(lambdah)
+        y = _stack_solve(B, np.eye(k), bhat, lambdah)
+        x = (V @ y).reshape((-1, 1))
+        x_history.append(x)
+    info = {"xHistory": x_history, "regParam": lambdah, "regParam_history": lambda_history, "relResidual": [], "its": ii,
+            "B": B, "U": U, "V": V}
+    if x_true is not None:
+        xt = x_true.reshape(-1, 1)
+        info["relError"] = [la.norm(xx - xt) / la.norm(xt) for xx in x_history]
+    return (x, info)
+
+
+def Hybrid_GMRES(A, b, n_iter, regparam="gcv", x_true=None, reorth="mgs", **kwargs):
+    """Hybrid_GMRES.py:33-87 (dp_stop=False).  relResidual holds ||bhat - H y|| (the reference's :80 broadcasts)."""
+    n = A.shape[1]
+    if A.shape[0] != n:
+        raise Exception("Please check the size of the matrx A: it should be square in order to apply hybrid GMRES")
+    x_history, lambda_history, residual_history = [], [], []
+    beta = np.linalg.norm(b)
+    V = b.reshape((-1, 1)) / beta
+    H = np.empty(1)
+    bhat = np.zeros(1)
+    bhat[0] = beta
+    step = arnoldi_update if reorth == "mgs" else arnoldi_update_cgs2
+    for ii in range(n_iter):
+        (V, H) = step(A, V, H)
+        bhat = np.append(bhat, 0)
+        k = H.shape[1]
+        if ii == 0:
+            lambdah = 0
+        elif regparam == "gcv":
+            Q_A, s, _ = la.svd(H, full_matrices=False)
+            lambdah = generalized_crossvalidation(Q_A, np.diag(s), IdentityOp(k), bhat, **kwargs)
+        elif regparam == "dp":
+            lambdah = discrepancy_principle(V, H, IdentityOp(k), b, **kwargs)
+        else:
+            lambdah = regparam
+        lambda_history.append(lambdah)
+        y = _stack_solve(H, np.eye(k), bhat, lambdah)
+        x = (V[:, :-1] @ y).reshape((-1, 1))
+        x_history.append(x)
+        residual_history.append(la.norm(bhat.reshape((-1, 1)) - H @ y))
+    info = {"xHistory": x_history, "regParam": lambdah, "regParam_history": lambda_history,
+            "relResidual": residual_history, "its": ii, "H": H, "V": V}
+    if x_true is not None:
+        xt = x_true.reshape(-1, 1)
+        info["relError"] = [la.norm(xx - xt) / la.norm(xt) for xx in x_history]
+    return (x, info)
+
+
+def GKS(A, b, L, projection_dim=3, n_iter=50, regparam="gcv", x_true=None, **kwargs):
+    """GKS.py:36-105, QR branch (L not the identity)."""
+    (U, B, V) = golub_kahan(A, b, projection_dim)
+    AV = A @ V
+    LV = L @ V
+    x_history, lambda_history, residual_history = [], [], []
+    for ii in range(n_iter):
+        (Q_A, R_A) = la.qr(AV, mode="economic")
+        _, R_L = la.qr(LV, mode="economic")
+        if regparam == "gcv":
+            lambdah = generalized_crossvalidation(Q_A, R_A, R_L, b, **kwargs)
+        elif regparam == "dp":
+            lambdah = discrepancy_principle(Q_A, R_A, R_L, b, **kwargs)
+        else:
+            lambdah = regparam
+        lambda_history.append(lambdah)
+        y, _, _, _ = np.linalg.lstsq(np.concatenate((R_A, np.sqrt(lambdah) * R_L)),
+                                     np.concatenate((Q_A.T @ b, np.zeros((R_L.shape[0], 1)))), rcond=None)
+        x = V @ y
+        x_history.append(x)
+        ra = AV @ y - b
+        ra = A.T @ ra
+        rb = (LV @ y)
+        rb = L.T @ rb
+        r = ra + lambdah * rb
+        r = r - V @ (V.T @ r)
+        r = r - V @ (V.T @ r)
+        r = r - V @ (V.T @ r)
+        residual_history.append(la.norm(r))
+        vn = r / np.linalg.norm(r)
+        V = np.column_stack((V, vn))
+        AV = np.column_stack((AV, A @ vn))
+        LV = np.column_stack((LV, L @ vn))
+    info = {"xHistory": x_history, "regParam": lambdah, "regParam_history": lambda_history,
+            "Residual": residual_history, "its": ii}
+    if x_true is not None:
+        xt = x_true.reshape(-1, 1)
+        info["relError"] = [la.norm(xx - xt) / la.norm(xt) for xx in x_history]
+    return (x, info)
+
+
+def smoothed_holder_weights(x, epsilon, p):
+    """weights.py:66-68."""
+    return (x ** 2 + epsilon ** 2) ** (p / 2 - 1)
+
+
+def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv", x_true=None, **kwargs):
+    """MMGKS.py:37-137, default (anisotropic) weights; isoTV via kwargs isoTV='isoTV', Ls=<2N x N gradient>."""
+    epsilon = kwargs["epsilon"] if ("epsilon" in kwargs) else 0.1
+    iso_L = kwargs.pop("iso_Ls", None)
+    (U, B, V) = golub_kahan(A, b, projection_dim)
+    x_history, lambda_history, residual_history = [], [], []
+    x = A.T @ b
+    AV = A @ V
+    LV = L @ V
+    for ii in range(n_iter):
+        v = A @ x - b
+        wf = (v ** 2 + epsilon ** 2) ** (pnorm / 2 - 1)
+        AA = AV * wf
+        (Q_A, R_A) = la.qr(AA, mode="economic")
+        u = L @ x
+        if iso_L is not None:
+            # MMGKS.py:64-78 with nt = 1 and an fp64 statement of the gradient operator
+            spacen = int(iso_L.shape[0] / 2)
+            LsX = iso_L @ x.reshape(-1, 1)
+            weightx = (LsX[:spacen, :] ** 2 + LsX[spacen:2 * spacen, :] ** 2 + epsilon ** 2) ** ((qnorm - 2) / 4)
+            weightx = np.concatenate((weightx.flatten(), weightx.flatten()))
+            weightt = (u[2 * spacen:] ** 2 + epsilon ** 2) ** ((qnorm - 2) / 4)
+            wr = np.concatenate((weightx.reshape(-1, 1), weightt))
+        else:
+            wr = smoothed_holder_weights(u, epsilon=epsilon, p=qnorm).reshape((-1, 1))
+        LL = LV * wr
+        (Q_L, R_L) = la.qr(LL, mode="economic")
+        if regparam == "gcv":
+            lambdah = generalized_crossvalidation(Q_A, R_A, R_L, wf * b, **kwargs)
+        elif regparam == "dp":
+            lambdah = discrepancy_principle(Q_A, R_A, R_L, wf * b, **kwargs)
+        else:
+            lambdah = regparam
+        lambda_history.append(lambdah)
+        y, _, _, _ = np.linalg.lstsq(np.concatenate((R_A, np.sqrt(lambdah) * R_L)),
+                                     np.concatenate((Q_A.T @ b, np.zeros((R_L.shape[0], 1)))), rcond=None)
+        x = V @ y
+        x_history.append(x)
+        if ii >= R_L.shape[0]:
+            break
+        ra = wf * (AV @ y - b)
+        ra = A.T @ ra
+        rb = wr * (LV @ y)
+        rb = L.T @ rb
+        r = ra + lambdah * rb
+        r = r - V @ (V.T @ r)
+        r = r - V @ (V.T @ r)
+        vn = r / np.linalg.norm(r)
+        V = np.column_stack((V, vn))
+        AV = np.column_stack((AV, A @ vn))
+        LV = np.column_stack((LV, L @ vn))
+        residual_history.append(la.norm(r))
+    info = {"xHistory": x_history, "regParam": lambdah, "regParam_history": lambda_history,
+            "Residual": residual_history, "its": ii}
+    if x_true is not None:
+        info["relError"] = [la.norm(xx - x_true) / la.norm(x_true) for xx in x_history]
+    return (x, info)
+
+
+# ======================================================================================================
+# operators
+# ======================================================================================================
+
+def first_derivative_1d(n):
+    """operators.py:24-28, built in CSR (the reference's DIA slicing raises under scipy >= 1.15: SURVEY.md F4):
+    rows i = 0..n-2 of I - shift(+1), i.e. (L x)_i = x_i - x_{i+1}."""
+    D = sp.diags(np.ones(n - 1), offsets=1, format="csr")
+    return (sp.identity(n, format="csr") - D).tocsr()[0:-1, :]
+
+
+def first_derivative_2d(nx, ny):
+    """operators.py:30-36."""
+    IDx = sp.kron(sp.identity(nx), first_derivative_1d(nx))
+    DyI = sp.kron(first_derivative_1d(ny), sp.identity(ny))
+    return sp.vstack((IDx, DyI)).tocsr()
+
+
+def spacetime_derivative(nx, ny, nt):
+    """operators.py:39-45."""
+    ITLs = sp.kron(sp.identity(nt), first_derivative_2d(nx, ny))
+    LTIN = sp.kron(first_derivative_1d(nt), sp.identity(nx ** 2))
+    return sp.vstack((ITLs, LTIN)).tocsr()
+
+
+def centered_derivative_2d(nx, ny):
+    """fp64 statement of operators_old.first_derivative_operator_2d (operators_old.py:35-45): pylops' 3-point centred
+    first derivative (zero rows at both ends) in VStack(Kronecker(I, D), Kronecker(D, I)) form; 2*nx*ny rows."""
+    def D(n):
+        M = sp.lil_matrix((n, n))
+        for i in range(1, n - 1):
+            M[i, i + 1] = 0.5
+            M[i, i - 1] = -0.5
+        return M.tocsr()
+    return sp.vstack((sp.kron(sp.identity(nx), D(nx)), sp.kron(D(ny), sp.identity(ny)))).tocsr()
+
+
+class FunctionOp:
+    """Matrix-free operator with `@` and `.T` (stands for pylops.FunctionOperator, Deblurring2D.py:72)."""
+
+    def __init__(self, f, fT, shape):
+        self.f, self.fT, self.shape = f, fT, shape
+
+    def _apply(self, fn, x):
+        x = np.asarray(x)
+        if x.ndim == 2 and x.shape[1] > 1:
+            return np.stack([fn(x[:, j]).reshape(-1) for j in range(x.shape[1])], axis=1)
+        y = fn(x).reshape(-1)
+        return y.reshape(-1, 1) if x.ndim == 2 else y
+
+    def __matmul__(self, x):
+        return self._apply(self.f, x)
+
+    @property
+    def T(self):
+        return FunctionOp(self.fT, self.f, (self.shape[1], self.shape[0]))
+
+
+def gauss_psf(dim, spread):
+    """Deblurring2D.py:48-64 (Gauss), without the centre lookup."""
+    m, n = dim[0], dim[1]
+    s1, s2 = (spread, spread) if type(spread) in [int] else (spread[0], spread[1])
+    x = np.arange(-np.fix(n / 2), np.ceil(n / 2))
+    y = np.arange(-np.fix(m / 2), np.ceil(m / 2))
+    X, Y = np.meshgrid(x, y)
+    PSF = np.exp(-0.5 * ((X ** 2) / (s1 ** 2) + (Y ** 2) / (s2 ** 2)))
+    PSF /= PSF.sum()
+    return PSF
+
+
+def blur_operator(PSF, nx, ny):
+    """Deblurring2D.py:66-73 (forward_Op)."""
+    fwd = lambda X: convolve(X.reshape([nx, ny]), PSF, mode="reflect").reshape((-1, 1))  # noqa: E731
+    bwd = lambda B: convolve(B.reshape([nx, ny]), np.flipud(np.fliplr(PSF)), mode="reflect").reshape((-1, 1))  # noqa: E731
+    return FunctionOp(fwd, bwd, (nx * ny, nx * ny))
+
+
+def blur_data(x, PSF, nx, ny):
+    """Deblurring2D.py:119-133 (gen_data, CommitCrime=False): blur on a zero-padded 2x image, crop the centre."""
+    big = np.zeros((2 * nx, 2 * ny))
+    px, py = nx // 2, ny // 2
+    big[px:px + nx, py:py + ny] = x.reshape((nx, ny))
+    b = convolve(big, PSF, mode="constant")
+    return b[px:px + nx, py:py + ny].reshape((-1, 1))
+
+
+# ---- parallel-beam CT matrix (new synthetic problem; geometry conventions of Tomography.py:53-56) --------------
+
+def ct_angles(views):
+    return np.linspace(0, np.pi, views, endpoint=False)
+
+
+def ct_num_detectors(nx):
+    return int(np.sqrt(2) * nx)
+
+
+def ct_matrix(nx, theta, ny=None, n_det=None):
+    """Dense-loop-free NumPy statement of the device builder (trips-py_b200/csrc/ct_builder.cu): entry = chord length
+    of ray (angle a, detector d) through unit pixel (iy, ix); row = a*n_det + d, column = iy*nx + ix.
+    Every arithmetic step is a separately rounded IEEE operation in the same order as the CUDA code."""
+    ny = nx if ny is None else ny
+    n_det = ct_num_detectors(nx) if n_det is None else n_det
+    theta = np.asarray(theta, dtype=np.float64)
+    cx = np.arange(nx) - 0.5 * (nx - 1)
+    cy = np.arange(ny) - 0.5 * (ny - 1)
+    sd = np.arange(n_det) - 0.5 * (n_det - 1)
+    rows, cols, vals = [], [], []
+    for a, (c, s) in enumerate(zip(np.cos(theta), np.sin(theta))):
+        hi, lo = max(abs(c), abs(s)), min(abs(c), abs(s))
+        d1, d2 = 0.5 * (hi - lo), 0.5 * (hi + lo)
+        proj = (cx[None, :] * c) + (cy[:, None] * s)          # (ny, nx): cx*c + cy*s
+        # candidate detectors around each pixel's projection
+        centre = proj + 0.5 * (n_det - 1)
+        base = np.floor(centre).astype(np.int64)
+        for off in (-1, 0, 1, 2):
+            d = base + off
+            ok = (d >= 0) & (d < n_det)
+            dd = np.clip(d, 0, n_det - 1)
+            t = sd[dd] - proj
+            at = np.abs(t)
+            hit = ok & (at < d2)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                w = np.where(at <= d1, 1.0 / hi, (d2 - at) / (hi * lo))
+            iy, ix = np.nonzero(hit)
+            rows.append(a * n_det + dd[iy, ix])
+            cols.append(iy * nx + ix)
+            vals.append(w[iy, ix])
+    A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                      shape=(len(theta) * n_det, nx * ny))
+    A.sort_indices()
+    return A
+
+
+def shepp_logan(n):
+    """Modified Shepp-Logan phantom: the standard ten-ellipse table on the grid [-1,1]^2 with spacing 2/(n-1),
+    negatives clipped - the construction of trips/utilities/phantoms.py:18-60; n x n, float64."""
+    ell = [(1.0, .69, .92, 0, 0, 0), (-.8, .6624, .8740, 0, -.0184, 0), (-.2, .1100, .3100, .22, 0, -18),
+           (-.2, .1600, .4100, -.22, 0, 18), (.1, .2100, .2500, 0, .35, 0), (.1, .0460, .0460, 0, .1, 0),
+           (.1, .0460, .0460, 0, -.1, 0), (.1, .0460, .0230, -.08, -.605, 0), (.1, .0230, .0230, 0, -.606, 0),
+           (.1, .0230, .0460, .06, -.605, 0)]
+    g = (np.arange(n) - (n - 1) / 2) / ((n - 1) / 2)
+    X, Y = np.meshgrid(g, -g)
+    img = np.zeros((n, n))
+    for A_, a, b, x0, y0, phi in ell:
+        ph = phi * np.pi / 180
+        xr = (X - x0) * np.cos(ph) + (Y - y0) * np.sin(ph)
+        yr = (Y - y0) * np.cos(ph) - (X - x0) * np.sin(ph)
+        img[(xr ** 2) / a ** 2 + (yr ** 2) / b ** 2 <= 1] += A_
+    img[img < 0] = 0
+    return img
+
+
+def add_noise(b_true, level, rng):
+    """Tomography.py:203-212 / Deblurring2D.py:141-147 with a seeded generator: e = level*||b||/||n|| * n."""
+    noise = rng.standard_normal(b_true.shape[0]).reshape((-1, 1))
+    e = level * np.linalg.norm(b_true) / np.linalg.norm(noise) * noise
+    return b_true.reshape((-1, 1)) + e, la.norm(e)

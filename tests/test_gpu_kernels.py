@@ -1,0 +1,320 @@
+"""Kernel-level parity on the B200: every CUDA kernel, called through the C ABI (trips_b200.kernels -> ctypes ->
+libtripsb200.so), against NumPy/SciPy (the arithmetic the reference delegates to) on the same seeded inputs.
+Integer/index results and the element-wise / stencil kernels must be bit-exact; reductions agree to rounding."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from scipy.ndimage import convolve
+
+import trips_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import torch
+    import trips_b200
+
+    assert torch.cuda.is_available()
+    return trips_b200
+
+
+def dev(a):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a).ravel() - np.asarray(b).ravel()) / max(np.linalg.norm(np.asarray(b).ravel()), 1e-300)
+
+
+def test_library_is_loaded_and_device_is_sm100(tb):
+    from trips_b200 import _lib
+
+    _lib.require_device()
+    import ctypes
+
+    sm, cc = ctypes.c_int(), ctypes.c_int()
+    l2, mem = ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(_lib.lib().tb200_device_info(ctypes.byref(sm), ctypes.byref(l2), ctypes.byref(mem), ctypes.byref(cc)))
+    assert cc.value // 10 == 10 and sm.value >= 100
+
+
+@pytest.mark.parametrize("shape,density", [((700, 500), 0.2), ((300, 400), 0.01), ((64, 64), 0.6), ((1000, 3), 0.5)])
+def test_spmv_matches_scipy(tb, shape, density):
+    K = tb.kernels
+    rng = np.random.default_rng(0)
+    A = sp.random(*shape, density=density, random_state=1, format="csr")
+    A.data[:] = rng.standard_normal(A.nnz)
+    op = tb.CSROperator.from_scipy(A)
+    x = rng.standard_normal(shape[1])
+    u = rng.standard_normal(shape[0])
+    z = rng.standard_normal(shape[0])
+    assert rel(host(op.apply_dev(dev(x))), A @ x) < 1e-14
+    assert rel(host(op.adjoint_dev(dev(u))), A.T @ u) < 1e-14
+    # fused recurrence epilogue + fused norm, scalar on the device
+    import torch
+
+    coef = torch.tensor([0.37], dtype=torch.float64, device="cuda")
+    nrm = torch.zeros(2, dtype=torch.float64, device="cuda")
+    y = op.apply_dev(dev(x), coef=coef, z=dev(z), norm_out=nrm)
+    want = A @ x - 0.37 * z
+    assert rel(host(y), want) < 1e-14
+    assert abs(host(nrm)[1] - np.linalg.norm(want)) < 1e-13 * np.linalg.norm(want)
+    assert abs(host(nrm)[0] - want @ want) < 1e-13 * (want @ want)
+    # deterministic: two runs are bitwise identical
+    y2 = op.apply_dev(dev(x), coef=coef, z=dev(z), norm_out=nrm)
+    assert np.array_equal(host(y), host(y2))
+    # numpy in -> numpy out through the operator surface, all input ranks the reference uses
+    assert rel(op @ x, A @ x) < 1e-14 and (op @ x.reshape(-1, 1)).shape == (shape[0], 1)
+    X = rng.standard_normal((shape[1], 3))
+    assert rel(op @ X, A @ X) < 1e-14 and rel(op.T @ u, A.T @ u) < 1e-14
+    assert rel(op * x.reshape(-1, 1), (A @ x).reshape(-1, 1)) < 1e-14
+
+
+def test_spmv_edge_cases_empty_rows_and_ragged(tb):
+    rng = np.random.default_rng(3)
+    # ragged: empty rows, rows of length 1..300 so every head/body/tail combination of the 4-wide loads occurs
+    lens = np.r_[0, 0, np.arange(1, 301), 0, 5, 0]
+    indptr = np.r_[0, np.cumsum(lens)]
+    n = 977
+    indices = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens]).astype(np.int32)
+    data = rng.standard_normal(indptr[-1])
+    A = sp.csr_matrix((data, indices, indptr), shape=(len(lens), n))
+    op = tb.CSROperator.from_scipy(A)
+    x = rng.standard_normal(n)
+    got = host(op.apply_dev(dev(x)))
+    assert rel(got, A @ x) < 1e-14 and got[0] == 0.0 and got[1] == 0.0
+    u = rng.standard_normal(len(lens))
+    assert rel(host(op.adjoint_dev(dev(u))), A.T @ u) < 1e-14
+    # fp32-storage / fp64-accumulate variant: exact on the rounded values
+    op32 = op.with_f32_storage()
+    A32 = A.copy()
+    A32.data = A.data.astype(np.float32).astype(np.float64)
+    assert rel(host(op32.apply_dev(dev(x))), A32 @ x) < 1e-14
+    # all-empty matrix
+    E = tb.CSROperator.from_scipy(sp.csr_matrix((5, 7)))
+    assert np.array_equal(host(E.apply_dev(dev(np.ones(7)))), np.zeros(5))
+
+
+def test_vector_kernels_round_like_numpy(tb):
+    K = tb.kernels
+    rng = np.random.default_rng(1)
+    n = 100_003
+    x, y, w = rng.standard_normal(n), rng.standard_normal(n), rng.uniform(0.1, 3, n)
+    a = 0.7310585786300049
+    assert np.array_equal(host(K.vec_div(dev(x), a)), x / a)
+    assert np.array_equal(host(K.vec_axpy(a, dev(x), dev(y))), y + a * x)
+    assert np.array_equal(host(K.vec_axpy(a, dev(x), dev(y), sign=-1.0)), y - a * x)
+    assert np.array_equal(host(K.vec_mul(dev(x), dev(w))), x * w)
+    assert np.array_equal(host(K.vec_sub(dev(x), dev(y))), x - y)
+    assert np.array_equal(host(K.vec_wsub(dev(w), dev(x), dev(y))), w * (x - y))
+    assert np.array_equal(host(K.vec_add(dev(x), dev(y))), x + y)
+    for expo in (-0.5, -0.25, 0.0, -0.3):
+        got = host(K.irls_weights(dev(x), 0.1, expo))
+        assert np.allclose(got, (x ** 2 + 0.1 ** 2) ** expo, rtol=1e-15, atol=0)
+    assert np.array_equal(host(K.irls_weights(dev(x), 0.1, 0.0)), np.ones(n))
+    nrm = host(K.vec_norm2(dev(x)))
+    assert abs(nrm[1] - np.linalg.norm(x)) < 1e-14 * np.linalg.norm(x) and abs(nrm[0] - x @ x) < 1e-13 * (x @ x)
+    assert abs(host(K.vec_dot(dev(x), dev(y)))[0] - x @ y) < 1e-12 * np.linalg.norm(x) * np.linalg.norm(y)
+    assert abs(host(K.vec_diffnorm2(dev(x), dev(y)))[1] - np.linalg.norm(x - y)) < 1e-14 * np.linalg.norm(x - y)
+    # fused norm of the axpy result; device-resident scalar
+    import torch
+
+    pair = torch.zeros(2, dtype=torch.float64, device="cuda")
+    ad = torch.tensor([a], dtype=torch.float64, device="cuda")
+    out = K.vec_axpy(ad, dev(x), dev(y), norm_out=pair)
+    assert np.array_equal(host(out), y + a * x)
+    assert abs(host(pair)[1] - np.linalg.norm(y + a * x)) < 1e-14 * np.linalg.norm(y + a * x)
+    # empty vectors
+    assert host(K.vec_norm2(dev(np.zeros(0))))[0] == 0.0
+
+
+@pytest.mark.parametrize("n,k", [(50_001, 1), (50_001, 7), (200_000, 19), (4096, 40)])
+def test_basis_kernels(tb, n, k):
+    K = tb.kernels
+    rng = np.random.default_rng(2)
+    V = rng.standard_normal((n, k))
+    w = rng.standard_normal(n)
+    basis = K.Basis(n, k + 2, "cuda")
+    for j in range(k):
+        basis.next_col().copy_(dev(V[:, j]))
+        basis.push()
+    h = host(K.basis_dots(basis, k, dev(w)))[:k]
+    assert np.allclose(h, V.T @ w, rtol=0, atol=1e-12 * np.linalg.norm(w) * np.sqrt(n))
+    hh = rng.standard_normal(k)
+    import torch
+
+    pair = torch.zeros(2, dtype=torch.float64, device="cuda")
+    out = host(K.basis_combine(basis, k, dev(hh), w=dev(w), sign=-1.0, norm_out=pair))
+    want = w - V @ hh
+    assert rel(out, want) < 1e-14 and abs(host(pair)[1] - np.linalg.norm(want)) < 1e-13 * np.linalg.norm(want)
+    assert rel(host(K.basis_combine(basis, k, dev(hh))), V @ hh) < 1e-14
+    assert np.array_equal(basis.to_numpy(), V)
+    # growth keeps the columns
+    for _ in range(4):
+        basis.next_col().zero_()
+        basis.push()
+    assert np.array_equal(basis.to_numpy()[:, :k], V)
+
+
+@pytest.mark.parametrize("m,k,weighted", [(5000, 3, False), (20_001, 10, True), (3000, 37, True)])
+def test_weighted_gram_and_factor_match_householder(tb, m, k, weighted):
+    K = tb.kernels
+    rng = np.random.default_rng(4)
+    # ill-conditioned basis: kappa ~ 1e6, so a plain-double Gram/Cholesky would lose ~12 digits
+    Uo = np.linalg.qr(rng.standard_normal((m, k)))[0]
+    Vo = np.linalg.qr(rng.standard_normal((k, k)))[0]
+    B = Uo @ np.diag(np.logspace(0, -6, k)) @ Vo.T
+    b = rng.standard_normal(m)
+    w = rng.uniform(0.5, 10, m) if weighted else None
+    basis = K.Basis(m, k, "cuda")
+    for j in range(k):
+        basis.next_col().copy_(dev(B[:, j]))
+        basis.push()
+    bd = dev(b)
+    Ghi, Glo = K.weighted_gram(basis, k, dev(w) if weighted else None, extras=(bd, bd), extra_weighted=(0, 1))
+    R, C, res2 = K.gram_factor(Ghi, Glo, k)
+    M = B * w[:, None] if weighted else B
+    Q, Rr = np.linalg.qr(M)
+    sg = np.sign(np.diag(Rr))
+    Q, Rr = Q * sg[None, :], Rr * sg[:, None]
+    assert np.allclose(R, Rr, rtol=0, atol=1e-9 * np.abs(Rr).max())
+    for i in range(k):
+        assert np.linalg.norm(R[i] - Rr[i]) <= 1e-8 * np.linalg.norm(Rr[i])
+    wb = b * w if weighted else b
+    assert np.allclose(C[:, 0], Q.T @ b, atol=1e-8 * np.linalg.norm(b))
+    assert np.allclose(C[:, 1], Q.T @ wb, atol=1e-8 * np.linalg.norm(wb))
+    assert abs(res2[1] - np.linalg.norm(wb - Q @ (Q.T @ wb)) ** 2) < 1e-8 * (wb @ wb)
+    # the quantity the solvers consume: y = argmin ||R y - c||^2 + lam ||y||^2 agrees with the Householder route
+    lam = 1e-3
+    y1 = np.linalg.lstsq(np.vstack((R, np.sqrt(lam) * np.eye(k))), np.r_[C[:, 0], np.zeros(k)], rcond=None)[0]
+    y2 = np.linalg.lstsq(np.vstack((Rr, np.sqrt(lam) * np.eye(k))), np.r_[Q.T @ b, np.zeros(k)], rcond=None)[0]
+    assert rel(y1, y2) < 1e-9
+
+
+@pytest.mark.parametrize("nx,views", [(24, 16), (64, 90), (33, 7)])
+def test_ct_builder_is_bit_identical_to_the_numpy_statement(tb, nx, views):
+    op = tb.ParallelBeamCT(nx, views)
+    A = op.to_scipy()
+    AT = op.transpose_to_scipy()
+    A0 = O.ct_matrix(nx, O.ct_angles(views))
+    assert A.shape == A0.shape and A.nnz == A0.nnz
+    assert np.array_equal(A.indptr, A0.indptr) and np.array_equal(A.indices, A0.indices)
+    assert np.array_equal(A.data, A0.data)
+    # the stored transpose is the exact transpose (same values, same pattern, sorted indices)
+    T0 = A0.T.tocsr()
+    T0.sort_indices()
+    assert np.array_equal(AT.indptr, T0.indptr) and np.array_equal(AT.indices, T0.indices)
+    assert np.array_equal(AT.data, T0.data)
+    # adjoint identity through the kernels
+    rng = np.random.default_rng(0)
+    x, u = rng.standard_normal(A.shape[1]), rng.standard_normal(A.shape[0])
+    lhs = u @ host(op.apply_dev(dev(x)))
+    rhs = host(op.adjoint_dev(dev(u))) @ x
+    assert abs(lhs - rhs) < 1e-12 * abs(lhs)
+
+
+def test_ct_builder_angle_subset_and_block_diagonal(tb):
+    nx, views = 32, 12
+    full = tb.ParallelBeamCT(nx, views).to_scipy()
+    n_det = O.ct_num_detectors(nx)
+    sub = tb.ParallelBeamCT(nx, views, angle_subset=np.arange(1, views, 2)).to_scipy()
+    rows = np.concatenate([np.arange(a * n_det, (a + 1) * n_det) for a in range(1, views, 2)])
+    assert (sub != full[rows]).nnz == 0
+    th = O.ct_angles(views)
+    frames = [th[0:4], th[4:8] + 0.01, th[8:12] + 0.02]
+    bd = tb.BlockDiagCT(nx, frames)
+    blocks = [O.ct_matrix(nx, f) for f in frames]
+    want = sp.block_diag(blocks, format="csr")
+    got = bd.to_scipy()
+    assert got.shape == want.shape and (got != want).nnz == 0
+    assert (bd.transpose_to_scipy() != want.T.tocsr()).nnz == 0
+
+
+@pytest.mark.parametrize("shape,psf_dim,spread", [((32, 32), (7, 7), (2, 2)), ((50, 37), (9, 5), (3, 1.5)),
+                                                   ((40, 40), (4, 6), (1.0, 2.0)), ((5, 6), (9, 9), (3, 3))])
+def test_psf_blur_is_bit_identical_to_ndimage(tb, shape, psf_dim, spread):
+    rng = np.random.default_rng(0)
+    nx, ny = shape
+    PSF = O.gauss_psf(psf_dim, spread)
+    PSF = PSF + 0.01 * rng.uniform(size=PSF.shape)  # not symmetric: tap ORDER and flips must be right
+    op = tb.PSFBlur2D(PSF, nx, ny)
+    X = rng.standard_normal((nx, ny))
+    got = host(op.apply_dev(dev(X.ravel()))).reshape(nx, ny)
+    assert np.array_equal(got, convolve(X, PSF, mode="reflect"))
+    got_t = host(op.adjoint_dev(dev(X.ravel()))).reshape(nx, ny)
+    assert np.array_equal(got_t, convolve(X, np.flipud(np.fliplr(PSF)), mode="reflect"))
+    opc = tb.PSFBlur2D(PSF, nx, ny, mode="constant")
+    assert np.array_equal(host(opc.apply_dev(dev(X.ravel()))).reshape(nx, ny), convolve(X, PSF, mode="constant"))
+
+
+def test_psf_blur_golden_and_adjointness(tb, golden_dir):
+    g = np.load(f"{golden_dir}/deblur32.npz")
+    n = int(g["n"])
+    op = tb.PSFBlur2D(g["PSF"], n, n)
+    assert np.array_equal(op @ g["probe"], g["fwd_probe"]) and np.array_equal(op.T @ g["probe"], g["adj_probe"])
+    rng = np.random.default_rng(1)
+    x, y = rng.standard_normal(n * n), rng.standard_normal(n * n)
+    assert abs(y @ (op @ x) - (op.T @ y) @ x) < 1e-12  # symmetric Gaussian PSF: the reference's A^T is the true adjoint
+
+
+@pytest.mark.parametrize("nx,nt", [(8, 1), (31, 1), (16, 5), (7, 2)])
+def test_difference_operators_bit_identical_to_the_sparse_matrices(tb, nx, nt):
+    rng = np.random.default_rng(0)
+    L = O.first_derivative_2d(nx, nx) if nt == 1 else O.spacetime_derivative(nx, nx, nt)
+    op = tb.SpaceTimeDerivative(nx, nx, nt)
+    assert op.shape == L.shape
+    x = rng.standard_normal(L.shape[1])
+    r = rng.standard_normal(L.shape[0])
+    assert np.array_equal(op @ x, L @ x)
+    assert np.array_equal(op.T @ r, L.T @ r)
+    # fused IRLS weights and weighted adjoint
+    import torch
+
+    wout = torch.empty(L.shape[0], dtype=torch.float64, device="cuda")
+    u = op.apply_dev(dev(x), wout=wout, eps=0.1, expo=-0.5)
+    assert np.array_equal(host(u), L @ x)
+    assert np.allclose(host(wout), ((L @ x) ** 2 + 0.01) ** (-0.5), rtol=1e-15, atol=0)
+    w = rng.uniform(0.5, 2, L.shape[0])
+    assert np.array_equal(host(op.adjoint_dev(dev(r), w=dev(w))), L.T @ (w * r))
+    if nt == 1:
+        L1 = O.first_derivative_1d(nx)
+        o1 = tb.FirstDerivative1D(nx)
+        z = rng.standard_normal(nx)
+        assert np.array_equal(o1 @ z, L1 @ z) and np.array_equal(o1.T @ z[:-1], L1.T @ z[:-1])
+
+
+def test_difference_operator_frame_sharding_with_halos(tb):
+    """Two 'ranks' each owning half of the frames reproduce the global operator given one-frame halos."""
+    import torch
+
+    nx, nt = 6, 6
+    N = nx * nx
+    rng = np.random.default_rng(0)
+    L = O.spacetime_derivative(nx, nx, nt)
+    x = rng.standard_normal(nt * N)
+    u_glob = L @ x
+    p2 = 2 * nx * (nx - 1)
+    lo = tb.SpaceTimeDerivative(nx, nx, 3, has_next=True)
+    hi = tb.SpaceTimeDerivative(nx, nx, 3)
+    x0, x1 = dev(x[:3 * N]), dev(x[3 * N:])
+    u0 = host(lo.apply_dev(x0, x_next=x1[:N].contiguous()))
+    u1 = host(hi.apply_dev(x1))
+    spatial = np.r_[u0[:3 * p2], u1[:3 * p2]]
+    temporal = np.r_[u0[3 * p2:], u1[3 * p2:]]
+    assert np.array_equal(spatial, u_glob[:nt * p2]) and np.array_equal(temporal, u_glob[nt * p2:])
+    r = rng.standard_normal(L.shape[0])
+    g_glob = L.T @ r
+    rs, rt = r[:nt * p2], r[nt * p2:].reshape(nt - 1, N)
+    r0 = dev(np.r_[rs[:3 * p2], rt[:3].ravel()])
+    r1 = dev(np.r_[rs[3 * p2:], rt[3:].ravel()])
+    g0 = host(lo.adjoint_dev(r0))
+    g1 = host(hi.adjoint_dev(r1, rt_prev=dev(rt[2])))
+    assert np.array_equal(np.r_[g0, g1], g_glob)

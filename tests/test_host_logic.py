@@ -1,0 +1,106 @@
+"""Host-side logic of the product that needs no GPU: the NumPy parameter-choice rules against the golden values
+of the reference, the reference's argument errors, operator bookkeeping."""
+import numpy as np
+import pytest
+
+import trips_oracle as O
+from conftest import GOLDEN
+
+
+def test_product_gcv_matches_reference_values():
+    from trips_b200.reg_param import generalized_crossvalidation
+    from trips_b200.reg_param.gcv import gcv_value
+
+    g = np.load(f"{GOLDEN}/regparam.npz")
+    B, bhat, k = g["B"], g["bhat"], g["B"].shape[1]
+    Q, s, _ = np.linalg.svd(B, full_matrices=False)
+    # the noise-free fixture has its minimum at the lower bound 1e-9, where the 'standard' objective is rounding
+    # noise (k - trace -> 0): compare the 'modified' minimiser, and objective VALUES for both variants
+    lam = generalized_crossvalidation(Q, np.diag(s), np.eye(k), bhat, variant="modified", fullsize=500)
+    assert lam == pytest.approx(float(g["lam_mod"]), rel=1e-6)
+    c = (Q.T @ bhat).reshape(-1, 1)
+    for lam in (1e-6, 1e-3, 1.0, 50.0):
+        ref = O.gcv_numerator(lam, Q, np.diag(s), np.eye(k), bhat) / O.gcv_denominator(lam, np.diag(s), np.eye(k), bhat)
+        assert gcv_value(lam, np.diag(s), np.eye(k), c, k) == pytest.approx(ref, rel=1e-9)
+    # an interior minimum: decaying spectrum, noisy right-hand side (Brent resolves ~1e-8 relative: SURVEY.md F11)
+    rng = np.random.default_rng(5)
+    m = 300
+    Qm = np.linalg.qr(rng.standard_normal((m, k)))[0]
+    RA = np.diag(np.logspace(0, -3, k)) @ (np.eye(k) + 0.1 * np.triu(rng.standard_normal((k, k)), 1))
+    bfull = Qm @ (RA @ np.ones((k, 1))) + 0.05 * rng.standard_normal((m, 1))
+    sg = np.diag([1, -1, 1, -1, -1, 1.0])
+    for RL in (np.eye(k), np.eye(k) + 0.3 * np.triu(np.ones((k, k)), 1)):
+        want = O.generalized_crossvalidation(Qm, RA, RL, bfull)
+        assert 1e-6 < want < 50  # interior minimum
+        got = generalized_crossvalidation(None, RA, RL, Qm.T @ bfull)
+        assert got == pytest.approx(want, rel=1e-6)
+        # row-sign changes of the triangular factors (Cholesky vs Householder convention) cannot change the rule
+        assert generalized_crossvalidation(None, sg @ RA, RL, sg @ (Qm.T @ bfull)) == pytest.approx(want, rel=1e-6)
+    # 'modified' denominator with the 'standard' numerator (the reference's mix) sits at the lower bound here
+    want = O.generalized_crossvalidation(Qm, RA, np.eye(k), bfull, variant="modified", fullsize=m)
+    assert generalized_crossvalidation(None, RA, np.eye(k), Qm.T @ bfull, variant="modified", fullsize=m) == pytest.approx(want, rel=1e-6)
+
+
+def test_product_discrepancy_principle_matches_reference_values():
+    from trips_b200.reg_param import discrepancy_principle, discrepancy_principle_projected
+
+    g = np.load(f"{GOLDEN}/regparam.npz")
+    B, k = g["B"], g["B"].shape[1]
+    assert discrepancy_principle(g["Qf"], B, None, g["bfull"], delta=0.5) == pytest.approx(float(g["lam_dp"]), rel=1e-11)
+    Qk = g["Qf"][:, :k]
+    lam = discrepancy_principle(Qk, g["RA"], g["RL"], g["bfull"], delta=0.8)
+    assert lam == pytest.approx(float(g["lam_dp_L"]), rel=1e-11)
+    bp = Qk.T @ g["bfull"]
+    res = np.linalg.norm(g["bfull"] - Qk @ bp)
+    assert discrepancy_principle_projected(g["RA"], g["RL"], bp, res, 0.8) == pytest.approx(float(g["lam_dp_L"]), rel=1e-11)
+    # unreachable discrepancy => lambda = 0, like the reference
+    assert discrepancy_principle_projected(g["RA"], g["RL"], bp, res, 1e-6) == 0
+    with pytest.raises(Exception, match="noise level delta"):
+        discrepancy_principle_projected(g["RA"], g["RL"], bp, res, None)
+
+
+def test_argument_errors_mirror_the_reference():
+    """Raised before any device work (Hybrid_LSQR.py:59-61, Hybrid_GMRES.py:29-31, GKS.py:32-34)."""
+    from trips_b200 import GKS, Hybrid_GMRES, Hybrid_LSQR
+
+    A = np.eye(4)
+    b = np.ones((4, 1))
+    for call in (lambda: Hybrid_LSQR(A, b, 5, regparam="dp"), lambda: Hybrid_GMRES(A, b, 5, regparam="dp"),
+                 lambda: GKS(A, b, A, regparam="dp")):
+        with pytest.raises(Exception, match="noise level delta"):
+            call()
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from trips_b200 import CGLS, as_operator
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        as_operator(np.eye(3))
+    with pytest.raises(RuntimeError):
+        CGLS(np.eye(3), np.ones(3), np.zeros((3, 1)), 2, 0)
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    import re
+
+    from conftest import ROOT
+
+    pkg = os.path.join(ROOT, "trips-py_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+(trips_oracle|ref_loader|oracle)\b", src, flags=re.M), f
+
+
+def test_gauss_psf_and_geometry_helpers_match_oracle():
+    from trips_b200.operators import ct_angles, ct_num_detectors, gauss_psf
+
+    for dim, spread in (((9, 9), (3, 3)), ((5, 7), (1.5, 2.5)), ((4, 6), 2)):
+        assert np.array_equal(gauss_psf(dim, spread), O.gauss_psf(dim, spread))
+    assert np.array_equal(ct_angles(90), O.ct_angles(90)) and ct_num_detectors(2048) == 2896 == O.ct_num_detectors(2048)

@@ -1,0 +1,258 @@
+// Parallel-beam CT system matrix, built directly on the device in CSR form, together with its explicitly
+// stored transpose (also CSR, i.e. one gather row per pixel).
+//
+// Role in the reference: the tomography operator comes from ASTRA (trips/test_problems/Tomography.py:49-88,
+// explicit-matrix idiom trips/utilities/cil_io.py:271-275, per-frame parallel beam trips/utilities/io.py:392-400).
+// ASTRA is not part of the reference tree, so this is a new synthetic problem generator with the same geometry
+// conventions (theta = linspace(0, pi, views, endpoint=False), n_det = int(sqrt(2)*nx), Tomography.py:53-56):
+// entry (ray, pixel) = length of the intersection of the ray with the unit pixel ("line" projector model).
+//
+// For a ray with unit normal (c, s) at signed distance t from the pixel centre the chord length through a unit
+// square is the trapezoid   len(t) = 1/hi                    |t| <= (hi-lo)/2
+//                                   ((hi+lo)/2 - |t|)/(hi*lo) (hi-lo)/2 < |t| < (hi+lo)/2,   hi/lo = max/min(|c|,|s|)
+// Both builders evaluate the SAME device function on the same (ray, pixel) arguments with explicitly rounded
+// arithmetic, so A and A^T hold bit-identical values and an identical sparsity pattern: the stored A^T is the
+// exact transpose of A, which the parity tests check against scipy's A.T.
+//
+// Row order of A: (local angle index)*n_det + detector; column = iy*nx + ix.  Both matrices have sorted indices.
+#include "tb200_common.cuh"
+
+namespace tb200 {
+
+struct RayGeom {
+  double c, s, hi, lo, d1, d2, inv_hi, hilo;
+};
+
+__device__ __forceinline__ RayGeom make_geom(double c, double s) {
+  RayGeom g;
+  g.c = c;
+  g.s = s;
+  const double ac = fabs(c), as = fabs(s);
+  g.hi = fmax(ac, as);
+  g.lo = fmin(ac, as);
+  g.d1 = __dmul_rn(0.5, __dsub_rn(g.hi, g.lo));
+  g.d2 = __dmul_rn(0.5, __dadd_rn(g.hi, g.lo));
+  g.inv_hi = __ddiv_rn(1.0, g.hi);
+  g.hilo = __dmul_rn(g.hi, g.lo);
+  return g;
+}
+
+// signed distance (along the detector axis) between ray offset sd and the projection of pixel centre (cx, cy)
+__device__ __forceinline__ double ray_pixel_t(const RayGeom& g, double sd, double cx, double cy) {
+  return __dsub_rn(sd, __dadd_rn(__dmul_rn(cx, g.c), __dmul_rn(cy, g.s)));
+}
+__device__ __forceinline__ bool hits(const RayGeom& g, double t) { return fabs(t) < g.d2; }
+__device__ __forceinline__ double chord(const RayGeom& g, double t) {
+  const double at = fabs(t);
+  if (at <= g.d1) return g.inv_hi;
+  return __ddiv_rn(__dsub_rn(g.d2, at), g.hilo);
+}
+
+// inclusive pixel range [lo, hi] of image row iy crossed by ray (g, sd); empty when hi < lo
+__device__ __forceinline__ void row_range(const RayGeom& g, double sd, int iy, int nx, int ny, int& lo, int& hi) {
+  const double cy = (double)iy - 0.5 * (double)(ny - 1);
+  const double x0 = 0.5 * (double)(nx - 1);
+  auto pred = [&](int ix) { return hits(g, ray_pixel_t(g, sd, (double)ix - x0, cy)); };
+  if (fabs(g.c) < 1e-9) {
+    // ray (numerically) parallel to the image rows: the footprint does not move along the row
+    lo = 0;
+    hi = nx - 1;
+    if (pred(0) && pred(nx - 1)) return;
+  } else {
+    const double q = sd - cy * g.s;
+    double e0 = (q - g.d2) / g.c, e1 = (q + g.d2) / g.c;
+    if (e0 > e1) {
+      const double tmp = e0;
+      e0 = e1;
+      e1 = tmp;
+    }
+    e0 = fmin(fmax(e0 + x0, -2.0), (double)nx + 1.0);
+    e1 = fmin(fmax(e1 + x0, -2.0), (double)nx + 1.0);
+    lo = (int)ceil(e0);
+    hi = (int)floor(e1);
+    if (lo < 0) lo = 0;
+    if (hi > nx - 1) hi = nx - 1;
+  }
+  // settle the estimate on the exact predicate (its true set is an interval: t is monotone in ix)
+  while (lo > 0 && pred(lo - 1)) --lo;
+  while (hi < nx - 1 && pred(hi + 1)) ++hi;
+  while (lo <= hi && !pred(lo)) ++lo;
+  while (hi >= lo && !pred(hi)) --hi;
+}
+
+// inclusive detector range hit by pixel (cx, cy) at angle g
+__device__ __forceinline__ void det_range(const RayGeom& g, double cx, double cy, int n_det, int& lo, int& hi) {
+  const double dc = 0.5 * (double)(n_det - 1);
+  auto pred = [&](int d) { return hits(g, ray_pixel_t(g, (double)d - dc, cx, cy)); };
+  const double p = cx * g.c + cy * g.s + dc;
+  double e0 = fmin(fmax(p - g.d2, -2.0), (double)n_det + 1.0);
+  double e1 = fmin(fmax(p + g.d2, -2.0), (double)n_det + 1.0);
+  lo = (int)ceil(e0);
+  hi = (int)floor(e1);
+  if (lo < 0) lo = 0;
+  if (hi > n_det - 1) hi = n_det - 1;
+  while (lo > 0 && pred(lo - 1)) --lo;
+  while (hi < n_det - 1 && pred(hi + 1)) ++hi;
+  while (lo <= hi && !pred(lo)) ++lo;
+  while (hi >= lo && !pred(hi)) --hi;
+}
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  total = __shfl_sync(0xffffffffu, inc, 31);
+  return inc - v;
+}
+
+// ---- A: one warp per ray -------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+ct_rows_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ cosv, const double* __restrict__ sinv,
+               int32_t* __restrict__ counts, const int64_t* __restrict__ rowptr, int32_t* __restrict__ col,
+               double* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ray >= (int64_t)n_ang * n_det) return;
+  const int a = (int)(ray / n_det), d = (int)(ray % n_det);
+  const RayGeom g = make_geom(cosv[a], sinv[a]);
+  const double sd = (double)d - 0.5 * (double)(n_det - 1);
+  const double x0 = 0.5 * (double)(nx - 1);
+  int64_t base = FILL ? rowptr[ray] : 0;
+  int total = 0;
+  for (int iy0 = 0; iy0 < ny; iy0 += 32) {
+    const int iy = iy0 + lane;
+    int lo = 0, hi = -1;
+    if (iy < ny) row_range(g, sd, iy, nx, ny, lo, hi);
+    const int cnt = (hi >= lo) ? (hi - lo + 1) : 0;
+    if (FILL) {
+      int chunk;
+      const int off = warp_excl_scan(cnt, lane, chunk);
+      const double cy = (double)iy - 0.5 * (double)(ny - 1);
+      int64_t pos = base + off;
+      for (int ix = lo; ix <= hi; ++ix, ++pos) {
+        col[pos] = iy * nx + ix;
+        val[pos] = chord(g, ray_pixel_t(g, sd, (double)ix - x0, cy));
+      }
+      base += chunk;
+    } else {
+      total += cnt;
+    }
+  }
+  if (!FILL) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) counts[ray] = total;
+  }
+}
+
+// ---- A^T: one warp per pixel ---------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+ct_cols_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ cosv, const double* __restrict__ sinv,
+               int32_t* __restrict__ counts, const int64_t* __restrict__ rowptr, int32_t* __restrict__ col,
+               double* __restrict__ val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t pix = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (pix >= (int64_t)nx * ny) return;
+  const int iy = (int)(pix / nx), ix = (int)(pix % nx);
+  const double cx = (double)ix - 0.5 * (double)(nx - 1), cy = (double)iy - 0.5 * (double)(ny - 1);
+  const double dc = 0.5 * (double)(n_det - 1);
+  int64_t base = FILL ? rowptr[pix] : 0;
+  int total = 0;
+  for (int a0 = 0; a0 < n_ang; a0 += 32) {
+    const int a = a0 + lane;
+    int lo = 0, hi = -1;
+    RayGeom g = make_geom(1.0, 0.0);
+    if (a < n_ang) {
+      g = make_geom(cosv[a], sinv[a]);
+      det_range(g, cx, cy, n_det, lo, hi);
+    }
+    const int cnt = (hi >= lo) ? (hi - lo + 1) : 0;
+    if (FILL) {
+      int chunk;
+      const int off = warp_excl_scan(cnt, lane, chunk);
+      int64_t pos = base + off;
+      for (int d = lo; d <= hi; ++d, ++pos) {
+        col[pos] = a * n_det + d;
+        val[pos] = chord(g, ray_pixel_t(g, (double)d - dc, cx, cy));
+      }
+      base += chunk;
+    } else {
+      total += cnt;
+    }
+  }
+  if (!FILL) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) counts[pix] = total;
+  }
+}
+
+}  // namespace tb200
+
+using namespace tb200;
+
+extern "C" {
+
+static int ct_args_ok(int nx, int ny, int n_det, int n_ang, const void* c, const void* s) {
+  TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0, "bad geometry");
+  TB200_REQUIRE((int64_t)nx * ny < ((int64_t)1 << 31) && (int64_t)n_ang * n_det < ((int64_t)1 << 31), "index space exceeds int32");
+  TB200_REQUIRE(n_ang == 0 || (c && s), "null angle tables");
+  return 0;
+}
+
+// counts[ray] = number of pixels crossed by ray (ray = angle*n_det + det), for the n_ang angles in cos/sin.
+int tb200_ct_count_rows(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
+                        void* stream) {
+  int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
+  if (rc) return rc;
+  const int64_t rays = (int64_t)n_ang * n_det;
+  if (rays == 0) return 0;
+  TB200_REQUIRE(counts, "null counts");
+  ct_rows_kernel<false><<<(unsigned)((rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, nullptr, nullptr);
+  return check_launch("ct_count_rows");
+}
+
+// Fills colidx/vals of A given rowptr = exclusive prefix sum of the counts.
+int tb200_ct_fill_rows(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
+                       const int64_t* rowptr, int32_t* colidx, double* vals, void* stream) {
+  int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
+  if (rc) return rc;
+  const int64_t rays = (int64_t)n_ang * n_det;
+  if (rays == 0) return 0;
+  TB200_REQUIRE(rowptr && colidx && vals, "null output");
+  ct_rows_kernel<true><<<(unsigned)((rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, colidx, vals);
+  return check_launch("ct_fill_rows");
+}
+
+// counts[pixel] = number of rays crossing the pixel (rows of A^T).
+int tb200_ct_count_cols(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
+                        void* stream) {
+  int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
+  if (rc) return rc;
+  TB200_REQUIRE(counts, "null counts");
+  const int64_t npix = (int64_t)nx * ny;
+  ct_cols_kernel<false><<<(unsigned)((npix * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, nullptr, nullptr);
+  return check_launch("ct_count_cols");
+}
+
+// Fills colidx/vals of A^T (CSR over pixels; column = angle*n_det + det) given its rowptr.
+int tb200_ct_fill_cols(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
+                       const int64_t* rowptr, int32_t* colidx, double* vals, void* stream) {
+  int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
+  if (rc) return rc;
+  TB200_REQUIRE(rowptr && colidx && vals, "null output");
+  const int64_t npix = (int64_t)nx * ny;
+  ct_cols_kernel<true><<<(unsigned)((npix * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, colidx, vals);
+  return check_launch("ct_fill_cols");
+}
+
+}  // extern "C"

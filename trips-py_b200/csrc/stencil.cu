@@ -1,0 +1,225 @@
+// Stencil operators: 2-D PSF blur (and the reference's "adjoint") and forward-difference regularisation
+// operators with the IRLS re-weighting fused in.
+//
+// PSF blur.  Reference: trips/test_problems/Deblurring2D.py:66-73
+//   A x  = scipy.ndimage.convolve(X, PSF, mode='reflect')
+//   A^T b = scipy.ndimage.convolve(B, flipud(fliplr(PSF)), mode='reflect')
+// ndimage.convolve is a correlation with the flipped kernel (origin moved by one for even sizes) and sums the
+// taps in C order with separately rounded multiply and add; the kernel below is that correlation, tap order and
+// rounding included, so the result is bit-identical to scipy's.  The host wrapper passes the flipped PSF for A
+// and the PSF itself for A^T (for centro-symmetric PSFs - every Gaussian PSF of Deblurring2D.Gauss - this is the
+// exact adjoint).  mode 0 = 'reflect' (half-sample symmetric), 1 = 'constant' (zeros; used by gen_data :121-133).
+//
+// Finite differences.  Reference: trips/utilities/operators.py:24-45 (sparse matrices there)
+//   1-D      (L x)_i = x_i - x_{i+1}, i = 0..n-2
+//   2-D      L = [ I (x) D ; D (x) I ]  on the row-major image: within-row differences first, then between rows
+//   space-time  L = [ I_t (x) L_2D ; D_t (x) I ]  on frame-major x
+// The kernels are matrix-free; L @ x can emit the IRLS weights (u^2+eps^2)^expo in the same pass
+// (MMGKS.py:60,93) and L.T @ r can apply the weights on the fly, L^T (w . r) (MMGKS.py:113-117).
+// The adjoint adds its (up to four / six) terms in the order scipy's CSC scatter does, so it is bit-identical.
+#include "tb200_common.cuh"
+
+namespace tb200 {
+
+__device__ __forceinline__ int reflect_index(int i, int n) {
+  // half-sample symmetric extension: ... b a | a b c ... y z | z y ...
+  while (i < 0 || i >= n) {
+    if (i < 0) i = -i - 1;
+    if (i >= n) i = 2 * n - 1 - i;
+  }
+  return i;
+}
+
+constexpr int kTileW = 32, kTileH = 32, kConvTy = 8;
+
+// out[i][j] = sum_{a,b in C order} W[a][b] * x[ext(i + a - ch)][ext(j + b - cw)]
+__global__ void __launch_bounds__(kTileW * kConvTy)
+correlate2d_kernel(int nrow, int ncol, const double* __restrict__ x, const double* __restrict__ W, int ph, int pw, int ch,
+                   int cw, int mode, double* __restrict__ out) {
+  extern __shared__ double sm[];
+  const int tw = kTileW + pw - 1, th = kTileH + ph - 1;
+  double* tile = sm;            // th x tw
+  double* wsm = sm + th * tw;   // ph x pw
+  const int j0 = blockIdx.x * kTileW, i0 = blockIdx.y * kTileH;
+  const int tid = threadIdx.y * kTileW + threadIdx.x, nthr = kTileW * kConvTy;
+  for (int t = tid; t < ph * pw; t += nthr) wsm[t] = W[t];
+  for (int t = tid; t < th * tw; t += nthr) {
+    const int ti = t / tw, tj = t % tw;
+    int gi = i0 + ti - ch, gj = j0 + tj - cw;
+    double v = 0.0;
+    if (mode == 0) {
+      gi = reflect_index(gi, nrow);
+      gj = reflect_index(gj, ncol);
+      v = x[(int64_t)gi * ncol + gj];
+    } else if (gi >= 0 && gi < nrow && gj >= 0 && gj < ncol) {
+      v = x[(int64_t)gi * ncol + gj];
+    }
+    tile[t] = v;
+  }
+  __syncthreads();
+  const int j = j0 + threadIdx.x;
+  if (j >= ncol) return;
+#pragma unroll
+  for (int r = 0; r < kTileH / kConvTy; ++r) {
+    const int li = threadIdx.y + r * kConvTy;
+    const int i = i0 + li;
+    if (i >= nrow) continue;
+    double acc = 0.0;
+    for (int a = 0; a < ph; ++a) {
+      const double* trow = tile + (li + a) * tw + threadIdx.x;
+      const double* wrow = wsm + a * pw;
+      for (int b = 0; b < pw; ++b) acc = __dadd_rn(acc, __dmul_rn(trow[b], wrow[b]));
+    }
+    out[(int64_t)i * ncol + j] = acc;
+  }
+}
+
+// ---- finite differences ------------------------------------------------------------------------------
+// Space-time operator on nt frames of nrow x ncol (nt = 1 and no temporal part => plain 2-D operator).
+// Output layout: [ nt * p2 spatial rows | ntr * N temporal rows ],  p2 = nrow*(ncol-1) + (nrow-1)*ncol, N = nrow*ncol,
+// ntr = nt - 1, or nt when x_next (the first frame owned by the next rank) is given.
+__global__ void __launch_bounds__(256)
+fd_apply_kernel(int nt, int nrow, int ncol, int ntr, const double* __restrict__ x, const double* __restrict__ x_next,
+                double* __restrict__ u, double* __restrict__ wout, double eps2, double expo) {
+  const int64_t N = (int64_t)nrow * ncol;
+  const int64_t p1 = (int64_t)nrow * (ncol - 1), p2 = p1 + (int64_t)(nrow - 1) * ncol;
+  const int64_t total = (int64_t)nt * p2 + (int64_t)ntr * N;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    double a, b;
+    if (q < (int64_t)nt * p2) {
+      const int64_t t = q / p2, rq = q % p2;
+      const double* xf = x + t * N;
+      if (rq < p1) {
+        const int64_t r = rq / (ncol - 1), c = rq % (ncol - 1);
+        a = xf[r * ncol + c];
+        b = xf[r * ncol + c + 1];
+      } else {
+        const int64_t e = rq - p1;
+        a = xf[e];
+        b = xf[e + ncol];
+      }
+    } else {
+      const int64_t e = q - (int64_t)nt * p2;
+      const int64_t t = e / N, p = e % N;
+      a = x[t * N + p];
+      b = (t + 1 < nt) ? x[(t + 1) * N + p] : x_next[p];
+    }
+    const double d = __dsub_rn(a, b);
+    u[q] = d;
+    if (wout != nullptr) wout[q] = pow(__dadd_rn(__dmul_rn(d, d), eps2), expo);
+  }
+}
+
+__device__ __forceinline__ double wr_at(const double* __restrict__ r, const double* __restrict__ w, int64_t i) {
+  return w ? __dmul_rn(w[i], r[i]) : r[i];
+}
+
+// out = L^T (w . r).  rt_prev: the temporal rows of the last frame owned by the previous rank (or NULL).
+__global__ void __launch_bounds__(256)
+fd_adjoint_kernel(int nt, int nrow, int ncol, int ntr, const double* __restrict__ r, const double* __restrict__ w,
+                  const double* __restrict__ rt_prev, const double* __restrict__ wt_prev, double* __restrict__ out) {
+  const int64_t N = (int64_t)nrow * ncol;
+  const int64_t p1 = (int64_t)nrow * (ncol - 1), p2 = p1 + (int64_t)(nrow - 1) * ncol;
+  const int64_t tbase = (int64_t)nt * p2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < (int64_t)nt * N; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = q / N, p = q % N;
+    const int64_t row = p / ncol, c = p % ncol;
+    const int64_t sb = t * p2;
+    double acc = 0.0;
+    // same order as scipy's csc scatter: ascending row index of L
+    if (c > 0) acc = __dsub_rn(acc, wr_at(r, w, sb + row * (ncol - 1) + c - 1));
+    if (c < ncol - 1) acc = __dadd_rn(acc, wr_at(r, w, sb + row * (ncol - 1) + c));
+    if (row > 0) acc = __dsub_rn(acc, wr_at(r, w, sb + p1 + (row - 1) * ncol + c));
+    if (row < nrow - 1) acc = __dadd_rn(acc, wr_at(r, w, sb + p1 + row * ncol + c));
+    if (t > 0) acc = __dsub_rn(acc, wr_at(r, w, tbase + (t - 1) * N + p));
+    else if (rt_prev != nullptr) acc = __dsub_rn(acc, wt_prev ? __dmul_rn(wt_prev[p], rt_prev[p]) : rt_prev[p]);
+    if (t < ntr) acc = __dadd_rn(acc, wr_at(r, w, tbase + t * N + p));
+    out[q] = acc;
+  }
+}
+
+// 1-D operator (n-1) x n and its adjoint
+__global__ void __launch_bounds__(256) fd1d_apply_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ u) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += (int64_t)gridDim.x * blockDim.x)
+    u[i] = __dsub_rn(x[i], x[i + 1]);
+}
+__global__ void __launch_bounds__(256) fd1d_adjoint_kernel(int64_t n, const double* __restrict__ r, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    if (i > 0) acc = __dsub_rn(acc, r[i - 1]);
+    if (i < n - 1) acc = __dadd_rn(acc, r[i]);
+    out[i] = acc;
+  }
+}
+
+}  // namespace tb200
+
+using namespace tb200;
+
+extern "C" {
+
+// out = correlate(x, W) with ndimage tap order; ch/cw = index of the tap that sits on the output pixel.
+// mode 0 reflect, 1 constant-zero.
+int tb200_correlate2d_f64(int nrow, int ncol, const double* x, const double* W, int ph, int pw, int ch, int cw, int mode,
+                          double* out, void* stream) {
+  TB200_REQUIRE(nrow > 0 && ncol > 0 && ph > 0 && pw > 0 && x && W && out, "bad argument");
+  TB200_REQUIRE(ch >= 0 && ch < ph && cw >= 0 && cw < pw && (mode == 0 || mode == 1), "bad centre or mode");
+  TB200_REQUIRE(x != out, "in-place convolution is not supported");
+  const size_t smem = ((size_t)(kTileW + pw - 1) * (kTileH + ph - 1) + (size_t)ph * pw) * sizeof(double);
+  TB200_REQUIRE(smem <= 200 * 1024, "PSF too large for the shared-memory tile");
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(correlate2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("correlate2d: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
+  dim3 grid((ncol + kTileW - 1) / kTileW, (nrow + kTileH - 1) / kTileH), block(kTileW, kConvTy);
+  correlate2d_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(nrow, ncol, x, W, ph, pw, ch, cw, mode, out);
+  return check_launch("correlate2d");
+}
+
+// Number of rows of the space-time operator for nt local frames (temporal rows: nt-1, or nt with a halo frame).
+int64_t tb200_fd_rows(int nt, int nrow, int ncol, int has_next) {
+  const int64_t p2 = (int64_t)nrow * (ncol - 1) + (int64_t)(nrow - 1) * ncol;
+  return (int64_t)nt * p2 + (int64_t)(has_next ? nt : nt - 1) * nrow * ncol;
+}
+
+// u = L x (space-time forward differences; nt = 1 => the 2-D operator). Optional fused weights
+// wout = (u^2 + eps^2)^expo.  x_next: first frame of the next rank (device pointer) or NULL.
+int tb200_fd_apply(int nt, int nrow, int ncol, const double* x, const double* x_next, double* u, double* wout, double eps,
+                   double expo, void* stream) {
+  TB200_REQUIRE(nt >= 1 && nrow >= 1 && ncol >= 1 && x && u, "bad argument");
+  const int ntr = x_next ? nt : nt - 1;
+  const int64_t total = tb200_fd_rows(nt, nrow, ncol, x_next != nullptr);
+  if (total == 0) return 0;
+  fd_apply_kernel<<<grid_for(total, 256 * 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(nt, nrow, ncol, ntr, x, x_next, u,
+                                                                                      wout, eps * eps, expo);
+  return check_launch("fd_apply");
+}
+
+// out = L^T (w . r)  (w may be NULL).  has_next selects the row layout used by tb200_fd_apply;
+// rt_prev / wt_prev: temporal rows (and their weights) of the previous rank's last frame, or NULL.
+int tb200_fd_adjoint(int nt, int nrow, int ncol, int has_next, const double* r, const double* w, const double* rt_prev,
+                     const double* wt_prev, double* out, void* stream) {
+  TB200_REQUIRE(nt >= 1 && nrow >= 1 && ncol >= 1 && r && out, "bad argument");
+  const int ntr = has_next ? nt : nt - 1;
+  const int64_t total = (int64_t)nt * nrow * ncol;
+  fd_adjoint_kernel<<<grid_for(total, 256 * 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(nt, nrow, ncol, ntr, r, w, rt_prev,
+                                                                                        wt_prev, out);
+  return check_launch("fd_adjoint");
+}
+
+int tb200_fd1d_apply(int64_t n, const double* x, double* u, void* stream) {
+  TB200_REQUIRE(n >= 1 && x && u, "bad argument");
+  if (n == 1) return 0;
+  fd1d_apply_kernel<<<grid_for(n, 256 * 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(n, x, u);
+  return check_launch("fd1d_apply");
+}
+int tb200_fd1d_adjoint(int64_t n, const double* r, double* out, void* stream) {
+  TB200_REQUIRE(n >= 1 && r && out, "bad argument");
+  fd1d_adjoint_kernel<<<grid_for(n, 256 * 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(n, r, out);
+  return check_launch("fd1d_adjoint");
+}
+
+}  // extern "C"

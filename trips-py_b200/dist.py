@@ -1,0 +1,125 @@
+"""Multi-GPU sharding for static CT: rows of A by projection angle, one process per GPU (torchrun / torch.distributed).
+
+The reference has no parallelism of any kind; this layer is new.
+
+Partition: angle a goes to rank a mod G (round robin: nnz per angle varies with
+|cos|+|sin|, contiguous blocks would be imbalanced).  Rank g holds A_g (its angles' rows), the explicit transpose
+A_g^T, b_g and its slice U_g of the left basis.  One Golub-Kahan step is
+    z_g = A_g^T u_g                      local SpMV (gather form, deterministic)
+    z   = sum_g z_g                      ONE all-reduce of an n-vector over NVLink (33.5 MB at 2048^2)
+    v   = z - beta v_prev ; alpha = ||v||; v /= alpha      replicated, bitwise identical on every rank
+    u_g = A_g v - alpha u_g              local SpMV with fused recurrence and local ||u_g||^2
+    beta^2 = sum_g ||u_g||^2             one scalar all-reduce
+There is no other data-path communication: u-space vectors never leave their rank.
+
+The arithmetic is delegated to a small backend object so the distributed algebra can be exercised on CPU with the
+gloo backend in tests (tests/test_dist_gloo.py supplies a NumPy stand-in); the product backend below is the CUDA
+kernels.  The package itself has no CPU path.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+from .kernels import F64
+
+
+def shard_angles(views, world_size, rank):
+    """Angle indices owned by `rank`: round robin over ranks."""
+    return np.arange(rank, views, world_size)
+
+
+def gather_sinogram_order(views, world_size, n_det):
+    """Permutation that maps the concatenation of the ranks' local sinograms back to angle-major order."""
+    order = np.concatenate([shard_angles(views, world_size, r) for r in range(world_size)])
+    inv = np.empty(views, dtype=np.int64)
+    inv[order] = np.arange(views)
+    return (inv[:, None] * n_det + np.arange(n_det)[None, :]).reshape(-1)
+
+
+class CudaBackend:
+    """Vector operations of the distributed step on the CUDA kernels (1-D float64 CUDA tensors)."""
+
+    def empty(self, n, like):
+        return torch.empty(n, dtype=F64, device=like.device)
+
+    def zeros(self, n, like):
+        return torch.zeros(n, dtype=F64, device=like.device)
+
+    def apply(self, op, x, out, coef=None, z=None, norm_out=None):
+        return op.apply_dev(x, out=out, coef=coef, z=z, norm_out=norm_out)
+
+    def adjoint(self, op, u, out):
+        return op.adjoint_dev(u, out=out)
+
+    def axpy_norm(self, a, x, y, out, norm_out, sign):
+        return K.vec_axpy(a, x, y, out=out, norm_out=norm_out, sign=sign)
+
+    def norm2(self, x, out):
+        return K.vec_norm2(x, out=out)
+
+    def div(self, x, d, out):
+        return K.vec_div(x, d, out=out)
+
+    def sqrt_(self, pair):
+        pair[1:2] = torch.sqrt(pair[0:1])
+
+
+class DistGKState:
+    """Golub-Kahan bidiagonalisation with rows sharded by angle.  `A_local` is this rank's CSROperator, `b_local`
+    its part of the right-hand side.  With world_size == 1 (or no process group) it degenerates to GKState."""
+
+    def __init__(self, A_local, b_local, kmax, backend=None, group=None):
+        self.A, self.be = A_local, backend or CudaBackend()
+        self.group = group
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        m, n = A_local.shape
+        be = self.be
+        self.kmax = kmax
+        self.U = [be.empty(m, b_local) for _ in range(kmax + 1)]
+        self.V = [be.empty(n, b_local) for _ in range(kmax)]
+        self.alpha = [be.zeros(2, b_local) for _ in range(kmax)]
+        self.beta = [be.zeros(2, b_local) for _ in range(kmax)]
+        self.beta0 = be.zeros(2, b_local)
+        self.k = 0
+        be.norm2(b_local, self.beta0)
+        self._allreduce_sq(self.beta0)
+        be.div(b_local, self.beta0[1:2], self.U[0])
+
+    def _allreduce_sq(self, pair):
+        """pair[0] holds a local sum of squares: make it global and refresh pair[1] = sqrt."""
+        if self.distributed:
+            dist.all_reduce(pair[0:1], op=dist.ReduceOp.SUM, group=self.group)
+            self.be.sqrt_(pair)
+
+    def step(self):
+        k, be = self.k, self.be
+        if k >= self.kmax:
+            raise RuntimeError("DistGKState capacity exceeded")
+        u_k, v = self.U[k], self.V[k]
+        be.adjoint(self.A, u_k, v)  # z_g = A_g^T u_g
+        if self.distributed:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)  # z = sum_g z_g
+        if k == 0:
+            be.norm2(v, self.alpha[k])
+        else:
+            be.axpy_norm(self.beta[k - 1][1:2], self.V[k - 1], v, v, self.alpha[k], -1.0)  # v = z - beta v_prev
+        be.div(v, self.alpha[k][1:2], v)
+        u = self.U[k + 1]
+        be.apply(self.A, v, u, coef=self.alpha[k][1:2], z=u_k, norm_out=self.beta[k])  # u_g = A_g v - alpha u_g
+        self._allreduce_sq(self.beta[k])
+        be.div(u, self.beta[k][1:2], u)
+        self.k += 1
+
+    def scalars_host(self):
+        k = self.k
+        to = lambda t: float(t[1])  # noqa: E731
+        return to(self.beta0), np.array([to(a) for a in self.alpha[:k]]), np.array([to(b) for b in self.beta[:k]])
+
+    def B_host(self):
+        _, al, be = self.scalars_host()
+        k = al.size
+        B = np.zeros((k + 1, k))
+        B[np.arange(k), np.arange(k)] = al
+        B[np.arange(1, k + 1), np.arange(k)] = be
+        return B

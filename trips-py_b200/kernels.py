@@ -1,0 +1,419 @@
+"""Thin torch-tensor front end over the C ABI: shape/dtype checks, workspaces, stream plumbing.
+
+PyTorch is used only for device memory and streams.  Every function enqueues on torch's current stream and
+returns without synchronising.  Vectors are 1-D float64 CUDA tensors; a Basis is a (kmax, n) row-major tensor,
+i.e. column j of the mathematical basis is the contiguous row j.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import c_ptr, check, lib
+
+F64 = torch.float64
+
+
+def _p(t):
+    return None if t is None else c_ptr(t.data_ptr())
+
+
+def _stream():
+    return c_ptr(torch.cuda.current_stream().cuda_stream)
+
+
+def _vec(t, n=None, name="vector"):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == F64 and t.dim() == 1 and t.is_contiguous()):
+        raise TypeError(f"{name} must be a contiguous 1-D float64 CUDA tensor")
+    if n is not None and t.numel() != n:
+        raise ValueError(f"{name} has {t.numel()} elements, expected {n}")
+    return t
+
+
+class Workspace:
+    """Caller-owned scratch the library asks for (tb200_*_workspace_len), cached per device."""
+
+    _cache = {}
+
+    def __init__(self, device):
+        self.device = device
+        self._bufs = {}
+        self.scalars = torch.zeros(64, dtype=F64, device=device)  # small pool of device scalars / norm pairs
+        self._next = 0
+
+    @classmethod
+    def get(cls, device):
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        ws = cls._cache.get(device)
+        if ws is None:
+            _lib.require_device()
+            ws = cls._cache[device] = Workspace(device)
+        return ws
+
+    def buf(self, key, length):
+        length = max(int(length), 1)
+        t = self._bufs.get(key)
+        if t is None or t.numel() < length:
+            t = self._bufs[key] = torch.empty(length, dtype=F64, device=self.device)
+        return t
+
+    def reduce(self):
+        return self.buf("reduce", lib().tb200_reduce_workspace_len())
+
+    def spmv(self, m):
+        return self.buf("spmv", lib().tb200_spmv_workspace_len(int(m)))
+
+    def basis(self, k):
+        return self.buf("basis", lib().tb200_basis_workspace_len(int(k)))
+
+    def gram(self, K):
+        return self.buf("gram", lib().tb200_gram_workspace_len(int(K)))
+
+    def pair(self):
+        """A fresh 2-double slot (sum of squares, norm) from a small ring."""
+        i = self._next
+        self._next = (i + 2) % 64
+        return self.scalars[i:i + 2]
+
+
+def new_pair(device):
+    return torch.zeros(2, dtype=F64, device=device)
+
+
+# ---- SpMV ---------------------------------------------------------------------------------------------------
+
+class CSRDevice:
+    """One CSR matrix resident in HBM: int64 rowptr, int32 colidx, fp64 (or fp32) vals."""
+
+    def __init__(self, shape, rowptr, colidx, vals):
+        self.shape = (int(shape[0]), int(shape[1]))
+        if rowptr.dtype != torch.int64 or colidx.dtype != torch.int32 or vals.dtype not in (F64, torch.float32):
+            raise TypeError("CSRDevice needs int64 rowptr, int32 colidx and float64/float32 vals")
+        if rowptr.numel() != self.shape[0] + 1:
+            raise ValueError("rowptr length must be m+1")
+        if self.shape[1] >= 2 ** 31:
+            raise ValueError("column count must fit int32")
+        self.rowptr, self.colidx, self.vals = rowptr.contiguous(), colidx.contiguous(), vals.contiguous()
+        self.nnz = int(colidx.numel())
+        if self.vals.numel() != self.nnz:
+            raise ValueError("colidx and vals differ in length")
+        if self.nnz and (self.vals.data_ptr() % 32 or self.colidx.data_ptr() % 16):
+            raise ValueError("vals must be 32-byte aligned and colidx 16-byte aligned")
+        self.device = self.vals.device
+
+    @property
+    def nbytes(self):
+        return self.nnz * (4 + self.vals.element_size()) + 8 * (self.shape[0] + 1)
+
+    def to_f32_storage(self):
+        return CSRDevice(self.shape, self.rowptr, self.colidx, self.vals.to(torch.float32))
+
+
+def spmv(A, x, out=None, coef=None, z=None, norm_out=None):
+    """out = A x - coef*z (z/coef optional), optionally norm_out[:] = (||out||^2, ||out||).
+
+    coef may be a Python float or a 1-element device tensor (kept on the device, no sync)."""
+    m, n = A.shape
+    _vec(x, n, "x")
+    if out is None:
+        out = torch.empty(m, dtype=F64, device=A.device)
+    _vec(out, m, "out")
+    coef_host, coef_dev = 0.0, None
+    if z is not None:
+        _vec(z, m, "z")
+        if isinstance(coef, torch.Tensor):
+            coef_dev = coef
+        else:
+            coef_host = float(coef)
+    ws = Workspace.get(A.device).spmv(m) if norm_out is not None else None
+    fn = lib().tb200_spmv_csr_f64 if A.vals.dtype == F64 else lib().tb200_spmv_csr_f32s
+    check(fn(m, n, A.nnz, _p(A.rowptr), _p(A.colidx), _p(A.vals), _p(x), _p(out), coef_host, _p(coef_dev), _p(z),
+             _p(norm_out), _p(ws), _stream()), "spmv")
+    _lib.count(2 if norm_out is not None else 1)
+    return out
+
+
+# ---- BLAS-1 -------------------------------------------------------------------------------------------------
+
+def _scalar(a):
+    if isinstance(a, torch.Tensor):
+        return 0.0, a
+    return float(a), None
+
+
+def vec_div(x, d, out=None):
+    n = x.numel()
+    out = torch.empty_like(x) if out is None else _vec(out, n, "out")
+    dh, dd = _scalar(d)
+    check(lib().tb200_vec_div(n, _p(_vec(x)), dh, _p(dd), _p(out), _stream()), "vec_div")
+    _lib.count()
+    return out
+
+
+def vec_axpy(a, x, y, out=None, norm_out=None, sign=1.0):
+    """out = y + sign*(a*x) with sign = +-1 (two roundings, as NumPy)."""
+    n = x.numel()
+    _vec(x), _vec(y, n, "y")
+    out = torch.empty_like(x) if out is None else _vec(out, n, "out")
+    ah, ad = _scalar(a)
+    ws = Workspace.get(x.device).reduce() if norm_out is not None else None
+    check(lib().tb200_vec_axpy(n, ah, _p(ad), float(sign), _p(x), _p(y), _p(out), _p(norm_out), _p(ws), _stream()), "vec_axpy")
+    _lib.count(2 if norm_out is not None else 1)
+    return out
+
+
+def _reduce(fn, name, x, y, out):
+    n = x.numel()
+    _vec(x)
+    if y is not None:
+        _vec(y, n, "y")
+    if out is None:
+        out = new_pair(x.device)
+    ws = Workspace.get(x.device).reduce()
+    if y is None:
+        check(fn(n, _p(x), _p(out), _p(ws), _stream()), name)
+    else:
+        check(fn(n, _p(x), _p(y), _p(out), _p(ws), _stream()), name)
+    _lib.count(2)
+    return out
+
+
+def vec_norm2(x, out=None):
+    """out = (sum x^2, ||x||) on the device."""
+    return _reduce(lib().tb200_vec_norm2, "vec_norm2", x, None, out)
+
+
+def vec_dot(x, y, out=None):
+    return _reduce(lib().tb200_vec_dot, "vec_dot", x, y, out)
+
+
+def vec_diffnorm2(x, y, out=None):
+    return _reduce(lib().tb200_vec_diffnorm2, "vec_diffnorm2", x, y, out)
+
+
+def vec_binary(mode, x, y, w=None, out=None):
+    n = x.numel()
+    _vec(x), _vec(y, n, "y")
+    if w is not None:
+        _vec(w, n, "w")
+    out = torch.empty_like(x) if out is None else _vec(out, n, "out")
+    check(lib().tb200_vec_binary(int(mode), n, _p(x), _p(y), _p(w), _p(out), _stream()), "vec_binary")
+    _lib.count()
+    return out
+
+
+def vec_mul(x, y, out=None):
+    return vec_binary(0, x, y, out=out)
+
+
+def vec_sub(x, y, out=None):
+    return vec_binary(1, x, y, out=out)
+
+
+def vec_wsub(w, x, y, out=None):
+    """out = w * (x - y)"""
+    return vec_binary(2, x, y, w=w, out=out)
+
+
+def vec_add(x, y, out=None):
+    return vec_binary(3, x, y, out=out)
+
+
+def irls_weights(v, eps, expo, out=None):
+    n = v.numel()
+    out = torch.empty_like(v) if out is None else _vec(out, n, "out")
+    check(lib().tb200_irls_weights(n, _p(_vec(v)), float(eps), float(expo), _p(out), _stream()), "irls_weights")
+    _lib.count()
+    return out
+
+
+# ---- basis ----------------------------------------------------------------------------------------------------
+
+class Basis:
+    """Pre-allocated column store: kmax columns of length n, column j = row j of a (kmax, n) tensor.
+
+    Appending is a pointer bump; the reference re-copies the whole basis with np.hstack / np.column_stack at
+    every iteration (decompositions.py:243-247, GKS.py:91-96)."""
+
+    def __init__(self, n, kmax, device):
+        self.n, self.kmax = int(n), int(kmax)
+        self.data = torch.empty((self.kmax, self.n), dtype=F64, device=device)
+        self.k = 0
+
+    def col(self, j):
+        if j < 0:
+            j += self.k
+        return self.data[j]
+
+    def next_col(self):
+        """The (not yet counted) slot a kernel should write the next column into."""
+        if self.k >= self.kmax:
+            self._grow()
+        return self.data[self.k]
+
+    def push(self):
+        self.k += 1
+
+    def _grow(self):
+        new = torch.empty((max(2 * self.kmax, 4), self.n), dtype=F64, device=self.data.device)
+        new[:self.k].copy_(self.data[:self.k])
+        self.data, self.kmax = new, new.shape[0]
+
+    def to_numpy(self, k=None):
+        k = self.k if k is None else k
+        return self.data[:k].T.cpu().numpy()
+
+
+def basis_dots(V, k, w, out=None):
+    """h[0:k] = V[:, :k]^T w"""
+    data = V.data if isinstance(V, Basis) else V
+    n = data.shape[1]
+    _vec(w, n, "w")
+    if out is None:
+        out = torch.empty(max(k, 1), dtype=F64, device=w.device)
+    if k == 0:
+        return out
+    ws = Workspace.get(w.device).basis(k)
+    check(lib().tb200_basis_dots(n, int(k), _p(data), n, _p(w), _p(out), _p(ws), _stream()), "basis_dots")
+    _lib.count(2)
+    return out
+
+
+def basis_combine(V, k, h, w=None, sign=1.0, out=None, norm_out=None):
+    """out = w + sign * V[:, :k] h  (w None: out = sign * V h)."""
+    data = V.data if isinstance(V, Basis) else V
+    n = data.shape[1]
+    if out is None:
+        out = torch.empty(n, dtype=F64, device=data.device)
+    _vec(out, n, "out")
+    if w is not None:
+        _vec(w, n, "w")
+    ws = Workspace.get(data.device).basis(1) if norm_out is not None else None
+    check(lib().tb200_basis_combine(n, int(k), _p(data), n, _p(h), _p(w), float(sign), _p(out), _p(norm_out), _p(ws),
+                                    _stream()), "basis_combine")
+    _lib.count(2 if norm_out is not None else 1)
+    return out
+
+
+def weighted_gram(B, k, w=None, extras=(), extra_weighted=()):
+    """Double-double Gram matrix of [diag(w) B[:, :k] | extras]; returns host arrays (Ghi, Glo) of shape (K, K)."""
+    data = B.data if isinstance(B, Basis) else B
+    m = data.shape[1]
+    ne = len(extras)
+    K = int(k) + ne
+    dev = data.device
+    Ghi = torch.empty((K, K), dtype=F64, device=dev)
+    Glo = torch.empty((K, K), dtype=F64, device=dev)
+    ws = Workspace.get(dev).gram(K)
+    ext = (ctypes.c_void_p * max(ne, 1))(*[e.data_ptr() for e in extras]) if ne else None
+    ewt = (ctypes.c_int * max(ne, 1))(*[int(bool(f)) for f in extra_weighted]) if ne else None
+    for e in extras:
+        _vec(e, m, "extra column")
+    if w is not None:
+        _vec(w, m, "w")
+    check(lib().tb200_weighted_gram(m, int(k), _p(data), m, _p(w), ne, ext, ewt, _p(Ghi), _p(Glo), _p(ws), _stream()),
+          "weighted_gram")
+    _lib.count(2)
+    both = torch.stack((Ghi, Glo)).cpu().numpy()  # one D2H, synchronises
+    return both[0], both[1]
+
+
+def gram_factor(Ghi, Glo, k):
+    """Host double-double Cholesky of the leading k x k block: returns (R, C, resid2) as in tb200_gram_factor_dd."""
+    K = Ghi.shape[0]
+    ne = K - k
+    Ghi = np.ascontiguousarray(Ghi, dtype=np.float64)
+    Glo = np.ascontiguousarray(Glo, dtype=np.float64)
+    R = np.zeros((k, k))
+    C = np.zeros((k, max(ne, 1)))
+    res = np.zeros(max(ne, 1))
+    rc = lib().tb200_gram_factor_dd(k, ne, Ghi.ctypes.data, Glo.ctypes.data, R.ctypes.data, C.ctypes.data, res.ctypes.data)
+    if rc != 0:
+        raise np.linalg.LinAlgError(f"Gram matrix is not positive definite at leading minor {rc}")
+    return R, C[:, :ne], res[:ne]
+
+
+# ---- CT builder ---------------------------------------------------------------------------------------------
+
+def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False):
+    """Build A (rows = rays) or A^T (rows = pixels) for the angles in the device tables cos_t/sin_t."""
+    dev = cos_t.device
+    n_ang = cos_t.numel()
+    rows = nx * ny if transpose else n_ang * n_det
+    counts = torch.zeros(rows, dtype=torch.int32, device=dev)
+    cnt_fn = lib().tb200_ct_count_cols if transpose else lib().tb200_ct_count_rows
+    fill_fn = lib().tb200_ct_fill_cols if transpose else lib().tb200_ct_fill_rows
+    check(cnt_fn(nx, ny, n_det, n_ang, _p(cos_t), _p(sin_t), _p(counts), _stream()), "ct_count")
+    rowptr = torch.zeros(rows + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=rowptr[1:])
+    del counts
+    nnz = int(rowptr[-1].item())
+    colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+    vals = torch.empty(max(nnz, 1), dtype=F64, device=dev)[:nnz]
+    check(fill_fn(nx, ny, n_det, n_ang, _p(cos_t), _p(sin_t), _p(rowptr), _p(colidx), _p(vals), _stream()), "ct_fill")
+    _lib.count(2)
+    shape = (nx * ny, n_ang * n_det) if transpose else (n_ang * n_det, nx * ny)
+    return CSRDevice(shape, rowptr, colidx, vals)
+
+
+# ---- stencils -------------------------------------------------------------------------------------------------
+
+def correlate2d(x, W, nrow, ncol, ch, cw, mode=0, out=None):
+    ph, pw = W.shape
+    _vec(x, nrow * ncol, "image")
+    out = torch.empty_like(x) if out is None else _vec(out, nrow * ncol, "out")
+    check(lib().tb200_correlate2d_f64(nrow, ncol, _p(x), _p(W), ph, pw, ch, cw, mode, _p(out), _stream()), "correlate2d")
+    _lib.count()
+    return out
+
+
+def fd_rows(nt, nrow, ncol, has_next=False):
+    return int(lib().tb200_fd_rows(nt, nrow, ncol, int(has_next)))
+
+
+def fd_apply(x, nt, nrow, ncol, x_next=None, out=None, wout=None, eps=0.0, expo=0.0):
+    rows = fd_rows(nt, nrow, ncol, x_next is not None)
+    _vec(x, nt * nrow * ncol, "x")
+    if out is None:
+        out = torch.empty(rows, dtype=F64, device=x.device)
+    _vec(out, rows, "out")
+    if wout is not None:
+        _vec(wout, rows, "wout")
+    check(lib().tb200_fd_apply(nt, nrow, ncol, _p(x), _p(x_next), _p(out), _p(wout), float(eps), float(expo), _stream()),
+          "fd_apply")
+    _lib.count()
+    return out
+
+
+def fd_adjoint(r, nt, nrow, ncol, has_next=False, w=None, rt_prev=None, wt_prev=None, out=None):
+    rows = fd_rows(nt, nrow, ncol, has_next)
+    _vec(r, rows, "r")
+    if w is not None:
+        _vec(w, rows, "w")
+    if out is None:
+        out = torch.empty(nt * nrow * ncol, dtype=F64, device=r.device)
+    check(lib().tb200_fd_adjoint(nt, nrow, ncol, int(has_next), _p(r), _p(w), _p(rt_prev), _p(wt_prev), _p(out), _stream()),
+          "fd_adjoint")
+    _lib.count()
+    return out
+
+
+def fd1d_apply(x, out=None):
+    n = x.numel()
+    if out is None:
+        out = torch.empty(max(n - 1, 0), dtype=F64, device=x.device)
+    check(lib().tb200_fd1d_apply(n, _p(x), _p(out), _stream()), "fd1d_apply")
+    _lib.count()
+    return out
+
+
+def fd1d_adjoint(r, out=None):
+    n = r.numel() + 1
+    if out is None:
+        out = torch.empty(n, dtype=F64, device=r.device)
+    check(lib().tb200_fd1d_adjoint(n, _p(r), _p(out), _stream()), "fd1d_adjoint")
+    _lib.count()
+    return out

@@ -1,0 +1,476 @@
+"""Operators for the reference's `A` / `L` arguments, backed by the sm_100a kernels.
+
+The reference has no plugin registry: the API is duck typing on the object passed as A or L
+(SURVEY.md section 8b).  The operations it uses are `.shape`, `A @ x`, `A.T @ y` with x 1-D, an (n,1) column or
+an n x k block, `L * v`, `.todense()`, and `isinstance(., pylops.LinearOperator)`
+(trips/solvers/Hybrid_LSQR.py:63,102; GKS.py:37-38,84,95; MMGKS.py:43-60,117,127;
+trips/utilities/decompositions.py:177-181,212,235-240).  `LinearOperator` below provides that surface (and
+subclasses pylops.LinearOperator when pylops is importable), so these objects can be handed to the reference's
+own solvers unchanged: NumPy in -> H2D -> kernel -> D2H -> NumPy out.  The solvers of this package call the
+device-level methods (`apply_dev` / `adjoint_dev`) on torch CUDA tensors with no host round trip.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import kernels as K
+from .kernels import F64, CSRDevice
+
+try:  # pragma: no cover - pylops is not installed in the build image
+    if os.environ.get("TRIPS_B200_NO_PYLOPS"):
+        raise ImportError
+    from pylops import LinearOperator as _PylopsBase
+except Exception:  # noqa: BLE001
+    _PylopsBase = None
+
+_Base = _PylopsBase if _PylopsBase is not None else object
+
+
+def default_device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("trips_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device_vector(x, device):
+    """1-D float64 CUDA tensor from a NumPy array / torch tensor of shape (n,) or (n,1)."""
+    if isinstance(x, torch.Tensor):
+        t = x.reshape(-1)
+        if t.device != device or t.dtype != F64:
+            t = t.to(device=device, dtype=F64)
+        return t.contiguous()
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+    return torch.from_numpy(a).to(device)
+
+
+class LinearOperator(_Base):
+    """pylops-style linear operator whose arithmetic runs on the GPU.
+
+    Subclasses implement `apply_dev(x, out=None)` and `adjoint_dev(y, out=None)` on 1-D float64 CUDA tensors."""
+
+    fused = False  # True: apply_dev/adjoint_dev accept coef=, z=, norm_out= (fused recurrence epilogue)
+
+    def __init__(self, shape, device=None, dtype=np.float64):
+        self._tb_shape = (int(shape[0]), int(shape[1]))
+        self._tb_dtype = np.dtype(dtype)
+        self.device = torch.device(device) if device is not None else default_device()
+        if _PylopsBase is not None:  # pragma: no cover
+            try:
+                _PylopsBase.__init__(self, dtype=self._tb_dtype, shape=self._tb_shape)
+            except Exception:  # noqa: BLE001
+                pass
+
+    # -- metadata ------------------------------------------------------------------------------------------
+    @property
+    def shape(self):
+        return self._tb_shape
+
+    @shape.setter
+    def shape(self, value):  # pylops' constructor assigns it
+        self._tb_shape = (int(value[0]), int(value[1]))
+
+    @property
+    def dtype(self):
+        return self._tb_dtype
+
+    @dtype.setter
+    def dtype(self, value):
+        self._tb_dtype = np.dtype(value)
+
+    # -- device level (subclasses) -----------------------------------------------------------------------------
+    def apply_dev(self, x, out=None):
+        raise NotImplementedError
+
+    def adjoint_dev(self, y, out=None):
+        raise NotImplementedError
+
+    # -- host/torch level ----------------------------------------------------------------------------------------
+    def _run(self, fn, x, n_in):
+        if isinstance(x, torch.Tensor):
+            if x.dim() == 2 and x.shape[1] > 1:
+                cols = [fn(to_device_vector(x[:, j], self.device)) for j in range(x.shape[1])]
+                return torch.stack(cols, dim=1)
+            y = fn(to_device_vector(x, self.device))
+            return y.reshape(-1, 1) if x.dim() == 2 else y
+        a = np.asarray(x)
+        if a.ndim == 2 and a.shape[1] > 1:
+            if a.shape[0] != n_in:
+                raise ValueError(f"dimension mismatch: operator expects {n_in} rows, got {a.shape}")
+            return np.stack([fn(to_device_vector(a[:, j], self.device)).cpu().numpy() for j in range(a.shape[1])], axis=1)
+        if a.size != n_in:
+            raise ValueError(f"dimension mismatch: operator expects {n_in} elements, got {a.shape}")
+        y = fn(to_device_vector(a, self.device)).cpu().numpy()
+        return y.reshape(-1, 1) if a.ndim == 2 else y
+
+    def matvec(self, x):
+        return self._run(self.apply_dev, x, self.shape[1])
+
+    def rmatvec(self, y):
+        return self._run(self.adjoint_dev, y, self.shape[0])
+
+    matmat = matvec
+    rmatmat = rmatvec
+    # pylops back ends call these
+    _matvec = matvec
+    _rmatvec = rmatvec
+
+    def dot(self, x):
+        if np.isscalar(x):
+            return _Scaled(self, float(x))
+        if isinstance(x, LinearOperator):
+            return _Product(self, x)
+        return self.matvec(x)
+
+    def __matmul__(self, x):
+        return self.dot(x)
+
+    def __mul__(self, x):
+        return self.dot(x)
+
+    def __rmul__(self, x):
+        if np.isscalar(x):
+            return _Scaled(self, float(x))
+        return NotImplemented
+
+    def __call__(self, x):
+        return self.dot(x)
+
+    @property
+    def T(self):
+        return _Adjoint(self)
+
+    @property
+    def H(self):
+        return _Adjoint(self)
+
+    def adjoint(self):
+        return _Adjoint(self)
+
+    def transpose(self):
+        return _Adjoint(self)
+
+    def todense(self):
+        """Dense matrix by applying the operator to the identity (as pylops does); for small operators only."""
+        m, n = self.shape
+        out = np.empty((m, n))
+        e = torch.zeros(n, dtype=F64, device=self.device)
+        for j in range(n):
+            e.zero_()
+            e[j] = 1.0
+            out[:, j] = self.apply_dev(e).cpu().numpy()
+        return out
+
+    def __repr__(self):
+        return f"<{self.shape[0]}x{self.shape[1]} {type(self).__name__} on {self.device}>"
+
+
+class _Adjoint(LinearOperator):
+    def __init__(self, op):
+        super().__init__((op.shape[1], op.shape[0]), op.device, op.dtype)
+        self.op = op
+        self.fused = op.fused
+
+    def apply_dev(self, x, out=None, **kw):
+        return self.op.adjoint_dev(x, out=out, **kw)
+
+    def adjoint_dev(self, y, out=None, **kw):
+        return self.op.apply_dev(y, out=out, **kw)
+
+    @property
+    def T(self):
+        return self.op
+
+    H = T
+
+
+class _Scaled(LinearOperator):
+    def __init__(self, op, a):
+        super().__init__(op.shape, op.device, op.dtype)
+        self.op, self.a = op, a
+
+    def apply_dev(self, x, out=None):
+        y = self.op.apply_dev(x, out=out)
+        return y.mul_(self.a)
+
+    def adjoint_dev(self, y, out=None):
+        x = self.op.adjoint_dev(y, out=out)
+        return x.mul_(self.a)
+
+
+class _Product(LinearOperator):
+    """A @ B as an operator (e.g. the square operator A^T A handed to Hybrid_GMRES)."""
+
+    def __init__(self, a, b):
+        if a.shape[1] != b.shape[0]:
+            raise ValueError("operator shapes do not chain")
+        super().__init__((a.shape[0], b.shape[1]), a.device, a.dtype)
+        self.a, self.b = a, b
+        self._tmp = None
+
+    def _mid(self):
+        if self._tmp is None:
+            self._tmp = torch.empty(self.a.shape[1], dtype=F64, device=self.device)
+        return self._tmp
+
+    def apply_dev(self, x, out=None):
+        return self.a.apply_dev(self.b.apply_dev(x, out=self._mid()), out=out)
+
+    def adjoint_dev(self, y, out=None):
+        return self.b.adjoint_dev(self.a.adjoint_dev(y, out=self._mid()), out=out)
+
+
+class Identity(LinearOperator):
+    def __init__(self, n, device=None):
+        super().__init__((n, n), device)
+
+    def apply_dev(self, x, out=None):
+        if out is None:
+            return x.clone()
+        out.copy_(x)
+        return out
+
+    adjoint_dev = apply_dev
+
+
+# ---- CSR tomography operator ------------------------------------------------------------------------------------
+
+class CSROperator(LinearOperator):
+    """Sparse matrix in CSR with an explicitly stored transpose (also CSR): both A x and A^T u are
+    gather-only, deterministic SpMVs.  Stands for the scipy.sparse matrices / ASTRA projector objects the
+    reference passes as A (demos: CT matrices from .mat files, `astra.OpTomo`)."""
+
+    fused = True
+
+    def __init__(self, A, AT):
+        if A.shape != (AT.shape[1], AT.shape[0]):
+            raise ValueError("AT must have the transposed shape of A")
+        super().__init__(A.shape, A.device)
+        self.A, self.AT = A, AT
+
+    @classmethod
+    def from_scipy(cls, A, device=None):
+        """Upload a scipy.sparse matrix; the transpose is formed once on the host (A.T.tocsr())."""
+        import scipy.sparse as sp
+
+        device = torch.device(device) if device is not None else default_device()
+        A = sp.csr_matrix(A, dtype=np.float64)
+        A.sort_indices()
+        AT = A.T.tocsr()
+        AT.sort_indices()
+        return cls(_upload_csr(A, device), _upload_csr(AT, device))
+
+    @classmethod
+    def from_dense(cls, A, device=None):
+        import scipy.sparse as sp
+
+        return cls.from_scipy(sp.csr_matrix(np.asarray(A, dtype=np.float64)), device)
+
+    def to_scipy(self):
+        """The same arrays as a scipy.sparse.csr_matrix (used to feed the oracle identical inputs)."""
+        return _download_csr(self.A)
+
+    def transpose_to_scipy(self):
+        return _download_csr(self.AT)
+
+    def with_f32_storage(self):
+        """fp32-storage / fp64-accumulate variant (16 instead of 24 B/nnz per Golub-Kahan iteration)."""
+        return CSROperator(self.A.to_f32_storage(), self.AT.to_f32_storage())
+
+    @property
+    def nnz(self):
+        return self.A.nnz
+
+    def apply_dev(self, x, out=None, coef=None, z=None, norm_out=None):
+        return K.spmv(self.A, x, out=out, coef=coef, z=z, norm_out=norm_out)
+
+    def adjoint_dev(self, y, out=None, coef=None, z=None, norm_out=None):
+        return K.spmv(self.AT, y, out=out, coef=coef, z=z, norm_out=norm_out)
+
+
+def _upload_csr(A, device):
+    rowptr = torch.from_numpy(np.ascontiguousarray(A.indptr, dtype=np.int64)).to(device)
+    colidx = torch.from_numpy(np.ascontiguousarray(A.indices, dtype=np.int32)).to(device)
+    vals = torch.from_numpy(np.ascontiguousarray(A.data, dtype=np.float64)).to(device)
+    return CSRDevice(A.shape, rowptr, colidx, vals)
+
+
+def _download_csr(A):
+    import scipy.sparse as sp
+
+    nnz = A.nnz
+    idx_dtype = np.int32 if nnz < 2 ** 31 else np.int64
+    return sp.csr_matrix((A.vals.to(F64).cpu().numpy(), A.colidx.cpu().numpy().astype(idx_dtype),
+                          A.rowptr.cpu().numpy().astype(idx_dtype)), shape=A.shape)
+
+
+def ct_angles(n_angles):
+    """theta = linspace(0, pi, views, endpoint=False)  (trips/test_problems/Tomography.py:56)."""
+    return np.linspace(0.0, np.pi, int(n_angles), endpoint=False)
+
+
+def ct_num_detectors(nx):
+    """p = int(sqrt(2) * nx)  (trips/test_problems/Tomography.py:53)."""
+    return int(np.sqrt(2) * nx)
+
+
+class ParallelBeamCT(CSROperator):
+    """2-D parallel-beam tomography matrix built on the device (line model: chord length per pixel).
+
+    Geometry follows the reference's conventions (Tomography.py:53-56, io.py:392-400): `views` angles in [0, pi),
+    n_det = int(sqrt(2)*nx) unit-spaced detector bins, sinogram ordered angle-major (row = angle*n_det + det),
+    image vectorised row-major.  `angle_subset` keeps only those angle indices (row sharding by projection angle)."""
+
+    def __init__(self, nx, views, ny=None, n_det=None, angles=None, angle_subset=None, device=None):
+        device = torch.device(device) if device is not None else default_device()
+        ny = nx if ny is None else ny
+        n_det = ct_num_detectors(nx) if n_det is None else int(n_det)
+        theta = ct_angles(views) if angles is None else np.asarray(angles, dtype=np.float64)
+        if angle_subset is not None:
+            theta = theta[np.asarray(angle_subset)]
+        self.nx, self.ny, self.n_det, self.theta = int(nx), int(ny), n_det, theta
+        cos_t = torch.from_numpy(np.cos(theta)).to(device)
+        sin_t = torch.from_numpy(np.sin(theta)).to(device)
+        K._lib.require_device()
+        A = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=False)
+        AT = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=True)
+        if A.nnz != AT.nnz:
+            raise RuntimeError(f"CT builder: nnz(A)={A.nnz} differs from nnz(A^T)={AT.nnz}")
+        super().__init__(A, AT)
+
+
+class BlockDiagCT(CSROperator):
+    """Block-diagonal dynamic-CT operator, one parallel-beam block per time frame, stored as ONE CSR matrix
+    (and one CSR transpose) so a frame-major x is applied in a single launch.  Mirrors `pylops.BlockDiag` of
+    per-frame projectors (trips/utilities/io.py:420) and the per-frame diagonal blocks of the CrossPhantom /
+    Emoji operators (io.py:206-225).  `frame_angles[t]` holds the angles (radians) of frame t."""
+
+    def __init__(self, nx, frame_angles, n_det=None, device=None):
+        device = torch.device(device) if device is not None else default_device()
+        n_det = ct_num_detectors(nx) if n_det is None else int(n_det)
+        self.nx, self.n_det, self.nt = int(nx), n_det, len(frame_angles)
+        K._lib.require_device()
+        parts, parts_t = [], []
+        for th in frame_angles:
+            th = np.asarray(th, dtype=np.float64)
+            c = torch.from_numpy(np.cos(th)).to(device)
+            s = torch.from_numpy(np.sin(th)).to(device)
+            parts.append(K.ct_build(nx, nx, n_det, c, s, transpose=False))
+            parts_t.append(K.ct_build(nx, nx, n_det, c, s, transpose=True))
+        super().__init__(_block_diag(parts), _block_diag(parts_t))
+
+
+def _block_diag(parts):
+    m = sum(p.shape[0] for p in parts)
+    n = sum(p.shape[1] for p in parts)
+    rowptrs, cols, vals = [], [], []
+    nnz_off, col_off = 0, 0
+    for i, p in enumerate(parts):
+        rp = p.rowptr if i == len(parts) - 1 else p.rowptr[:-1]
+        rowptrs.append(rp + nnz_off)
+        cols.append(p.colidx + col_off)
+        vals.append(p.vals)
+        nnz_off += p.nnz
+        col_off += p.shape[1]
+    return CSRDevice((m, n), torch.cat(rowptrs), torch.cat(cols).to(torch.int32), torch.cat(vals))
+
+
+# ---- PSF blur ----------------------------------------------------------------------------------------------------
+
+def gauss_psf(dim, spread):
+    """Normalised Gaussian PSF, same formula as trips/test_problems/Deblurring2D.py:48-64 (Gauss)."""
+    m, n = int(dim[0]), int(dim[1])
+    s1, s2 = (spread, spread) if np.isscalar(spread) else (spread[0], spread[1])
+    gx = np.arange(-np.fix(n / 2), np.ceil(n / 2))
+    gy = np.arange(-np.fix(m / 2), np.ceil(m / 2))
+    X, Y = np.meshgrid(gx, gy)
+    psf = np.exp(-0.5 * ((X ** 2) / (s1 ** 2) + (Y ** 2) / (s2 ** 2)))
+    psf /= psf.sum()
+    return psf
+
+
+class PSFBlur2D(LinearOperator):
+    """Deblurring operator of Deblurring2D.forward_Op (Deblurring2D.py:66-73):
+    A x = ndimage.convolve(X, PSF, mode='reflect'), A^T b = ndimage.convolve(B, flipud(fliplr(PSF)), 'reflect')."""
+
+    def __init__(self, psf, nx, ny, device=None, mode="reflect"):
+        super().__init__((nx * ny, nx * ny), device)
+        psf = np.ascontiguousarray(psf, dtype=np.float64)
+        self.psf, self.nx, self.ny = psf, int(nx), int(ny)
+        self.mode = {"reflect": 0, "constant": 1}[mode]
+        ph, pw = psf.shape
+        # ndimage.convolve(x, w) == correlate(x, w[::-1, ::-1]) with the origin moved by one for even sizes
+        self.ch = ph // 2 - (1 if ph % 2 == 0 else 0)
+        self.cw = pw // 2 - (1 if pw % 2 == 0 else 0)
+        self._w_fwd = torch.from_numpy(np.ascontiguousarray(psf[::-1, ::-1])).to(self.device)
+        self._w_adj = torch.from_numpy(psf).to(self.device)
+
+    def apply_dev(self, x, out=None):
+        return K.correlate2d(x, self._w_fwd, self.nx, self.ny, self.ch, self.cw, self.mode, out=out)
+
+    def adjoint_dev(self, y, out=None):
+        return K.correlate2d(y, self._w_adj, self.nx, self.ny, self.ch, self.cw, self.mode, out=out)
+
+
+# ---- finite-difference regularisation operators -------------------------------------------------------------------
+
+class FirstDerivative1D(LinearOperator):
+    """(n-1) x n forward difference, (L x)_i = x_i - x_{i+1}  (trips/utilities/operators.py:24-28)."""
+
+    def __init__(self, n, device=None):
+        super().__init__((n - 1, n), device)
+
+    def apply_dev(self, x, out=None):
+        return K.fd1d_apply(x, out=out)
+
+    def adjoint_dev(self, r, out=None):
+        return K.fd1d_adjoint(r, out=out)
+
+
+class SpaceTimeDerivative(LinearOperator):
+    """L = [ I_t (x) L_2D ; D_t (x) I ] on frame-major x (trips/utilities/operators.py:39-45); nt = 1 gives the 2-D
+    operator [ I (x) D ; D (x) I ] of operators.py:30-36.  Matrix-free, with the IRLS weights fused:
+      apply_dev(x, wout=, eps=, expo=)  also writes (u^2+eps^2)^expo       (MMGKS.py:60,93)
+      adjoint_dev(r, w=)                computes L^T (w . r)                (MMGKS.py:113-117)
+    For frame-sharded dynamic CT, `x_next` / `rt_prev` / `wt_prev` carry the one-frame halos."""
+
+    def __init__(self, nx, ny, nt=1, device=None, has_next=False):
+        self.nx, self.ny, self.nt, self.has_next = int(nx), int(ny), int(nt), bool(has_next)
+        p2 = self.nx * (self.ny - 1) + (self.nx - 1) * self.ny
+        rows = self.nt * p2 + (self.nt if self.has_next else self.nt - 1) * self.nx * self.ny
+        super().__init__((rows, self.nt * self.nx * self.ny), device)
+
+    def apply_dev(self, x, out=None, wout=None, eps=0.0, expo=0.0, x_next=None):
+        if self.has_next and x_next is None:
+            raise ValueError("this shard needs the next rank's first frame (x_next)")
+        return K.fd_apply(x, self.nt, self.nx, self.ny, x_next=x_next, out=out, wout=wout, eps=eps, expo=expo)
+
+    def adjoint_dev(self, r, out=None, w=None, rt_prev=None, wt_prev=None):
+        return K.fd_adjoint(r, self.nt, self.nx, self.ny, has_next=self.has_next, w=w, rt_prev=rt_prev, wt_prev=wt_prev,
+                            out=out)
+
+
+class FirstDerivative2D(SpaceTimeDerivative):
+    """2-D forward-difference operator of gen_first_derivative_operator_2D (operators.py:30-36)."""
+
+    def __init__(self, nx, ny, device=None):
+        super().__init__(nx, ny, 1, device)
+
+
+def as_operator(A, device=None):
+    """Accept what the reference accepts for A / L and return a GPU operator: our operators pass through;
+    scipy.sparse matrices and (small) dense arrays are uploaded as CSR with an explicit transpose."""
+    if isinstance(A, LinearOperator):
+        return A
+    try:
+        import scipy.sparse as sp
+
+        if sp.issparse(A):
+            return CSROperator.from_scipy(A, device)
+    except ImportError:  # pragma: no cover
+        pass
+    if isinstance(A, np.ndarray) and A.ndim == 2:
+        return CSROperator.from_dense(A, device)
+    raise TypeError(
+        f"cannot run {type(A).__name__} on the GPU: pass a trips_b200 operator, a scipy.sparse matrix or a dense "
+        "ndarray (host callbacks such as pylops.FunctionOperator would be a CPU fallback, which this package refuses)")

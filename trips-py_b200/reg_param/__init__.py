@@ -1,0 +1,5 @@
+"""Host-side (NumPy) regularisation-parameter rules for the projected problems."""
+from .discrepancy_principle import discrepancy_principle, discrepancy_principle_projected
+from .gcv import generalized_crossvalidation
+
+__all__ = ["generalized_crossvalidation", "discrepancy_principle", "discrepancy_principle_projected"]

@@ -1,0 +1,51 @@
+"""Generalised cross validation for the projected problem (host, NumPy - stays on the CPU as in the reference).
+
+Follows trips/utilities/reg_param/gcv.py:
+  gcv_numerator :25-49, gcv_denominator :51-78, generalized_crossvalidation :80-95 (gcvtype 'tikhonov').
+Behaviour that changes numbers and is therefore replicated:
+  * the numerator is always the 'standard' one - the reference calls it without forwarding kwargs (:94) - while the
+    denominator honours variant='modified' with fullsize=m (Hybrid_LSQR.py:84);
+  * the minimiser is scipy.optimize.fminbound on [1e-9, 1e2] with xtol=1e-12, maxfun=1000 (:95).
+The only structural change: the big operand enters as c = Q_A^T b (a k-vector the device computes in one pass),
+not as Q_A and b separately - the reference re-does the O(k m) product at every objective evaluation (:43).
+Brent's method cannot resolve the minimiser below ~1e-8 relative, so GCV agreement with the
+reference is reported at that level; the 1e-10 parity gate runs with a fixed or discrepancy-principle lambda.
+"""
+import numpy as np
+import scipy.linalg as la
+import scipy.optimize as op
+
+
+def _dense(M):
+    return M.todense() if hasattr(M, "todense") and not isinstance(M, np.ndarray) else np.asarray(M)
+
+
+def gcv_value(lam, R_A, R_L, c, trace_size):
+    """GCV objective at lam:  ||R_A y(lam) - c||^2 / (trace_size - trace(R_A (R_A^T R_A + lam R_L^T R_L)^-1 R_A^T))^2."""
+    RA2 = R_A.T @ R_A
+    RL2 = R_L.T @ R_L
+    M = RA2 + lam * RL2
+    y = la.solve(M, R_A.T @ c)
+    num = np.linalg.norm(R_A @ y - c) ** 2
+    infl = la.solve(M, R_A.T)
+    den = (trace_size - np.trace(R_A @ infl)) ** 2
+    return num / den
+
+
+def generalized_crossvalidation(Q_A, R_A, R_L, b, **kwargs):
+    """Same call as the reference's generalized_crossvalidation(Q_A, R_A, R_L, b, **kwargs).
+
+    Q_A may be None when `b` already holds the projected right-hand side c = Q_A^T b."""
+    gcvtype = kwargs.get("gcvtype", "tikhonov")
+    if gcvtype != "tikhonov":
+        raise NotImplementedError("only gcvtype='tikhonov' is on the Krylov hot path (tsvd/tgsvd belong to the direct solvers)")
+    R_A = _dense(R_A)
+    R_L = _dense(R_L)
+    b = np.asarray(b, dtype=np.float64)
+    c = b.reshape(-1, 1) if Q_A is None else np.asarray(Q_A).T @ b.reshape(-1, 1)
+    if kwargs.get("variant", "standard") == "modified":
+        trace_size = kwargs["fullsize"]
+    else:
+        trace_size = R_A.shape[0]
+    f = lambda lam: gcv_value(lam, R_A, R_L, c, trace_size)  # noqa: E731
+    return op.fminbound(func=f, x1=1e-09, x2=1e2, args=(), xtol=1e-12, maxfun=1000, full_output=0, disp=0)

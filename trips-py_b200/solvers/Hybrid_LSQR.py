@@ -1,0 +1,84 @@
+"""Hybrid LSQR on the GPU - signature and returns of trips/solvers/Hybrid_LSQR.py:25-114.
+
+Each iteration: one device Golub-Kahan step (2 fused SpMVs + 2 scalings, no host traffic), one small D2H of the
+bidiagonal entries, the (k+1) x k Tikhonov problem and its parameter rule on the host in NumPy (as in the
+reference), and the lift x = V y as one stream of the device basis.
+
+Reference behaviour kept because it changes results: at ii == 0 lambda = 0 and NO iterate is formed (:77-78), so
+n_iter = 1 fails like the reference (UnboundLocalError there, ValueError here); GCV is called with
+variant='modified', fullsize=m (:84) while its numerator stays 'standard' (gcv.py:94); info['its'] is the last
+loop index.  Refused: dp_stop=True (the reference path at :88-94 raises a shape error before it can stop).
+"""
+import numpy as np
+from scipy import linalg as la
+
+from .. import kernels as K
+from ..decompositions import GKState
+from ..operators import as_operator, to_device_vector
+from ..reg_param.discrepancy_principle import discrepancy_principle_projected
+from ..reg_param.gcv import generalized_crossvalidation
+from ._common import ErrorTracker, LazyHistory, dev_scalar, host_column, need_delta, tikhonov_projected
+
+
+def Hybrid_LSQR(A, b, n_iter=100, regparam="gcv", x_true=None, **kwargs):
+    delta, dp_stop = need_delta(regparam, kwargs, "gcv.")
+    if dp_stop is not False:
+        raise NotImplementedError("dp_stop=True is not supported: the reference implementation of that branch "
+                                  "(Hybrid_LSQR.py:88-94) fails with a shape error")
+    A = as_operator(A)
+    dev = A.device
+    m, n = A.shape
+    bd = to_device_vector(b, dev)
+    st = GKState(A, bd, n_iter)
+    x_history = LazyHistory()
+    lambda_history, residual_history = [], []
+    err = ErrorTracker(x_true, dev)
+    keep = kwargs.get("b200_history", "lazy")
+    rp_kwargs = {k: v for k, v in kwargs.items() if not k.startswith("b200_")}
+    xd = None
+    lambdah = 0
+    ii = -1
+    for ii in range(n_iter):
+        st.step()  # (U, B, V) = golub_kahan_update(A, U, B, V)                          (Hybrid_LSQR.py:74)
+        if ii == 0:
+            lambdah = 0
+            continue
+        beta0, al, be = st.scalars_host()
+        k = al.size
+        B = np.zeros((k + 1, k))
+        B[np.arange(k), np.arange(k)] = al
+        B[np.arange(1, k + 1), np.arange(k)] = be
+        bhat = np.zeros(k + 1)
+        bhat[0] = beta0
+        eye = np.eye(k)
+        if isinstance(regparam, str) and regparam == "gcv":
+            Q_A, s, _ = la.svd(B, full_matrices=False)
+            lambdah = generalized_crossvalidation(Q_A, np.diag(s), eye, bhat, variant="modified", fullsize=m, **rp_kwargs)
+        elif isinstance(regparam, str) and regparam == "dp":
+            # discrepancy_principle(U, B, L, b): U^T b and ||b - U U^T b|| come from the device basis
+            h = K.basis_dots(st.U, k + 1, bd)
+            explicit = rp_kwargs.get("explicitProj", False)
+            resid = 0.0
+            if explicit:  # ||b - U U^T b|| is only consulted by the explicitProj variant (discrepancy_principle.py:69,82)
+                res = K.new_pair(dev)
+                K.basis_combine(st.U, k + 1, h, w=bd, sign=-1.0, norm_out=res)
+                resid = float(res.cpu()[1])
+            lambdah = discrepancy_principle_projected(B, None, h.cpu().numpy()[:k + 1], resid, delta,
+                                                      rp_kwargs.get("eta", 1.01), explicit)
+        elif isinstance(regparam, str):
+            raise NotImplementedError(f"regparam={regparam!r}: only 'gcv', 'dp' or a number are on the hot path")
+        else:
+            lambdah = regparam
+        lambda_history.append(lambdah)
+        y = tikhonov_projected(B, eye, bhat, lambdah)
+        xd = K.basis_combine(st.V, k, dev_scalar(y, dev), out=xd)  # x = V @ y                (:105)
+        if keep != "none":
+            x_history.append_lift(st.V, k, y)
+        err.add(xd)
+    if xd is None:
+        raise ValueError("Hybrid_LSQR forms no iterate when n_iter < 2 (the reference raises UnboundLocalError)")
+    info = {"xHistory": x_history, "regParam": lambdah, "regParam_history": lambda_history,
+            "relResidual": residual_history, "its": ii}
+    if x_true is not None:
+        info["relError"] = err.values()
+    return (host_column(xd), info)

@@ -1,0 +1,115 @@
+"""Machinery shared by GKS and MMGKS: the generalised Krylov bases V, AV, LV on the device, the Gram-based
+replacement of the per-iteration tall-skinny QRs, and the normal-equations residual + reorthogonalisation.
+
+Reference loops: trips/solvers/GKS.py:36-105 and trips/solvers/MMGKS.py:37-137.
+
+Replacing the QRs.  The reference factors AV*wf (m x k) and LV*wr (p x k) with Householder QR on the host at every
+iteration and then only uses R_A, R_L, Q_A^T b, Q_A^T(wf*b) and ||wf*b - Q_A Q_A^T wf*b||.  Those are obtained here
+from one double-double Gram pass per basis (tb200_weighted_gram) and a k x k double-double Cholesky on the host
+(tb200_gram_factor_dd): R = chol(G) is the Householder R up to the signs of its rows, which neither the
+regularisation-parameter rules nor y = argmin ||R_A y - Q_A^T b||^2 + lam ||R_L y||^2 can see.
+"""
+import numpy as np
+
+from .. import kernels as K
+from ..decompositions import GKState
+from ..kernels import Basis
+from ..operators import SpaceTimeDerivative
+from ..reg_param.discrepancy_principle import discrepancy_principle_projected
+from ..reg_param.gcv import generalized_crossvalidation
+
+
+class GKSBases:
+    def __init__(self, A, L, bd, projection_dim, n_iter):
+        self.A, self.L = A, L
+        dev = bd.device
+        kmax = projection_dim + n_iter + 1
+        st = GKState(A, bd, projection_dim)  # golub_kahan(A, b, projection_dim)          (GKS.py:36, MMGKS.py:37)
+        for _ in range(projection_dim):
+            st.step()
+        self.V = Basis(A.shape[1], kmax, dev)
+        self.AV = Basis(A.shape[0], kmax, dev)
+        self.LV = Basis(L.shape[0], kmax, dev)
+        for j in range(projection_dim):  # AV = A@V ; LV = L@V                            (GKS.py:37-38)
+            self.V.next_col().copy_(st.V.col(j))
+            self.V.push()
+            self.append_images()
+        del st
+
+    @property
+    def k(self):
+        return self.V.k
+
+    def append_images(self):
+        """AV, LV gain the images of the newest column of V  (GKS.py:92-96, MMGKS.py:124-128)."""
+        vn = self.V.col(self.V.k - 1)
+        self.A.apply_dev(vn, out=self.AV.next_col())
+        self.AV.push()
+        self.L.apply_dev(vn, out=self.LV.next_col())
+        self.LV.push()
+
+
+def apply_L_with_weights(L, x, eps, expo):
+    """u = L x and wr = (u^2 + eps^2)^expo, in one pass when L is a matrix-free difference operator."""
+    import torch
+
+    if isinstance(L, SpaceTimeDerivative):
+        wr = torch.empty(L.shape[0], dtype=K.F64, device=x.device)
+        u = L.apply_dev(x, wout=wr, eps=eps, expo=expo)
+        return u, wr
+    u = L.apply_dev(x)
+    return u, K.irls_weights(u, eps, expo)
+
+
+def adjoint_L_weighted(L, r, w, out=None):
+    """L^T (w . r)   (w None: L^T r)."""
+    if w is None:
+        return L.adjoint_dev(r, out=out)
+    if isinstance(L, SpaceTimeDerivative):
+        return L.adjoint_dev(r, out=out, w=w)
+    return L.adjoint_dev(K.vec_mul(w, r), out=out)
+
+
+def factor_pair(bases, bd, wf=None, wr=None):
+    """R_A, R_L, c_plain = Q_A^T b, c_w = Q_A^T (wf*b), resid_w = ||wf*b - Q_A Q_A^T wf*b||."""
+    k = bases.k
+    if wf is None:
+        Ghi, Glo = K.weighted_gram(bases.AV, k, None, extras=(bd,), extra_weighted=(0,))
+        R_A, C, res2 = K.gram_factor(Ghi, Glo, k)
+        c_plain = c_w = C[:, 0:1]
+        resid_w = float(np.sqrt(res2[0]))
+    else:
+        Ghi, Glo = K.weighted_gram(bases.AV, k, wf, extras=(bd, bd), extra_weighted=(0, 1))
+        R_A, C, res2 = K.gram_factor(Ghi, Glo, k)
+        c_plain, c_w = C[:, 0:1], C[:, 1:2]
+        resid_w = float(np.sqrt(res2[1]))
+    Ghi, Glo = K.weighted_gram(bases.LV, k, wr)
+    R_L, _, _ = K.gram_factor(Ghi, Glo, k)
+    return R_A, R_L, c_plain, c_w, resid_w
+
+
+def choose_lambda(regparam, R_A, R_L, c_w, resid_w, delta, rp_kwargs):
+    """GKS.py:60-69 / MMGKS.py:96-103 with the long-vector products already projected."""
+    if isinstance(regparam, str) and regparam == "gcv":
+        return generalized_crossvalidation(None, R_A, R_L, c_w, **rp_kwargs)
+    if isinstance(regparam, str) and regparam == "dp":
+        return discrepancy_principle_projected(R_A, R_L, c_w, resid_w, delta, rp_kwargs.get("eta", 1.01),
+                                               rp_kwargs.get("explicitProj", False))
+    if isinstance(regparam, str):
+        raise NotImplementedError(f"regparam={regparam!r}: only 'gcv', 'dp' or a number are on the hot path")
+    return regparam
+
+
+def expand(bases, r, n_reorth, residual_history):
+    """r -= V (V^T r) n_reorth times, record ||r||, append r/||r|| and its images  (GKS.py:86-96, MMGKS.py:119-129)."""
+    k = bases.k
+    nrm = K.new_pair(r.device)
+    for it in range(n_reorth):
+        h = K.basis_dots(bases.V, k, r)
+        K.basis_combine(bases.V, k, h, w=r, sign=-1.0, out=r, norm_out=nrm if it == n_reorth - 1 else None)
+    if n_reorth == 0:
+        K.vec_norm2(r, out=nrm)
+    K.vec_div(r, nrm[1:2], out=bases.V.next_col())
+    bases.V.push()
+    bases.append_images()
+    residual_history.append(nrm)  # device pair; converted once at the end
