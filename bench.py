@@ -48,6 +48,10 @@ def parse():
     ap.add_argument("--cpu-sample-views", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--f32-storage", action="store_true", help="fp32-storage / fp64-accumulate variant (reported separately)")
+    ap.add_argument("--order", default="sequential", choices=["sequential", "tree"],
+                    help="SpMV row-sum order: 'sequential' = scipy's (bit-identical to the reference, the parity build); "
+                         "'tree' = per-row tree reduction (reported separately)")
+    ap.add_argument("--variant", type=int, default=0, help="tile configuration of the sequential kernel (tuning)")
     return ap.parse_args()
 
 
@@ -177,6 +181,10 @@ def main():
     if args.f32_storage:
         A = A.with_f32_storage()
         torch.cuda.empty_cache()
+    if args.order != "sequential":
+        A = A.with_order(args.order)
+    _lib.check(_lib.lib().tb200_spmv_set_variant(args.variant))
+    kernel_name = {"sequential": "spmv_seq_tile_kernel", "tree": "spmv_warp_kernel"}[args.order]
     m_loc = A.shape[0]
     nnz_loc = A.nnz
     nnz_t = torch.tensor([nnz_loc], dtype=torch.int64, device=dev)
@@ -254,7 +262,7 @@ def main():
     spmv_share = sum(spmv_ms) / ms
     B_GK = 2 * (val_bytes + 4) * nnz + 8 * (m_full + 1) + 8 * (n + 1) + 48 * (m_full + n)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "spmv_warp_kernel<double,8>",
+                "traffic": None, "peak_source": peak_src, "kernel": kernel_name,
                 "launch_ms": mean_spmv_ms, "alg_bytes_per_launch": alg_bytes, "share_of_step": spmv_share,
                 "gk_iteration": {"alg_bytes": B_GK, "achieved": B_GK / (ms_per_step * 1e-3) / 1e9 / world,
                                  "frac": B_GK / (ms_per_step * 1e-3) / 1e9 / world / hbm_peak, "note": "per GPU"}}
@@ -320,6 +328,7 @@ def main():
                 "dtype": "f64" if not args.f32_storage else "f32-storage/f64-accumulate", "data": "synthetic",
                 "config": {"workload": workload, "nnz": nnz, "m": m_full, "n": n, "matrix_bytes": 2 * (val_bytes + 4) * nnz,
                            "parallelism": f"rows by angle x{world}" if world > 1 else "single GPU",
+                           "spmv_order": args.order, "spmv_variant": args.variant,
                            "l2_note": "inputs (2 x 46 GB matrix streams per step) exceed L2 by >300x; no flush needed",
                            "build_s": t_build},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}

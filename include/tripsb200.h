@@ -13,7 +13,8 @@
  *   - a "basis" is kmax columns, column j contiguous at V + j*ld (ld >= column length).
  *   - scalars that may live on the device come as a (x_host, x_dev) pair: x_dev wins when it is not NULL.
  *   - norm outputs are two doubles: out[0] = sum of squares, out[1] = its square root.
- *   - reductions are two-stage fixed-order trees (no atomics): results are bitwise reproducible run to run.
+ *   - norms and dot products are accumulated in double-double and return the CORRECTLY ROUNDED exact sum (no
+ *     atomics): bitwise reproducible run to run, independent of grid size, and reproducible by a CPU oracle.
  */
 #ifndef TRIPSB200_H
 #define TRIPSB200_H
@@ -40,14 +41,18 @@ int tb200_require_sm100(void);
  * i.e. scipy sparsetools csr_matvec / csc_matvec behind scipy.sparse `__matmul__`.
  * The epilogue `- coef*z` is the three-term recurrence of decompositions.py:237,240 (z = NULL: plain product).
  * rowptr: int64[m+1]; colidx: int32[nnz] (16-byte aligned); vals: fp64 (or fp32 for _f32s; 32-byte aligned).
- * norm_out (nullable): 2 doubles; ws: tb200_spmv_workspace_len(m) doubles, required iff norm_out != NULL. */
+ * norm_out (nullable): 2 doubles; ws: tb200_spmv_workspace_len(m) doubles, required iff norm_out != NULL.
+ * order 0: products of a row are added one after the other in index order with separately rounded multiply and
+ *          add - the arithmetic of scipy's csr_matvec (and of csc_matvec when applied to the stored transpose):
+ *          results are BIT-IDENTICAL to the reference's.  order 1: per-row tree reduction with FMA (fastest). */
 int64_t tb200_spmv_workspace_len(int64_t m);
 int tb200_spmv_launches(int with_norm);
-int tb200_spmv_csr_f64(int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx,
+int tb200_spmv_set_variant(int variant);
+int tb200_spmv_csr_f64(int order, int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx,
                        const double* vals, const double* x, double* y, double coef_host, const double* coef_dev,
                        const double* z, double* norm_out, double* ws, void* stream);
 /* fp32-storage / fp64-accumulate variant (reported separately from the fp64 parity build). */
-int tb200_spmv_csr_f32s(int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx,
+int tb200_spmv_csr_f32s(int order, int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx,
                         const float* vals, const double* x, double* y, double coef_host, const double* coef_dev,
                         const double* z, double* norm_out, double* ws, void* stream);
 int tb200_reduce_finalize(const double* partials, int64_t n, double* out, void* stream);

@@ -43,8 +43,10 @@ def test_workspace_queries_and_error_channel():
     assert L.tb200_fd_rows(1, 4, 4, 0) == 2 * 4 * 3
     assert L.tb200_fd_rows(3, 4, 4, 0) == 3 * 24 + 2 * 16
     # argument errors come back as status codes with a message, never as a crash
-    rc = L.tb200_spmv_csr_f64(-1, 1, 0, None, None, None, None, None, 0.0, None, None, None, None, None)
+    rc = L.tb200_spmv_csr_f64(0, -1, 1, 0, None, None, None, None, None, 0.0, None, None, None, None, None)
     assert rc == 1001 and b"negative" in L.tb200_last_error()
+    rc = L.tb200_spmv_csr_f64(7, 1, 1, 0, None, None, None, None, None, 0.0, None, None, None, None, None)
+    assert rc == 1001 and b"order" in L.tb200_last_error()
 
 
 def test_gram_factor_dd_matches_householder_qr():
@@ -78,3 +80,14 @@ def test_gram_factor_dd_matches_householder_qr():
         assert np.linalg.norm(R[i] - Rr[i]) <= 1e-6 * np.linalg.norm(Rr[i])
     assert np.allclose(C[:, 0], Qr.T @ z, atol=1e-7)
     assert abs(res2[0] - np.linalg.norm(z - Qr @ (Qr.T @ z)) ** 2) < 1e-7  # Householder itself carries eps*kappa here
+
+
+def test_library_is_not_older_than_its_sources():
+    """A stale libtripsb200.so (sources edited, `make` not re-run) silently mis-binds arguments: refuse it."""
+    import glob
+
+    from trips_b200 import _lib
+
+    srcs = glob.glob(os.path.join(ROOT, "trips-py_b200", "csrc", "*.cu*"))
+    newest = max(os.path.getmtime(p) for p in srcs)
+    assert os.path.getmtime(_lib.LIB_PATH) >= newest, "rebuild: make -C trips-py_b200/csrc"

@@ -23,8 +23,9 @@ SIGNATURES = {
     "tb200_require_sm100": (c_int, []),
     "tb200_spmv_workspace_len": (c_i64, [c_i64]),
     "tb200_spmv_launches": (c_int, [c_int]),
-    "tb200_spmv_csr_f64": (c_int, [c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "tb200_spmv_csr_f32s": (c_int, [c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_spmv_set_variant": (c_int, [c_int]),
+    "tb200_spmv_csr_f64": (c_int, [c_int, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_spmv_csr_f32s": (c_int, [c_int, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_reduce_finalize": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "tb200_reduce_workspace_len": (c_i64, []),
     "tb200_vec_div": (c_int, [c_i64, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr]),

@@ -13,6 +13,7 @@
 // cores.  basis_dots streams V once for h = V^T w with the w segment resident in L1; basis_combine streams V
 // once for  out = w + sign * V h  with the squared norm of the result fused into the same pass.
 #include "tb200_common.cuh"
+#include "tb200_dd.cuh"
 
 namespace tb200 {
 
@@ -89,10 +90,10 @@ __global__ void __launch_bounds__(kBThreads)
 basis_combine_kernel(int64_t n, int k, const double* __restrict__ V, int64_t ld, const double* __restrict__ h,
                      const double* __restrict__ w, double sign, double* __restrict__ out, double* __restrict__ partials) {
   extern __shared__ double hs[];
-  __shared__ double red[32];
+  __shared__ double red[64];
   for (int j = threadIdx.x; j < k; j += kBThreads) hs[j] = h[j];
   __syncthreads();
-  double nrm = 0.0;
+  dd_t nrm = dd_zero();
   for (int64_t i = (int64_t)blockIdx.x * kBThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBThreads) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int j = 0;
@@ -111,11 +112,14 @@ basis_combine_kernel(int64_t n, int k, const double* __restrict__ V, int64_t ld,
     double r = (sign < 0.0) ? -vh : vh;
     if (w != nullptr) r = (sign < 0.0) ? __dsub_rn(w[i], vh) : __dadd_rn(w[i], vh);
     out[i] = r;
-    nrm = fma(r, r, nrm);
+    if (partials != nullptr) nrm = dd_fma(nrm, r, r);
   }
   if (partials != nullptr) {
-    const double tot = block_sum(nrm, red);
-    if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+    const dd_t tot = dd_block_sum(nrm, red);
+    if (threadIdx.x == 0) {
+      partials[2 * blockIdx.x] = tot.hi;
+      partials[2 * blockIdx.x + 1] = tot.lo;
+    }
   }
 }
 
@@ -126,7 +130,7 @@ using namespace tb200;
 extern "C" {
 
 // Doubles of workspace needed by tb200_basis_dots for k columns (and by basis_combine's fused norm).
-int64_t tb200_basis_workspace_len(int64_t k) { return (int64_t)kBMaxBlocks * (k > 1 ? k : 1); }
+int64_t tb200_basis_workspace_len(int64_t k) { return (int64_t)kBMaxBlocks * (k > 2 ? k : 2); }
 
 // h[0..k) = V[:, 0..k)^T w.  Deterministic (fixed two-stage tree).  2 launches.
 int tb200_basis_dots(int64_t n, int64_t k, const double* V, int64_t ld, const double* w, double* h, double* ws,
@@ -157,7 +161,7 @@ int tb200_basis_combine(int64_t n, int64_t k, const double* V, int64_t ld, const
                                                                          norm_out ? ws : nullptr);
   int rc = check_launch("basis_combine");
   if (rc || !norm_out) return rc;
-  finalize_sum_kernel<<<1, 1024, 0, st>>>(ws, g, norm_out);
+  finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, g, norm_out);
   return check_launch("basis_combine finalize");
 }
 

@@ -5,24 +5,218 @@
 // A.T is never applied by scatter: the caller stores A^T as a second CSR matrix and calls the same kernel,
 // so both directions are gather-only and bitwise reproducible (no atomics).
 //
-// Kernel shape (HBM-bound, 12 B/nnz streamed once):
-//  * CT rows are long (~900-1800 nnz): one warp per row, lanes take groups of four consecutive non-zeros;
-//    values arrive as one 256-bit LDG (evict-first in L2, not allocated in L1), column indices as one 128-bit
-//    LDG, and the four x[col] gathers go through the read-only path with an evict-last L2 policy so the
-//    dense vector (33.5 MB at 2048^2) stays L2/L1 resident while 46 GB of matrix streams past it.
-//  * the row start is peeled to a multiple of four non-zeros so the wide loads are aligned for any rowptr.
-//  * warps of one CTA work on neighbouring rows (neighbouring rays / pixels) at the same time, which is what
-//    makes the x gathers hit L1: adjacent rays cross adjacent pixels.
-//  * fused epilogue  y = A x - coef * z  (the Golub-Kahan three-term recurrences) and fused ||y||^2:
-//    one partial per CTA, then a single-CTA fixed-order finalize => deterministic norms without atomics.
-//  * short-row matrices (generic CSR passed by a user) take a sub-warp path with T threads per row.
+// Two summation orders (argument `order`):
+//
+//  order 0, "sequential" (default, the parity build).  Golub-Kahan and CGLS run WITHOUT reorthogonalisation in the
+//    reference; on CT problems the bases lose orthogonality within ~15 steps and a 1-ulp change anywhere moves the
+//    reference's own iterate by ~1e-3 after 50 iterations (measured).  Matching it to 1e-10 therefore
+//    needs the SAME arithmetic, not a similar one.  scipy's csr_matvec adds the products of a row one after the
+//    other in index order, each multiply and add rounded separately (baseline x86-64 build: no FMA); csc_matvec
+//    (A.T @ u) adds the contributions to an output entry in increasing row index, which is the order of the sorted
+//    rows of the stored transpose.  The sequential kernels do exactly that, one thread per row for the summation,
+//    and are bit-identical to scipy.
+//    Bandwidth shape: a warp owns 32 consecutive rows.  Row chunks of CH non-zeros are copied global->shared with
+//    cp.async (LDGSTS, fully coalesced: one row chunk = CH consecutive entries), STAGES chunks deep, into a
+//    [32][CH+1] tile; lane r then walks row r of the tile (conflict-free: odd pitch), gathers x[col] through the
+//    read-only path and extends its own rounding chain.  Warps never synchronise with each other (per-warp tiles,
+//    __syncwarp only), so the 8 warps of an SM are 8 independent copy/compute pipelines.  Neighbouring rows are
+//    neighbouring rays (or pixels): the 32 gathers of one step hit neighbouring pixels, i.e. few sectors.
+//
+//  order 1, "tree".  One warp per row, 128-/256-bit streaming loads, FMA, butterfly reduction.  Fastest; differs
+//    from scipy by summation order only (rel. 1e-16 per product).
+//
+// Both fuse the recurrence epilogue  y = A x - coef * z  (decompositions.py:237,240) and ||y||^2.  The norm is
+// accumulated in double-double and is the correctly rounded value of the exact sum of squares (tb200_dd.cuh).
 #include "tb200_common.cuh"
+#include "tb200_dd.cuh"
 
 namespace tb200 {
 
+// ---------------------------------------------------------------------------------------------------------
+// cp.async helpers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <typename VT>
+__device__ __forceinline__ void cp_async_val(VT* dst, const VT* src, bool valid);
+template <>
+__device__ __forceinline__ void cp_async_val<double>(double* dst, const double* src, bool valid) {
+  cp_async_8(dst, src, valid ? 8 : 0);
+}
+template <>
+__device__ __forceinline__ void cp_async_val<float>(float* dst, const float* src, bool valid) {
+  cp_async_4(dst, src, valid ? 4 : 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// order 0: sequential (scipy) summation order
+// ---------------------------------------------------------------------------------------------------------
+template <typename VT, int WARPS, int CH, int STAGES>
+struct SeqTileCfg {
+  static constexpr int CHP = CH + 1;  // odd pitch: lane r reading column k of row r is bank-conflict free
+  static constexpr int RPI = 32 / CH;  // rows copied per warp-wide cp.async instruction
+  static constexpr size_t kValsPerWarp = (size_t)STAGES * 32 * CHP;
+  static constexpr size_t kSmemBytes = (size_t)WARPS * kValsPerWarp * (sizeof(VT) + sizeof(int32_t)) +
+                                       (size_t)WARPS * 32 * (sizeof(int64_t) + sizeof(int32_t));
+};
+
+template <typename VT, int WARPS, int CH, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32)
+spmv_seq_tile_kernel(int64_t m, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                     const VT* __restrict__ val, const double* __restrict__ x, double* __restrict__ y, double coef_host,
+                     const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials) {
+  using Cfg = SeqTileCfg<VT, WARPS, CH, STAGES>;
+  constexpr int CHP = Cfg::CHP, RPI = Cfg::RPI;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // carve: [all warps' value tiles][all warps' column tiles][row starts][row lengths]
+  VT* svals = reinterpret_cast<VT*>(smem_raw) + (size_t)warp * Cfg::kValsPerWarp;
+  int32_t* scols = reinterpret_cast<int32_t*>(smem_raw + (size_t)WARPS * Cfg::kValsPerWarp * sizeof(VT)) +
+                   (size_t)warp * Cfg::kValsPerWarp;
+  unsigned char* meta = smem_raw + (size_t)WARPS * Cfg::kValsPerWarp * (sizeof(VT) + sizeof(int32_t));
+  int64_t* sstart = reinterpret_cast<int64_t*>(meta) + warp * 32;
+  int32_t* slen = reinterpret_cast<int32_t*>(meta + (size_t)WARPS * 32 * sizeof(int64_t)) + warp * 32;
+
+  const uint64_t pol_keep = policy_evict_last();
+  const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
+  const int64_t row = ((int64_t)blockIdx.x * WARPS + warp) * 32 + lane;
+  int64_t s = 0;
+  int len = 0;
+  if (row < m) {
+    s = rowptr[row];
+    len = (int)(rowptr[row + 1] - s);
+  }
+  sstart[lane] = s;
+  slen[lane] = len;
+  const int maxlen = __reduce_max_sync(0xffffffffu, len);
+  const int nit = (maxlen + CH - 1) / CH;
+  __syncwarp();
+
+  auto issue = [&](int it) {
+    const int slot = it % STAGES;
+    VT* tv = svals + (size_t)slot * 32 * CHP;
+    int32_t* tc = scols + (size_t)slot * 32 * CHP;
+    const int sub = lane / CH, k = lane % CH;
+    const int idx = it * CH + k;
+#pragma unroll 4
+    for (int rr = 0; rr < 32; rr += RPI) {
+      const int r = rr + sub;
+      const bool valid = idx < slen[r];
+      const int64_t src = valid ? sstart[r] + idx : 0;
+      cp_async_4(tc + r * CHP + k, col + src, valid ? 4 : 0);
+      cp_async_val<VT>(tv + r * CHP + k, val + src, valid);
+    }
+  };
+
+  // Software pipeline, per warp:  cp.async of chunk it+STAGES-1  |  x-gathers of chunk it+1  |  add chain of chunk it.
+  // The gathered values of chunk it+1 are live across the loop back-edge, so all CH gathers of a lane are in flight
+  // while the (latency-bound, strictly ordered) rounding chain of chunk it runs.
+  static_assert(STAGES >= 3, "the gather prefetch needs the tile of chunk it+1 landed while chunk it is consumed");
+#pragma unroll
+  for (int p = 0; p < STAGES - 1; ++p) {
+    if (p < nit) issue(p);
+    cp_async_commit();
+  }
+  double xn[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) xn[k] = 0.0;
+  if (nit > 0) {
+    cp_async_wait<STAGES - 2>();  // chunk 0 has landed
+    __syncwarp();
+    const int32_t* tc = scols + (size_t)lane * CHP;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) xn[k] = ld_gather_f64(x + tc[k], pol_keep);
+  }
+  double acc = 0.0;
+  for (int it = 0; it < nit; ++it) {
+    // slot (it-1) % STAGES was fully consumed in the previous iteration (trailing __syncwarp)
+    if (it + STAGES - 1 < nit) issue(it + STAGES - 1);
+    cp_async_commit();
+    const int slot = it % STAGES;
+    const VT* tv = svals + ((size_t)slot * 32 + lane) * CHP;
+    const int rem = len - it * CH;
+    // products of chunk it: values from the tile, x from the registers filled one iteration ago.
+    // Entries past the end of the row contribute +0.0, which leaves the running sum unchanged bit for bit
+    // (the sum is never -0.0).
+    double p[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const double prod = __dmul_rn((double)tv[k], xn[k]);
+      p[k] = (k < rem) ? prod : 0.0;
+    }
+    // gathers of chunk it+1 (its tile landed: at most STAGES-2 younger groups may still be pending)
+    cp_async_wait<STAGES - 2>();
+    __syncwarp();
+    if (it + 1 < nit) {
+      const int32_t* tc = scols + ((size_t)((it + 1) % STAGES) * 32 + lane) * CHP;
+#pragma unroll
+      for (int k = 0; k < CH; ++k) xn[k] = ld_gather_f64(x + tc[k], pol_keep);
+    }
+    // the rounding chain, in index order
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc = __dadd_rn(acc, p[k]);
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+
+  dd_t nrm = dd_zero();
+  if (row < m) {
+    if (z != nullptr) acc = __dsub_rn(acc, __dmul_rn(coef, z[row]));
+    y[row] = acc;
+    nrm = dd_fma(nrm, acc, acc);
+  }
+  if (partials != nullptr) {
+    const dd_t tot = dd_block_sum(nrm, red);
+    if (threadIdx.x == 0) {
+      partials[2 * (int64_t)blockIdx.x] = tot.hi;
+      partials[2 * (int64_t)blockIdx.x + 1] = tot.lo;
+    }
+  }
+}
+
+// One thread per row, for short rows (generic CSR handed in by a user, e.g. a sparse regularisation matrix).
+template <typename VT>
+__global__ void __launch_bounds__(256)
+spmv_seq_scalar_kernel(int64_t m, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                       const VT* __restrict__ val, const double* __restrict__ x, double* __restrict__ y, double coef_host,
+                       const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials) {
+  __shared__ double red[64];
+  const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
+  dd_t nrm = dd_zero();
+  if (row < m) {
+    double acc = 0.0;
+    const int64_t s = rowptr[row], e = rowptr[row + 1];
+    for (int64_t i = s; i < e; ++i) acc = __dadd_rn(acc, __dmul_rn((double)val[i], x[col[i]]));
+    if (z != nullptr) acc = __dsub_rn(acc, __dmul_rn(coef, z[row]));
+    y[row] = acc;
+    nrm = dd_fma(nrm, acc, acc);
+  }
+  if (partials != nullptr) {
+    const dd_t tot = dd_block_sum(nrm, red);
+    if (threadIdx.x == 0) {
+      partials[2 * (int64_t)blockIdx.x] = tot.hi;
+      partials[2 * (int64_t)blockIdx.x + 1] = tot.lo;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// order 1: tree summation (one warp per row, wide streaming loads)
+// ---------------------------------------------------------------------------------------------------------
 template <typename VT>
 struct StreamVals;
-
 template <>
 struct StreamVals<double> {
   __device__ __forceinline__ static void load4(const double* p, uint64_t, double (&v)[4]) { ld_stream_f64x4(p, v); }
@@ -37,20 +231,18 @@ struct StreamVals<float> {
   }
 };
 
-// One warp per row; WARPS warps per CTA; each CTA owns `rows_per_cta` consecutive rows, visited so that at any
-// time the CTA's warps sit on WARPS adjacent rows.
 template <typename VT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 spmv_warp_kernel(int64_t m, int rows_per_cta, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                  const VT* __restrict__ val, const double* __restrict__ x, double* __restrict__ y, double coef_host,
                  const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials) {
-  __shared__ double red[32];
+  __shared__ double red[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t pol_stream = policy_evict_first();
   const uint64_t pol_keep = policy_evict_last();
   const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
   const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
-  double nrm = 0.0;
+  dd_t nrm = dd_zero();
 
   for (int r = warp; r < rows_per_cta; r += WARPS) {
     const int64_t row = row0 + r;
@@ -59,7 +251,6 @@ spmv_warp_kernel(int64_t m, int rows_per_cta, const int64_t* __restrict__ rowptr
     int64_t a = (s + 3) & ~(int64_t)3;
     if (a > e) a = e;
     double acc0 = 0.0, acc1 = 0.0;
-    // head: up to three unaligned leading entries
     if (s + lane < a) acc0 = (double)val[s + lane] * ld_gather_f64(x + col[s + lane], pol_keep);
     const int64_t ngrp = (e - a) >> 2;
     int64_t g = lane;
@@ -88,30 +279,31 @@ spmv_warp_kernel(int64_t m, int rows_per_cta, const int64_t* __restrict__ rowptr
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc0 = fma(v0[i], ld_gather_f64(x + c0[i], pol_keep), acc0);
     }
-    // tail: up to three trailing entries
     const int64_t t0 = a + 4 * ngrp;
     if (t0 + lane < e) acc1 = fma((double)val[t0 + lane], ld_gather_f64(x + col[t0 + lane], pol_keep), acc1);
-
     double sum = warp_sum(acc0 + acc1);
     if (lane == 0) {
       if (z != nullptr) sum = __dsub_rn(sum, __dmul_rn(coef, z[row]));
       y[row] = sum;
-      nrm = fma(sum, sum, nrm);
+      nrm = dd_fma(nrm, sum, sum);
     }
   }
   if (partials != nullptr) {
-    const double tot = block_sum(nrm, red);
-    if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+    const dd_t tot = dd_block_sum(nrm, red);
+    if (threadIdx.x == 0) {
+      partials[2 * (int64_t)blockIdx.x] = tot.hi;
+      partials[2 * (int64_t)blockIdx.x + 1] = tot.lo;
+    }
   }
 }
 
-// T threads per row (T in {2,4,8,16}); scalar loads. For generic short-row CSR matrices.
+// T threads per row (T in {2,4,8,16}); scalar loads; tree order.
 template <typename VT, int T>
 __global__ void __launch_bounds__(256)
 spmv_subwarp_kernel(int64_t m, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                     const VT* __restrict__ val, const double* __restrict__ x, double* __restrict__ y, double coef_host,
                     const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials) {
-  __shared__ double red[32];
+  __shared__ double red[64];
   const int sub = threadIdx.x % T;
   const int64_t row = ((int64_t)blockIdx.x * 256 + threadIdx.x) / T;
   const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
@@ -122,71 +314,88 @@ spmv_subwarp_kernel(int64_t m, const int64_t* __restrict__ rowptr, const int32_t
   }
 #pragma unroll
   for (int o = T / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  double nrm = 0.0;
+  dd_t nrm = dd_zero();
   if (row < m && sub == 0) {
     if (z != nullptr) acc = __dsub_rn(acc, __dmul_rn(coef, z[row]));
     y[row] = acc;
-    nrm = acc * acc;
+    nrm = dd_fma(nrm, acc, acc);
   }
   if (partials != nullptr) {
-    const double tot = block_sum(nrm, red);
-    if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+    const dd_t tot = dd_block_sum(nrm, red);
+    if (threadIdx.x == 0) {
+      partials[2 * (int64_t)blockIdx.x] = tot.hi;
+      partials[2 * (int64_t)blockIdx.x + 1] = tot.lo;
+    }
   }
 }
 
-struct SpmvPlan {
-  int threads_per_row;  // 32 => warp kernel
-  int rows_per_cta;
-  int64_t nblocks;
-};
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+static int g_seq_variant = 0;  // tuning knob (tb200_spmv_set_variant): which tile configuration order 0 uses
 
-static SpmvPlan make_plan(int64_t m, int64_t nnz) {
-  SpmvPlan p;
-  const double avg = (m > 0) ? (double)nnz / (double)m : 0.0;
-  if (avg >= 48.0) {
-    p.threads_per_row = 32;
-    p.rows_per_cta = 32;  // 8 warps x 4 rows
-  } else {
-    int t = 2;
-    while (t < 16 && t < avg) t <<= 1;
-    p.threads_per_row = t;
-    p.rows_per_cta = 256 / t;
+template <typename VT, int WARPS, int CH, int STAGES>
+static int launch_seq_tile(int64_t m, const int64_t* rowptr, const int32_t* col, const VT* val, const double* x, double* y,
+                           double coef_host, const double* coef_dev, const double* z, double* partials, int64_t* nblocks,
+                           cudaStream_t st) {
+  using Cfg = SeqTileCfg<VT, WARPS, CH, STAGES>;
+  auto kern = spmv_seq_tile_kernel<VT, WARPS, CH, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("spmv_seq_tile: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
   }
-  p.nblocks = (m + p.rows_per_cta - 1) / p.rows_per_cta;
-  if (p.nblocks < 1) p.nblocks = 1;
-  return p;
+  const int64_t rows_per_cta = (int64_t)WARPS * 32;
+  *nblocks = (m + rows_per_cta - 1) / rows_per_cta;
+  kern<<<(unsigned)*nblocks, WARPS * 32, Cfg::kSmemBytes, st>>>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials);
+  return check_launch("spmv_seq_tile");
 }
 
 template <typename VT>
-static int spmv_launch(int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* col, const VT* val,
+static int spmv_launch(int order, int64_t m, int64_t nnz, const int64_t* rowptr, const int32_t* col, const VT* val,
                        const double* x, double* y, double coef_host, const double* coef_dev, const double* z,
                        double* norm_out, double* ws, cudaStream_t st) {
-  (void)n;
-  const SpmvPlan p = make_plan(m, nnz);
   double* partials = norm_out ? ws : nullptr;
-  if (p.threads_per_row == 32) {
-    spmv_warp_kernel<VT, 8><<<(unsigned)p.nblocks, 256, 0, st>>>(m, p.rows_per_cta, rowptr, col, val, x, y, coef_host,
-                                                                 coef_dev, z, partials);
-  } else {
-    switch (p.threads_per_row) {
-      case 2:
-        spmv_subwarp_kernel<VT, 2><<<(unsigned)p.nblocks, 256, 0, st>>>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials);
-        break;
-      case 4:
-        spmv_subwarp_kernel<VT, 4><<<(unsigned)p.nblocks, 256, 0, st>>>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials);
-        break;
-      case 8:
-        spmv_subwarp_kernel<VT, 8><<<(unsigned)p.nblocks, 256, 0, st>>>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials);
-        break;
-      default:
-        spmv_subwarp_kernel<VT, 16><<<(unsigned)p.nblocks, 256, 0, st>>>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials);
-        break;
+  const double avg = (m > 0) ? (double)nnz / (double)m : 0.0;
+  int64_t nblocks = 1;
+  int rc = 0;
+  if (order == 0) {
+    if (avg >= 24.0) {
+      switch (g_seq_variant) {
+        case 1: rc = launch_seq_tile<VT, 8, 16, 3>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
+        case 2: rc = launch_seq_tile<VT, 4, 32, 3>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
+        case 3: rc = launch_seq_tile<VT, 8, 8, 3>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
+        default: rc = launch_seq_tile<VT, 4, 16, 3>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
+      }
+    } else {
+      nblocks = (m + 255) / 256;
+      spmv_seq_scalar_kernel<VT><<<(unsigned)nblocks, 256, 0, st>>>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials);
+      rc = check_launch("spmv_seq_scalar");
     }
+  } else if (avg >= 48.0) {
+    const int rows_per_cta = 32;
+    nblocks = (m + rows_per_cta - 1) / rows_per_cta;
+    spmv_warp_kernel<VT, 8><<<(unsigned)nblocks, 256, 0, st>>>(m, rows_per_cta, rowptr, col, val, x, y, coef_host, coef_dev, z, partials);
+    rc = check_launch("spmv_warp");
+  } else {
+    int t = 2;
+    while (t < 16 && t < avg) t <<= 1;
+    nblocks = (m * t + 255) / 256;
+    switch (t) {
+      case 2: spmv_subwarp_kernel<VT, 2><<<(unsigned)nblocks, 256, 0, st>>>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials); break;
+      case 4: spmv_subwarp_kernel<VT, 4><<<(unsigned)nblocks, 256, 0, st>>>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials); break;
+      case 8: spmv_subwarp_kernel<VT, 8><<<(unsigned)nblocks, 256, 0, st>>>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials); break;
+      default: spmv_subwarp_kernel<VT, 16><<<(unsigned)nblocks, 256, 0, st>>>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials); break;
+    }
+    rc = check_launch("spmv_subwarp");
   }
-  int rc = check_launch("spmv");
   if (rc) return rc;
   if (norm_out) {
-    finalize_sum_kernel<<<1, 1024, 0, st>>>(ws, p.nblocks, norm_out);
+    finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, nblocks, norm_out);
     rc = check_launch("spmv finalize");
   }
   return rc;
@@ -198,14 +407,24 @@ using namespace tb200;
 
 extern "C" {
 
-// Number of doubles of workspace a fused-norm SpMV over m rows may need (upper bound over all plans).
-int64_t tb200_spmv_workspace_len(int64_t m) { return (m + 7) / 8 + 8; }
+// Number of doubles of workspace a fused-norm SpMV over m rows may need (upper bound over all plans):
+// one double-double partial per CTA, smallest CTA footprint is 16 rows.
+int64_t tb200_spmv_workspace_len(int64_t m) { return 2 * ((m + 15) / 16 + 8); }
 
 // How many of this library's kernels one call enqueues (for launch accounting in bench.py).
 int tb200_spmv_launches(int with_norm) { return with_norm ? 2 : 1; }
 
-static int check_spmv_args(int64_t m, int64_t n, int64_t nnz, const void* rowptr, const void* col, const void* val,
-                           const void* x, const void* y, const void* norm_out, const void* ws) {
+// Tuning knob for the order-0 tile kernel: 0 = 4 warps x 16-entry chunks x 3 stages (default),
+// 1 = 8 x 16 x 3, 2 = 4 x 32 x 3, 3 = 8 x 8 x 3.  Results are bit-identical across variants.
+int tb200_spmv_set_variant(int v) {
+  TB200_REQUIRE(v >= 0 && v <= 3, "variant must be 0..3");
+  g_seq_variant = v;
+  return 0;
+}
+
+static int check_spmv_args(int order, int64_t m, int64_t n, int64_t nnz, const void* rowptr, const void* col,
+                           const void* val, const void* x, const void* y, const void* norm_out, const void* ws) {
+  TB200_REQUIRE(order == 0 || order == 1, "order must be 0 (sequential) or 1 (tree)");
   TB200_REQUIRE(m >= 0 && n >= 0 && nnz >= 0, "negative size");
   TB200_REQUIRE(n < ((int64_t)1 << 31), "n must fit int32 column indices");
   TB200_REQUIRE(rowptr && x && y, "null pointer");
@@ -215,30 +434,30 @@ static int check_spmv_args(int64_t m, int64_t n, int64_t nnz, const void* rowptr
   return 0;
 }
 
-int tb200_spmv_csr_f64(int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx,
+int tb200_spmv_csr_f64(int order, int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx,
                        const double* vals, const double* x, double* y, double coef_host, const double* coef_dev,
                        const double* z, double* norm_out, double* ws, void* stream) {
-  int rc = check_spmv_args(m, n, nnz, rowptr, colidx, vals, x, y, norm_out, ws);
+  int rc = check_spmv_args(order, m, n, nnz, rowptr, colidx, vals, x, y, norm_out, ws);
   if (rc) return rc;
   if (m == 0) return 0;
-  return spmv_launch<double>(m, n, nnz, rowptr, colidx, vals, x, y, coef_host, coef_dev, z, norm_out, ws,
+  return spmv_launch<double>(order, m, nnz, rowptr, colidx, vals, x, y, coef_host, coef_dev, z, norm_out, ws,
                              (cudaStream_t)stream);
 }
 
-int tb200_spmv_csr_f32s(int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx,
+int tb200_spmv_csr_f32s(int order, int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx,
                         const float* vals, const double* x, double* y, double coef_host, const double* coef_dev,
                         const double* z, double* norm_out, double* ws, void* stream) {
-  int rc = check_spmv_args(m, n, nnz, rowptr, colidx, vals, x, y, norm_out, ws);
+  int rc = check_spmv_args(order, m, n, nnz, rowptr, colidx, vals, x, y, norm_out, ws);
   if (rc) return rc;
   if (m == 0) return 0;
-  return spmv_launch<float>(m, n, nnz, rowptr, colidx, vals, x, y, coef_host, coef_dev, z, norm_out, ws,
+  return spmv_launch<float>(order, m, nnz, rowptr, colidx, vals, x, y, coef_host, coef_dev, z, norm_out, ws,
                             (cudaStream_t)stream);
 }
 
-// out[0] = sum(partials[0..n)), out[1] = sqrt(out[0]); fixed order, one CTA.
+// out[0] = round(sum of the n double-double partials (hi, lo interleaved)), out[1] = sqrt(out[0]); one CTA.
 int tb200_reduce_finalize(const double* partials, int64_t n, double* out, void* stream) {
   TB200_REQUIRE(partials && out && n >= 0, "bad argument");
-  finalize_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, n, out);
+  finalize_dd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(partials, n, out);
   return check_launch("reduce_finalize");
 }
 

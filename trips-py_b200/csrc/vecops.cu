@@ -6,8 +6,10 @@
 //   (v**2 + eps**2)**(p/2-1)             trips/solvers/MMGKS.py:57, trips/utilities/weights.py:66-68
 //   wf*(AV@y - b), wr*(LV@y)             trips/solvers/MMGKS.py:111-113
 // NumPy rounds every elementary operation, so the element-wise kernels use the *_rn intrinsics (no FMA
-// contraction).  Reductions (norms, dots) use a fixed two-stage tree: per-CTA partials, then one CTA.
+// contraction).  Reductions (norms, dots) are accumulated in double-double and return the correctly rounded value of
+// the exact sum (tb200_dd.cuh): independent of the reduction tree, reproducible bit for bit by the CPU oracle.
 #include "tb200_common.cuh"
+#include "tb200_dd.cuh"
 
 namespace tb200 {
 
@@ -30,17 +32,20 @@ __global__ void __launch_bounds__(kVecThreads) vec_div_kernel(int64_t n, const d
 __global__ void __launch_bounds__(kVecThreads) vec_axpy_kernel(int64_t n, double ah, const double* __restrict__ ad, double sign,
                                                                const double* __restrict__ x, const double* __restrict__ y,
                                                                double* __restrict__ out, double* __restrict__ partials) {
-  __shared__ double red[32];
+  __shared__ double red[64];
   const double a = sign * scalar_of(ah, ad);  // sign = +-1: exact
-  double acc = 0.0;
+  dd_t acc = dd_zero();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double v = __dadd_rn(y[i], __dmul_rn(a, x[i]));
     out[i] = v;
-    acc = fma(v, v, acc);
+    if (partials) acc = dd_fma(acc, v, v);
   }
   if (partials) {
-    const double tot = block_sum(acc, red);
-    if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+    const dd_t tot = dd_block_sum(acc, red);
+    if (threadIdx.x == 0) {
+      partials[2 * blockIdx.x] = tot.hi;
+      partials[2 * blockIdx.x + 1] = tot.lo;
+    }
   }
 }
 
@@ -48,21 +53,24 @@ __global__ void __launch_bounds__(kVecThreads) vec_axpy_kernel(int64_t n, double
 template <int MODE>
 __global__ void __launch_bounds__(kVecThreads) vec_reduce_kernel(int64_t n, const double* __restrict__ x,
                                                                  const double* __restrict__ y, double* __restrict__ partials) {
-  __shared__ double red[32];
-  double acc = 0.0;
+  __shared__ double red[64];
+  dd_t acc = dd_zero();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     if (MODE == 0) {
       const double v = x[i];
-      acc = fma(v, v, acc);
+      acc = dd_fma(acc, v, v);
     } else if (MODE == 1) {
-      acc = fma(x[i], y[i], acc);
+      acc = dd_fma(acc, x[i], y[i]);
     } else {
       const double d = __dsub_rn(x[i], y[i]);
-      acc = fma(d, d, acc);
+      acc = dd_fma(acc, d, d);
     }
   }
-  const double tot = block_sum(acc, red);
-  if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+  const dd_t tot = dd_block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = tot.hi;
+    partials[2 * blockIdx.x + 1] = tot.lo;
+  }
 }
 
 // mode 0: out = x*y ; 1: out = x-y ; 2: out = w*(x-y) ; 3: out = x + y
@@ -96,7 +104,7 @@ using namespace tb200;
 extern "C" {
 
 // Doubles of workspace any reduction in this file needs.
-int64_t tb200_reduce_workspace_len(void) { return kMaxReduceBlocks; }
+int64_t tb200_reduce_workspace_len(void) { return 2 * kMaxReduceBlocks; }
 
 int tb200_vec_div(int64_t n, const double* x, double d_host, const double* d_dev, double* out, void* stream) {
   TB200_REQUIRE(n >= 0 && (n == 0 || (x && out)), "bad argument");
@@ -116,7 +124,7 @@ int tb200_vec_axpy(int64_t n, double a_host, const double* a_dev, double sign, c
   vec_axpy_kernel<<<g, kVecThreads, 0, st>>>(n, a_host, a_dev, sign, x, y, out, norm_out ? ws : nullptr);
   int rc = check_launch("vec_axpy");
   if (rc || !norm_out) return rc;
-  finalize_sum_kernel<<<1, 1024, 0, st>>>(ws, g, norm_out);
+  finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, g, norm_out);
   return check_launch("vec_axpy finalize");
 }
 
@@ -129,7 +137,7 @@ static int reduce_common(int mode, int64_t n, const double* x, const double* y, 
   else vec_reduce_kernel<2><<<g, kVecThreads, 0, st>>>(n, x, y, ws);
   int rc = check_launch("vec_reduce");
   if (rc) return rc;
-  finalize_sum_kernel<<<1, 1024, 0, st>>>(ws, g, out);
+  finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, g, out);
   return check_launch("vec_reduce finalize");
 }
 

@@ -112,10 +112,14 @@ class CSRDevice:
         return CSRDevice(self.shape, self.rowptr, self.colidx, self.vals.to(torch.float32))
 
 
-def spmv(A, x, out=None, coef=None, z=None, norm_out=None):
+ORDERS = {"sequential": 0, "tree": 1}
+
+
+def spmv(A, x, out=None, coef=None, z=None, norm_out=None, order="sequential"):
     """out = A x - coef*z (z/coef optional), optionally norm_out[:] = (||out||^2, ||out||).
 
-    coef may be a Python float or a 1-element device tensor (kept on the device, no sync)."""
+    coef may be a Python float or a 1-element device tensor (kept on the device, no sync).
+    order 'sequential' reproduces scipy's csr_matvec bit for bit; 'tree' is the fastest reduction order."""
     m, n = A.shape
     _vec(x, n, "x")
     if out is None:
@@ -130,8 +134,8 @@ def spmv(A, x, out=None, coef=None, z=None, norm_out=None):
             coef_host = float(coef)
     ws = Workspace.get(A.device).spmv(m) if norm_out is not None else None
     fn = lib().tb200_spmv_csr_f64 if A.vals.dtype == F64 else lib().tb200_spmv_csr_f32s
-    check(fn(m, n, A.nnz, _p(A.rowptr), _p(A.colidx), _p(A.vals), _p(x), _p(out), coef_host, _p(coef_dev), _p(z),
-             _p(norm_out), _p(ws), _stream()), "spmv")
+    check(fn(ORDERS[order], m, n, A.nnz, _p(A.rowptr), _p(A.colidx), _p(A.vals), _p(x), _p(out), coef_host, _p(coef_dev),
+             _p(z), _p(norm_out), _p(ws), _stream()), "spmv")
     _lib.count(2 if norm_out is not None else 1)
     return out
 

@@ -242,11 +242,17 @@ class CSROperator(LinearOperator):
 
     fused = True
 
-    def __init__(self, A, AT):
+    def __init__(self, A, AT, order="sequential"):
         if A.shape != (AT.shape[1], AT.shape[0]):
             raise ValueError("AT must have the transposed shape of A")
+        if order not in K.ORDERS:
+            raise ValueError("order must be 'sequential' (bit-identical to scipy's SpMV) or 'tree' (fastest)")
         super().__init__(A.shape, A.device)
-        self.A, self.AT = A, AT
+        self.A, self.AT, self.order = A, AT, order
+
+    def with_order(self, order):
+        """Same matrices, different summation order of the row sums ('sequential' = scipy's, 'tree' = fastest)."""
+        return CSROperator(self.A, self.AT, order)
 
     @classmethod
     def from_scipy(cls, A, device=None):
@@ -275,17 +281,17 @@ class CSROperator(LinearOperator):
 
     def with_f32_storage(self):
         """fp32-storage / fp64-accumulate variant (16 instead of 24 B/nnz per Golub-Kahan iteration)."""
-        return CSROperator(self.A.to_f32_storage(), self.AT.to_f32_storage())
+        return CSROperator(self.A.to_f32_storage(), self.AT.to_f32_storage(), self.order)
 
     @property
     def nnz(self):
         return self.A.nnz
 
     def apply_dev(self, x, out=None, coef=None, z=None, norm_out=None):
-        return K.spmv(self.A, x, out=out, coef=coef, z=z, norm_out=norm_out)
+        return K.spmv(self.A, x, out=out, coef=coef, z=z, norm_out=norm_out, order=self.order)
 
     def adjoint_dev(self, y, out=None, coef=None, z=None, norm_out=None):
-        return K.spmv(self.AT, y, out=out, coef=coef, z=z, norm_out=norm_out)
+        return K.spmv(self.AT, y, out=out, coef=coef, z=z, norm_out=norm_out, order=self.order)
 
 
 def _upload_csr(A, device):
