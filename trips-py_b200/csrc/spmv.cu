@@ -36,93 +36,188 @@ namespace tb200 {
 // cp.async helpers
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async_4(void* dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_8(void* dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+// 16-byte global->shared copy, L2 only (no L1 allocation); bytes beyond src_bytes are zero-filled.
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst), "l"(src), "r"(src_bytes),
+               "l"(policy)
+               : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-template <typename VT>
-__device__ __forceinline__ void cp_async_val(VT* dst, const VT* src, bool valid);
-template <>
-__device__ __forceinline__ void cp_async_val<double>(double* dst, const double* src, bool valid) {
-  cp_async_8(dst, src, valid ? 8 : 0);
-}
-template <>
-__device__ __forceinline__ void cp_async_val<float>(float* dst, const float* src, bool valid) {
-  cp_async_4(dst, src, valid ? 4 : 0);
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // order 0: sequential (scipy) summation order
 // ---------------------------------------------------------------------------------------------------------
+// Tile geometry.  Every row stream is taken from its start rounded DOWN to a multiple of four entries, so that
+// column indices (4 B) and values (8 or 4 B) both arrive in 16-byte pieces that are 16-byte aligned in global
+// memory; the up to three leading entries that belong to the previous row, and whatever follows the row's end in
+// its last piece, are masked to zero in registers (only the first and last chunk of a row take that path).
 template <typename VT, int WARPS, int CH, int STAGES>
 struct SeqTileCfg {
-  static constexpr int CHP = CH + 1;  // odd pitch: lane r reading column k of row r is bank-conflict free
-  static constexpr int RPI = 32 / CH;  // rows copied per warp-wide cp.async instruction
-  static constexpr size_t kValsPerWarp = (size_t)STAGES * 32 * CHP;
-  static constexpr size_t kSmemBytes = (size_t)WARPS * kValsPerWarp * (sizeof(VT) + sizeof(int32_t)) +
-                                       (size_t)WARPS * 32 * (sizeof(int64_t) + sizeof(int32_t));
+  static constexpr int VPP = 16 / (int)sizeof(VT);  // values per 16-byte piece
+  static constexpr int NC = CH / 4;                 // column pieces per row chunk
+  static constexpr int NV = CH / VPP;               // value pieces per row chunk
+  static constexpr int PC = NC + 1;                 // row pitch in pieces: odd => 128-bit reads by 8 consecutive
+  static constexpr int PV = NV + 1;                 //   lanes (one row each) hit 8 distinct 16-byte bank groups
+  static_assert((PC & 1) && (PV & 1), "pitches must be odd");
+  static constexpr int CSTAGES = STAGES - 1;        // column tiles are dead once their gathers are issued
+  static constexpr size_t kColBytesPerWarp = (size_t)CSTAGES * 32 * PC * 16;
+  static constexpr size_t kValBytesPerWarp = (size_t)STAGES * 32 * PV * 16;
+  static constexpr size_t kSmemBytes = (size_t)WARPS * (kColBytesPerWarp + kValBytesPerWarp);
 };
+
+template <typename VT, int CH>
+__device__ __forceinline__ void load_vals(const unsigned char* rowbase, double (&v)[CH]);
+template <>
+__device__ __forceinline__ void load_vals<double, 8>(const unsigned char* rowbase, double (&v)[8]) {
+  const double2* p = reinterpret_cast<const double2*>(rowbase);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double2 t = p[j];
+    v[2 * j] = t.x;
+    v[2 * j + 1] = t.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load_vals<double, 16>(const unsigned char* rowbase, double (&v)[16]) {
+  const double2* p = reinterpret_cast<const double2*>(rowbase);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double2 t = p[j];
+    v[2 * j] = t.x;
+    v[2 * j + 1] = t.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load_vals<double, 32>(const unsigned char* rowbase, double (&v)[32]) {
+  const double2* p = reinterpret_cast<const double2*>(rowbase);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const double2 t = p[j];
+    v[2 * j] = t.x;
+    v[2 * j + 1] = t.y;
+  }
+}
+template <>
+__device__ __forceinline__ void load_vals<float, 8>(const unsigned char* rowbase, double (&v)[8]) {
+  const float4* p = reinterpret_cast<const float4*>(rowbase);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float4 t = p[j];
+    v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+  }
+}
+template <>
+__device__ __forceinline__ void load_vals<float, 16>(const unsigned char* rowbase, double (&v)[16]) {
+  const float4* p = reinterpret_cast<const float4*>(rowbase);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = p[j];
+    v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+  }
+}
+template <>
+__device__ __forceinline__ void load_vals<float, 32>(const unsigned char* rowbase, double (&v)[32]) {
+  const float4* p = reinterpret_cast<const float4*>(rowbase);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = p[j];
+    v[4 * j] = t.x, v[4 * j + 1] = t.y, v[4 * j + 2] = t.z, v[4 * j + 3] = t.w;
+  }
+}
 
 template <typename VT, int WARPS, int CH, int STAGES>
 __global__ void __launch_bounds__(WARPS * 32)
-spmv_seq_tile_kernel(int64_t m, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+spmv_seq_tile_kernel(int64_t m, int64_t nnz, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const VT* __restrict__ val, const double* __restrict__ x, double* __restrict__ y, double coef_host,
                      const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials) {
   using Cfg = SeqTileCfg<VT, WARPS, CH, STAGES>;
-  constexpr int CHP = Cfg::CHP, RPI = Cfg::RPI;
+  constexpr int NC = Cfg::NC, NV = Cfg::NV, PC = Cfg::PC, PV = Cfg::PV, VPP = Cfg::VPP, CSTAGES = Cfg::CSTAGES;
+  constexpr int RPI = 32 / NC;  // rows covered by one warp-wide copy instruction (NC lanes per row)
+  constexpr int VH = NV / NC;   // value pieces each lane copies per row (2 for fp64, 1 for fp32)
+  static_assert(STAGES >= 3, "the gather prefetch needs the tile of chunk it+1 landed while chunk it is consumed");
+  static_assert(32 % NC == 0 && NV % NC == 0, "pieces per row must divide the warp");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double red[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // carve: [all warps' value tiles][all warps' column tiles][row starts][row lengths]
-  VT* svals = reinterpret_cast<VT*>(smem_raw) + (size_t)warp * Cfg::kValsPerWarp;
-  int32_t* scols = reinterpret_cast<int32_t*>(smem_raw + (size_t)WARPS * Cfg::kValsPerWarp * sizeof(VT)) +
-                   (size_t)warp * Cfg::kValsPerWarp;
-  unsigned char* meta = smem_raw + (size_t)WARPS * Cfg::kValsPerWarp * (sizeof(VT) + sizeof(int32_t));
-  int64_t* sstart = reinterpret_cast<int64_t*>(meta) + warp * 32;
-  int32_t* slen = reinterpret_cast<int32_t*>(meta + (size_t)WARPS * 32 * sizeof(int64_t)) + warp * 32;
+  // carve: [col tiles of all warps][val tiles of all warps]
+  unsigned char* ctile = smem_raw + (size_t)warp * Cfg::kColBytesPerWarp;
+  unsigned char* vtile = smem_raw + (size_t)WARPS * Cfg::kColBytesPerWarp + (size_t)warp * Cfg::kValBytesPerWarp;
+  const uint32_t ctile_s = smem_u32(ctile), vtile_s = smem_u32(vtile);
 
-  const uint64_t pol_keep = policy_evict_last();
+  const uint64_t pol_keep = policy_evict_last();     // the gathered vector: the only data with reuse
+  const uint64_t pol_stream = policy_evict_first();  // the matrix stream: read once, must not displace x in L2
   const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
   const int64_t row = ((int64_t)blockIdx.x * WARPS + warp) * 32 + lane;
-  int64_t s = 0;
-  int len = 0;
+  int64_t a = 0;  // row start rounded down to a multiple of 4 entries
+  int off = 0;    // leading entries of the stream that belong to the previous row
+  int tot = 0;    // stream length = off + row length
   if (row < m) {
-    s = rowptr[row];
-    len = (int)(rowptr[row + 1] - s);
+    const int64_t s = rowptr[row];
+    a = s & ~(int64_t)3;
+    off = (int)(s - a);
+    tot = (int)(rowptr[row + 1] - a);
+    if (tot == off) tot = 0, off = 0;  // empty row
   }
-  sstart[lane] = s;
-  slen[lane] = len;
-  const int maxlen = __reduce_max_sync(0xffffffffu, len);
-  const int nit = (maxlen + CH - 1) / CH;
-  __syncwarp();
+  const int nit = (__reduce_max_sync(0xffffffffu, tot) + CH - 1) / CH;
 
+  // Producer role of this lane: piece (lane % NC) of the rows q*RPI + lane/NC, q = 0..NC-1 (the same rows for the
+  // column and the value tiles), whose stream descriptors are fetched once from the owning lanes.
+  const int pc = lane % NC, rsub = lane / NC;
+  int64_t pa[NC];  // aligned stream start of my q-th row
+  int ptot[NC];    // its stream length
+  int pavail[NC];  // entries left in the arrays from its start (clamped): no read beyond the end of colidx / vals
+#pragma unroll
+  for (int q = 0; q < NC; ++q) {
+    const int r = q * RPI + rsub;
+    pa[q] = __shfl_sync(0xffffffffu, a, r);
+    ptot[q] = __shfl_sync(0xffffffffu, tot, r);
+    const int64_t left = nnz - pa[q];
+    pavail[q] = left > (int64_t)0x3fffffff ? 0x3fffffff : (int)left;
+  }
+
+  // One chunk = CH stream positions of each of the 32 rows: NC column pieces + NV value pieces per row.
   auto issue = [&](int it) {
-    const int slot = it % STAGES;
-    VT* tv = svals + (size_t)slot * 32 * CHP;
-    int32_t* tc = scols + (size_t)slot * 32 * CHP;
-    const int sub = lane / CH, k = lane % CH;
-    const int idx = it * CH + k;
-#pragma unroll 4
-    for (int rr = 0; rr < 32; rr += RPI) {
-      const int r = rr + sub;
-      const bool valid = idx < slen[r];
-      const int64_t src = valid ? sstart[r] + idx : 0;
-      cp_async_4(tc + r * CHP + k, col + src, valid ? 4 : 0);
-      cp_async_val<VT>(tv + r * CHP + k, val + src, valid);
+    const int cslot = it % CSTAGES, vslot = it % STAGES;
+    const int pos0 = it * CH;
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+      const int r = q * RPI + rsub;
+      {
+        const int pos = pos0 + 4 * pc;
+        const int left = (pavail[q] - pos) * 4;
+        const int bytes = (pos < ptot[q]) ? (left < 16 ? left : 16) : 0;
+        cp_async_16(ctile_s + (uint32_t)(((cslot * 32 + r) * PC + pc) * 16), col + (bytes ? pa[q] + pos : 0), bytes, pol_stream);
+      }
+#pragma unroll
+      for (int h = 0; h < VH; ++h) {
+        const int pv = h * NC + pc;
+        const int pos = pos0 + VPP * pv;
+        const int left = (pavail[q] - pos) * (int)sizeof(VT);
+        const int bytes = (pos < ptot[q]) ? (left < 16 ? left : 16) : 0;
+        cp_async_16(vtile_s + (uint32_t)(((vslot * 32 + r) * PV + pv) * 16), val + (bytes ? pa[q] + pos : 0), bytes, pol_stream);
+      }
+    }
+  };
+  auto gather = [&](int it, double (&xv)[CH]) {
+    const int4* tc = reinterpret_cast<const int4*>(ctile + (size_t)(((it % CSTAGES) * 32 + lane) * PC) * 16);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int4 c = tc[j];
+      xv[4 * j + 0] = ld_gather_f64(x + c.x, pol_keep);
+      xv[4 * j + 1] = ld_gather_f64(x + c.y, pol_keep);
+      xv[4 * j + 2] = ld_gather_f64(x + c.z, pol_keep);
+      xv[4 * j + 3] = ld_gather_f64(x + c.w, pol_keep);
     }
   };
 
   // Software pipeline, per warp:  cp.async of chunk it+STAGES-1  |  x-gathers of chunk it+1  |  add chain of chunk it.
   // The gathered values of chunk it+1 are live across the loop back-edge, so all CH gathers of a lane are in flight
-  // while the (latency-bound, strictly ordered) rounding chain of chunk it runs.
-  static_assert(STAGES >= 3, "the gather prefetch needs the tile of chunk it+1 landed while chunk it is consumed");
+  // while the (latency-bound, strictly ordered) rounding chain of chunk it runs.  Column tiles need one slot less
+  // than value tiles: the columns of chunk it are dead once its gathers were issued (iteration it-1).
 #pragma unroll
   for (int p = 0; p < STAGES - 1; ++p) {
     if (p < nit) issue(p);
@@ -134,38 +229,32 @@ spmv_seq_tile_kernel(int64_t m, const int64_t* __restrict__ rowptr, const int32_
   if (nit > 0) {
     cp_async_wait<STAGES - 2>();  // chunk 0 has landed
     __syncwarp();
-    const int32_t* tc = scols + (size_t)lane * CHP;
-#pragma unroll
-    for (int k = 0; k < CH; ++k) xn[k] = ld_gather_f64(x + tc[k], pol_keep);
+    gather(0, xn);
   }
   double acc = 0.0;
   for (int it = 0; it < nit; ++it) {
-    // slot (it-1) % STAGES was fully consumed in the previous iteration (trailing __syncwarp)
+    // value slot (it-1) % STAGES and column slot it % CSTAGES were fully consumed (trailing __syncwarp of it-1)
     if (it + STAGES - 1 < nit) issue(it + STAGES - 1);
     cp_async_commit();
-    const int slot = it % STAGES;
-    const VT* tv = svals + ((size_t)slot * 32 + lane) * CHP;
-    const int rem = len - it * CH;
-    // products of chunk it: values from the tile, x from the registers filled one iteration ago.
-    // Entries past the end of the row contribute +0.0, which leaves the running sum unchanged bit for bit
-    // (the sum is never -0.0).
-    double p[CH];
+    double v[CH];
+    load_vals<VT, CH>(vtile + (size_t)(((it % STAGES) * 32 + lane) * PV) * 16, v);
+    // positions outside [lo, hi) are not this row's: zero their value (adds +-0.0: the running sum keeps its bits)
+    const int lo = (it == 0) ? off : 0;
+    const int hi = tot - it * CH;
+    if (lo > 0 || hi < CH) {
 #pragma unroll
-    for (int k = 0; k < CH; ++k) {
-      const double prod = __dmul_rn((double)tv[k], xn[k]);
-      p[k] = (k < rem) ? prod : 0.0;
+      for (int k = 0; k < CH; ++k)
+        if (k < lo || k >= hi) v[k] = 0.0, xn[k] = 0.0;
     }
-    // gathers of chunk it+1 (its tile landed: at most STAGES-2 younger groups may still be pending)
+#pragma unroll
+    for (int k = 0; k < CH; ++k) v[k] = __dmul_rn(v[k], xn[k]);
+    // gathers of chunk it+1 (its tile has landed: at most STAGES-2 younger groups may still be pending)
     cp_async_wait<STAGES - 2>();
     __syncwarp();
-    if (it + 1 < nit) {
-      const int32_t* tc = scols + ((size_t)((it + 1) % STAGES) * 32 + lane) * CHP;
-#pragma unroll
-      for (int k = 0; k < CH; ++k) xn[k] = ld_gather_f64(x + tc[k], pol_keep);
-    }
+    if (it + 1 < nit) gather(it + 1, xn);
     // the rounding chain, in index order
 #pragma unroll
-    for (int k = 0; k < CH; ++k) acc = __dadd_rn(acc, p[k]);
+    for (int k = 0; k < CH; ++k) acc = __dadd_rn(acc, v[k]);
     __syncwarp();
   }
   cp_async_wait<0>();
@@ -177,10 +266,10 @@ spmv_seq_tile_kernel(int64_t m, const int64_t* __restrict__ rowptr, const int32_
     nrm = dd_fma(nrm, acc, acc);
   }
   if (partials != nullptr) {
-    const dd_t tot = dd_block_sum(nrm, red);
+    const dd_t tot2 = dd_block_sum(nrm, red);
     if (threadIdx.x == 0) {
-      partials[2 * (int64_t)blockIdx.x] = tot.hi;
-      partials[2 * (int64_t)blockIdx.x + 1] = tot.lo;
+      partials[2 * (int64_t)blockIdx.x] = tot2.hi;
+      partials[2 * (int64_t)blockIdx.x + 1] = tot2.lo;
     }
   }
 }
@@ -335,7 +424,7 @@ spmv_subwarp_kernel(int64_t m, const int64_t* __restrict__ rowptr, const int32_t
 static int g_seq_variant = 0;  // tuning knob (tb200_spmv_set_variant): which tile configuration order 0 uses
 
 template <typename VT, int WARPS, int CH, int STAGES>
-static int launch_seq_tile(int64_t m, const int64_t* rowptr, const int32_t* col, const VT* val, const double* x, double* y,
+static int launch_seq_tile(int64_t m, int64_t nnz, const int64_t* rowptr, const int32_t* col, const VT* val, const double* x, double* y,
                            double coef_host, const double* coef_dev, const double* z, double* partials, int64_t* nblocks,
                            cudaStream_t st) {
   using Cfg = SeqTileCfg<VT, WARPS, CH, STAGES>;
@@ -351,7 +440,7 @@ static int launch_seq_tile(int64_t m, const int64_t* rowptr, const int32_t* col,
   }
   const int64_t rows_per_cta = (int64_t)WARPS * 32;
   *nblocks = (m + rows_per_cta - 1) / rows_per_cta;
-  kern<<<(unsigned)*nblocks, WARPS * 32, Cfg::kSmemBytes, st>>>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials);
+  kern<<<(unsigned)*nblocks, WARPS * 32, Cfg::kSmemBytes, st>>>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials);
   return check_launch("spmv_seq_tile");
 }
 
@@ -366,10 +455,10 @@ static int spmv_launch(int order, int64_t m, int64_t nnz, const int64_t* rowptr,
   if (order == 0) {
     if (avg >= 24.0) {
       switch (g_seq_variant) {
-        case 1: rc = launch_seq_tile<VT, 8, 16, 3>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
-        case 2: rc = launch_seq_tile<VT, 4, 32, 3>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
-        case 3: rc = launch_seq_tile<VT, 8, 8, 3>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
-        default: rc = launch_seq_tile<VT, 4, 16, 3>(m, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
+        case 1: rc = launch_seq_tile<VT, 2, 16, 3>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
+        case 2: rc = launch_seq_tile<VT, 4, 16, 3>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
+        case 3: rc = launch_seq_tile<VT, 1, 8, 4>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
+        default: rc = launch_seq_tile<VT, 1, 16, 3>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
       }
     } else {
       nblocks = (m + 255) / 256;
@@ -409,13 +498,13 @@ extern "C" {
 
 // Number of doubles of workspace a fused-norm SpMV over m rows may need (upper bound over all plans):
 // one double-double partial per CTA, smallest CTA footprint is 16 rows.
-int64_t tb200_spmv_workspace_len(int64_t m) { return 2 * ((m + 15) / 16 + 8); }
+int64_t tb200_spmv_workspace_len(int64_t m) { return 2 * ((m + 15) / 16 + 8); }  // >= one dd partial per 32 rows
 
 // How many of this library's kernels one call enqueues (for launch accounting in bench.py).
 int tb200_spmv_launches(int with_norm) { return with_norm ? 2 : 1; }
 
-// Tuning knob for the order-0 tile kernel: 0 = 4 warps x 16-entry chunks x 3 stages (default),
-// 1 = 8 x 16 x 3, 2 = 4 x 32 x 3, 3 = 8 x 8 x 3.  Results are bit-identical across variants.
+// Tuning knob for the order-0 tile kernel (warps per CTA x entries per chunk x stages): 0 = 1 x 16 x 3 (default),
+// 1 = 2 x 16 x 3, 2 = 4 x 16 x 3, 3 = 1 x 8 x 4.  Results are bit-identical across variants.
 int tb200_spmv_set_variant(int v) {
   TB200_REQUIRE(v >= 0 && v <= 3, "variant must be 0..3");
   g_seq_variant = v;
