@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=2048)
     ap.add_argument("--views", type=int, default=720)
-    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-sample-views", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--f32-storage", action="store_true", help="fp32-storage / fp64-accumulate variant (reported separately)")
@@ -64,34 +64,50 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (started early, filtered by timestamp)."""
+
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:  # noqa: BLE001
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is not None:
+            time.sleep(0.12)  # let the last samples arrive
             self.proc.terminate()
-        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 - 0.05 <= t <= self.t1 + 0.1 and len(r) >= 8]
+        rows = inside if inside else [r for _, r in self.rows if len(r) >= 8]
+        num = lambda s: float(s) if s.replace(".", "", 1).isdigit() else None  # noqa: E731
+        sm = sorted(v for v in (num(r[1]) for r in rows) if v is not None)
+        mx = [v for v in (num(r[2]) for r in rows) if v is not None]
+        pw = [v for v in (num(r[3]) for r in rows) if v is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": int(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": int(max(mx)) if mx else None,
+                "reasons": reasons, "samples": len(sm), "samples_in_timed_region": len(inside),
+                "power_w_max": max(pw) if pw else None}
 
 
 def cpu_gk_rate(A_sample, b_sample, steps, warmup, nnz_full):
@@ -224,13 +240,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(W):
         st.step()
     barrier()
     KM.spmv = timed_spmv
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     launches0 = _lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -238,6 +255,7 @@ def main():
         st.step()
     ev1.record()
     barrier()
+    sampler.mark_end()
     KM.spmv = orig_spmv
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count - launches0

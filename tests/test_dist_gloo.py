@@ -1,0 +1,121 @@
+"""N > 1 path on CPU: world_size-2 `gloo` run of the row-sharded Golub-Kahan step (trips_b200.dist.DistGKState).
+
+The product's arithmetic backend is CUDA only; here the distributed ALGEBRA and the torch.distributed plumbing are
+exercised with a NumPy stand-in backend that lives in this test (it implements the same six vector operations on
+CPU tensors).  Checked: round-robin angle sharding, the n-vector all-reduce + scalar all-reduce per step, and
+agreement of the sharded factors with the oracle's single-process Golub-Kahan on the full matrix."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import trips_oracle as O
+
+
+class NumpyBackend:
+    """Same interface as trips_b200.dist.CudaBackend, on CPU float64 tensors."""
+
+    def empty(self, n, like):
+        return torch.empty(n, dtype=torch.float64)
+
+    def zeros(self, n, like):
+        return torch.zeros(n, dtype=torch.float64)
+
+    def apply(self, op, x, out, coef=None, z=None, norm_out=None):
+        y = op @ x.numpy()
+        if z is not None:
+            y = y - float(coef) * z.numpy()
+        out.copy_(torch.from_numpy(y))
+        if norm_out is not None:
+            norm_out[0] = float(y @ y)
+            norm_out[1] = float(np.sqrt(y @ y))
+        return out
+
+    def adjoint(self, op, u, out):
+        out.copy_(torch.from_numpy(op.T @ u.numpy()))
+        return out
+
+    def axpy_norm(self, a, x, y, out, norm_out, sign):
+        r = y.numpy() + sign * (float(a) * x.numpy())
+        out.copy_(torch.from_numpy(r))
+        norm_out[0] = float(r @ r)
+        norm_out[1] = float(np.sqrt(r @ r))
+        return out
+
+    def norm2(self, x, out):
+        v = x.numpy()
+        out[0] = float(v @ v)
+        out[1] = float(np.sqrt(v @ v))
+        return out
+
+    def div(self, x, d, out):
+        out.copy_(x / float(d))
+        return out
+
+    def sqrt_(self, pair):
+        pair[1] = float(np.sqrt(float(pair[0])))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, nx, views, steps, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from trips_b200.dist import DistGKState, shard_angles
+
+        theta = O.ct_angles(views)
+        mine = shard_angles(views, world, rank)
+        A_loc = O.ct_matrix(nx, theta[mine])
+        x_true = O.shepp_logan(nx).reshape(-1)
+        b_loc = A_loc @ x_true + 0.01 * np.random.default_rng(100 + rank).standard_normal(A_loc.shape[0])
+        st = DistGKState(A_loc, torch.from_numpy(b_loc), steps, backend=NumpyBackend())
+        assert st.distributed
+        for _ in range(steps):
+            st.step()
+        V = torch.stack(st.V[:steps]).numpy()
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), B=st.B_host(), V=V, b=b_loc, angles=mine,
+                 U=torch.stack(st.U[:steps + 1]).numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_angles_round_robin_and_inverse_permutation():
+    from trips_b200.dist import gather_sinogram_order, shard_angles
+
+    parts = [shard_angles(10, 4, r) for r in range(4)]
+    assert [p.tolist() for p in parts] == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]
+    n_det = 3
+    order = gather_sinogram_order(10, 4, n_det)
+    local = np.concatenate([(p[:, None] * n_det + np.arange(n_det)).reshape(-1) for p in parts])  # global ray ids, rank-major
+    assert np.array_equal(local[order], np.arange(10 * n_det))
+
+
+def test_dist_gk_world2_gloo_matches_single_process_oracle(tmp_path):
+    nx, views, steps, world = 24, 16, 6, 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, nx, views, steps, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    # replicated quantities are bitwise identical on both ranks
+    assert np.array_equal(parts[0]["B"], parts[1]["B"]) and np.array_equal(parts[0]["V"], parts[1]["V"])
+    # assemble the global problem in angle-major order and run the oracle on one process
+    n_det = O.ct_num_detectors(nx)
+    A = O.ct_matrix(nx, O.ct_angles(views))
+    b = np.empty(views * n_det)
+    U = np.empty((steps + 1, views * n_det))
+    for p in parts:
+        rows = (p["angles"][:, None] * n_det + np.arange(n_det)).reshape(-1)
+        b[rows] = p["b"]
+        U[:, rows] = p["U"]
+    Uo, Bo, Vo = O.golub_kahan(A, b, steps)
+    assert np.allclose(parts[0]["B"], Bo, rtol=1e-10, atol=1e-12)
+    assert np.allclose(parts[0]["V"].T, Vo, atol=1e-9) and np.allclose(U.T, Uo, atol=1e-9)
