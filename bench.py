@@ -51,7 +51,10 @@ def parse():
     ap.add_argument("--order", default="sequential", choices=["sequential", "tree"],
                     help="SpMV row-sum order: 'sequential' = scipy's (bit-identical to the reference, the parity build); "
                          "'tree' = per-row tree reduction (reported separately)")
-    ap.add_argument("--variant", type=int, default=0, help="tile configuration of the sequential kernel (tuning)")
+    ap.add_argument("--variant", type=int, default=0, help="kernel tuning knob (tb200_spmv_set_variant)")
+    ap.add_argument("--layout", default="auto", choices=["auto", "sell", "csr"],
+                    help="device layout of A / A^T: 'sell' = row-interleaved CSR (SELL-32-4, the fast path for the "
+                         "sequential order), 'csr' = plain CSR; auto = sell for sequential, csr for tree")
     return ap.parse_args()
 
 
@@ -191,7 +194,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     t_build = time.perf_counter()
     my_angles = shard_angles(views, world, rank)
-    A = tb.ParallelBeamCT(nx, views, angle_subset=my_angles if world > 1 else None, device=dev)
+    layout = args.layout if args.layout != "auto" else ("sell" if args.order == "sequential" else "csr")
+    A = tb.ParallelBeamCT(nx, views, angle_subset=my_angles if world > 1 else None, device=dev, layout=layout)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
     if args.f32_storage:
@@ -200,7 +204,9 @@ def main():
     if args.order != "sequential":
         A = A.with_order(args.order)
     _lib.check(_lib.lib().tb200_spmv_set_variant(args.variant))
-    kernel_name = {"sequential": "spmv_seq_tile_kernel", "tree": "spmv_warp_kernel"}[args.order]
+    kernel_name = {("sequential", "sell"): "spmv_sell_kernel", ("sequential", "csr"): "spmv_seq_tile_kernel",
+                   ("tree", "csr"): "spmv_warp_kernel"}[(args.order, layout)]
+    stored = (A.A_sell.stored if layout == "sell" else A.A.nnz)
     m_loc = A.shape[0]
     nnz_loc = A.nnz
     nnz_t = torch.tensor([nnz_loc], dtype=torch.int64, device=dev)
@@ -281,7 +287,9 @@ def main():
     B_GK = 2 * (val_bytes + 4) * nnz + 8 * (m_full + 1) + 8 * (n + 1) + 48 * (m_full + n)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": None, "peak_source": peak_src, "kernel": kernel_name,
-                "launch_ms": mean_spmv_ms, "alg_bytes_per_launch": alg_bytes, "share_of_step": spmv_share,
+                "launch_ms": mean_spmv_ms, "launch_ms_AT": sum(spmv_ms[0::2]) / max(len(spmv_ms[0::2]), 1),
+                "launch_ms_A": sum(spmv_ms[1::2]) / max(len(spmv_ms[1::2]), 1),
+                "alg_bytes_per_launch": alg_bytes, "share_of_step": spmv_share,
                 "gk_iteration": {"alg_bytes": B_GK, "achieved": B_GK / (ms_per_step * 1e-3) / 1e9 / world,
                                  "frac": B_GK / (ms_per_step * 1e-3) / 1e9 / world / hbm_peak, "note": "per GPU"}}
 
@@ -346,7 +354,8 @@ def main():
                 "dtype": "f64" if not args.f32_storage else "f32-storage/f64-accumulate", "data": "synthetic",
                 "config": {"workload": workload, "nnz": nnz, "m": m_full, "n": n, "matrix_bytes": 2 * (val_bytes + 4) * nnz,
                            "parallelism": f"rows by angle x{world}" if world > 1 else "single GPU",
-                           "spmv_order": args.order, "spmv_variant": args.variant,
+                           "spmv_order": args.order, "spmv_variant": args.variant, "layout": layout,
+                           "stored_entries_per_matrix": stored, "padding_frac": stored / max(nnz_loc, 1) - 1.0,
                            "l2_note": "inputs (2 x 46 GB matrix streams per step) exceed L2 by >300x; no flush needed",
                            "build_s": t_build},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}

@@ -55,6 +55,17 @@ int tb200_spmv_csr_f64(int order, int64_t m, int64_t n, int64_t nnz, const int64
 int tb200_spmv_csr_f32s(int order, int64_t m, int64_t n, int64_t nnz, const int64_t* rowptr, const int32_t* colidx,
                         const float* vals, const double* x, double* y, double coef_host, const double* coef_dev,
                         const double* z, double* norm_out, double* ws, void* stream);
+/* Same product on the SELL-32-4 layout ("row-interleaved CSR"): rows in slices of 32, entry j of row r at
+ * sliceptr[r/32] + (j/4)*128 + (r%32)*4 + j%4, rows of a slice zero-padded to the longest (rounded up to 4).
+ * Every row is still summed in index order with separately rounded multiply/add: bit-identical to
+ * tb200_spmv_csr_f64(order 0) and to scipy.  This is the production layout for the CT matrices: the 32 lanes of
+ * a warp (lane = row) read contiguous 512 B / 1 KB per load.  sliceptr: int64[ceil(m/32)+1], rowlen: int32[m]. */
+int tb200_spmv_sell_f64(int64_t m, int64_t n, const int64_t* sliceptr, const int32_t* rowlen, const int32_t* colidx,
+                        const double* vals, const double* x, double* y, double coef_host, const double* coef_dev,
+                        const double* z, double* norm_out, double* ws, void* stream);
+int tb200_spmv_sell_f32s(int64_t m, int64_t n, const int64_t* sliceptr, const int32_t* rowlen, const int32_t* colidx,
+                         const float* vals, const double* x, double* y, double coef_host, const double* coef_dev,
+                         const double* z, double* norm_out, double* ws, void* stream);
 int tb200_reduce_finalize(const double* partials, int64_t n, double* out, void* stream);
 
 /* ---- BLAS-1 between operator applies -------------------------------------------------------------------
@@ -97,15 +108,16 @@ int tb200_gram_factor_dd(int k, int ne, const double* Ghi_host, const double* Gl
  * Stands where ASTRA does in the reference (trips/test_problems/Tomography.py:49-88, utilities/io.py:392-400,
  * utilities/cil_io.py:271-275): theta = linspace(0, pi, views, endpoint=False), n_det = int(sqrt(2)*nx),
  * unit detector spacing, entry = chord length of the ray through the unit pixel.
- * Row of A = angle*n_det + det over the n_ang angles given by the cos/sin tables; column = iy*nx + ix. */
+ * Row of A = angle*n_det + det over the n_ang angles given by the cos/sin tables; column = iy*nx + ix.
+ * Fill: sell = 0 writes CSR (ptr = rowptr), sell = 1 writes SELL-32-4 (ptr = slice pointers; arrays pre-zeroed). */
 int tb200_ct_count_rows(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
                         void* stream);
 int tb200_ct_fill_rows(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
-                       const int64_t* rowptr, int32_t* colidx, double* vals, void* stream);
+                       const int64_t* ptr, int sell, int32_t* colidx, double* vals, void* stream);
 int tb200_ct_count_cols(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
                         void* stream);
 int tb200_ct_fill_cols(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
-                       const int64_t* rowptr, int32_t* colidx, double* vals, void* stream);
+                       const int64_t* ptr, int sell, int32_t* colidx, double* vals, void* stream);
 
 /* ---- stencils ---------------------------------------------------------------------------------------------
  * PSF blur and its reference "adjoint": trips/test_problems/Deblurring2D.py:66-73 (scipy.ndimage.convolve,

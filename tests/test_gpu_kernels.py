@@ -56,9 +56,15 @@ def test_spmv_matches_scipy(tb, shape, density):
     x = rng.standard_normal(shape[1])
     u = rng.standard_normal(shape[0])
     z = rng.standard_normal(shape[0])
-    # default order = scipy's summation order: bit-identical to csr_matvec, and to csc_matvec for the transpose
-    assert np.array_equal(host(op.apply_dev(dev(x))), A @ x)
-    assert np.array_equal(host(op.adjoint_dev(dev(u))), A.T @ u)
+    # default order = scipy's summation order: bit-identical to csr_matvec, and to csc_matvec for the transpose,
+    # in both device layouts (SELL-32-4 = the default fast path, plain CSR)
+    assert op.A_sell is not None and op.A is not None
+    for lay in (op, op.with_layout("sell"), op.with_layout("csr")):
+        assert np.array_equal(host(lay.apply_dev(dev(x))), A @ x)
+        assert np.array_equal(host(lay.adjoint_dev(dev(u))), A.T @ u)
+    # the SELL container converts back to exactly the CSR it was made from
+    back = op.with_layout("sell").to_scipy()
+    assert np.array_equal(back.indptr, A.indptr) and np.array_equal(back.indices, A.indices) and np.array_equal(back.data, A.data)
     tree = op.with_order("tree")
     assert rel(host(tree.apply_dev(dev(x))), A @ x) < 1e-14 and rel(host(tree.adjoint_dev(dev(u))), A.T @ u) < 1e-14
     # fused recurrence epilogue + fused norm, scalar on the device
@@ -103,9 +109,13 @@ def test_spmv_edge_cases_empty_rows_and_ragged(tb):
     # every tile configuration of the sequential kernel gives the same bits
     from trips_b200 import _lib
 
-    for variant in (1, 2, 3, 0):
+    # (tile kernels 0-3, direct register-streaming kernels 4-6, forced gather mappings 8*mode)
+    csr_only, sell_only = op.with_layout("csr"), op.with_layout("sell")
+    for variant in (1, 2, 3, 4, 5, 6, 8 + 1, 16 + 1, 256, 512, 768, 0):
         _lib.check(_lib.lib().tb200_spmv_set_variant(variant))
-        assert np.array_equal(host(op.apply_dev(dev(x))), A @ x), variant
+        for lay in (csr_only, sell_only):
+            assert np.array_equal(host(lay.apply_dev(dev(x))), A @ x), variant
+            assert np.array_equal(host(lay.adjoint_dev(dev(u))), A.T @ u), variant
     # fp32-storage / fp64-accumulate variant: exact on the rounded values
     op32 = op.with_f32_storage()
     A32 = A.copy()
@@ -231,9 +241,17 @@ def test_ct_builder_is_bit_identical_to_the_numpy_statement(tb, nx, views):
     T0.sort_indices()
     assert np.array_equal(AT.indptr, T0.indptr) and np.array_equal(AT.indices, T0.indices)
     assert np.array_equal(AT.data, T0.data)
+    # the natively built SELL-32-4 matrices hold exactly the same rows (and little padding)
+    sell = tb.ParallelBeamCT(nx, views, layout="sell")
+    assert sell.A is None and sell.AT is None
+    As, ATs = sell.to_scipy(), sell.transpose_to_scipy()
+    assert np.array_equal(As.indptr, A0.indptr) and np.array_equal(As.indices, A0.indices) and np.array_equal(As.data, A0.data)
+    assert np.array_equal(ATs.indptr, T0.indptr) and np.array_equal(ATs.indices, T0.indices) and np.array_equal(ATs.data, T0.data)
+    assert sell.AT_sell.stored <= 1.15 * A0.nnz + 4096
     # adjoint identity through the kernels
     rng = np.random.default_rng(0)
     x, u = rng.standard_normal(A.shape[1]), rng.standard_normal(A.shape[0])
+    assert np.array_equal(host(sell.apply_dev(dev(x))), A0 @ x) and np.array_equal(host(sell.adjoint_dev(dev(u))), A0.T @ u)
     lhs = u @ host(op.apply_dev(dev(x)))
     rhs = host(op.adjoint_dev(dev(u))) @ x
     assert abs(lhs - rhs) < 1e-12 * abs(lhs)

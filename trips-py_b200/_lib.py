@@ -26,6 +26,8 @@ SIGNATURES = {
     "tb200_spmv_set_variant": (c_int, [c_int]),
     "tb200_spmv_csr_f64": (c_int, [c_int, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_spmv_csr_f32s": (c_int, [c_int, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_spmv_sell_f64": (c_int, [c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_spmv_sell_f32s": (c_int, [c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_reduce_finalize": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "tb200_reduce_workspace_len": (c_i64, []),
     "tb200_vec_div": (c_int, [c_i64, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr]),
@@ -42,9 +44,9 @@ SIGNATURES = {
     "tb200_weighted_gram": (c_int, [c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_gram_factor_dd": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_count_rows": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "tb200_ct_fill_rows": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_ct_fill_rows": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_count_cols": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "tb200_ct_fill_cols": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_ct_fill_cols": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "tb200_correlate2d_f64": (c_int, [c_int, c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "tb200_fd_rows": (c_i64, [c_int, c_int, c_int, c_int]),
     "tb200_fd_apply": (c_int, [c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr]),

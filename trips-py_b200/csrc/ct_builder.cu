@@ -15,6 +15,11 @@
 // exact transpose of A, which the parity tests check against scipy's A.T.
 //
 // Row order of A: (local angle index)*n_det + detector; column = iy*nx + ix.  Both matrices have sorted indices.
+//
+// Two storage layouts for the same rows (argument `sell`):
+//   CSR      entry j of row r at rowptr[r] + j
+//   SELL-32-4 ("row-interleaved CSR", see spmv.cu): rows in slices of 32, entry j of row r at
+//            sliceptr[r/32] + (j/4)*128 + (r%32)*4 + j%4 ; the caller zero-fills the arrays (padding = 0.0 * x[0]).
 #include "tb200_common.cuh"
 
 namespace tb200 {
@@ -97,6 +102,12 @@ __device__ __forceinline__ void det_range(const RayGeom& g, double cx, double cy
   while (hi >= lo && !pred(hi)) --hi;
 }
 
+// address of entry j of `row` in either layout (ptr = rowptr for CSR, slice pointers for SELL-32-4)
+__device__ __forceinline__ int64_t entry_addr(const int64_t* __restrict__ ptr, int sell, int64_t row, int64_t j) {
+  if (!sell) return ptr[row] + j;
+  return ptr[row >> 5] + (j >> 2) * 128 + (row & 31) * 4 + (j & 3);
+}
+
 __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
   int inc = v;
 #pragma unroll
@@ -112,7 +123,7 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 ct_rows_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ cosv, const double* __restrict__ sinv,
-               int32_t* __restrict__ counts, const int64_t* __restrict__ rowptr, int32_t* __restrict__ col,
+               int32_t* __restrict__ counts, const int64_t* __restrict__ rowptr, int sell, int32_t* __restrict__ col,
                double* __restrict__ val) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -121,7 +132,7 @@ ct_rows_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ 
   const RayGeom g = make_geom(cosv[a], sinv[a]);
   const double sd = (double)d - 0.5 * (double)(n_det - 1);
   const double x0 = 0.5 * (double)(nx - 1);
-  int64_t base = FILL ? rowptr[ray] : 0;
+  int64_t base = 0;  // entries of this row written so far
   int total = 0;
   for (int iy0 = 0; iy0 < ny; iy0 += 32) {
     const int iy = iy0 + lane;
@@ -132,8 +143,9 @@ ct_rows_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ 
       int chunk;
       const int off = warp_excl_scan(cnt, lane, chunk);
       const double cy = (double)iy - 0.5 * (double)(ny - 1);
-      int64_t pos = base + off;
-      for (int ix = lo; ix <= hi; ++ix, ++pos) {
+      int64_t j = base + off;
+      for (int ix = lo; ix <= hi; ++ix, ++j) {
+        const int64_t pos = entry_addr(rowptr, sell, ray, j);
         col[pos] = iy * nx + ix;
         val[pos] = chord(g, ray_pixel_t(g, sd, (double)ix - x0, cy));
       }
@@ -153,7 +165,7 @@ ct_rows_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ 
 template <bool FILL>
 __global__ void __launch_bounds__(256)
 ct_cols_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ cosv, const double* __restrict__ sinv,
-               int32_t* __restrict__ counts, const int64_t* __restrict__ rowptr, int32_t* __restrict__ col,
+               int32_t* __restrict__ counts, const int64_t* __restrict__ rowptr, int sell, int32_t* __restrict__ col,
                double* __restrict__ val) {
   const int lane = threadIdx.x & 31;
   const int64_t pix = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -161,7 +173,7 @@ ct_cols_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ 
   const int iy = (int)(pix / nx), ix = (int)(pix % nx);
   const double cx = (double)ix - 0.5 * (double)(nx - 1), cy = (double)iy - 0.5 * (double)(ny - 1);
   const double dc = 0.5 * (double)(n_det - 1);
-  int64_t base = FILL ? rowptr[pix] : 0;
+  int64_t base = 0;  // entries of this row written so far
   int total = 0;
   for (int a0 = 0; a0 < n_ang; a0 += 32) {
     const int a = a0 + lane;
@@ -175,8 +187,9 @@ ct_cols_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ 
     if (FILL) {
       int chunk;
       const int off = warp_excl_scan(cnt, lane, chunk);
-      int64_t pos = base + off;
-      for (int d = lo; d <= hi; ++d, ++pos) {
+      int64_t j = base + off;
+      for (int d = lo; d <= hi; ++d, ++j) {
+        const int64_t pos = entry_addr(rowptr, sell, pix, j);
         col[pos] = a * n_det + d;
         val[pos] = chord(g, ray_pixel_t(g, (double)d - dc, cx, cy));
       }
@@ -214,20 +227,21 @@ int tb200_ct_count_rows(int nx, int ny, int n_det, int n_ang, const double* cosv
   if (rays == 0) return 0;
   TB200_REQUIRE(counts, "null counts");
   ct_rows_kernel<false><<<(unsigned)((rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, nullptr, nullptr);
+      nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, 0, nullptr, nullptr);
   return check_launch("ct_count_rows");
 }
 
-// Fills colidx/vals of A given rowptr = exclusive prefix sum of the counts.
+// Fills colidx/vals of A.  sell = 0: CSR, ptr = rowptr (exclusive prefix sum of the counts).
+// sell = 1: SELL-32-4, ptr = slice pointers; colidx/vals must have been zero-filled by the caller.
 int tb200_ct_fill_rows(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
-                       const int64_t* rowptr, int32_t* colidx, double* vals, void* stream) {
+                       const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream) {
   int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
   if (rc) return rc;
   const int64_t rays = (int64_t)n_ang * n_det;
   if (rays == 0) return 0;
   TB200_REQUIRE(rowptr && colidx && vals, "null output");
   ct_rows_kernel<true><<<(unsigned)((rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, colidx, vals);
+      nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, sell, colidx, vals);
   return check_launch("ct_fill_rows");
 }
 
@@ -239,19 +253,19 @@ int tb200_ct_count_cols(int nx, int ny, int n_det, int n_ang, const double* cosv
   TB200_REQUIRE(counts, "null counts");
   const int64_t npix = (int64_t)nx * ny;
   ct_cols_kernel<false><<<(unsigned)((npix * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, nullptr, nullptr);
+      nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, 0, nullptr, nullptr);
   return check_launch("ct_count_cols");
 }
 
-// Fills colidx/vals of A^T (CSR over pixels; column = angle*n_det + det) given its rowptr.
+// Fills colidx/vals of A^T (rows = pixels; column = angle*n_det + det); layouts as for tb200_ct_fill_rows.
 int tb200_ct_fill_cols(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
-                       const int64_t* rowptr, int32_t* colidx, double* vals, void* stream) {
+                       const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream) {
   int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
   if (rc) return rc;
   TB200_REQUIRE(rowptr && colidx && vals, "null output");
   const int64_t npix = (int64_t)nx * ny;
   ct_cols_kernel<true><<<(unsigned)((npix * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, colidx, vals);
+      nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, sell, colidx, vals);
   return check_launch("ct_fill_cols");
 }
 

@@ -66,7 +66,10 @@ struct SeqTileCfg {
   static constexpr int CSTAGES = STAGES - 1;        // column tiles are dead once their gathers are issued
   static constexpr size_t kColBytesPerWarp = (size_t)CSTAGES * 32 * PC * 16;
   static constexpr size_t kValBytesPerWarp = (size_t)STAGES * 32 * PV * 16;
-  static constexpr size_t kSmemBytes = (size_t)WARPS * (kColBytesPerWarp + kValBytesPerWarp);
+  static constexpr int PX = CH / 2 + 1;              // x-transpose tile (row-major gather mode): pitch in pieces, odd
+  static_assert(PX & 1, "x tile pitch must be odd");
+  static constexpr size_t kXBytesPerWarp = (size_t)32 * PX * 16;
+  static constexpr size_t kSmemBytes = (size_t)WARPS * (kColBytesPerWarp + kValBytesPerWarp + kXBytesPerWarp);
 };
 
 template <typename VT, int CH>
@@ -133,7 +136,8 @@ template <typename VT, int WARPS, int CH, int STAGES>
 __global__ void __launch_bounds__(WARPS * 32)
 spmv_seq_tile_kernel(int64_t m, int64_t nnz, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                      const VT* __restrict__ val, const double* __restrict__ x, double* __restrict__ y, double coef_host,
-                     const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials) {
+                     const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials,
+                     int force_mode) {
   using Cfg = SeqTileCfg<VT, WARPS, CH, STAGES>;
   constexpr int NC = Cfg::NC, NV = Cfg::NV, PC = Cfg::PC, PV = Cfg::PV, VPP = Cfg::VPP, CSTAGES = Cfg::CSTAGES;
   constexpr int RPI = 32 / NC;  // rows covered by one warp-wide copy instruction (NC lanes per row)
@@ -146,6 +150,8 @@ spmv_seq_tile_kernel(int64_t m, int64_t nnz, const int64_t* __restrict__ rowptr,
   // carve: [col tiles of all warps][val tiles of all warps]
   unsigned char* ctile = smem_raw + (size_t)warp * Cfg::kColBytesPerWarp;
   unsigned char* vtile = smem_raw + (size_t)WARPS * Cfg::kColBytesPerWarp + (size_t)warp * Cfg::kValBytesPerWarp;
+  unsigned char* xtile = smem_raw + (size_t)WARPS * (Cfg::kColBytesPerWarp + Cfg::kValBytesPerWarp) +
+                         (size_t)warp * Cfg::kXBytesPerWarp;
   const uint32_t ctile_s = smem_u32(ctile), vtile_s = smem_u32(vtile);
 
   const uint64_t pol_keep = policy_evict_last();     // the gathered vector: the only data with reuse
@@ -163,6 +169,31 @@ spmv_seq_tile_kernel(int64_t m, int64_t nnz, const int64_t* __restrict__ rowptr,
     if (tot == off) tot = 0, off = 0;  // empty row
   }
   const int nit = (__reduce_max_sync(0xffffffffu, tot) + CH - 1) / CH;
+
+  // Gather mapping for this group of 32 rows.  L1TEX spends one tag cycle per distinct 128-byte line of a gather
+  // request, so the request shape should follow the matrix: if the same-position entries of NEIGHBOURING ROWS are
+  // close in x (near-vertical rays, pixels of the transpose), lane r gathers for row r (one request = one position
+  // of 32 rows); if CONSECUTIVE ENTRIES OF A ROW are close in x (near-horizontal rays: runs of adjacent pixels), a
+  // request covers 32 consecutive entries of a row pair and the values reach their owner lanes through shared
+  // memory.  Decided once per group by probing the column stride in both directions in the middle of the rows.
+  bool row_major = false;
+  {
+    const int len = tot - off;
+    int c0 = 0, c1 = 0;
+    const bool ok = len >= 2;
+    if (ok) {
+      const int64_t i0 = a + off + ((len - 2) >> 1);
+      c0 = col[i0];
+      c1 = col[i0 + 1];
+    }
+    const int cn = __shfl_xor_sync(0xffffffffu, c0, 1);
+    const bool okn = __shfl_xor_sync(0xffffffffu, (int)ok, 1) != 0;
+    const unsigned along = __ballot_sync(0xffffffffu, ok && (c1 - c0) <= 2);
+    const unsigned across = __ballot_sync(0xffffffffu, ok && okn && abs(c0 - cn) <= 8);
+    row_major = __popc(along) > __popc(across);
+    if (force_mode == 1) row_major = false;
+    if (force_mode == 2) row_major = true;
+  }
 
   // Producer role of this lane: piece (lane % NC) of the rows q*RPI + lane/NC, q = 0..NC-1 (the same rows for the
   // column and the value tiles), whose stream descriptors are fetched once from the owning lanes.
@@ -202,15 +233,49 @@ spmv_seq_tile_kernel(int64_t m, int64_t nnz, const int64_t* __restrict__ rowptr,
       }
     }
   };
+  constexpr int RPR = 32 / CH;  // rows per request in row-major mode (a request = CH consecutive entries of RPR rows)
   auto gather = [&](int it, double (&xv)[CH]) {
-    const int4* tc = reinterpret_cast<const int4*>(ctile + (size_t)(((it % CSTAGES) * 32 + lane) * PC) * 16);
+    if (force_mode == 3) {  // measurement only: no gathers (pipeline ceiling of the stream + rounding chain)
 #pragma unroll
-    for (int j = 0; j < NC; ++j) {
-      const int4 c = tc[j];
-      xv[4 * j + 0] = ld_gather_f64(x + c.x, pol_keep);
-      xv[4 * j + 1] = ld_gather_f64(x + c.y, pol_keep);
-      xv[4 * j + 2] = ld_gather_f64(x + c.z, pol_keep);
-      xv[4 * j + 3] = ld_gather_f64(x + c.w, pol_keep);
+      for (int j = 0; j < CH; ++j) xv[j] = 1.0;
+    } else if (!row_major) {
+      const int4* tc = reinterpret_cast<const int4*>(ctile + (size_t)(((it % CSTAGES) * 32 + lane) * PC) * 16);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) {
+        const int4 c = tc[j];
+        xv[4 * j + 0] = ld_gather_f64(x + c.x, pol_keep);
+        xv[4 * j + 1] = ld_gather_f64(x + c.y, pol_keep);
+        xv[4 * j + 2] = ld_gather_f64(x + c.z, pol_keep);
+        xv[4 * j + 3] = ld_gather_f64(x + c.w, pol_keep);
+      }
+    } else {
+      // request j: lanes -> entries (lane % CH) of rows j*RPR + lane / CH; xv[j] is delivered to its owner later
+      const int32_t* tc = reinterpret_cast<const int32_t*>(ctile + (size_t)((it % CSTAGES) * 32 * PC) * 16);
+      const int k = lane % CH, rs = lane / CH;
+#pragma unroll
+      for (int j = 0; j < 32 / RPR; ++j) {
+        const int r = j * RPR + rs;
+        if (j < CH) xv[j] = ld_gather_f64(x + tc[r * (PC * 4) + k], pol_keep);
+      }
+    }
+  };
+  // row-major mode: hand the gathered values to the lanes that own the rows (through the x tile)
+  auto deliver = [&](double (&xv)[CH]) {
+    if (row_major) {
+      double* xt = reinterpret_cast<double*>(xtile);
+      const int k = lane % CH, rs = lane / CH;
+#pragma unroll
+      for (int j = 0; j < 32 / RPR; ++j)
+        if (j < CH) xt[(j * RPR + rs) * (Cfg::PX * 2) + k] = xv[j];
+      __syncwarp();
+      const double2* xr = reinterpret_cast<const double2*>(xtile + (size_t)(lane * Cfg::PX) * 16);
+#pragma unroll
+      for (int j = 0; j < CH / 2; ++j) {
+        const double2 t = xr[j];
+        xv[2 * j] = t.x;
+        xv[2 * j + 1] = t.y;
+      }
+      __syncwarp();
     }
   };
 
@@ -236,6 +301,7 @@ spmv_seq_tile_kernel(int64_t m, int64_t nnz, const int64_t* __restrict__ rowptr,
     // value slot (it-1) % STAGES and column slot it % CSTAGES were fully consumed (trailing __syncwarp of it-1)
     if (it + STAGES - 1 < nit) issue(it + STAGES - 1);
     cp_async_commit();
+    deliver(xn);
     double v[CH];
     load_vals<VT, CH>(vtile + (size_t)(((it % STAGES) * 32 + lane) * PV) * 16, v);
     // positions outside [lo, hi) are not this row's: zero their value (adds +-0.0: the running sum keeps its bits)
@@ -258,6 +324,302 @@ spmv_seq_tile_kernel(int64_t m, int64_t nnz, const int64_t* __restrict__ rowptr,
     __syncwarp();
   }
   cp_async_wait<0>();
+
+  dd_t nrm = dd_zero();
+  if (row < m) {
+    if (z != nullptr) acc = __dsub_rn(acc, __dmul_rn(coef, z[row]));
+    y[row] = acc;
+    nrm = dd_fma(nrm, acc, acc);
+  }
+  if (partials != nullptr) {
+    const dd_t tot2 = dd_block_sum(nrm, red);
+    if (threadIdx.x == 0) {
+      partials[2 * (int64_t)blockIdx.x] = tot2.hi;
+      partials[2 * (int64_t)blockIdx.x + 1] = tot2.lo;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// order 0, direct variant: no shared memory.
+// ncu on the tile kernel above shows the L1TEX data pipe saturated (92 %), 56 % of its wavefronts being the
+// shared-memory round trip of the matrix stream (LDGSTS in, LDS out).  Here lane r streams row r straight into
+// registers with 256-bit loads: 32 bytes = one full sector per lane per load (8 column indices or 4 values), L2
+// prefetch granularity 128 B so the next three loads of the lane hit L2, no L1 allocation.  That is ~4x fewer data
+// pipe wavefronts for the stream; what remains are the x-gathers.  Software pipeline per lane:
+//   stream loads of chunk it+2  |  gathers of chunk it+1  |  rounding chain of chunk it        (16 entries each)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld_row_i32x8(const int32_t* p, int32_t* c) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7])
+               : "l"(p));
+}
+template <typename VT>
+struct RowVals;
+template <>
+struct RowVals<double> {
+  static constexpr int VPP = 4;  // values per 32-byte piece
+  __device__ __forceinline__ static void piece(const double* p, double* v) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+                 : "l"(p));
+  }
+};
+template <>
+struct RowVals<float> {
+  static constexpr int VPP = 8;
+  __device__ __forceinline__ static void piece(const float* p, double* v) {
+    float f[8];
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7])
+                 : "l"(p));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (double)f[i];
+  }
+};
+
+template <typename VT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+spmv_seq_direct_kernel(int64_t m, int64_t nnz, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                       const VT* __restrict__ val, const double* __restrict__ x, double* __restrict__ y, double coef_host,
+                       const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials) {
+  constexpr int CH = 16;
+  constexpr int VPP = RowVals<VT>::VPP;
+  __shared__ double red[64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t pol_keep = policy_evict_last();
+  const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
+  const int64_t row = ((int64_t)blockIdx.x * WARPS + warp) * 32 + lane;
+  int64_t a = 0;  // row start rounded down to 8 entries: 32-byte aligned for both arrays
+  int off = 0, tot = 0;
+  if (row < m) {
+    const int64_t s = rowptr[row];
+    a = s & ~(int64_t)7;
+    off = (int)(s - a);
+    tot = (int)(rowptr[row + 1] - a);
+    if (tot == off) tot = 0, off = 0;
+  }
+  const int nit = (__reduce_max_sync(0xffffffffu, tot) + CH - 1) / CH;
+  const int32_t* cp = col + a;
+  const VT* vp = val + a;
+  const int64_t room64 = nnz - a;  // entries between the stream start and the end of the arrays
+  const int room = room64 > (int64_t)0x3fffffff ? 0x3fffffff : (int)room64;
+
+  // A piece is loaded when it starts inside the row's stream; positions it covers beyond the row (or, for the very
+  // last pieces of the arrays, beyond nnz) are masked by position later, so their content is irrelevant - but no
+  // byte outside [0, nnz) is ever read.
+  auto load_cols = [&](int it, int32_t (&c)[CH]) {
+#pragma unroll
+    for (int q = 0; q < CH / 8; ++q) {
+      const int pos = it * CH + 8 * q;
+      if (pos < tot) {
+        if (pos + 8 <= room) {
+          ld_row_i32x8(cp + pos, &c[8 * q]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) c[8 * q + j] = (pos + j < room) ? cp[pos + j] : 0;
+        }
+      }
+    }
+  };
+  auto load_vals = [&](int it, double (&v)[CH]) {
+#pragma unroll
+    for (int q = 0; q < CH / VPP; ++q) {
+      const int pos = it * CH + VPP * q;
+      if (pos < tot) {
+        if (pos + VPP <= room) {
+          RowVals<VT>::piece(vp + pos, &v[VPP * q]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < VPP; ++j) v[VPP * q + j] = (pos + j < room) ? (double)vp[pos + j] : 0.0;
+        }
+      }
+    }
+  };
+
+  int32_t c1[CH];
+  double v0[CH], v1[CH], x0[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) c1[k] = 0, v0[k] = 0.0, v1[k] = 0.0, x0[k] = 0.0;
+  if (nit > 0) {
+    load_cols(0, c1);
+    load_vals(0, v0);
+#pragma unroll
+    for (int k = 0; k < CH; ++k) x0[k] = ld_gather_f64(x + c1[k], pol_keep);
+  }
+  if (nit > 1) {
+    load_cols(1, c1);
+    load_vals(1, v1);
+  }
+  double acc = 0.0;
+  for (int it = 0; it < nit; ++it) {
+    // products of chunk it; positions outside [lo, hi) are not this row's and contribute +0.0
+    const int lo = (it == 0) ? off : 0;
+    const int hi = tot - it * CH;
+    double p[CH];
+    if (lo > 0 || hi < CH) {
+#pragma unroll
+      for (int k = 0; k < CH; ++k) p[k] = (k < lo || k >= hi) ? 0.0 : __dmul_rn(v0[k], x0[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < CH; ++k) p[k] = __dmul_rn(v0[k], x0[k]);
+    }
+    // gathers of chunk it+1 (its columns arrived during the previous iteration)
+    if (it + 1 < nit) {
+#pragma unroll
+      for (int k = 0; k < CH; ++k) x0[k] = ld_gather_f64(x + c1[k], pol_keep);
+    }
+    // stream loads of chunk it+2
+    double v2[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) v2[k] = 0.0;
+    if (it + 2 < nit) {
+      load_cols(it + 2, c1);
+      load_vals(it + 2, v2);
+    }
+    // the rounding chain, in index order
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc = __dadd_rn(acc, p[k]);
+#pragma unroll
+    for (int k = 0; k < CH; ++k) v0[k] = v1[k], v1[k] = v2[k];
+  }
+
+  dd_t nrm = dd_zero();
+  if (row < m) {
+    if (z != nullptr) acc = __dsub_rn(acc, __dmul_rn(coef, z[row]));
+    y[row] = acc;
+    nrm = dd_fma(nrm, acc, acc);
+  }
+  if (partials != nullptr) {
+    const dd_t tot2 = dd_block_sum(nrm, red);
+    if (threadIdx.x == 0) {
+      partials[2 * (int64_t)blockIdx.x] = tot2.hi;
+      partials[2 * (int64_t)blockIdx.x + 1] = tot2.lo;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// order 0 on the SELL-32-4 layout ("row-interleaved CSR"): the production path for the tomography matrices.
+//
+// Measured on the CSR kernels above (profiles/): lane-per-row streaming is what the
+// sequential rounding chain wants, but on plain CSR it costs the L1TEX data pipe one 32-byte sector per lane per
+// load (scattered rows) or a shared-memory round trip; the pipe moves only ~2 such sectors per clock per SM and
+// saturates (92 %) below the HBM roofline.  Interleaving the rows of each group of 32 removes that cost without
+// touching the arithmetic: entry j of row r lives at  sliceptr[r/32] + (j/4)*128 + (r%32)*4 + j%4,  so the 32
+// lanes of a warp (lane = row) read 512 contiguous bytes of column indices / 1 KB of values per load, every lane
+// still walks ITS row in index order, and the result is bit-identical to the CSR kernels and to scipy.  Rows of a
+// slice are padded to the slice's longest row rounded up to 4 (zeros; < 2 % for the CT matrices).
+// Software pipeline per lane, 16 entries per stage:
+//   stream loads of chunk it+2  |  x-gathers of chunk it+1  |  rounding chain of chunk it
+// ---------------------------------------------------------------------------------------------------------
+template <typename VT>
+struct SellVals;
+template <>
+struct SellVals<double> {
+  __device__ __forceinline__ static void piece(const double* p, uint64_t, double* v) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3])
+                 : "l"(p));
+  }
+};
+template <>
+struct SellVals<float> {
+  __device__ __forceinline__ static void piece(const float* p, uint64_t pol, double* v) {
+    float f[4];
+    ld_stream_f32x4(p, pol, f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (double)f[i];
+  }
+};
+
+template <typename VT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t* __restrict__ rowlen,
+                 const int32_t* __restrict__ col, const VT* __restrict__ val, const double* __restrict__ x,
+                 double* __restrict__ y, double coef_host, const double* __restrict__ coef_dev,
+                 const double* __restrict__ z, double* __restrict__ partials) {
+  constexpr int CH = 16;
+  __shared__ double red[64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t pol_keep = policy_evict_last();
+  const uint64_t pol_stream = policy_evict_first();
+  const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
+  const int64_t slice = (int64_t)blockIdx.x * WARPS + warp;
+  const int64_t nslices = (m + 31) >> 5;
+  const int64_t row = slice * 32 + lane;
+  int64_t base = 0;
+  int w = 0, len = 0;  // slice width (entries per row, multiple of 4), length of this lane's row
+  if (slice < nslices) {
+    base = sliceptr[slice];
+    w = (int)((sliceptr[slice + 1] - base) >> 5);
+    if (row < m) len = rowlen[row];
+  }
+  const int nit = (w + CH - 1) / CH;
+  const int32_t* cp = col + base + lane * 4;
+  const VT* vp = val + base + lane * 4;
+
+  auto load_cols = [&](int it, int32_t (&c)[CH]) {
+#pragma unroll
+    for (int q = 0; q < CH / 4; ++q)
+      if (it * CH + 4 * q < w) {
+        int32_t t[4];
+        ld_stream_i32x4(cp + (int64_t)(it * (CH / 4) + q) * 128, pol_stream, t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[4 * q + i] = t[i];
+      }
+  };
+  auto load_vals = [&](int it, double (&v)[CH]) {
+#pragma unroll
+    for (int q = 0; q < CH / 4; ++q)
+      if (it * CH + 4 * q < w) SellVals<VT>::piece(vp + (int64_t)(it * (CH / 4) + q) * 128, pol_stream, &v[4 * q]);
+  };
+
+  int32_t c1[CH];
+  double v0[CH], v1[CH], x0[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) c1[k] = 0, v0[k] = 0.0, v1[k] = 0.0, x0[k] = 0.0;
+  if (nit > 0) {
+    load_cols(0, c1);
+    load_vals(0, v0);
+#pragma unroll
+    for (int k = 0; k < CH; ++k) x0[k] = ld_gather_f64(x + c1[k], pol_keep);
+  }
+  if (nit > 1) {
+    load_cols(1, c1);
+    load_vals(1, v1);
+  }
+  double acc = 0.0;
+  for (int it = 0; it < nit; ++it) {
+    // products of chunk it; positions at or beyond the row's length are padding and contribute +0.0
+    const int hi = len - it * CH;
+    double p[CH];
+    if (hi < CH) {
+#pragma unroll
+      for (int k = 0; k < CH; ++k) p[k] = (k >= hi) ? 0.0 : __dmul_rn(v0[k], x0[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < CH; ++k) p[k] = __dmul_rn(v0[k], x0[k]);
+    }
+    // gathers of chunk it+1 (its columns arrived during the previous iteration)
+    if (it + 1 < nit) {
+#pragma unroll
+      for (int k = 0; k < CH; ++k) x0[k] = ld_gather_f64(x + c1[k], pol_keep);
+    }
+    // stream loads of chunk it+2
+    double v2[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) v2[k] = 0.0;
+    if (it + 2 < nit) {
+      load_cols(it + 2, c1);
+      load_vals(it + 2, v2);
+    }
+    // the rounding chain, in index order
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc = __dadd_rn(acc, p[k]);
+#pragma unroll
+    for (int k = 0; k < CH; ++k) v0[k] = v1[k], v1[k] = v2[k];
+  }
 
   dd_t nrm = dd_zero();
   if (row < m) {
@@ -422,6 +784,7 @@ spmv_subwarp_kernel(int64_t m, const int64_t* __restrict__ rowptr, const int32_t
 // host side
 // ---------------------------------------------------------------------------------------------------------
 static int g_seq_variant = 0;  // tuning knob (tb200_spmv_set_variant): which tile configuration order 0 uses
+static int g_seq_gather_mode = 0;  // 0 = decide per row group, 1 = always lane-per-row gathers, 2 = always row-major gathers
 
 template <typename VT, int WARPS, int CH, int STAGES>
 static int launch_seq_tile(int64_t m, int64_t nnz, const int64_t* rowptr, const int32_t* col, const VT* val, const double* x, double* y,
@@ -440,8 +803,20 @@ static int launch_seq_tile(int64_t m, int64_t nnz, const int64_t* rowptr, const 
   }
   const int64_t rows_per_cta = (int64_t)WARPS * 32;
   *nblocks = (m + rows_per_cta - 1) / rows_per_cta;
-  kern<<<(unsigned)*nblocks, WARPS * 32, Cfg::kSmemBytes, st>>>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials);
+  kern<<<(unsigned)*nblocks, WARPS * 32, Cfg::kSmemBytes, st>>>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials,
+                                                                g_seq_gather_mode);
   return check_launch("spmv_seq_tile");
+}
+
+template <typename VT, int WARPS>
+static int launch_seq_direct(int64_t m, int64_t nnz, const int64_t* rowptr, const int32_t* col, const VT* val,
+                             const double* x, double* y, double coef_host, const double* coef_dev, const double* z,
+                             double* partials, int64_t* nblocks, cudaStream_t st) {
+  const int64_t rows_per_cta = (int64_t)WARPS * 32;
+  *nblocks = (m + rows_per_cta - 1) / rows_per_cta;
+  spmv_seq_direct_kernel<VT, WARPS><<<(unsigned)*nblocks, WARPS * 32, 0, st>>>(m, nnz, rowptr, col, val, x, y, coef_host,
+                                                                              coef_dev, z, partials);
+  return check_launch("spmv_seq_direct");
 }
 
 template <typename VT>
@@ -455,6 +830,9 @@ static int spmv_launch(int order, int64_t m, int64_t nnz, const int64_t* rowptr,
   if (order == 0) {
     if (avg >= 24.0) {
       switch (g_seq_variant) {
+        case 4: rc = launch_seq_direct<VT, 2>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
+        case 5: rc = launch_seq_direct<VT, 4>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
+        case 6: rc = launch_seq_direct<VT, 1>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
         case 1: rc = launch_seq_tile<VT, 2, 16, 3>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
         case 2: rc = launch_seq_tile<VT, 4, 16, 3>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
         case 3: rc = launch_seq_tile<VT, 1, 8, 4>(m, nnz, rowptr, col, val, x, y, coef_host, coef_dev, z, partials, &nblocks, st); break;
@@ -490,6 +868,31 @@ static int spmv_launch(int order, int64_t m, int64_t nnz, const int64_t* rowptr,
   return rc;
 }
 
+static int g_sell_warps = 4;  // tuning knob (tb200_spmv_set_variant, bits 8-9 -> 1/2/4/8 warps per CTA)
+
+template <typename VT>
+static int sell_launch(int64_t m, const int64_t* sliceptr, const int32_t* rowlen, const int32_t* col, const VT* val,
+                       const double* x, double* y, double coef_host, const double* coef_dev, const double* z,
+                       double* norm_out, double* ws, cudaStream_t st) {
+  double* partials = norm_out ? ws : nullptr;
+  const int64_t nslices = (m + 31) / 32;
+  const int warps = g_sell_warps;
+  const int64_t nblocks = (nslices + warps - 1) / warps;
+  switch (warps) {
+    case 1: spmv_sell_kernel<VT, 1><<<(unsigned)nblocks, 32, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials); break;
+    case 2: spmv_sell_kernel<VT, 2><<<(unsigned)nblocks, 64, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials); break;
+    case 8: spmv_sell_kernel<VT, 8><<<(unsigned)nblocks, 256, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials); break;
+    default: spmv_sell_kernel<VT, 4><<<(unsigned)nblocks, 128, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials); break;
+  }
+  int rc = check_launch("spmv_sell");
+  if (rc) return rc;
+  if (norm_out) {
+    finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, nblocks, norm_out);
+    rc = check_launch("spmv_sell finalize");
+  }
+  return rc;
+}
+
 }  // namespace tb200
 
 using namespace tb200;
@@ -504,10 +907,15 @@ int64_t tb200_spmv_workspace_len(int64_t m) { return 2 * ((m + 15) / 16 + 8); } 
 int tb200_spmv_launches(int with_norm) { return with_norm ? 2 : 1; }
 
 // Tuning knob for the order-0 tile kernel (warps per CTA x entries per chunk x stages): 0 = 1 x 16 x 3 (default),
-// 1 = 2 x 16 x 3, 2 = 4 x 16 x 3, 3 = 1 x 8 x 4.  Results are bit-identical across variants.
+// 1 = 2 x 16 x 3, 2 = 4 x 16 x 3, 3 = 1 x 8 x 4; 4/5/6 = direct (no shared memory) kernel with 2/4/1 warps per CTA;
+// plus 8 * gather mode of the tile kernel (0 = per row group, 1 = lane-per-row, 2 = row-major, 3 = no gathers:
+// measurement only).  Results are bit-identical across variants (except gather mode 3).
 int tb200_spmv_set_variant(int v) {
-  TB200_REQUIRE(v >= 0 && v <= 3, "variant must be 0..3");
-  g_seq_variant = v;
+  TB200_REQUIRE(v >= 0 && (v & 7) <= 6 && ((v >> 3) & 3) <= 3 && (v >> 8) <= 3,
+                "variant = CSR kernel (0..6) + 8 * gather mode (0..3) + 256 * log2(SELL warps per CTA) (0..3)");
+  g_seq_variant = v & 7;
+  g_seq_gather_mode = (v >> 3) & 3;
+  g_sell_warps = (v >> 8) ? (1 << (v >> 8)) : 4;
   return 0;
 }
 
@@ -540,6 +948,38 @@ int tb200_spmv_csr_f32s(int order, int64_t m, int64_t n, int64_t nnz, const int6
   if (rc) return rc;
   if (m == 0) return 0;
   return spmv_launch<float>(order, m, nnz, rowptr, colidx, vals, x, y, coef_host, coef_dev, z, norm_out, ws,
+                            (cudaStream_t)stream);
+}
+
+// SELL-32-4 ("row-interleaved CSR") SpMV, scipy summation order: y = A x - coef*z, optional fused ||y||^2.
+// sliceptr: int64[ceil(m/32)+1] (multiples of 128), rowlen: int32[m], colidx/vals: sliceptr[last] entries, entry j of
+// row r at sliceptr[r/32] + (j/4)*128 + (r%32)*4 + j%4, padding zero-filled.  colidx 512-byte, vals 1024-byte aligned.
+static int check_sell_args(int64_t m, int64_t n, const void* sliceptr, const void* rowlen, const void* col,
+                           const void* val, const void* x, const void* y, const void* norm_out, const void* ws) {
+  TB200_REQUIRE(m >= 0 && n >= 0 && n < ((int64_t)1 << 31), "bad size");
+  TB200_REQUIRE(sliceptr && rowlen && x && y, "null pointer");
+  TB200_REQUIRE(((uintptr_t)val % 32) == 0 && ((uintptr_t)col % 16) == 0, "vals must be 32-byte and colidx 16-byte aligned");
+  TB200_REQUIRE(norm_out == nullptr || ws != nullptr, "norm_out requires a workspace");
+  return 0;
+}
+
+int tb200_spmv_sell_f64(int64_t m, int64_t n, const int64_t* sliceptr, const int32_t* rowlen, const int32_t* colidx,
+                        const double* vals, const double* x, double* y, double coef_host, const double* coef_dev,
+                        const double* z, double* norm_out, double* ws, void* stream) {
+  int rc = check_sell_args(m, n, sliceptr, rowlen, colidx, vals, x, y, norm_out, ws);
+  if (rc) return rc;
+  if (m == 0) return 0;
+  return sell_launch<double>(m, sliceptr, rowlen, colidx, vals, x, y, coef_host, coef_dev, z, norm_out, ws,
+                             (cudaStream_t)stream);
+}
+
+int tb200_spmv_sell_f32s(int64_t m, int64_t n, const int64_t* sliceptr, const int32_t* rowlen, const int32_t* colidx,
+                         const float* vals, const double* x, double* y, double coef_host, const double* coef_dev,
+                         const double* z, double* norm_out, double* ws, void* stream) {
+  int rc = check_sell_args(m, n, sliceptr, rowlen, colidx, vals, x, y, norm_out, ws);
+  if (rc) return rc;
+  if (m == 0) return 0;
+  return sell_launch<float>(m, sliceptr, rowlen, colidx, vals, x, y, coef_host, coef_dev, z, norm_out, ws,
                             (cudaStream_t)stream);
 }
 

@@ -186,7 +186,8 @@ class _HostBasis:
         hb = cls.registry.get(M.__array_interface__["data"][0])
         if hb is not None and hb.rows == rows and M.strides == (8, 8 * rows) and k + extra <= hb.cap:
             return hb, k
-        hb = cls(rows, max(2 * (k + extra), 8))
+        # pinning is expensive (page-locking): start with room for a typical run and double from there
+        hb = cls(rows, max(2 * (k + extra), 64 if rows * 64 * 8 <= (4 << 30) else 16))
         hb.arr[:, :k] = M
         return hb, k
 

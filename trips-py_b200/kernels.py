@@ -115,12 +115,100 @@ class CSRDevice:
 ORDERS = {"sequential": 0, "tree": 1}
 
 
+def _sell_addresses(sliceptr, rowlen):
+    """Device tensors (row, addr) for every stored entry of a SELL-32-4 matrix, in CSR (row-major) order."""
+    m = rowlen.numel()
+    rows = torch.repeat_interleave(torch.arange(m, device=rowlen.device, dtype=torch.int64), rowlen.to(torch.int64))
+    start = torch.zeros(m + 1, dtype=torch.int64, device=rowlen.device)
+    torch.cumsum(rowlen.to(torch.int64), 0, out=start[1:])
+    j = torch.arange(rows.numel(), device=rowlen.device, dtype=torch.int64) - start[rows]
+    addr = sliceptr[rows >> 5] + (j >> 2) * 128 + (rows & 31) * 4 + (j & 3)
+    return rows, addr, start
+
+
+def sell_slice_pointers(rowlen):
+    """Slice widths (longest row of each 32-row slice, rounded up to 4) -> int64 slice pointers."""
+    m = rowlen.numel()
+    nsl = (m + 31) // 32
+    padded = torch.zeros(nsl * 32, dtype=torch.int64, device=rowlen.device)
+    padded[:m] = rowlen
+    w = (padded.view(nsl, 32).max(dim=1).values + 3) // 4 * 4
+    sliceptr = torch.zeros(nsl + 1, dtype=torch.int64, device=rowlen.device)
+    torch.cumsum(w * 32, 0, out=sliceptr[1:])
+    return sliceptr
+
+
+class SellDevice:
+    """The same rows as a CSR matrix, interleaved in groups of 32 ("SELL-32-4", see csrc/spmv.cu): entry j of row r at
+    sliceptr[r//32] + (j//4)*128 + (r%32)*4 + j%4.  Per-row order is CSR order, so products are bit-identical."""
+
+    def __init__(self, shape, sliceptr, rowlen, colidx, vals):
+        self.shape = (int(shape[0]), int(shape[1]))
+        if sliceptr.dtype != torch.int64 or rowlen.dtype != torch.int32 or colidx.dtype != torch.int32 \
+                or vals.dtype not in (F64, torch.float32):
+            raise TypeError("SellDevice needs int64 sliceptr, int32 rowlen/colidx and float64/float32 vals")
+        self.sliceptr, self.rowlen, self.colidx, self.vals = sliceptr, rowlen, colidx, vals
+        self.stored = int(colidx.numel())
+        self.nnz = int(rowlen.sum().item())
+        self.device = vals.device
+
+    @classmethod
+    def from_csr(cls, A):
+        rowlen = (A.rowptr[1:] - A.rowptr[:-1]).to(torch.int32)
+        sliceptr = sell_slice_pointers(rowlen)
+        total = int(sliceptr[-1].item())
+        colidx = torch.zeros(max(total, 1), dtype=torch.int32, device=A.device)[:total]
+        vals = torch.zeros(max(total, 1), dtype=A.vals.dtype, device=A.device)[:total]
+        _, addr, _ = _sell_addresses(sliceptr, rowlen)
+        colidx[addr] = A.colidx
+        vals[addr] = A.vals
+        return cls(A.shape, sliceptr, rowlen, colidx, vals)
+
+    def to_csr(self):
+        _, addr, start = _sell_addresses(self.sliceptr, self.rowlen)
+        return CSRDevice(self.shape, start, self.colidx[addr].contiguous(), self.vals[addr].contiguous())
+
+    @property
+    def nbytes(self):
+        return self.stored * (4 + self.vals.element_size()) + 8 * self.sliceptr.numel() + 4 * self.rowlen.numel()
+
+    def to_f32_storage(self):
+        return SellDevice(self.shape, self.sliceptr, self.rowlen, self.colidx, self.vals.to(torch.float32))
+
+
+def _spmv_sell(A, x, out, coef, z, norm_out):
+    m, n = A.shape
+    coef_host, coef_dev = 0.0, None
+    if z is not None:
+        if isinstance(coef, torch.Tensor):
+            coef_dev = coef
+        else:
+            coef_host = float(coef)
+    ws = Workspace.get(A.device).spmv(m) if norm_out is not None else None
+    fn = lib().tb200_spmv_sell_f64 if A.vals.dtype == F64 else lib().tb200_spmv_sell_f32s
+    check(fn(m, n, _p(A.sliceptr), _p(A.rowlen), _p(A.colidx), _p(A.vals), _p(x), _p(out), coef_host, _p(coef_dev), _p(z),
+             _p(norm_out), _p(ws), _stream()), "spmv_sell")
+    _lib.count(2 if norm_out is not None else 1)
+    return out
+
+
 def spmv(A, x, out=None, coef=None, z=None, norm_out=None, order="sequential"):
     """out = A x - coef*z (z/coef optional), optionally norm_out[:] = (||out||^2, ||out||).
 
     coef may be a Python float or a 1-element device tensor (kept on the device, no sync).
-    order 'sequential' reproduces scipy's csr_matvec bit for bit; 'tree' is the fastest reduction order."""
+    order 'sequential' reproduces scipy's csr_matvec bit for bit; 'tree' is the fastest reduction order on CSR.
+    A may be a CSRDevice or a SellDevice (sequential order only)."""
     m, n = A.shape
+    if isinstance(A, SellDevice):
+        if order != "sequential":
+            raise ValueError("the SELL layout implements the sequential (scipy) summation order only")
+        _vec(x, n, "x")
+        if out is None:
+            out = torch.empty(m, dtype=F64, device=A.device)
+        _vec(out, m, "out")
+        if z is not None:
+            _vec(z, m, "z")
+        return _spmv_sell(A, x, out, coef, z, norm_out)
     _vec(x, n, "x")
     if out is None:
         out = torch.empty(m, dtype=F64, device=A.device)
@@ -342,8 +430,9 @@ def gram_factor(Ghi, Glo, k):
 
 # ---- CT builder ---------------------------------------------------------------------------------------------
 
-def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False):
-    """Build A (rows = rays) or A^T (rows = pixels) for the angles in the device tables cos_t/sin_t."""
+def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False, layout="csr"):
+    """Build A (rows = rays) or A^T (rows = pixels) for the angles in the device tables cos_t/sin_t, directly in the
+    requested device layout ('csr' -> CSRDevice, 'sell' -> SellDevice)."""
     dev = cos_t.device
     n_ang = cos_t.numel()
     rows = nx * ny if transpose else n_ang * n_det
@@ -351,15 +440,24 @@ def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False):
     cnt_fn = lib().tb200_ct_count_cols if transpose else lib().tb200_ct_count_rows
     fill_fn = lib().tb200_ct_fill_cols if transpose else lib().tb200_ct_fill_rows
     check(cnt_fn(nx, ny, n_det, n_ang, _p(cos_t), _p(sin_t), _p(counts), _stream()), "ct_count")
+    shape = (nx * ny, n_ang * n_det) if transpose else (n_ang * n_det, nx * ny)
+    _lib.count(2)
+    if layout == "sell":
+        sliceptr = sell_slice_pointers(counts)
+        total = int(sliceptr[-1].item())
+        colidx = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)[:total]
+        vals = torch.zeros(max(total, 1), dtype=F64, device=dev)[:total]
+        check(fill_fn(nx, ny, n_det, n_ang, _p(cos_t), _p(sin_t), _p(sliceptr), 1, _p(colidx), _p(vals), _stream()), "ct_fill")
+        return SellDevice(shape, sliceptr, counts, colidx, vals)
+    if layout != "csr":
+        raise ValueError("layout must be 'csr' or 'sell'")
     rowptr = torch.zeros(rows + 1, dtype=torch.int64, device=dev)
     torch.cumsum(counts, 0, out=rowptr[1:])
     del counts
     nnz = int(rowptr[-1].item())
     colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
     vals = torch.empty(max(nnz, 1), dtype=F64, device=dev)[:nnz]
-    check(fill_fn(nx, ny, n_det, n_ang, _p(cos_t), _p(sin_t), _p(rowptr), _p(colidx), _p(vals), _stream()), "ct_fill")
-    _lib.count(2)
-    shape = (nx * ny, n_ang * n_det) if transpose else (n_ang * n_det, nx * ny)
+    check(fill_fn(nx, ny, n_det, n_ang, _p(cos_t), _p(sin_t), _p(rowptr), 0, _p(colidx), _p(vals), _stream()), "ct_fill")
     return CSRDevice(shape, rowptr, colidx, vals)
 
 

@@ -236,27 +236,61 @@ class Identity(LinearOperator):
 # ---- CSR tomography operator ------------------------------------------------------------------------------------
 
 class CSROperator(LinearOperator):
-    """Sparse matrix in CSR with an explicitly stored transpose (also CSR): both A x and A^T u are
-    gather-only, deterministic SpMVs.  Stands for the scipy.sparse matrices / ASTRA projector objects the
-    reference passes as A (demos: CT matrices from .mat files, `astra.OpTomo`)."""
+    """Sparse matrix with an explicitly stored transpose: both A x and A^T u are gather-only, deterministic SpMVs.
+    Stands for the scipy.sparse matrices / ASTRA projector objects the reference passes as A (demos: CT matrices
+    from .mat files, `astra.OpTomo`).
+
+    Device layouts (either or both, per matrix): CSR (`A`, `AT`: CSRDevice) and SELL-32-4, the row-interleaved form
+    of the same rows (`A_sell`, `AT_sell`: SellDevice).  order='sequential' (default) sums every row in index order
+    with separately rounded multiply/add - bit-identical to scipy's csr_matvec / csc_matvec - and prefers the SELL
+    layout (the fast path); order='tree' is a per-row tree reduction on CSR (differs from scipy by rounding)."""
 
     fused = True
 
-    def __init__(self, A, AT, order="sequential"):
-        if A.shape != (AT.shape[1], AT.shape[0]):
+    def __init__(self, A=None, AT=None, order="sequential", A_sell=None, AT_sell=None):
+        ref, ref_t = (A if A is not None else A_sell), (AT if AT is not None else AT_sell)
+        if ref is None or ref_t is None:
+            raise ValueError("need A and A^T, each in at least one layout")
+        if ref.shape != (ref_t.shape[1], ref_t.shape[0]):
             raise ValueError("AT must have the transposed shape of A")
         if order not in K.ORDERS:
-            raise ValueError("order must be 'sequential' (bit-identical to scipy's SpMV) or 'tree' (fastest)")
-        super().__init__(A.shape, A.device)
-        self.A, self.AT, self.order = A, AT, order
+            raise ValueError("order must be 'sequential' (bit-identical to scipy's SpMV) or 'tree' (fastest on CSR)")
+        super().__init__(ref.shape, ref.device)
+        self.A, self.AT, self.A_sell, self.AT_sell, self.order = A, AT, A_sell, AT_sell, order
+
+    def _csr(self, transposed):
+        """CSR form of A (or A^T), converting from SELL on first use."""
+        if transposed:
+            if self.AT is None:
+                self.AT = self.AT_sell.to_csr()
+            return self.AT
+        if self.A is None:
+            self.A = self.A_sell.to_csr()
+        return self.A
+
+    def _active(self, transposed):
+        sell = self.AT_sell if transposed else self.A_sell
+        if self.order == "sequential" and sell is not None:
+            return sell
+        return self._csr(transposed)
 
     def with_order(self, order):
-        """Same matrices, different summation order of the row sums ('sequential' = scipy's, 'tree' = fastest)."""
-        return CSROperator(self.A, self.AT, order)
+        """Same matrices, different summation order of the row sums ('sequential' = scipy's, 'tree' = fastest CSR)."""
+        return CSROperator(self.A, self.AT, order, self.A_sell, self.AT_sell)
+
+    def with_layout(self, layout):
+        """Restrict to one device layout ('csr' or 'sell'); the other is dropped (converted first if missing)."""
+        if layout == "csr":
+            return CSROperator(self._csr(False), self._csr(True), self.order)
+        if layout == "sell":
+            a = self.A_sell if self.A_sell is not None else K.SellDevice.from_csr(self.A)
+            at = self.AT_sell if self.AT_sell is not None else K.SellDevice.from_csr(self.AT)
+            return CSROperator(None, None, self.order, a, at)
+        raise ValueError("layout must be 'csr' or 'sell'")
 
     @classmethod
     def from_scipy(cls, A, device=None):
-        """Upload a scipy.sparse matrix; the transpose is formed once on the host (A.T.tocsr())."""
+        """Upload a scipy.sparse matrix (both layouts); the transpose is formed once on the host (A.T.tocsr())."""
         import scipy.sparse as sp
 
         device = torch.device(device) if device is not None else default_device()
@@ -264,7 +298,8 @@ class CSROperator(LinearOperator):
         A.sort_indices()
         AT = A.T.tocsr()
         AT.sort_indices()
-        return cls(_upload_csr(A, device), _upload_csr(AT, device))
+        a, at = _upload_csr(A, device), _upload_csr(AT, device)
+        return cls(a, at, "sequential", K.SellDevice.from_csr(a), K.SellDevice.from_csr(at))
 
     @classmethod
     def from_dense(cls, A, device=None):
@@ -274,24 +309,25 @@ class CSROperator(LinearOperator):
 
     def to_scipy(self):
         """The same arrays as a scipy.sparse.csr_matrix (used to feed the oracle identical inputs)."""
-        return _download_csr(self.A)
+        return _download_csr(self._csr(False))
 
     def transpose_to_scipy(self):
-        return _download_csr(self.AT)
+        return _download_csr(self._csr(True))
 
     def with_f32_storage(self):
         """fp32-storage / fp64-accumulate variant (16 instead of 24 B/nnz per Golub-Kahan iteration)."""
-        return CSROperator(self.A.to_f32_storage(), self.AT.to_f32_storage(), self.order)
+        f = lambda M: None if M is None else M.to_f32_storage()  # noqa: E731
+        return CSROperator(f(self.A), f(self.AT), self.order, f(self.A_sell), f(self.AT_sell))
 
     @property
     def nnz(self):
-        return self.A.nnz
+        return (self.A if self.A is not None else self.A_sell).nnz
 
     def apply_dev(self, x, out=None, coef=None, z=None, norm_out=None):
-        return K.spmv(self.A, x, out=out, coef=coef, z=z, norm_out=norm_out, order=self.order)
+        return K.spmv(self._active(False), x, out=out, coef=coef, z=z, norm_out=norm_out, order=self.order)
 
     def adjoint_dev(self, y, out=None, coef=None, z=None, norm_out=None):
-        return K.spmv(self.AT, y, out=out, coef=coef, z=z, norm_out=norm_out, order=self.order)
+        return K.spmv(self._active(True), y, out=out, coef=coef, z=z, norm_out=norm_out, order=self.order)
 
 
 def _upload_csr(A, device):
@@ -327,7 +363,7 @@ class ParallelBeamCT(CSROperator):
     n_det = int(sqrt(2)*nx) unit-spaced detector bins, sinogram ordered angle-major (row = angle*n_det + det),
     image vectorised row-major.  `angle_subset` keeps only those angle indices (row sharding by projection angle)."""
 
-    def __init__(self, nx, views, ny=None, n_det=None, angles=None, angle_subset=None, device=None):
+    def __init__(self, nx, views, ny=None, n_det=None, angles=None, angle_subset=None, device=None, layout="auto"):
         device = torch.device(device) if device is not None else default_device()
         ny = nx if ny is None else ny
         n_det = ct_num_detectors(nx) if n_det is None else int(n_det)
@@ -338,11 +374,19 @@ class ParallelBeamCT(CSROperator):
         cos_t = torch.from_numpy(np.cos(theta)).to(device)
         sin_t = torch.from_numpy(np.sin(theta)).to(device)
         K._lib.require_device()
-        A = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=False)
-        AT = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=True)
-        if A.nnz != AT.nnz:
-            raise RuntimeError(f"CT builder: nnz(A)={A.nnz} differs from nnz(A^T)={AT.nnz}")
-        super().__init__(A, AT)
+        if layout == "auto":  # SELL is the fast path; keep CSR too while it is cheap (tests, export, 'tree' order)
+            layout = "both" if 1.3 * len(theta) * self.nx * self.ny <= 2e8 else "sell"
+        if layout not in ("csr", "sell", "both"):
+            raise ValueError("layout must be 'auto', 'csr', 'sell' or 'both'")
+        mats = {}
+        for lay in (("csr", "sell") if layout == "both" else (layout,)):
+            a = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=False, layout=lay)
+            at = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=True, layout=lay)
+            if a.nnz != at.nnz:
+                raise RuntimeError(f"CT builder: nnz(A)={a.nnz} differs from nnz(A^T)={at.nnz}")
+            mats[lay] = (a, at)
+        csr, sell = mats.get("csr", (None, None)), mats.get("sell", (None, None))
+        super().__init__(csr[0], csr[1], "sequential", sell[0], sell[1])
 
 
 class BlockDiagCT(CSROperator):
@@ -363,7 +407,8 @@ class BlockDiagCT(CSROperator):
             s = torch.from_numpy(np.sin(th)).to(device)
             parts.append(K.ct_build(nx, nx, n_det, c, s, transpose=False))
             parts_t.append(K.ct_build(nx, nx, n_det, c, s, transpose=True))
-        super().__init__(_block_diag(parts), _block_diag(parts_t))
+        a, at = _block_diag(parts), _block_diag(parts_t)
+        super().__init__(a, at, "sequential", K.SellDevice.from_csr(a), K.SellDevice.from_csr(at))
 
 
 def _block_diag(parts):
