@@ -133,6 +133,11 @@ int tb200_fd_apply(int nt, int nrow, int ncol, const double* x, const double* x_
                    double expo, void* stream);
 int tb200_fd_adjoint(int nt, int nrow, int ncol, int has_next, const double* r, const double* w, const double* rt_prev,
                      const double* wt_prev, double* out, void* stream);
+/* Centred-difference gradient [I (x) D ; D (x) I], D = 3-point centred first derivative with zero end rows: the fp64
+ * statement of first_derivative_operator_2d (trips/utilities/operators_old.py:35-45, float32 pylops there), with the
+ * isotropic-TV weights (u1^2+u2^2+eps^2)^expo of MMGKS.py:64-78 fused into the apply pass. */
+int tb200_cd2d_apply(int nrow, int ncol, const double* x, double* u, double* wout, double eps, double expo, void* stream);
+int tb200_cd2d_adjoint(int nrow, int ncol, const double* r, const double* w, double* out, void* stream);
 int tb200_fd1d_apply(int64_t n, const double* x, double* u, void* stream);
 int tb200_fd1d_adjoint(int64_t n, const double* r, double* out, void* stream);
 

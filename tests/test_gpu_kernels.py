@@ -327,6 +327,33 @@ def test_difference_operators_bit_identical_to_the_sparse_matrices(tb, nx, nt):
         assert np.array_equal(o1 @ z, L1 @ z) and np.array_equal(o1.T @ z[:-1], L1.T @ z[:-1])
 
 
+@pytest.mark.parametrize("nx,ny", [(6, 6), (17, 17), (9, 14)])
+def test_centred_gradient_and_iso_weights_bit_identical(tb, nx, ny):
+    import torch
+
+    rng = np.random.default_rng(0)
+    if nx == ny:
+        L = O.centered_derivative_2d(nx, ny)
+    else:  # general rectangle: [I_nx (x) D(ny) ; D(nx) (x) I_ny]
+        def D(n):
+            M = sp.lil_matrix((n, n))
+            for i in range(1, n - 1):
+                M[i, i + 1], M[i, i - 1] = 0.5, -0.5
+            return M.tocsr()
+        L = sp.vstack((sp.kron(sp.identity(nx), D(ny)), sp.kron(D(nx), sp.identity(ny)))).tocsr()
+    op = tb.CenteredDerivative2D(nx, ny)
+    assert op.shape == L.shape
+    x, r = rng.standard_normal(nx * ny), rng.standard_normal(2 * nx * ny)
+    assert np.array_equal(op @ x, L @ x) and np.array_equal(op.T @ r, L.T @ r)
+    w = rng.uniform(0.5, 2, 2 * nx * ny)
+    assert np.array_equal(host(op.adjoint_dev(dev(r), w=dev(w))), L.T @ (w * r))
+    u = L @ x
+    N = nx * ny
+    want = (u[:N] ** 2 + u[N:] ** 2 + 0.1 ** 2) ** ((1 - 2) / 4)
+    got = host(op.iso_weights(dev(x), 0.1, (1 - 2) / 4))
+    assert np.allclose(got[:N], want, rtol=1e-15, atol=0) and np.array_equal(got[:N], got[N:])
+
+
 def test_difference_operator_frame_sharding_with_halos(tb):
     """Two 'ranks' each owning half of the frames reproduce the global operator given one-frame halos."""
     import torch

@@ -285,6 +285,22 @@ def test_cfg3_mmgks_deblurring_128(tb):
     assert np.allclose(info["relError"], io["relError"], rtol=1e-8)
     x, info = tb.GKS(op, b, L, projection_dim=3, n_iter=30, regparam="dp", delta=float(delta))
     assert rel(x, xg) < TOL
+    # isotropic TV (configs[2] names it): MMGKS.py:61-78 with the fp64 statement of the reference's centred gradient
+    # as L (the reference builds that operator in float32 pylops: SURVEY.md F12 - deviation stated in DESIGN.md)
+    Lc = tb.CenteredDerivative2D(n, n)
+    Lco = O.centered_derivative_2d(n, n)
+    with O.reductions("blas"):
+        xi, ii = O.MMGKS(Ao, b, Lco, pnorm=2, qnorm=1, projection_dim=3, n_iter=30, regparam="dp", delta=float(delta),
+                         iso_Ls=Lco)
+    x, info = tb.MMGKS(op, b, Lc, pnorm=2, qnorm=1, projection_dim=3, n_iter=30, regparam="dp", delta=float(delta),
+                       isoTV="isoTV", prob_dims=(n, n, 1))
+    print("cfg3 MMGKS isoTV 30 it: rel iterate dev", rel(x, xi))
+    assert rel(x, xi) < TOL
+    assert np.allclose(np.array(info["regParam_history"], dtype=float), np.array(ii["regParam_history"], dtype=float), rtol=1e-7)
+    with pytest.raises(TypeError, match="Isotropic TV"):
+        tb.MMGKS(op, b, Lc, isoTV="isoTV")
+    with pytest.raises(TypeError, match="CenteredDerivative2D"):
+        tb.MMGKS(op, b, L, isoTV="isoTV", prob_dims=(n, n, 1))
 
 
 def test_cfg5_dynamic_ct_spacetime_tv_small(tb):

@@ -51,6 +51,8 @@ SIGNATURES = {
     "tb200_fd_rows": (c_i64, [c_int, c_int, c_int, c_int]),
     "tb200_fd_apply": (c_int, [c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr]),
     "tb200_fd_adjoint": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_cd2d_apply": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr]),
+    "tb200_cd2d_adjoint": (c_int, [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_fd1d_apply": (c_int, [c_i64, c_ptr, c_ptr, c_ptr]),
     "tb200_fd1d_adjoint": (c_int, [c_i64, c_ptr, c_ptr, c_ptr]),
 }

@@ -138,6 +138,51 @@ fd_adjoint_kernel(int nt, int nrow, int ncol, int ntr, const double* __restrict_
   }
 }
 
+// ---- centred differences (isotropic TV) ------------------------------------------------------------------
+// fp64 statement of the reference's first_derivative_operator_2d (trips/utilities/operators_old.py:35-45):
+// pylops' 3-point centred FirstDerivative (y[1:-1] = (x[2:] - x[:-2]) / 2, zero at both ends) in
+// VStack(Kronecker(I, D), Kronecker(D, I)) form: 2*nrow*ncol rows, [within-row part | between-row part].
+// The reference builds it in float32; the isoTV weights of MMGKS.py:64-78,
+//   w = (u1^2 + u2^2 + eps^2)^((q-2)/4) for both halves, are fused into the apply pass.
+__global__ void __launch_bounds__(256)
+cd2d_apply_kernel(int nrow, int ncol, const double* __restrict__ x, double* __restrict__ u, double* __restrict__ wout,
+                  double eps2, double expo) {
+  const int64_t N = (int64_t)nrow * ncol;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = q / ncol, c = q % ncol;
+    double u1 = 0.0, u2 = 0.0;
+    if (c >= 1 && c <= ncol - 2) u1 = __dsub_rn(__dmul_rn(0.5, x[q + 1]), __dmul_rn(0.5, x[q - 1]));
+    if (r >= 1 && r <= nrow - 2) u2 = __dsub_rn(__dmul_rn(0.5, x[q + ncol]), __dmul_rn(0.5, x[q - ncol]));
+    if (u != nullptr) {
+      u[q] = u1;
+      u[N + q] = u2;
+    }
+    if (wout != nullptr) {
+      const double t = __dadd_rn(__dadd_rn(__dmul_rn(u1, u1), __dmul_rn(u2, u2)), eps2);
+      const double w = pow(t, expo);
+      wout[q] = w;
+      wout[N + q] = w;
+    }
+  }
+}
+
+// out = L^T (w . r), terms added in the order of scipy's CSC scatter (ascending row index of L)
+__global__ void __launch_bounds__(256)
+cd2d_adjoint_kernel(int nrow, int ncol, const double* __restrict__ r, const double* __restrict__ w,
+                    double* __restrict__ out) {
+  const int64_t N = (int64_t)nrow * ncol;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = q / ncol, c = q % ncol;
+    double acc = 0.0;
+    // within-row part: L-row (row, c') is non-zero for 1 <= c' <= ncol-2 with -0.5 at c'-1 and +0.5 at c'+1
+    if (c - 1 >= 1 && c - 1 <= ncol - 2) acc = __dadd_rn(acc, __dmul_rn(0.5, wr_at(r, w, q - 1)));
+    if (c + 1 >= 1 && c + 1 <= ncol - 2) acc = __dsub_rn(acc, __dmul_rn(0.5, wr_at(r, w, q + 1)));
+    if (row - 1 >= 1 && row - 1 <= nrow - 2) acc = __dadd_rn(acc, __dmul_rn(0.5, wr_at(r, w, N + q - ncol)));
+    if (row + 1 >= 1 && row + 1 <= nrow - 2) acc = __dsub_rn(acc, __dmul_rn(0.5, wr_at(r, w, N + q + ncol)));
+    out[q] = acc;
+  }
+}
+
 // 1-D operator (n-1) x n and its adjoint
 __global__ void __launch_bounds__(256) fd1d_apply_kernel(int64_t n, const double* __restrict__ x, double* __restrict__ u) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n - 1; i += (int64_t)gridDim.x * blockDim.x)
@@ -208,6 +253,22 @@ int tb200_fd_adjoint(int nt, int nrow, int ncol, int has_next, const double* r, 
   fd_adjoint_kernel<<<grid_for(total, 256 * 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(nt, nrow, ncol, ntr, r, w, rt_prev,
                                                                                         wt_prev, out);
   return check_launch("fd_adjoint");
+}
+
+// Centred-difference gradient (2*nrow*ncol rows): u = L x (u may be NULL) and, if wout != NULL, the isotropic-TV
+// weights wout = (u1^2 + u2^2 + eps^2)^expo written to both halves (MMGKS.py:64-78 with nt = 1).
+int tb200_cd2d_apply(int nrow, int ncol, const double* x, double* u, double* wout, double eps, double expo, void* stream) {
+  TB200_REQUIRE(nrow >= 1 && ncol >= 1 && x && (u || wout), "bad argument");
+  const int64_t N = (int64_t)nrow * ncol;
+  cd2d_apply_kernel<<<grid_for(N, 256 * 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(nrow, ncol, x, u, wout, eps * eps, expo);
+  return check_launch("cd2d_apply");
+}
+// out = L^T (w . r) for the centred-difference gradient (w may be NULL).
+int tb200_cd2d_adjoint(int nrow, int ncol, const double* r, const double* w, double* out, void* stream) {
+  TB200_REQUIRE(nrow >= 1 && ncol >= 1 && r && out, "bad argument");
+  const int64_t N = (int64_t)nrow * ncol;
+  cd2d_adjoint_kernel<<<grid_for(N, 256 * 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(nrow, ncol, r, w, out);
+  return check_launch("cd2d_adjoint");
 }
 
 int tb200_fd1d_apply(int64_t n, const double* x, double* u, void* stream) {

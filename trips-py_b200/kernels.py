@@ -503,6 +503,33 @@ def fd_adjoint(r, nt, nrow, ncol, has_next=False, w=None, rt_prev=None, wt_prev=
     return out
 
 
+def cd2d_apply(x, nrow, ncol, out=None, wout=None, eps=0.0, expo=0.0, want_u=True):
+    """u = [I (x) D ; D (x) I] x with centred differences; optional fused isoTV weights into wout (both halves)."""
+    n = nrow * ncol
+    _vec(x, n, "x")
+    if want_u and out is None:
+        out = torch.empty(2 * n, dtype=F64, device=x.device)
+    if out is not None:
+        _vec(out, 2 * n, "out")
+    if wout is not None:
+        _vec(wout, 2 * n, "wout")
+    check(lib().tb200_cd2d_apply(nrow, ncol, _p(x), _p(out), _p(wout), float(eps), float(expo), _stream()), "cd2d_apply")
+    _lib.count()
+    return out
+
+
+def cd2d_adjoint(r, nrow, ncol, w=None, out=None):
+    n = nrow * ncol
+    _vec(r, 2 * n, "r")
+    if w is not None:
+        _vec(w, 2 * n, "w")
+    if out is None:
+        out = torch.empty(n, dtype=F64, device=r.device)
+    check(lib().tb200_cd2d_adjoint(nrow, ncol, _p(r), _p(w), _p(out), _stream()), "cd2d_adjoint")
+    _lib.count()
+    return out
+
+
 def fd1d_apply(x, out=None):
     n = x.numel()
     if out is None:

@@ -508,6 +508,29 @@ class FirstDerivative2D(SpaceTimeDerivative):
         super().__init__(nx, ny, 1, device)
 
 
+class CenteredDerivative2D(LinearOperator):
+    """Centred-difference gradient [I (x) D ; D (x) I] (2*nx*ny rows): the fp64 statement of the reference's
+    `first_derivative_operator_2d` (trips/utilities/operators_old.py:35-45; pylops FirstDerivative(kind='centered') in
+    float32 there - SURVEY.md F12).  It is the operator MMGKS' isoTV branch (MMGKS.py:61-78) is written for: the
+    regulariser passed as L must have 2*nx*ny rows.  `iso_weights` fuses L x with (u1^2+u2^2+eps^2)^expo."""
+
+    def __init__(self, nx, ny, device=None):
+        self.nx, self.ny = int(nx), int(ny)
+        super().__init__((2 * self.nx * self.ny, self.nx * self.ny), device)
+
+    def apply_dev(self, x, out=None):
+        return K.cd2d_apply(x, self.nx, self.ny, out=out)
+
+    def adjoint_dev(self, r, out=None, w=None):
+        return K.cd2d_adjoint(r, self.nx, self.ny, w=w, out=out)
+
+    def iso_weights(self, x, eps, expo, out=None):
+        if out is None:
+            out = torch.empty(self.shape[0], dtype=F64, device=x.device)
+        K.cd2d_apply(x, self.nx, self.ny, out=None, wout=out, eps=eps, expo=expo, want_u=False)
+        return out
+
+
 def as_operator(A, device=None):
     """Accept what the reference accepts for A / L and return a GPU operator: our operators pass through;
     scipy.sparse matrices and (small) dense arrays are uploaded as CSR with an explicit transpose."""

@@ -14,7 +14,7 @@ import numpy as np
 from .. import kernels as K
 from ..decompositions import GKState
 from ..kernels import Basis
-from ..operators import SpaceTimeDerivative
+from ..operators import CenteredDerivative2D, SpaceTimeDerivative
 from ..reg_param.discrepancy_principle import discrepancy_principle_projected
 from ..reg_param.gcv import generalized_crossvalidation
 
@@ -65,7 +65,7 @@ def adjoint_L_weighted(L, r, w, out=None):
     """L^T (w . r)   (w None: L^T r)."""
     if w is None:
         return L.adjoint_dev(r, out=out)
-    if isinstance(L, SpaceTimeDerivative):
+    if isinstance(L, (SpaceTimeDerivative, CenteredDerivative2D)):
         return L.adjoint_dev(r, out=out, w=w)
     return L.adjoint_dev(K.vec_mul(w, r), out=out)
 
