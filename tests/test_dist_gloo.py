@@ -119,3 +119,45 @@ def test_dist_gk_world2_gloo_matches_single_process_oracle(tmp_path):
     Uo, Bo, Vo = O.golub_kahan(A, b, steps)
     assert np.allclose(parts[0]["B"], Bo, rtol=1e-10, atol=1e-12)
     assert np.allclose(parts[0]["V"].T, Vo, atol=1e-9) and np.allclose(U.T, Uo, atol=1e-9)
+
+
+def _comm_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from trips_b200.dist import FrameComm, shard_frames
+
+        comm = FrameComm()
+        assert (comm.first, comm.last) == (rank == 0, rank == world - 1)
+        lo, hi = shard_frames(7, world, rank)
+        frames = torch.arange(lo, hi, dtype=torch.float64).repeat_interleave(4)  # 4 "pixels" per frame, value = frame id
+        nxt = comm.halo_from_next(frames[:4])
+        prv = comm.halo_from_prev(frames[-4:])
+        pair = torch.tensor([float(rank + 1), 0.0], dtype=torch.float64)
+        comm.sync_norm_(pair)
+        gathered = comm.allgather(torch.full((2, 2), float(rank), dtype=torch.float64))
+        np.savez(os.path.join(out_dir, f"comm{rank}.npz"), lo=lo, hi=hi, nxt=-1 if nxt is None else nxt.numpy(),
+                 prv=-1 if prv is None else prv.numpy(), pair=pair.numpy(), gathered=gathered.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_comm_halos_and_reductions_world3_gloo(tmp_path):
+    """One-frame halos in both directions, scalar all-reduce and all-gather of the frame-sharded (dynamic CT) path."""
+    world = 3
+    mp.spawn(_comm_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"comm{r}.npz") for r in range(world)]
+    bounds = [(int(p["lo"]), int(p["hi"])) for p in parts]
+    assert bounds[0][0] == 0 and bounds[-1][1] == 7 and all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
+    for r, p in enumerate(parts):
+        if r < world - 1:
+            assert np.array_equal(p["nxt"], np.full(4, float(bounds[r + 1][0])))  # next rank's FIRST frame
+        else:
+            assert p["nxt"] == -1
+        if r > 0:
+            assert np.array_equal(p["prv"], np.full(4, float(bounds[r - 1][1] - 1)))  # previous rank's LAST frame
+        else:
+            assert p["prv"] == -1
+        assert p["pair"][0] == 6.0 and p["pair"][1] == np.sqrt(6.0)
+        assert np.array_equal(p["gathered"][:, 0, 0], np.arange(world, dtype=float))

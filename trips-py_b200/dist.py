@@ -37,6 +37,77 @@ def gather_sinogram_order(views, world_size, n_det):
     return (inv[:, None] * n_det + np.arange(n_det)[None, :]).reshape(-1)
 
 
+def shard_frames(nt, world_size, rank):
+    """Contiguous block of time frames owned by `rank` (contiguous so the time derivative needs neighbours only)."""
+    lo = rank * nt // world_size
+    hi = (rank + 1) * nt // world_size
+    return lo, hi
+
+
+class FrameComm:
+    """Communication of the frame-sharded (dynamic CT) solvers: the operator is block diagonal
+    over time frames, so A, A^T, the bases and every vector are local to the rank that owns the frames; what crosses
+    ranks is (i) scalars, k-vectors and k x k Gram matrices (all-reduce / all-gather of a few hundred doubles) and
+    (ii) ONE FRAME of halo per application of the temporal difference operator or its adjoint (0.5 MB at 256^2)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._bufs = {}
+
+    @property
+    def first(self):
+        return self.rank == 0
+
+    @property
+    def last(self):
+        return self.rank == self.world - 1
+
+    def allreduce_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def sync_norm_(self, pair):
+        """pair[0] = local sum of squares -> global; pair[1] = its square root."""
+        dist.all_reduce(pair[0:1], op=dist.ReduceOp.SUM, group=self.group)
+        pair[1:2] = torch.sqrt(pair[0:1])
+        return pair
+
+    def allgather(self, t):
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t.contiguous(), group=self.group)
+        return torch.stack(parts)
+
+    def _buf(self, key, like, n):
+        b = self._bufs.get(key)
+        if b is None or b.numel() != n or b.device != like.device:
+            b = self._bufs[key] = torch.empty(n, dtype=like.dtype, device=like.device)
+        return b
+
+    def _exchange(self, send, send_to, recv_from, key):
+        ops, buf = [], None
+        if send_to is not None:
+            ops.append(dist.P2POp(dist.isend, send.contiguous(), send_to, self.group))
+        if recv_from is not None:
+            buf = self._buf(key, send, send.numel())
+            ops.append(dist.P2POp(dist.irecv, buf, recv_from, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return buf
+
+    def halo_from_next(self, my_first_frame):
+        """Every rank hands its first frame to the previous rank; returns the next rank's first frame (None on the last)."""
+        return self._exchange(my_first_frame, None if self.first else self.rank - 1,
+                              None if self.last else self.rank + 1, "next")
+
+    def halo_from_prev(self, my_last_block):
+        """Every rank hands a block to the next rank; returns the previous rank's block (None on the first)."""
+        return self._exchange(my_last_block, None if self.last else self.rank + 1,
+                              None if self.first else self.rank - 1, "prev")
+
+
 class CudaBackend:
     """Vector operations of the distributed step on the CUDA kernels (1-D float64 CUDA tensors)."""
 

@@ -390,8 +390,10 @@ def basis_combine(V, k, h, w=None, sign=1.0, out=None, norm_out=None):
     return out
 
 
-def weighted_gram(B, k, w=None, extras=(), extra_weighted=()):
-    """Double-double Gram matrix of [diag(w) B[:, :k] | extras]; returns host arrays (Ghi, Glo) of shape (K, K)."""
+def weighted_gram(B, k, w=None, extras=(), extra_weighted=(), comm=None):
+    """Double-double Gram matrix of [diag(w) B[:, :k] | extras]; returns host arrays (Ghi, Glo) of shape (K, K).
+    With a communicator (row-sharded bases) the per-rank double-double partials are all-gathered and summed in
+    double-double on the host, so the result keeps its accuracy and is identical on every rank."""
     data = B.data if isinstance(B, Basis) else B
     m = data.shape[1]
     ne = len(extras)
@@ -409,8 +411,20 @@ def weighted_gram(B, k, w=None, extras=(), extra_weighted=()):
     check(lib().tb200_weighted_gram(m, int(k), _p(data), m, _p(w), ne, ext, ewt, _p(Ghi), _p(Glo), _p(ws), _stream()),
           "weighted_gram")
     _lib.count(2)
-    both = torch.stack((Ghi, Glo)).cpu().numpy()  # one D2H, synchronises
-    return both[0], both[1]
+    both = torch.stack((Ghi, Glo))
+    if comm is None:
+        both = both.cpu().numpy()  # one D2H, synchronises
+        return both[0], both[1]
+    parts = comm.allgather(both).cpu().numpy()  # (world, 2, K, K)
+    hi, lo = np.zeros((K, K)), np.zeros((K, K))
+    for p in parts:  # double-double accumulation (TwoSum), fixed rank order
+        s = hi + p[0]
+        bb = s - hi
+        e = (hi - (s - bb)) + (p[0] - bb)
+        lo = lo + (e + p[1])
+        hi = s
+    s = hi + lo
+    return s, lo - (s - hi)
 
 
 def gram_factor(Ghi, Glo, k):

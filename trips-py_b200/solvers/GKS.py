@@ -26,10 +26,11 @@ def GKS(A, b, L, projection_dim=3, n_iter=50, regparam="gcv", x_true=None, **kwa
     L = as_operator(L, A.device)
     dev = A.device
     bd = to_device_vector(b, dev)
-    bases = GKSBases(A, L, bd, projection_dim, n_iter)
+    comm = kwargs.get("b200_comm")  # dist.FrameComm: frame-sharded dynamic CT (A block diagonal over the ranks' frames)
+    bases = GKSBases(A, L, bd, projection_dim, n_iter, comm=comm)
     x_history = LazyHistory()
     lambda_history, residuals = [], []
-    err = ErrorTracker(x_true, dev)
+    err = ErrorTracker(x_true, dev, comm=kwargs.get("b200_comm"))
     keep = kwargs.get("b200_history", "lazy")
     rp_kwargs = {k: v for k, v in kwargs.items() if not k.startswith("b200_")}
     m, n = A.shape
@@ -55,7 +56,7 @@ def GKS(A, b, L, projection_dim=3, n_iter=50, regparam="gcv", x_true=None, **kwa
         K.vec_sub(tm, bd, out=tm)  # ra = AV@y - b                                               (:81)
         A.adjoint_dev(tm, out=ra)  # ra = A.T @ ra                                               (:82)
         K.basis_combine(bases.LV, k, yd, out=tp)  # rb = LV @ y                                  (:83)
-        adjoint_L_weighted(L, tp, None, out=rb)  # rb = L.T @ rb                                 (:84)
+        adjoint_L_weighted(L, tp, None, out=rb, comm=comm)  # rb = L.T @ rb                                 (:84)
         K.vec_axpy(float(lambdah), rb, ra, out=ra)  # r = ra + lambdah*rb                        (:85)
         expand(bases, ra, 3, residuals)  #                                                       (:86-96)
     info = {"xHistory": x_history, "regParam": lambdah, "regParam_history": lambda_history,

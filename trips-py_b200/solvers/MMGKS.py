@@ -54,10 +54,11 @@ def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv",
         if not isinstance(L, CenteredDerivative2D) or p != 2 * n:
             raise TypeError("isoTV needs L = CenteredDerivative2D(nx, ny) (the fp64 statement of the reference's "
                             "first_derivative_operator_2d), single frame")
-    bases = GKSBases(A, L, bd, projection_dim, n_iter)
+    comm = kwargs.get("b200_comm")  # dist.FrameComm: frame-sharded dynamic CT (A block diagonal over the ranks' frames)
+    bases = GKSBases(A, L, bd, projection_dim, n_iter, comm=comm)
     x_history = LazyHistory()
     lambda_history, residuals = [], []
-    err = ErrorTracker(x_true, dev)
+    err = ErrorTracker(x_true, dev, comm=kwargs.get("b200_comm"))
     keep = kwargs.get("b200_history", "lazy")
     rp_kwargs = {k: v for k, v in kwargs.items() if not k.startswith("b200_")}
     tm = torch.empty(m, dtype=K.F64, device=dev)
@@ -78,7 +79,7 @@ def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv",
         if iso:
             wr = L.iso_weights(xd, epsilon, (qnorm - 2) / 4)  #                                  (:64-78)
         else:
-            _, wr = apply_L_with_weights(L, xd, epsilon, qnorm / 2 - 1)  # u = L@x; wr           (:60,93)
+            _, wr = apply_L_with_weights(L, xd, epsilon, qnorm / 2 - 1, comm=comm)  # u = L@x; wr           (:60,93)
         R_A, R_L, c_plain, c_w, resid_w = factor_pair(bases, bd, wf=wf, wr=wr)  #               (:58-59,94-95)
         lambdah = choose_lambda(regparam, R_A, R_L, c_w, resid_w, delta, rp_kwargs)  #           (:96-103)
         lambda_history.append(lambdah)
@@ -97,7 +98,7 @@ def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv",
             K.vec_wsub(wf, tm, bd, out=tm)  # ra = wf*(AV@y - b)                                  (:111)
         A.adjoint_dev(tm, out=ra)  # ra = A.T @ ra                                               (:115)
         K.basis_combine(bases.LV, k, yd, out=tp)
-        adjoint_L_weighted(L, tp, wr, out=rb)  # rb = L.T @ (wr*(LV@y))                          (:113-117)
+        adjoint_L_weighted(L, tp, wr, out=rb, comm=comm)  # rb = L.T @ (wr*(LV@y))                          (:113-117)
         K.vec_axpy(float(lambdah), rb, ra, out=ra)  # r = ra + lambdah*rb                        (:118)
         expand(bases, ra, 2, residuals)  #                                                       (:119-129)
     info = {"xHistory": x_history, "regParam": lambdah, "regParam_history": lambda_history,

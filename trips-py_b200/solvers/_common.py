@@ -52,18 +52,25 @@ class ErrorTracker:
     """||x - x_true|| / ||x_true|| per iterate, computed on the device (one fused difference-norm pass).
     The reference recomputes the whole history at every iteration (Hybrid_LSQR.py:108-111); the final list is the same."""
 
-    def __init__(self, x_true, device):
+    def __init__(self, x_true, device, comm=None):
         self.enabled = x_true is not None
+        self.comm = comm
         if self.enabled:
             from ..operators import to_device_vector
 
             self.xt = to_device_vector(x_true, device)
-            self.xt_norm = float(K.vec_norm2(self.xt).cpu()[1])
+            pair = K.vec_norm2(self.xt)
+            if comm is not None:
+                comm.sync_norm_(pair)
+            self.xt_norm = float(pair.cpu()[1])
             self._pairs = []
 
     def add(self, x_dev):
         if self.enabled:
-            self._pairs.append(K.vec_diffnorm2(x_dev, self.xt))
+            pair = K.vec_diffnorm2(x_dev, self.xt)
+            if self.comm is not None:
+                self.comm.sync_norm_(pair)
+            self._pairs.append(pair)
 
     def values(self, denominators=None):
         if not self.enabled or not self._pairs:

@@ -20,11 +20,11 @@ from ..reg_param.gcv import generalized_crossvalidation
 
 
 class GKSBases:
-    def __init__(self, A, L, bd, projection_dim, n_iter):
-        self.A, self.L = A, L
+    def __init__(self, A, L, bd, projection_dim, n_iter, comm=None):
+        self.A, self.L, self.comm = A, L, comm
         dev = bd.device
         kmax = projection_dim + n_iter + 1
-        st = GKState(A, bd, projection_dim)  # golub_kahan(A, b, projection_dim)          (GKS.py:36, MMGKS.py:37)
+        st = GKState(A, bd, projection_dim, comm=comm)  # golub_kahan(A, b, projection_dim) (GKS.py:36, MMGKS.py:37)
         for _ in range(projection_dim):
             st.step()
         self.V = Basis(A.shape[1], kmax, dev)
@@ -45,27 +45,51 @@ class GKSBases:
         vn = self.V.col(self.V.k - 1)
         self.A.apply_dev(vn, out=self.AV.next_col())
         self.AV.push()
-        self.L.apply_dev(vn, out=self.LV.next_col())
+        apply_L(self.L, vn, self.comm, out=self.LV.next_col())
         self.LV.push()
 
 
-def apply_L_with_weights(L, x, eps, expo):
+def apply_L(L, x, comm=None, out=None, wout=None, eps=0.0, expo=0.0):
+    """u = L x (optionally with fused IRLS weights); frame-sharded difference operators fetch their one-frame halo."""
+    if isinstance(L, SpaceTimeDerivative):
+        x_next = None
+        if comm is not None:
+            N = L.nx * L.ny
+            x_next = comm.halo_from_next(x[:N])
+        return L.apply_dev(x, out=out, wout=wout, eps=eps, expo=expo, x_next=x_next)
+    if wout is not None:
+        raise TypeError("fused weights need a matrix-free difference operator")
+    return L.apply_dev(x, out=out)
+
+
+def apply_L_with_weights(L, x, eps, expo, comm=None):
     """u = L x and wr = (u^2 + eps^2)^expo, in one pass when L is a matrix-free difference operator."""
     import torch
 
     if isinstance(L, SpaceTimeDerivative):
         wr = torch.empty(L.shape[0], dtype=K.F64, device=x.device)
-        u = L.apply_dev(x, wout=wr, eps=eps, expo=expo)
+        u = apply_L(L, x, comm, wout=wr, eps=eps, expo=expo)
         return u, wr
     u = L.apply_dev(x)
     return u, K.irls_weights(u, eps, expo)
 
 
-def adjoint_L_weighted(L, r, w, out=None):
-    """L^T (w . r)   (w None: L^T r)."""
+def adjoint_L_weighted(L, r, w, out=None, comm=None):
+    """L^T (w . r)   (w None: L^T r).  Frame-sharded: the temporal rows of my last frame also act on the next rank."""
+    if isinstance(L, SpaceTimeDerivative):
+        rt_prev = None
+        if comm is not None:
+            N = L.nx * L.ny
+            if L.has_next:
+                lo = L.shape[0] - N  # temporal rows of my last frame: the final N rows
+                blk = r[lo:lo + N] if w is None else K.vec_mul(w[lo:lo + N].contiguous(), r[lo:lo + N].contiguous())
+            else:
+                blk = r[:N]  # nothing to hand on (last rank); participates for the receive only
+            rt_prev = comm.halo_from_prev(blk.contiguous())
+        return L.adjoint_dev(r, out=out, w=w, rt_prev=rt_prev, wt_prev=None)
     if w is None:
         return L.adjoint_dev(r, out=out)
-    if isinstance(L, (SpaceTimeDerivative, CenteredDerivative2D)):
+    if isinstance(L, CenteredDerivative2D):
         return L.adjoint_dev(r, out=out, w=w)
     return L.adjoint_dev(K.vec_mul(w, r), out=out)
 
@@ -73,17 +97,18 @@ def adjoint_L_weighted(L, r, w, out=None):
 def factor_pair(bases, bd, wf=None, wr=None):
     """R_A, R_L, c_plain = Q_A^T b, c_w = Q_A^T (wf*b), resid_w = ||wf*b - Q_A Q_A^T wf*b||."""
     k = bases.k
+    comm = bases.comm
     if wf is None:
-        Ghi, Glo = K.weighted_gram(bases.AV, k, None, extras=(bd,), extra_weighted=(0,))
+        Ghi, Glo = K.weighted_gram(bases.AV, k, None, extras=(bd,), extra_weighted=(0,), comm=comm)
         R_A, C, res2 = K.gram_factor(Ghi, Glo, k)
         c_plain = c_w = C[:, 0:1]
         resid_w = float(np.sqrt(res2[0]))
     else:
-        Ghi, Glo = K.weighted_gram(bases.AV, k, wf, extras=(bd, bd), extra_weighted=(0, 1))
+        Ghi, Glo = K.weighted_gram(bases.AV, k, wf, extras=(bd, bd), extra_weighted=(0, 1), comm=comm)
         R_A, C, res2 = K.gram_factor(Ghi, Glo, k)
         c_plain, c_w = C[:, 0:1], C[:, 1:2]
         resid_w = float(np.sqrt(res2[1]))
-    Ghi, Glo = K.weighted_gram(bases.LV, k, wr)
+    Ghi, Glo = K.weighted_gram(bases.LV, k, wr, comm=comm)
     R_L, _, _ = K.gram_factor(Ghi, Glo, k)
     return R_A, R_L, c_plain, c_w, resid_w
 
@@ -104,11 +129,16 @@ def expand(bases, r, n_reorth, residual_history):
     """r -= V (V^T r) n_reorth times, record ||r||, append r/||r|| and its images  (GKS.py:86-96, MMGKS.py:119-129)."""
     k = bases.k
     nrm = K.new_pair(r.device)
+    comm = bases.comm
     for it in range(n_reorth):
         h = K.basis_dots(bases.V, k, r)
+        if comm is not None:
+            comm.allreduce_(h)
         K.basis_combine(bases.V, k, h, w=r, sign=-1.0, out=r, norm_out=nrm if it == n_reorth - 1 else None)
     if n_reorth == 0:
         K.vec_norm2(r, out=nrm)
+    if comm is not None:
+        comm.sync_norm_(nrm)
     K.vec_div(r, nrm[1:2], out=bases.V.next_col())
     bases.V.push()
     bases.append_images()
