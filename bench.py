@@ -285,8 +285,15 @@ def main():
     achieved = alg_bytes / (mean_spmv_ms * 1e-3) / 1e9
     spmv_share = sum(spmv_ms) / ms
     B_GK = 2 * (val_bytes + 4) * nnz + 8 * (m_full + 1) + 8 * (n + 1) + 48 * (m_full + n)
+    traffic = None  # DRAM bytes per launch from the committed ncu capture of this exact configuration, if there is one
+    if world == 1 and (nx, views) == (2048, 720) and layout == "sell" and not args.f32_storage:
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                traffic = json.load(f)["cfg4_sell_sequential_n1"]["mean_bytes"]
+        except Exception:  # noqa: BLE001
+            traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "kernel": kernel_name,
+                "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name,
                 "launch_ms": mean_spmv_ms, "launch_ms_AT": sum(spmv_ms[0::2]) / max(len(spmv_ms[0::2]), 1),
                 "launch_ms_A": sum(spmv_ms[1::2]) / max(len(spmv_ms[1::2]), 1),
                 "alg_bytes_per_launch": alg_bytes, "share_of_step": spmv_share,
