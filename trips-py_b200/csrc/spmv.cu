@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t* __restrict__ rowlen,
                  const int32_t* __restrict__ col, const VT* __restrict__ val, const double* __restrict__ x,
                  double* __restrict__ y, double coef_host, const double* __restrict__ coef_dev,
-                 const double* __restrict__ z, double* __restrict__ partials) {
+                 const double* __restrict__ z, double* __restrict__ partials, int gather_mode) {
   constexpr int CH = 16;
   __shared__ double red[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -575,15 +575,67 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
       if (it * CH + 4 * q < w) SellVals<VT>::piece(vp + (int64_t)(it * (CH / 4) + q) * 128, pol_stream, &v[4 * q]);
   };
 
+  // Gather mapping of this slice.  The L1TEX data pipe pays per distinct 32-byte sector of a gather request, so the
+  // request shape should follow the matrix.  Lane-per-row requests (one position of 32 rows) are cheap when the rows
+  // are near-vertical rays or pixels of the transpose: neighbouring rows hit neighbouring x.  For near-horizontal rays
+  // (runs of adjacent pixels along the row, neighbouring rays in DIFFERENT image rows) they touch 32 sectors each:
+  // there a request is re-shaped to 16 consecutive entries of two rows (2-3 sectors) and the values are handed to
+  // the owner lanes through a per-warp shared-memory tile.  Arithmetic and order are unchanged (bit-identical).
+  // Decided once per slice by probing the column stride along the row and across the rows in the first chunk.
+  __shared__ __align__(16) int32_t ctile_all[WARPS][32 * 20];  // [row][16 cols + 4 pad]: 16-byte aligned rows
+  __shared__ __align__(16) double xtile_all[WARPS][32 * 18];   // [row][16 x + 2 pad]: odd number of 16-byte pieces
+  int32_t* ctile = ctile_all[warp];
+  double* xtile = xtile_all[warp];
+  const int gk = lane & 15, gr = lane >> 4;  // row-major mode: my entry / which row of the pair
+  auto gather_lane_per_row = [&](const int32_t (&c)[CH], double (&xv)[CH]) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k) xv[k] = ld_gather_f64(x + c[k], pol_keep);
+  };
+  auto gather_row_major = [&](const int32_t (&c)[CH], double (&xv)[CH]) {
+    // publish my row's columns, then request j gathers entries 0..15 of rows 2j and 2j+1
+#pragma unroll
+    for (int q = 0; q < CH / 4; ++q)
+      *reinterpret_cast<int4*>(ctile + lane * 20 + 4 * q) = make_int4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < CH; ++j) xv[j] = ld_gather_f64(x + ctile[(2 * j + gr) * 20 + gk], pol_keep);
+    __syncwarp();
+  };
+  auto deliver_row_major = [&](double (&xv)[CH]) {
+    // xv[j] currently holds x for (row 2j + gr, entry gk): hand every value to the lane that owns its row
+#pragma unroll
+    for (int j = 0; j < CH; ++j) xtile[(2 * j + gr) * 18 + gk] = xv[j];
+    __syncwarp();
+    const double2* xr = reinterpret_cast<const double2*>(xtile + lane * 18);
+#pragma unroll
+    for (int j = 0; j < CH / 2; ++j) {
+      const double2 t = xr[j];
+      xv[2 * j] = t.x;
+      xv[2 * j + 1] = t.y;
+    }
+    __syncwarp();
+  };
+
   int32_t c1[CH];
   double v0[CH], v1[CH], x0[CH];
 #pragma unroll
   for (int k = 0; k < CH; ++k) c1[k] = 0, v0[k] = 0.0, v1[k] = 0.0, x0[k] = 0.0;
+  bool row_major = false;
   if (nit > 0) {
     load_cols(0, c1);
     load_vals(0, v0);
-#pragma unroll
-    for (int k = 0; k < CH; ++k) x0[k] = ld_gather_f64(x + c1[k], pol_keep);
+    {
+      const bool ok = len >= 10;
+      const int cn = __shfl_xor_sync(0xffffffffu, c1[8], 1);
+      const bool okn = __shfl_xor_sync(0xffffffffu, (int)ok, 1) != 0;
+      const unsigned along = __ballot_sync(0xffffffffu, ok && (c1[9] - c1[8]) <= 2 && (c1[8] - c1[7]) <= 2);
+      const unsigned across = __ballot_sync(0xffffffffu, ok && okn && abs(c1[8] - cn) <= 6);
+      row_major = __popc(along) > __popc(across) + 8;
+      if (gather_mode == 1) row_major = false;
+      if (gather_mode == 2) row_major = true;
+    }
+    if (row_major) gather_row_major(c1, x0);
+    else gather_lane_per_row(c1, x0);
   }
   if (nit > 1) {
     load_cols(1, c1);
@@ -591,6 +643,7 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
   }
   double acc = 0.0;
   for (int it = 0; it < nit; ++it) {
+    if (row_major) deliver_row_major(x0);
     // products of chunk it; positions at or beyond the row's length are padding and contribute +0.0
     const int hi = len - it * CH;
     double p[CH];
@@ -603,8 +656,8 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
     }
     // gathers of chunk it+1 (its columns arrived during the previous iteration)
     if (it + 1 < nit) {
-#pragma unroll
-      for (int k = 0; k < CH; ++k) x0[k] = ld_gather_f64(x + c1[k], pol_keep);
+      if (row_major) gather_row_major(c1, x0);
+      else gather_lane_per_row(c1, x0);
     }
     // stream loads of chunk it+2
     double v2[CH];
@@ -868,7 +921,7 @@ static int spmv_launch(int order, int64_t m, int64_t nnz, const int64_t* rowptr,
   return rc;
 }
 
-static int g_sell_warps = 4;  // tuning knob (tb200_spmv_set_variant, bits 8-9 -> 1/2/4/8 warps per CTA)
+static int g_sell_warps = 4;  // tuning knob (tb200_spmv_set_variant, bits 8-9: 0/2 -> 4, 1 -> 2, 3 -> 1 warps per CTA)
 
 template <typename VT>
 static int sell_launch(int64_t m, const int64_t* sliceptr, const int32_t* rowlen, const int32_t* col, const VT* val,
@@ -879,10 +932,9 @@ static int sell_launch(int64_t m, const int64_t* sliceptr, const int32_t* rowlen
   const int warps = g_sell_warps;
   const int64_t nblocks = (nslices + warps - 1) / warps;
   switch (warps) {
-    case 1: spmv_sell_kernel<VT, 1><<<(unsigned)nblocks, 32, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials); break;
-    case 2: spmv_sell_kernel<VT, 2><<<(unsigned)nblocks, 64, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials); break;
-    case 8: spmv_sell_kernel<VT, 8><<<(unsigned)nblocks, 256, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials); break;
-    default: spmv_sell_kernel<VT, 4><<<(unsigned)nblocks, 128, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials); break;
+    case 1: spmv_sell_kernel<VT, 1><<<(unsigned)nblocks, 32, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials, g_seq_gather_mode); break;
+    case 2: spmv_sell_kernel<VT, 2><<<(unsigned)nblocks, 64, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials, g_seq_gather_mode); break;
+    default: spmv_sell_kernel<VT, 4><<<(unsigned)nblocks, 128, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials, g_seq_gather_mode); break;
   }
   int rc = check_launch("spmv_sell");
   if (rc) return rc;
@@ -915,7 +967,7 @@ int tb200_spmv_set_variant(int v) {
                 "variant = CSR kernel (0..6) + 8 * gather mode (0..3) + 256 * log2(SELL warps per CTA) (0..3)");
   g_seq_variant = v & 7;
   g_seq_gather_mode = (v >> 3) & 3;
-  g_sell_warps = (v >> 8) ? (1 << (v >> 8)) : 4;
+  g_sell_warps = ((v >> 8) == 1) ? 2 : ((v >> 8) == 3) ? 1 : 4;
   return 0;
 }
 
