@@ -66,6 +66,15 @@ int tb200_spmv_sell_f64(int64_t m, int64_t n, const int64_t* sliceptr, const int
 int tb200_spmv_sell_f32s(int64_t m, int64_t n, const int64_t* sliceptr, const int32_t* rowlen, const int32_t* colidx,
                          const float* vals, const double* x, double* y, double coef_host, const double* coef_dev,
                          const double* z, double* norm_out, double* ws, void* stream);
+/* One complete Golub-Kahan step = the reference's golub_kahan_update (trips/utilities/decompositions.py:230-255) on
+ * SELL-32-4 matrices A (m x n) and A^T (n x m): 6 kernels enqueued on `stream`, all scalars stay on the device.
+ * v_prev / beta_prev_dev are NULL on the first step.  alpha_pair, beta_pair: 2 doubles each (sum of squares, norm).
+ * events_host (nullable): four cudaEvent_t recorded around the A^T and the A launch (live per-launch timing). */
+int tb200_gk_step_sell_f64(int64_t m, int64_t n, const int64_t* a_sliceptr, const int32_t* a_rowlen, const int32_t* a_col,
+                           const double* a_val, const int64_t* at_sliceptr, const int32_t* at_rowlen,
+                           const int32_t* at_col, const double* at_val, const double* u_k, const double* v_prev,
+                           const double* beta_prev_dev, double* v_out, double* u_out, double* alpha_pair,
+                           double* beta_pair, double* ws, void* const* events_host, void* stream);
 int tb200_reduce_finalize(const double* partials, int64_t n, double* out, void* stream);
 
 /* ---- BLAS-1 between operator applies -------------------------------------------------------------------

@@ -28,6 +28,7 @@ SIGNATURES = {
     "tb200_spmv_csr_f32s": (c_int, [c_int, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_spmv_sell_f64": (c_int, [c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_spmv_sell_f32s": (c_int, [c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_gk_step_sell_f64": (c_int, [c_i64, c_i64] + [c_ptr] * 18),
     "tb200_reduce_finalize": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "tb200_reduce_workspace_len": (c_i64, []),
     "tb200_vec_div": (c_int, [c_i64, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr]),

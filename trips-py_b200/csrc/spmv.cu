@@ -1035,6 +1035,40 @@ int tb200_spmv_sell_f32s(int64_t m, int64_t n, const int64_t* sliceptr, const in
                             (cudaStream_t)stream);
 }
 
+// One Golub-Kahan step (the reference's golub_kahan_update, trips/utilities/decompositions.py:230-255) on SELL-32-4
+// matrices, enqueued as 6 kernels on `stream` with every scalar kept on the device:
+//   v = A^T u_k - beta_prev * v_prev ; alpha = ||v|| ; v /= alpha ; u = A v - alpha * u_k ; beta = ||u|| ; u /= beta
+// v_prev / beta_prev_dev are NULL on the first step.  alpha_pair / beta_pair: 2 doubles each (sum of squares, norm).
+// ws: tb200_spmv_workspace_len(max(m, n)) doubles.  events_host (nullable): host array of four cudaEvent_t recorded on
+// `stream` before/after the A^T launch (+ its norm finalize) and before/after the A launch, for live per-launch timing.
+int tb200_vec_div(int64_t n, const double* x, double d_host, const double* d_dev, double* out, void* stream);
+
+int tb200_gk_step_sell_f64(int64_t m, int64_t n, const int64_t* a_sliceptr, const int32_t* a_rowlen, const int32_t* a_col,
+                           const double* a_val, const int64_t* at_sliceptr, const int32_t* at_rowlen,
+                           const int32_t* at_col, const double* at_val, const double* u_k, const double* v_prev,
+                           const double* beta_prev_dev, double* v_out, double* u_out, double* alpha_pair,
+                           double* beta_pair, double* ws, void* const* events_host, void* stream) {
+  TB200_REQUIRE(u_k && v_out && u_out && alpha_pair && beta_pair && ws, "null pointer");
+  TB200_REQUIRE((v_prev == nullptr) == (beta_prev_dev == nullptr), "v_prev and beta_prev_dev go together");
+  cudaStream_t st = (cudaStream_t)stream;
+  auto mark = [&](int i) {
+    if (events_host != nullptr && events_host[i] != nullptr) cudaEventRecord((cudaEvent_t)events_host[i], st);
+  };
+  mark(0);
+  int rc = tb200_spmv_sell_f64(n, m, at_sliceptr, at_rowlen, at_col, at_val, u_k, v_out, 0.0, beta_prev_dev, v_prev,
+                               alpha_pair, ws, stream);
+  mark(1);
+  if (rc) return rc;
+  rc = tb200_vec_div(n, v_out, 0.0, alpha_pair + 1, v_out, stream);
+  if (rc) return rc;
+  mark(2);
+  rc = tb200_spmv_sell_f64(m, n, a_sliceptr, a_rowlen, a_col, a_val, v_out, u_out, 0.0, alpha_pair + 1, u_k, beta_pair, ws,
+                           stream);
+  mark(3);
+  if (rc) return rc;
+  return tb200_vec_div(m, u_out, 0.0, beta_pair + 1, u_out, stream);
+}
+
 // out[0] = round(sum of the n double-double partials (hi, lo interleaved)), out[1] = sqrt(out[0]); one CTA.
 int tb200_reduce_finalize(const double* partials, int64_t n, double* out, void* stream) {
   TB200_REQUIRE(partials && out && n >= 0, "bad argument");

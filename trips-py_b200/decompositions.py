@@ -80,6 +80,16 @@ class GKState:
             self.beta[:k + 1].copy_(old_b[:k + 1])
         u_k = self.U.col(k)
         v = self.V.next_col()
+        A = self.A
+        if self.comm is None and getattr(A, "A_sell", None) is not None and A.order == "sequential" \
+                and A.A_sell.vals.dtype == F64:
+            # the whole step behind one C-ABI call (tb200_gk_step_sell_f64)
+            self.V.push()
+            u = self.U.next_col()
+            K.gk_step_sell(A.A_sell, A.AT_sell, u_k, self.V.col(k - 1) if k else None,
+                           self.beta[k - 1, 1:2] if k else None, v, u, self.alpha[k], self.beta[k])
+            self.U.push()
+            return
         # v = A^T u_k - beta_{k-1} v_{k-1} ; alpha = ||v|| ; v /= alpha      (decompositions.py:234-239)
         if k == 0:
             apply_fused(self.A, u_k, v, adjoint=True, norm_out=self.alpha[k])
@@ -183,7 +193,7 @@ class _HostBasis:
         self.cap, self.rows = cap, rows
         self.arr = self.t.numpy().T  # (rows, cap), Fortran order: column j contiguous
         _HostBasis.registry[self.arr.__array_interface__["data"][0]] = self
-        if len(_HostBasis.registry) > 64:
+        if len(_HostBasis.registry) > 4:  # each entry pins up to GBs of host memory: keep only the live pair(s)
             _HostBasis.registry.pop(next(iter(_HostBasis.registry)))
 
     @classmethod

@@ -192,6 +192,22 @@ def _spmv_sell(A, x, out, coef, z, norm_out):
     return out
 
 
+GK_STEP_EVENTS = None  # bench.py: callable returning four torch.cuda.Event to be recorded around the two SpMV launches
+
+
+def gk_step_sell(A, AT, u_k, v_prev, beta_prev, v_out, u_out, alpha_pair, beta_pair):
+    """One Golub-Kahan step in a single C-ABI call (6 kernels) on SELL matrices; scalars stay on the device."""
+    m, n = A.shape
+    ws = Workspace.get(A.device).spmv(max(m, n))
+    ev = None
+    if GK_STEP_EVENTS is not None:
+        ev = (ctypes.c_void_p * 4)(*[e.cuda_event for e in GK_STEP_EVENTS()])
+    check(lib().tb200_gk_step_sell_f64(m, n, _p(A.sliceptr), _p(A.rowlen), _p(A.colidx), _p(A.vals), _p(AT.sliceptr),
+                                       _p(AT.rowlen), _p(AT.colidx), _p(AT.vals), _p(u_k), _p(v_prev), _p(beta_prev),
+                                       _p(v_out), _p(u_out), _p(alpha_pair), _p(beta_pair), _p(ws), ev, _stream()), "gk_step")
+    _lib.count(6)
+
+
 def spmv(A, x, out=None, coef=None, z=None, norm_out=None, order="sequential"):
     """out = A x - coef*z (z/coef optional), optionally norm_out[:] = (||out||^2, ||out||).
 
