@@ -11,5 +11,7 @@ from .operators import (BlockDiagCT, CenteredDerivative2D, CSROperator, FirstDer
                         FirstDerivative2D, Identity, LinearOperator, ParallelBeamCT, PSFBlur2D, SpaceTimeDerivative,
                         as_operator, gauss_psf)
 from .solvers import CGLS, GKS, MMGKS, Hybrid_GMRES, Hybrid_LSQR  # noqa: F401
+from . import test_problems  # noqa: F401
+from .test_problems import Deblurring2D, Tomography  # noqa: F401
 
 __version__ = "0.1.0"
