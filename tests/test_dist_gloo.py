@@ -161,3 +161,38 @@ def test_frame_comm_halos_and_reductions_world3_gloo(tmp_path):
             assert p["prv"] == -1
         assert p["pair"][0] == 6.0 and p["pair"][1] == np.sqrt(6.0)
         assert np.array_equal(p["gathered"][:, 0, 0], np.arange(world, dtype=float))
+
+
+def _row_comm_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from trips_b200.dist import FrameComm, RowComm
+
+        rc, fc = RowComm(), FrameComm()
+        out = {}
+        for name, comm in (("row", rc), ("frame", fc)):
+            for space in ("data", "model", "reg"):
+                pair = torch.tensor([float(rank + 1), -1.0], dtype=torch.float64)
+                comm.sync_norm_(pair, space)
+                h = comm.sum_(torch.tensor([1.0, 2.0], dtype=torch.float64), space)
+                out[f"{name}_{space}"] = np.concatenate((pair.numpy(), h.numpy(), [comm.total(10 + rank, space)]))
+        np.savez(os.path.join(out_dir, f"rc{rank}.npz"), **out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_comm_sums_only_the_sharded_space_world2_gloo(tmp_path):
+    """RowComm (static CT, rows by angle): only data-space reductions cross ranks; model / regulariser space are
+    replicated and must be left alone.  FrameComm: every space is split."""
+    world = 2
+    mp.spawn(_row_comm_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        p = np.load(tmp_path / f"rc{r}.npz")
+        summed = np.array([3.0, np.sqrt(3.0), 2.0, 4.0, 21.0])
+        alone = np.array([r + 1.0, -1.0, 1.0, 2.0, 10.0 + r])
+        assert np.array_equal(p["row_data"], summed)
+        assert np.array_equal(p["row_model"], alone) and np.array_equal(p["row_reg"], alone)
+        for space in ("data", "model", "reg"):
+            assert np.array_equal(p[f"frame_{space}"], summed)

@@ -41,8 +41,8 @@ def apply_fused(op, x, out, adjoint=False, coef=None, z=None, norm_out=None):
 class GKState:
     """Golub-Kahan bidiagonalisation state on the device (one `step()` == one golub_kahan_update).
 
-    `comm` (a dist.FrameComm) selects the frame-sharded mode for block-diagonal operators: A, A^T and all vectors are
-    local to the rank, only the squared norms are all-reduced."""
+    `comm` selects a sharded mode (dist.FrameComm: block-diagonal operators, every vector local; dist.RowComm: rows of
+    A by angle, u-space local and v-space replicated): only the squared norms over split spaces are all-reduced."""
 
     def __init__(self, A, b_dev, kmax, comm=None):
         self.A, self.comm = A, comm
@@ -54,13 +54,13 @@ class GKState:
         # U[:,0] = b / ||b||   (Hybrid_LSQR.py:64-65, decompositions.py:159)
         self.beta0 = torch.zeros(2, dtype=F64, device=dev)
         K.vec_norm2(b_dev, out=self.beta0)
-        self._sync(self.beta0)
+        self._sync(self.beta0, "data")
         K.vec_div(b_dev, self.beta0[1:2], out=self.U.next_col())
         self.U.push()
 
-    def _sync(self, pair):
+    def _sync(self, pair, space):
         if self.comm is not None:
-            self.comm.sync_norm_(pair)
+            self.comm.sync_norm_(pair, space)
 
     def _alloc_scalars(self, kmax):
         dev = self.U.data.device
@@ -96,13 +96,13 @@ class GKState:
         else:
             apply_fused(self.A, u_k, v, adjoint=True, coef=self.beta[k - 1, 1:2], z=self.V.col(k - 1),
                         norm_out=self.alpha[k])
-        self._sync(self.alpha[k])
+        self._sync(self.alpha[k], "model")
         K.vec_div(v, self.alpha[k, 1:2], out=v)
         self.V.push()
         # u = A v - alpha u_k ; beta = ||u|| ; u /= beta                      (decompositions.py:240-242)
         u = self.U.next_col()
         apply_fused(self.A, v, u, coef=self.alpha[k, 1:2], z=u_k, norm_out=self.beta[k])
-        self._sync(self.beta[k])
+        self._sync(self.beta[k], "data")
         K.vec_div(u, self.beta[k, 1:2], out=u)
         self.U.push()
 

@@ -44,17 +44,73 @@ def shard_frames(nt, world_size, rank):
     return lo, hi
 
 
-class FrameComm:
-    """Communication of the frame-sharded (dynamic CT) solvers (SURVEY.md section 8e): the operator is block diagonal
-    over time frames, so A, A^T, the bases and every vector are local to the rank that owns the frames; what crosses
-    ranks is (i) scalars, k-vectors and k x k Gram matrices (all-reduce / all-gather of a few hundred doubles) and
-    (ii) ONE FRAME of halo per application of the temporal difference operator or its adjoint (0.5 MB at 256^2)."""
+class _Comm:
+    """What the solvers ask of a communicator.  Vectors live in one of three spaces - 'data' (rows of A), 'model'
+    (columns of A) and 'reg' (rows of L) - and a communicator says which of them are split over the ranks:
+    reductions (norms, dots, Gram matrices) over a split space are summed across ranks, the others are already
+    replicated and must NOT be summed."""
+
+    SHARDED = ()
+    frames = False  # True: difference operators need one-frame halos (FrameComm)
 
     def __init__(self, group=None):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self._bufs = {}
+
+    def is_sharded(self, space):
+        return space in self.SHARDED
+
+    def allreduce_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def sum_(self, t, space):
+        """Sum a vector of partial reductions taken over `space`."""
+        return self.allreduce_(t) if self.is_sharded(space) else t
+
+    def sync_norm_(self, pair, space="data"):
+        """pair[0] = local sum of squares over `space` -> global; pair[1] = its square root."""
+        if self.is_sharded(space):
+            dist.all_reduce(pair[0:1], op=dist.ReduceOp.SUM, group=self.group)
+            pair[1:2] = torch.sqrt(pair[0:1])
+        return pair
+
+    def total(self, count, space):
+        """Global length of a `space` vector whose local length is `count`."""
+        if not self.is_sharded(space):
+            return int(count)
+        t = torch.tensor([int(count)], dtype=torch.int64, device=self._device())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return int(t.item())
+
+    def _device(self):
+        return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+
+    def allgather(self, t):
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t.contiguous(), group=self.group)
+        return torch.stack(parts)
+
+
+class RowComm(_Comm):
+    """Static CT, rows of A sharded by projection angle: data-space vectors (b, u,
+    residuals, AV) are local slices; model-space vectors (x, v, V) and regulariser-space vectors (L x, LV) are
+    replicated and bitwise identical on every rank.  The only large exchange is the sum of the partial back-projections
+    A_g^T u_g (ShardedRowsOperator.adjoint_dev); everything else is a scalar, a k-vector or a k x k Gram matrix."""
+
+    SHARDED = ("data",)
+
+
+class FrameComm(_Comm):
+    """Communication of the frame-sharded (dynamic CT) solvers (SURVEY.md section 8e): the operator is block diagonal
+    over time frames, so A, A^T, the bases and every vector are local to the rank that owns the frames; what crosses
+    ranks is (i) scalars, k-vectors and k x k Gram matrices (all-reduce / all-gather of a few hundred doubles) and
+    (ii) ONE FRAME of halo per application of the temporal difference operator or its adjoint (0.5 MB at 256^2)."""
+
+    SHARDED = ("data", "model", "reg")
+    frames = True
 
     @property
     def first(self):
@@ -63,21 +119,6 @@ class FrameComm:
     @property
     def last(self):
         return self.rank == self.world - 1
-
-    def allreduce_(self, t):
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-        return t
-
-    def sync_norm_(self, pair):
-        """pair[0] = local sum of squares -> global; pair[1] = its square root."""
-        dist.all_reduce(pair[0:1], op=dist.ReduceOp.SUM, group=self.group)
-        pair[1:2] = torch.sqrt(pair[0:1])
-        return pair
-
-    def allgather(self, t):
-        parts = [torch.empty_like(t) for _ in range(self.world)]
-        dist.all_gather(parts, t.contiguous(), group=self.group)
-        return torch.stack(parts)
 
     def _buf(self, key, like, n):
         b = self._bufs.get(key)
@@ -194,3 +235,43 @@ class DistGKState:
         B[np.arange(k), np.arange(k)] = al
         B[np.arange(1, k + 1), np.arange(k)] = be
         return B
+
+
+# ---- static CT behind the solver interface -------------------------------------------------------------------------
+
+from .operators import LinearOperator, ParallelBeamCT  # noqa: E402  (operators does not import this module)
+
+
+class ShardedRowsOperator(LinearOperator):
+    """This rank's row block A_g of a row-sharded operator, presented to the solvers as the whole operator:
+    shape (m_g, n); `apply_dev` is local (x replicated -> local rows), `adjoint_dev` sums the ranks' partial
+    back-projections with ONE all-reduce of an n-vector before the fused recurrence/norm epilogue, so its result
+    is replicated and bitwise identical on every rank.  Pass the matching RowComm as `b200_comm=` to the solver;
+    `A.T @ A` of this operator is a replicated square operator and needs no communicator (Hybrid_GMRES)."""
+
+    fused = True
+
+    def __init__(self, local_op, comm):
+        super().__init__(local_op.shape, local_op.device)
+        self.local, self.comm = local_op, comm
+
+    def apply_dev(self, x, out=None, coef=None, z=None, norm_out=None):
+        return self.local.apply_dev(x, out=out, coef=coef, z=z, norm_out=norm_out)  # norm_out: LOCAL sum of squares
+
+    def adjoint_dev(self, u, out=None, coef=None, z=None, norm_out=None):
+        out = self.local.adjoint_dev(u, out=out)
+        self.comm.allreduce_(out)
+        if z is not None:
+            K.vec_axpy(coef, z, out, out=out, norm_out=norm_out, sign=-1.0)
+        elif norm_out is not None:
+            K.vec_norm2(out, out=norm_out)
+        return out
+
+
+def sharded_ct(nx, views, comm, **kwargs):
+    """(operator, row index) of this rank's share of ParallelBeamCT(nx, views): angles round robin over the ranks.
+    `rows` selects the rank's entries of a full angle-major sinogram: b_local = b_full[rows]."""
+    mine = shard_angles(views, comm.world, comm.rank)
+    op = ParallelBeamCT(nx, views, angle_subset=mine, **kwargs)
+    rows = (mine[:, None] * op.n_det + np.arange(op.n_det)[None, :]).reshape(-1)
+    return ShardedRowsOperator(op, comm), rows

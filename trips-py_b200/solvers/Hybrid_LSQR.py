@@ -29,10 +29,12 @@ def Hybrid_LSQR(A, b, n_iter=100, regparam="gcv", x_true=None, **kwargs):
     dev = A.device
     m, n = A.shape
     bd = to_device_vector(b, dev)
-    st = GKState(A, bd, n_iter)
+    comm = kwargs.get("b200_comm")  # dist.RowComm (static CT, rows by angle) or dist.FrameComm (block-diagonal A)
+    m_total = m if comm is None else comm.total(m, "data")
+    st = GKState(A, bd, n_iter, comm=comm)
     x_history = LazyHistory()
     lambda_history, residual_history = [], []
-    err = ErrorTracker(x_true, dev)
+    err = ErrorTracker(x_true, dev, comm=comm)
     keep = kwargs.get("b200_history", "lazy")
     rp_kwargs = {k: v for k, v in kwargs.items() if not k.startswith("b200_")}
     xd = None
@@ -53,15 +55,19 @@ def Hybrid_LSQR(A, b, n_iter=100, regparam="gcv", x_true=None, **kwargs):
         eye = np.eye(k)
         if isinstance(regparam, str) and regparam == "gcv":
             Q_A, s, _ = la.svd(B, full_matrices=False)
-            lambdah = generalized_crossvalidation(Q_A, np.diag(s), eye, bhat, variant="modified", fullsize=m, **rp_kwargs)
+            lambdah = generalized_crossvalidation(Q_A, np.diag(s), eye, bhat, variant="modified", fullsize=m_total, **rp_kwargs)
         elif isinstance(regparam, str) and regparam == "dp":
             # discrepancy_principle(U, B, L, b): U^T b and ||b - U U^T b|| come from the device basis
             h = K.basis_dots(st.U, k + 1, bd)
+            if comm is not None:
+                comm.sum_(h, "data")
             explicit = rp_kwargs.get("explicitProj", False)
             resid = 0.0
             if explicit:  # ||b - U U^T b|| is only consulted by the explicitProj variant (discrepancy_principle.py:69,82)
                 res = K.new_pair(dev)
                 K.basis_combine(st.U, k + 1, h, w=bd, sign=-1.0, norm_out=res)
+                if comm is not None:
+                    comm.sync_norm_(res, "data")
                 resid = float(res.cpu()[1])
             lambdah = discrepancy_principle_projected(B, None, h.cpu().numpy()[:k + 1], resid, delta,
                                                       rp_kwargs.get("eta", 1.01), explicit)

@@ -61,7 +61,7 @@ class ErrorTracker:
             self.xt = to_device_vector(x_true, device)
             pair = K.vec_norm2(self.xt)
             if comm is not None:
-                comm.sync_norm_(pair)
+                comm.sync_norm_(pair, "model")
             self.xt_norm = float(pair.cpu()[1])
             self._pairs = []
 
@@ -69,7 +69,7 @@ class ErrorTracker:
         if self.enabled:
             pair = K.vec_diffnorm2(x_dev, self.xt)
             if self.comm is not None:
-                self.comm.sync_norm_(pair)
+                self.comm.sync_norm_(pair, "model")
             self._pairs.append(pair)
 
     def values(self, denominators=None):

@@ -53,7 +53,7 @@ def apply_L(L, x, comm=None, out=None, wout=None, eps=0.0, expo=0.0):
     """u = L x (optionally with fused IRLS weights); frame-sharded difference operators fetch their one-frame halo."""
     if isinstance(L, SpaceTimeDerivative):
         x_next = None
-        if comm is not None:
+        if comm is not None and comm.frames:
             N = L.nx * L.ny
             x_next = comm.halo_from_next(x[:N])
         return L.apply_dev(x, out=out, wout=wout, eps=eps, expo=expo, x_next=x_next)
@@ -78,7 +78,7 @@ def adjoint_L_weighted(L, r, w, out=None, comm=None):
     """L^T (w . r)   (w None: L^T r).  Frame-sharded: the temporal rows of my last frame also act on the next rank."""
     if isinstance(L, SpaceTimeDerivative):
         rt_prev = None
-        if comm is not None:
+        if comm is not None and comm.frames:
             N = L.nx * L.ny
             if L.has_next:
                 lo = L.shape[0] - N  # temporal rows of my last frame: the final N rows
@@ -94,21 +94,26 @@ def adjoint_L_weighted(L, r, w, out=None, comm=None):
     return L.adjoint_dev(K.vec_mul(w, r), out=out)
 
 
+def _gram_comm(comm, space):
+    """The communicator to sum a Gram matrix with, or None when the basis' space is replicated."""
+    return comm if (comm is not None and comm.is_sharded(space)) else None
+
+
 def factor_pair(bases, bd, wf=None, wr=None):
     """R_A, R_L, c_plain = Q_A^T b, c_w = Q_A^T (wf*b), resid_w = ||wf*b - Q_A Q_A^T wf*b||."""
     k = bases.k
     comm = bases.comm
     if wf is None:
-        Ghi, Glo = K.weighted_gram(bases.AV, k, None, extras=(bd,), extra_weighted=(0,), comm=comm)
+        Ghi, Glo = K.weighted_gram(bases.AV, k, None, extras=(bd,), extra_weighted=(0,), comm=_gram_comm(comm, "data"))
         R_A, C, res2 = K.gram_factor(Ghi, Glo, k)
         c_plain = c_w = C[:, 0:1]
         resid_w = float(np.sqrt(res2[0]))
     else:
-        Ghi, Glo = K.weighted_gram(bases.AV, k, wf, extras=(bd, bd), extra_weighted=(0, 1), comm=comm)
+        Ghi, Glo = K.weighted_gram(bases.AV, k, wf, extras=(bd, bd), extra_weighted=(0, 1), comm=_gram_comm(comm, "data"))
         R_A, C, res2 = K.gram_factor(Ghi, Glo, k)
         c_plain, c_w = C[:, 0:1], C[:, 1:2]
         resid_w = float(np.sqrt(res2[1]))
-    Ghi, Glo = K.weighted_gram(bases.LV, k, wr, comm=comm)
+    Ghi, Glo = K.weighted_gram(bases.LV, k, wr, comm=_gram_comm(comm, "reg"))
     R_L, _, _ = K.gram_factor(Ghi, Glo, k)
     return R_A, R_L, c_plain, c_w, resid_w
 
@@ -133,12 +138,12 @@ def expand(bases, r, n_reorth, residual_history):
     for it in range(n_reorth):
         h = K.basis_dots(bases.V, k, r)
         if comm is not None:
-            comm.allreduce_(h)
+            comm.sum_(h, "model")
         K.basis_combine(bases.V, k, h, w=r, sign=-1.0, out=r, norm_out=nrm if it == n_reorth - 1 else None)
     if n_reorth == 0:
         K.vec_norm2(r, out=nrm)
     if comm is not None:
-        comm.sync_norm_(nrm)
+        comm.sync_norm_(nrm, "model")
     K.vec_div(r, nrm[1:2], out=bases.V.next_col())
     bases.V.push()
     bases.append_images()
