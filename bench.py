@@ -52,9 +52,11 @@ def parse():
                     help="SpMV row-sum order: 'sequential' = scipy's (bit-identical to the reference, the parity build); "
                          "'tree' = per-row tree reduction (reported separately)")
     ap.add_argument("--variant", type=int, default=0, help="kernel tuning knob (tb200_spmv_set_variant)")
-    ap.add_argument("--layout", default="auto", choices=["auto", "sell", "csr"],
-                    help="device layout of A / A^T: 'sell' = row-interleaved CSR (SELL-32-4, the fast path for the "
-                         "sequential order), 'csr' = plain CSR; auto = sell for sequential, csr for tree")
+    ap.add_argument("--layout", default="auto", choices=["auto", "implicit", "sell", "csr"],
+                    help="device layout of A / A^T: 'implicit' = values re-evaluated on the fly (A: column indices only, "
+                         "A^T: matrix-free), 'sell' = stored row-interleaved CSR (SELL-32-4), 'csr' = plain CSR; "
+                         "auto = implicit for the fp64 sequential order, sell for fp32 storage, csr for tree. "
+                         "All give bit-identical results in the sequential order")
     return ap.parse_args()
 
 
@@ -147,7 +149,7 @@ def main():
     n_det = O.ct_num_detectors(nx)
     n = nx * nx
     m_full = views * n_det
-    workload = f"cfg4 geometry: parallel-beam CT {nx}^2, {views} angles, {n_det} detectors, CSR A + explicit A^T"
+    workload = f"cfg4 geometry: parallel-beam CT {nx}^2, {views} angles, {n_det} detectors, one Golub-Kahan step per step"
     hbm_peak, peak_src = peaks()
     sub = np.linspace(0, views, args.cpu_sample_views, endpoint=False).astype(int)
 
@@ -194,7 +196,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     t_build = time.perf_counter()
     my_angles = shard_angles(views, world, rank)
-    layout = args.layout if args.layout != "auto" else ("sell" if args.order == "sequential" else "csr")
+    layout = args.layout
+    if layout == "auto":
+        layout = "csr" if args.order != "sequential" else ("sell" if args.f32_storage else "implicit")
+    if layout == "implicit" and (args.f32_storage or args.order != "sequential"):
+        raise SystemExit("--layout implicit is the fp64 sequential-order path")
     A = tb.ParallelBeamCT(nx, views, angle_subset=my_angles if world > 1 else None, device=dev, layout=layout)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
@@ -205,8 +211,9 @@ def main():
         A = A.with_order(args.order)
     _lib.check(_lib.lib().tb200_spmv_set_variant(args.variant))
     kernel_name = {("sequential", "sell"): "spmv_sell_kernel", ("sequential", "csr"): "spmv_seq_tile_kernel",
-                   ("tree", "csr"): "spmv_warp_kernel"}[(args.order, layout)]
-    stored = (A.A_sell.stored if layout == "sell" else A.A.nnz)
+                   ("tree", "csr"): "spmv_warp_kernel",
+                   ("sequential", "implicit"): "spmv_sell_kernel<GEOM> (A) + ct_backproject_kernel (A^T)"}[(args.order, layout)]
+    stored = A.projector.stored if layout == "implicit" else (A.A_sell.stored if layout == "sell" else A.A.nnz)
     m_loc = A.shape[0]
     nnz_loc = A.nnz
     nnz_t = torch.tensor([nnz_loc], dtype=torch.int64, device=dev)
@@ -233,13 +240,19 @@ def main():
 
     orig_spmv = KM.spmv
 
-    def timed_spmv(*a, **k):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = orig_spmv(*a, **k)
-        e1.record()
-        spmv_events.append((e0, e1))
-        return out
+    def timed(fn):
+        def run(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            spmv_events.append((e0, e1))
+            return out
+        return run
+
+    timed_spmv = timed(orig_spmv)
+    proj = getattr(A, "projector", None)  # matrix-free layout: the two launches are projector calls, not KM.spmv
+    orig_proj = (proj.forward, proj.backproject) if proj is not None else None
 
     def barrier():
         if world > 1:
@@ -263,6 +276,8 @@ def main():
     barrier()
     KM.spmv = timed_spmv
     KM.GK_STEP_EVENTS = step_events
+    if proj is not None and world > 1:  # (single GPU: tb200_gk_step_ct_f64 records the events itself)
+        proj.forward, proj.backproject = timed(orig_proj[0]), timed(orig_proj[1])
     sampler.mark_begin()
     launches0 = _lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -274,6 +289,8 @@ def main():
     sampler.mark_end()
     KM.spmv = orig_spmv
     KM.GK_STEP_EVENTS = None
+    if proj is not None:
+        proj.forward, proj.backproject = orig_proj
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count - launches0
     ms = ev0.elapsed_time(ev1)
@@ -296,20 +313,46 @@ def main():
     achieved = alg_bytes / (mean_spmv_ms * 1e-3) / 1e9
     spmv_share = sum(spmv_ms) / ms
     B_GK = 2 * (val_bytes + 4) * nnz + 8 * (m_full + 1) + 8 * (n + 1) + 48 * (m_full + n)
-    traffic = None  # DRAM bytes per launch from the committed ncu capture of this exact configuration, if there is one
-    if world == 1 and (nx, views) == (2048, 720) and layout == "sell" and not args.f32_storage:
+    ms_AT = sum(spmv_ms[0::2]) / max(len(spmv_ms[0::2]), 1)
+    ms_A = sum(spmv_ms[1::2]) / max(len(spmv_ms[1::2]), 1)
+    traffic, traffic_AT = None, None  # DRAM bytes per launch from the committed ncu capture of this exact configuration
+    if world == 1 and (nx, views) == (2048, 720) and not args.f32_storage and layout in ("sell", "implicit"):
         try:
             with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                traffic = json.load(f)["cfg4_sell_sequential_n1"]["mean_bytes"]
+                tj = json.load(f)
+            if layout == "sell":
+                traffic = tj["cfg4_sell_sequential_n1"]["mean_bytes"]
+            else:
+                traffic = tj["cfg4_implicit_n1"]["A_launch_bytes"]
+                traffic_AT = tj["cfg4_implicit_n1"]["AT_launch_bytes"]
         except Exception:  # noqa: BLE001
             traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name,
-                "launch_ms": mean_spmv_ms, "launch_ms_AT": sum(spmv_ms[0::2]) / max(len(spmv_ms[0::2]), 1),
-                "launch_ms_A": sum(spmv_ms[1::2]) / max(len(spmv_ms[1::2]), 1),
-                "alg_bytes_per_launch": alg_bytes, "share_of_step": spmv_share,
-                "gk_iteration": {"alg_bytes": B_GK, "achieved": B_GK / (ms_per_step * 1e-3) / 1e9 / world,
-                                 "frac": B_GK / (ms_per_step * 1e-3) / 1e9 / world / hbm_peak, "note": "per GPU"}}
+    gk_it = {"alg_bytes": B_GK, "achieved": B_GK / (ms_per_step * 1e-3) / 1e9 / world,
+             "frac": B_GK / (ms_per_step * 1e-3) / 1e9 / world / hbm_peak, "note": "per GPU"}
+    if layout == "implicit":
+        # Two different kernels per step.  The dominant one is the forward projection (index stream + gathers + values
+        # re-evaluated); the back-projection reads no matrix at all.  `achieved` keeps SURVEY.md 8(d)'s ALGORITHMIC
+        # bytes (stored fp64 values + int32 indices) so the figures stay comparable with the stored layouts: what the
+        # kernels really move is `traffic`, far less - that is the point of this layout.
+        ach_A = bytes_A / (ms_A * 1e-3) / 1e9
+        ach_AT = bytes_AT / (ms_AT * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach_A, "peak": hbm_peak, "unit": "GB/s", "frac": ach_A / hbm_peak,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "kernel": "spmv_sell_kernel<GEOM> (forward projection A v, the longer launch)",
+                    "launch_ms": ms_A, "launch_ms_A": ms_A, "launch_ms_AT": ms_AT, "alg_bytes_per_launch": bytes_A,
+                    "share_of_step": ms_A * len(spmv_ms[1::2]) / ms,
+                    "note": "alg bytes = stored-matrix figure of SURVEY 8(d); this layout streams 4 B/entry (A) or nothing "
+                            "(A^T) and re-evaluates the values (fp64-issue bound), so achieved/peak is not a DRAM utilisation",
+                    "back_projection": {"kernel": "ct_backproject_kernel (matrix-free A^T u)", "launch_ms": ms_AT,
+                                        "alg_bytes_per_launch": bytes_AT, "achieved": ach_AT, "frac": ach_AT / hbm_peak,
+                                        "traffic": traffic_AT, "bound": "fp64 issue",
+                                        "share_of_step": ms_AT * len(spmv_ms[0::2]) / ms},
+                    "gk_iteration": gk_it}
+    else:
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name,
+                    "launch_ms": mean_spmv_ms, "launch_ms_AT": ms_AT, "launch_ms_A": ms_A,
+                    "alg_bytes_per_launch": alg_bytes, "share_of_step": spmv_share, "gk_iteration": gk_it}
 
     # parity property at full size, outside the timed region: the bidiagonal relation A^T u_1 = alpha_1 v_1 etc. is
     # covered by tests; here only a cheap sanity check that the factors are finite
@@ -370,11 +413,13 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64" if not args.f32_storage else "f32-storage/f64-accumulate", "data": "synthetic",
-                "config": {"workload": workload, "nnz": nnz, "m": m_full, "n": n, "matrix_bytes": 2 * (val_bytes + 4) * nnz,
+                "config": {"workload": workload, "nnz": nnz, "m": m_full, "n": n,
+                           "matrix_bytes": (4 * stored if layout == "implicit" else 2 * (val_bytes + 4) * nnz),
                            "parallelism": f"rows by angle x{world}" if world > 1 else "single GPU",
                            "spmv_order": args.order, "spmv_variant": args.variant, "layout": layout,
                            "stored_entries_per_matrix": stored, "padding_frac": stored / max(nnz_loc, 1) - 1.0,
-                           "l2_note": "inputs (2 x 46 GB matrix streams per step) exceed L2 by >300x; no flush needed",
+                           "l2_note": ("inputs (15 GB index stream per step) exceed L2 by >100x; no flush needed" if layout == "implicit"
+                                       else "inputs (2 x 46 GB matrix streams per step) exceed L2 by >300x; no flush needed"),
                            "build_s": t_build},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line))

@@ -128,6 +128,29 @@ int tb200_ct_count_cols(int nx, int ny, int n_det, int n_ang, const double* cosv
 int tb200_ct_fill_cols(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
                        const int64_t* ptr, int sell, int32_t* colidx, double* vals, void* stream);
 
+/* ---- parallel-beam CT projectors with the matrix values re-evaluated on the fly ---------------------------
+ * The reference's tomography operator is matrix-free (astra.OpTomo behind pylops.FunctionOperator,
+ * trips/test_problems/Tomography.py:73-83); SURVEY.md section 8(f) item 1.  Same matrix as the builder above, same
+ * bits as the sequential-order SpMV on the stored matrices, but an entry costs ~10 fp64 instructions instead of
+ * 12 streamed bytes: the forward projector reads only A's SELL-32-4 column indices (tb200_ct_fill_rows with
+ * vals = NULL), the back-projector reads no matrix at all.
+ * geom: 6 doubles per angle (c, s, d2, 1/hi, 1/(hi*lo), 0) written by tb200_ct_geometry, 16-byte aligned.
+ * coef / z / norm_out / ws as for tb200_spmv_sell_f64; back-projector ws: tb200_ct_backproject_workspace_len. */
+int tb200_ct_geometry(int n_ang, const double* cosv, const double* sinv, double* geom, void* stream);
+int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
+                         const int32_t* rowlen, const int32_t* colidx, const double* x, double* y, double coef_host,
+                         const double* coef_dev, const double* z, double* norm_out, double* ws, void* stream);
+int64_t tb200_ct_backproject_workspace_len(int nx, int ny);
+int tb200_ct_backproject_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* u, double* y,
+                             double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
+                             void* stream);
+/* One Golub-Kahan step (trips/utilities/decompositions.py:230-255) on the matrix-free operator, as
+ * tb200_gk_step_sell_f64; ws: max(tb200_spmv_workspace_len(m), tb200_ct_backproject_workspace_len(nx, ny)). */
+int tb200_gk_step_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
+                         const int32_t* rowlen, const int32_t* colidx, const double* u_k, const double* v_prev,
+                         const double* beta_prev_dev, double* v_out, double* u_out, double* alpha_pair, double* beta_pair,
+                         double* ws, void* const* events_host, void* stream);
+
 /* ---- stencils ---------------------------------------------------------------------------------------------
  * PSF blur and its reference "adjoint": trips/test_problems/Deblurring2D.py:66-73 (scipy.ndimage.convolve,
  * mode='reflect'); zero-padded variant for gen_data :121-133 (mode 1).  Bit-identical to ndimage (tap order and

@@ -633,7 +633,9 @@ def ct_matrix(nx, theta, ny=None, n_det=None):
     rows, cols, vals = [], [], []
     for a, (c, s) in enumerate(zip(np.cos(theta), np.sin(theta))):
         hi, lo = max(abs(c), abs(s)), min(abs(c), abs(s))
-        d1, d2 = 0.5 * (hi - lo), 0.5 * (hi + lo)
+        d2 = 0.5 * (hi + lo)
+        with np.errstate(divide="ignore"):
+            inv_hi, inv_hilo = 1.0 / hi, 1.0 / (hi * lo)  # lo == 0: inf, the min below returns the plateau
         proj = (cx[None, :] * c) + (cy[:, None] * s)          # (ny, nx): cx*c + cy*s
         # candidate detectors around each pixel's projection
         centre = proj + 0.5 * (n_det - 1)
@@ -645,8 +647,8 @@ def ct_matrix(nx, theta, ny=None, n_det=None):
             t = sd[dd] - proj
             at = np.abs(t)
             hit = ok & (at < d2)
-            with np.errstate(divide="ignore", invalid="ignore"):
-                w = np.where(at <= d1, 1.0 / hi, (d2 - at) / (hi * lo))
+            with np.errstate(invalid="ignore"):
+                w = np.minimum(inv_hi, (d2 - at) * inv_hilo)  # trapezoid: plateau 1/hi, slopes (d2-|t|)/(hi*lo)
             iy, ix = np.nonzero(hit)
             rows.append(a * n_det + dd[iy, ix])
             cols.append(iy * nx + ix)

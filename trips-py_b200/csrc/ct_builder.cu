@@ -7,9 +7,7 @@
 // conventions (theta = linspace(0, pi, views, endpoint=False), n_det = int(sqrt(2)*nx), Tomography.py:53-56):
 // entry (ray, pixel) = length of the intersection of the ray with the unit pixel ("line" projector model).
 //
-// For a ray with unit normal (c, s) at signed distance t from the pixel centre the chord length through a unit
-// square is the trapezoid   len(t) = 1/hi                    |t| <= (hi-lo)/2
-//                                   ((hi+lo)/2 - |t|)/(hi*lo) (hi-lo)/2 < |t| < (hi+lo)/2,   hi/lo = max/min(|c|,|s|)
+// The entry definition (trapezoid chord length, every step separately rounded) lives in tb200_ctgeom.cuh.
 // Both builders evaluate the SAME device function on the same (ray, pixel) arguments with explicitly rounded
 // arithmetic, so A and A^T hold bit-identical values and an identical sparsity pattern: the stored A^T is the
 // exact transpose of A, which the parity tests check against scipy's A.T.
@@ -21,37 +19,9 @@
 //   SELL-32-4 ("row-interleaved CSR", see spmv.cu): rows in slices of 32, entry j of row r at
 //            sliceptr[r/32] + (j/4)*128 + (r%32)*4 + j%4 ; the caller zero-fills the arrays (padding = 0.0 * x[0]).
 #include "tb200_common.cuh"
+#include "tb200_ctgeom.cuh"
 
 namespace tb200 {
-
-struct RayGeom {
-  double c, s, hi, lo, d1, d2, inv_hi, hilo;
-};
-
-__device__ __forceinline__ RayGeom make_geom(double c, double s) {
-  RayGeom g;
-  g.c = c;
-  g.s = s;
-  const double ac = fabs(c), as = fabs(s);
-  g.hi = fmax(ac, as);
-  g.lo = fmin(ac, as);
-  g.d1 = __dmul_rn(0.5, __dsub_rn(g.hi, g.lo));
-  g.d2 = __dmul_rn(0.5, __dadd_rn(g.hi, g.lo));
-  g.inv_hi = __ddiv_rn(1.0, g.hi);
-  g.hilo = __dmul_rn(g.hi, g.lo);
-  return g;
-}
-
-// signed distance (along the detector axis) between ray offset sd and the projection of pixel centre (cx, cy)
-__device__ __forceinline__ double ray_pixel_t(const RayGeom& g, double sd, double cx, double cy) {
-  return __dsub_rn(sd, __dadd_rn(__dmul_rn(cx, g.c), __dmul_rn(cy, g.s)));
-}
-__device__ __forceinline__ bool hits(const RayGeom& g, double t) { return fabs(t) < g.d2; }
-__device__ __forceinline__ double chord(const RayGeom& g, double t) {
-  const double at = fabs(t);
-  if (at <= g.d1) return g.inv_hi;
-  return __ddiv_rn(__dsub_rn(g.d2, at), g.hilo);
-}
 
 // inclusive pixel range [lo, hi] of image row iy crossed by ray (g, sd); empty when hi < lo
 __device__ __forceinline__ void row_range(const RayGeom& g, double sd, int iy, int nx, int ny, int& lo, int& hi) {
@@ -147,7 +117,7 @@ ct_rows_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ 
       for (int ix = lo; ix <= hi; ++ix, ++j) {
         const int64_t pos = entry_addr(rowptr, sell, ray, j);
         col[pos] = iy * nx + ix;
-        val[pos] = chord(g, ray_pixel_t(g, sd, (double)ix - x0, cy));
+        if (val != nullptr) val[pos] = chord(g, ray_pixel_t(g, sd, (double)ix - x0, cy));
       }
       base += chunk;
     } else {
@@ -233,13 +203,14 @@ int tb200_ct_count_rows(int nx, int ny, int n_det, int n_ang, const double* cosv
 
 // Fills colidx/vals of A.  sell = 0: CSR, ptr = rowptr (exclusive prefix sum of the counts).
 // sell = 1: SELL-32-4, ptr = slice pointers; colidx/vals must have been zero-filled by the caller.
+// vals may be NULL: only the column indices are written (index-only matrix for tb200_ct_forward_f64).
 int tb200_ct_fill_rows(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
                        const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream) {
   int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
   if (rc) return rc;
   const int64_t rays = (int64_t)n_ang * n_det;
   if (rays == 0) return 0;
-  TB200_REQUIRE(rowptr && colidx && vals, "null output");
+  TB200_REQUIRE(rowptr && colidx, "null output");
   ct_rows_kernel<true><<<(unsigned)((rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, sell, colidx, vals);
   return check_launch("ct_fill_rows");

@@ -1,0 +1,216 @@
+// Matrix-free parallel-beam back-projection  y = A^T u - coef*z  for the CT matrix of ct_builder.cu, bit-identical to
+// the sequential-order SpMV on the stored transpose (and so to scipy's A.T @ u on the same matrix).
+//
+// Role in the reference: the tomography operator is matrix-free there too (astra.OpTomo behind a pylops
+// FunctionOperator, trips/test_problems/Tomography.py:73-83); SURVEY.md section 8(f) item 1.
+//
+// Why: streaming the stored transpose costs 12 bytes per entry and bounds a Golub-Kahan step at the HBM roofline.
+// An entry of this matrix is a closed-form function of (pixel, angle, detector) - tb200_ctgeom.cuh - and a pixel
+// meets at most TWO detector bins per angle (footprint (|c|+|s|) <= sqrt(2) bins wide), always the two that bracket
+// its projection.  So one thread per pixel walks the angles in order, evaluates the two candidate entries
+// (~20 fp64 instructions per angle), gathers the two neighbouring sinogram samples (L1/L2 resident: the sinogram is
+// 16.7 MB at 2048^2 x 720) and adds the products that lie inside the footprint, in ascending (angle, detector) order -
+// exactly the row order of the stored transpose.  No matrix bytes are read at all; the kernel is fp64-pipe bound.
+//
+// Pattern equivalence.  Stored pattern of pixel p at angle a: { d in [0, n_det) : |t_d| < d2 },  t_d = (d - dc) - proj.
+// With d0 = any integer within 1 of floor(proj + dc), every d outside {d0, d0+1} that is not one of the bracketing
+// pair has |t_d| >= 1 - 1e-12 > d2 (d2 <= 0.7072), so testing the pair {d0, d0+1} with the SAME predicate on the SAME
+// separately rounded t_d reproduces the pattern; rounding in the estimate of d0 can only swap in a neighbour that fails
+// the predicate.
+#include "tb200_common.cuh"
+#include "tb200_ctgeom.cuh"
+#include "tb200_dd.cuh"
+
+namespace tb200 {
+
+__global__ void ct_geometry_kernel(int n_ang, const double* __restrict__ cosv, const double* __restrict__ sinv,
+                                   double* __restrict__ geom) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_ang) return;
+  const RayGeom g = make_geom(cosv[a], sinv[a]);
+  double* o = geom + 6 * (int64_t)a;
+  o[0] = g.c, o[1] = g.s, o[2] = g.d2, o[3] = g.inv_hi, o[4] = g.inv_hilo, o[5] = 0.0;
+}
+
+// CTA = 4 warps side by side, each warp an 8 x 4 pixel tile (32 x 4 pixels per CTA): a compact tile keeps the two
+// gather requests of an angle within 2-3 sectors whatever the angle.
+constexpr int BP_TA = 256;  // angles per shared-memory tile of the geometry table (12 KB)
+
+// acc + p when flag > 0, else acc: one predicated DADD (the C form compiles to an add and two selects)
+__device__ __forceinline__ double add_if_positive(double acc, double p, int flag) {
+  asm("{\n\t.reg .pred q;\n\tsetp.gt.s32 q, %2, 0;\n\t@q add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(p), "r"(flag));
+  return acc;
+}
+
+// One tile of angles for one pixel.  CHECKED = false is the path of warps whose pixels project at least two bins
+// inside the detector at every angle (all but the image corners): no bounds tests, unconditional gathers.
+template <bool CHECKED, int UNROLL>
+__device__ __forceinline__ double bp_tile(double acc, const double* __restrict__ gtab, int na, const double* __restrict__ u, int row0,
+                                          int n_det, double cx, double cy, double dcm, double sbias, uint64_t pol_keep) {
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (v + MAGIC) - MAGIC = v rounded to an integer
+  const unsigned und = (unsigned)n_det;
+#pragma unroll UNROLL
+  for (int j = 0; j < na; ++j) {
+    const double2 cs = reinterpret_cast<const double2*>(gtab)[3 * j];      // c, s
+    const double2 dh = reinterpret_cast<const double2*>(gtab)[3 * j + 1];  // d2, 1/hi
+    const double inv_hilo = gtab[6 * j + 4];
+    const double proj = __dadd_rn(__dmul_rn(cx, cs.x), __dmul_rn(cy, cs.y));
+    const double w = __dadd_rn(__dadd_rn(proj, dcm), MAGIC);
+    const int d0 = __double2loint(w);  // low word of MAGIC is 0: the integer, in two's complement
+    // (d - dc) for d0 and d0 + 1: the integer goes into the mantissa of 2^51 (ulp 0.5), one exact subtraction
+    // removes the bias and the detector centre; wrong only for d < 0, where CHECKED masks the candidate anyway
+    const double sd0 = __dsub_rn(__hiloint2double(0x43200000, d0 << 1), sbias);
+    const double sd1 = __dsub_rn(__hiloint2double(0x43200000, (d0 + 1) << 1), sbias);
+    const double e0 = __dsub_rn(dh.x, fabs(__dsub_rn(sd0, proj)));  // d2 - |t|: positive inside the footprint
+    const double e1 = __dsub_rn(dh.x, fabs(__dsub_rn(sd1, proj)));
+    // e > 0 (never denormal here: |t| and d2 are O(1)) <=> the high word, read as an int, is positive
+    if (CHECKED) {
+      const double* up = u + ((int64_t)row0 + (int64_t)j * n_det + d0);
+      const bool in0 = (unsigned)d0 < und, in1 = (unsigned)(d0 + 1) < und;
+      const double u0 = in0 ? ld_gather_f64(up, pol_keep) : 0.0;
+      const double u1 = in1 ? ld_gather_f64(up + 1, pol_keep) : 0.0;
+      const double p0 = __dmul_rn(chord_from_margin(e0, dh.y, inv_hilo), u0);
+      const double p1 = __dmul_rn(chord_from_margin(e1, dh.y, inv_hilo), u1);
+      if (in0 && __double2hiint(e0) > 0) acc = __dadd_rn(acc, p0);
+      if (in1 && __double2hiint(e1) > 0) acc = __dadd_rn(acc, p1);
+    } else {
+      const double* up = u + (unsigned)(row0 + j * n_det + d0);  // n_ang * n_det < 2^31 is checked at launch
+      const double p0 = __dmul_rn(chord_from_margin(e0, dh.y, inv_hilo), ld_gather_f64(up, pol_keep));
+      const double p1 = __dmul_rn(chord_from_margin(e1, dh.y, inv_hilo), ld_gather_f64(up + 1, pol_keep));
+      acc = add_if_positive(acc, p0, __double2hiint(e0));
+      acc = add_if_positive(acc, p1, __double2hiint(e1));
+    }
+  }
+  return acc;
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(128, 8)
+ct_backproject_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ geom, const double* __restrict__ u,
+                      double* __restrict__ y, double coef_host, const double* __restrict__ coef_dev,
+                      const double* __restrict__ z, double* __restrict__ partials) {
+  __shared__ __align__(16) double gtab[BP_TA * 6];
+  __shared__ double red[64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ix = blockIdx.x * 32 + warp * 8 + (lane & 7);
+  const int iy = blockIdx.y * 4 + (lane >> 3);
+  const bool valid = ix < nx && iy < ny;
+  const uint64_t pol_keep = policy_evict_last();
+  const double cx = (double)ix - 0.5 * (double)(nx - 1), cy = (double)iy - 0.5 * (double)(ny - 1);
+  const double dc = 0.5 * (double)(n_det - 1);
+  const double dcm = dc - 0.5;                      // exact: multiples of 0.5
+  const double sbias = 2251799813685248.0 + dc;     // 2^51 + dc, exact
+  // |proj| <= |(cx, cy)|: with two bins of slack every candidate of every angle is a valid detector index
+  const bool interior = __all_sync(0xffffffffu, sqrt(cx * cx + cy * cy) + 2.5 <= dc);
+  double acc = 0.0;
+
+  for (int a0 = 0; a0 < n_ang; a0 += BP_TA) {
+    const int na = min(BP_TA, n_ang - a0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < na * 3; i += 128)
+      reinterpret_cast<double2*>(gtab)[i] = reinterpret_cast<const double2*>(geom + 6 * (int64_t)a0)[i];
+    __syncthreads();
+    if (interior) acc = bp_tile<false, UNROLL>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dcm, sbias, pol_keep);
+    else acc = bp_tile<true, UNROLL>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dcm, sbias, pol_keep);
+  }
+
+  const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
+  dd_t nrm = dd_zero();
+  if (valid) {
+    const int64_t pix = (int64_t)iy * nx + ix;
+    if (z != nullptr) acc = __dsub_rn(acc, __dmul_rn(coef, z[pix]));
+    y[pix] = acc;
+    nrm = dd_fma(nrm, acc, acc);
+  }
+  if (partials != nullptr) {
+    const dd_t tot2 = dd_block_sum(nrm, red);
+    if (threadIdx.x == 0) {
+      const int64_t b = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+      partials[2 * b] = tot2.hi;
+      partials[2 * b + 1] = tot2.lo;
+    }
+  }
+}
+
+}  // namespace tb200
+
+using namespace tb200;
+
+extern "C" {
+
+// geom[6*a .. 6*a+5] = (c, s, d2, 1/hi, 1/(hi*lo), 0) for angle a: the per-angle constants of the entry function.
+int tb200_ct_geometry(int n_ang, const double* cosv, const double* sinv, double* geom, void* stream) {
+  TB200_REQUIRE(n_ang >= 0, "bad size");
+  if (n_ang == 0) return 0;
+  TB200_REQUIRE(cosv && sinv && geom, "null pointer");
+  TB200_REQUIRE(((uintptr_t)geom % 16) == 0, "geom must be 16-byte aligned");
+  ct_geometry_kernel<<<(n_ang + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_ang, cosv, sinv, geom);
+  return check_launch("ct_geometry");
+}
+
+// Doubles of workspace tb200_ct_backproject_f64 needs for its fused norm (one double-double partial per CTA).
+int64_t tb200_ct_backproject_workspace_len(int nx, int ny) {
+  return 2 * ((int64_t)((nx + 31) / 32) * ((ny + 3) / 4) + 8);
+}
+
+// y = A^T u - coef*z (z nullable; coef from coef_dev if non-null), optional norm_out = (||y||^2, ||y||), for the
+// parallel-beam matrix of n_ang angles (geom from tb200_ct_geometry), u angle-major (angle*n_det + detector),
+// y row-major (iy*nx + ix).  No matrix is read.  Same bits as tb200_spmv_sell_f64 on tb200_ct_fill_cols' matrix.
+int tb200_ct_backproject_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* u, double* y,
+                             double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
+                             void* stream) {
+  TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0, "bad geometry");
+  TB200_REQUIRE((int64_t)nx * ny < ((int64_t)1 << 31) && (int64_t)n_ang * n_det < ((int64_t)1 << 31), "index space exceeds int32");
+  TB200_REQUIRE(y && (n_ang == 0 || (geom && u)), "null pointer");
+  TB200_REQUIRE(((uintptr_t)geom % 16) == 0, "geom must be 16-byte aligned");
+  TB200_REQUIRE(norm_out == nullptr || ws != nullptr, "norm_out requires a workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ny + 3) / 4));
+  TB200_REQUIRE(grid.y <= 65535u, "ny too large for this launch shape");
+  ct_backproject_kernel<4><<<grid, 128, 0, st>>>(nx, ny, n_det, n_ang, geom, u, y, coef_host, coef_dev, z,
+                                                 norm_out ? ws : nullptr);
+  int rc = check_launch("ct_backproject");
+  if (rc) return rc;
+  if (norm_out) {
+    finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, (int64_t)grid.x * grid.y, norm_out);
+    rc = check_launch("ct_backproject finalize");
+  }
+  return rc;
+}
+
+// One Golub-Kahan step (the reference's golub_kahan_update, trips/utilities/decompositions.py:230-255) on the
+// matrix-free CT operator, enqueued as 6 kernels on `stream` with every scalar kept on the device:
+//   v = A^T u_k - beta_prev * v_prev ; alpha = ||v|| ; v /= alpha ; u = A v - alpha * u_k ; beta = ||u|| ; u /= beta
+// Arguments as tb200_gk_step_sell_f64, the operator as tb200_ct_forward_f64 / tb200_ct_backproject_f64.
+// ws: max(tb200_spmv_workspace_len(n_ang*n_det), tb200_ct_backproject_workspace_len(nx, ny)) doubles.
+int tb200_vec_div(int64_t n, const double* x, double d_host, const double* d_dev, double* out, void* stream);
+int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
+                         const int32_t* rowlen, const int32_t* colidx, const double* x, double* y, double coef_host,
+                         const double* coef_dev, const double* z, double* norm_out, double* ws, void* stream);
+
+int tb200_gk_step_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
+                         const int32_t* rowlen, const int32_t* colidx, const double* u_k, const double* v_prev,
+                         const double* beta_prev_dev, double* v_out, double* u_out, double* alpha_pair, double* beta_pair,
+                         double* ws, void* const* events_host, void* stream) {
+  TB200_REQUIRE(u_k && v_out && u_out && alpha_pair && beta_pair && ws, "null pointer");
+  TB200_REQUIRE((v_prev == nullptr) == (beta_prev_dev == nullptr), "v_prev and beta_prev_dev go together");
+  cudaStream_t st = (cudaStream_t)stream;
+  auto mark = [&](int i) {
+    if (events_host != nullptr && events_host[i] != nullptr) cudaEventRecord((cudaEvent_t)events_host[i], st);
+  };
+  const int64_t m = (int64_t)n_ang * n_det, n = (int64_t)nx * ny;
+  mark(0);
+  int rc = tb200_ct_backproject_f64(nx, ny, n_det, n_ang, geom, u_k, v_out, 0.0, beta_prev_dev, v_prev, alpha_pair, ws, stream);
+  mark(1);
+  if (rc) return rc;
+  rc = tb200_vec_div(n, v_out, 0.0, alpha_pair + 1, v_out, stream);
+  if (rc) return rc;
+  mark(2);
+  rc = tb200_ct_forward_f64(nx, ny, n_det, n_ang, geom, sliceptr, rowlen, colidx, v_out, u_out, 0.0, alpha_pair + 1, u_k,
+                            beta_pair, ws, stream);
+  mark(3);
+  if (rc) return rc;
+  return tb200_vec_div(m, u_out, 0.0, beta_pair + 1, u_out, stream);
+}
+
+}  // extern "C"

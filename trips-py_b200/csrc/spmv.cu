@@ -29,6 +29,7 @@
 // accumulated in double-double and is the correctly rounded value of the exact sum of squares (tb200_dd.cuh).
 #include "tb200_common.cuh"
 #include "tb200_dd.cuh"
+#include "tb200_ctgeom.cuh"
 
 namespace tb200 {
 
@@ -533,13 +534,27 @@ struct SellVals<float> {
   }
 };
 
-template <typename VT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+// GEOM = true: the matrix is the parallel-beam CT matrix A (rows = rays) and its VALUES ARE NOT STORED: an entry is
+// re-evaluated from its column index and the ray's geometry (tb200_ctgeom.cuh, ~9 fp64 instructions, same bits as the
+// builder writes) while the index stream - 4 bytes per entry instead of 12 - and the gathers are in flight.
+struct CtRays {
+  const double* geom;  // 6 doubles per angle: c, s, d2, 1/hi, 1/(hi*lo), 0
+  int nx, ny, n_det;
+  uint32_t nx_magic;   // floor(2^(32+nx_shift) / nx) clipped to 2^32-1: col / nx = umulhi(col, magic) >> shift (+1 fix-up)
+  int nx_shift;
+};
+
+template <typename VT, int WARPS, bool GEOM, int CH>
+__global__ void __launch_bounds__(WARPS * 32, GEOM ? 512 / (WARPS * 32) : 1)
 spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t* __restrict__ rowlen,
                  const int32_t* __restrict__ col, const VT* __restrict__ val, const double* __restrict__ x,
                  double* __restrict__ y, double coef_host, const double* __restrict__ coef_dev,
-                 const double* __restrict__ z, double* __restrict__ partials, int gather_mode) {
-  constexpr int CH = 16;
+                 const double* __restrict__ z, double* __restrict__ partials, int gather_mode, CtRays ct) {
+  // CH = entries per pipeline stage and lane: 16 for stored values (deep stream prefetch, HBM bound), 8 when the
+  // values are computed (GEOM: issue bound, wants four times the warps, so half the registers per lane)
+  constexpr int RPR = 32 / CH;        // row-major gathers: rows covered by one request
+  constexpr int CT_LD = CH + 4;       // ctile row pitch (ints): 16-byte aligned rows
+  constexpr int XT_LD = CH + 2;       // xtile row pitch (doubles): odd number of 16-byte pieces
   __shared__ double red[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t pol_keep = policy_evict_last();
@@ -558,6 +573,27 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
   const int nit = (w + CH - 1) / CH;
   const int32_t* cp = col + base + lane * 4;
   const VT* vp = val + base + lane * 4;
+
+  // GEOM: this lane's ray
+  RayGeom g = {1.0, 0.0, 0.5, 1.0, 1.0};
+  double sd = 0.0, bx = 0.0, by = 0.0;
+  if (GEOM) {
+    const int64_t r = (row < m) ? row : 0;
+    const int a = (int)(r / ct.n_det), d = (int)(r - (int64_t)a * ct.n_det);
+    const double* gp = ct.geom + 6 * (int64_t)a;
+    g.c = gp[0], g.s = gp[1], g.d2 = gp[2], g.inv_hi = gp[3], g.inv_hilo = gp[4];
+    sd = (double)d - 0.5 * (double)(ct.n_det - 1);
+    bx = centred_bias(ct.nx), by = centred_bias(ct.ny);
+  }
+  auto entry_values = [&](const int32_t (&c)[CH], double (&v)[CH]) {
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      int iy = (int)(__umulhi((uint32_t)c[k], ct.nx_magic) >> ct.nx_shift);
+      int ix = c[k] - iy * ct.nx;
+      if (ix >= ct.nx) ix -= ct.nx, ++iy;
+      v[k] = chord(g, ray_pixel_t(g, sd, centred_coord(ix, bx), centred_coord(iy, by)));
+    }
+  };
 
   auto load_cols = [&](int it, int32_t (&c)[CH]) {
 #pragma unroll
@@ -582,31 +618,31 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
   // there a request is re-shaped to 16 consecutive entries of two rows (2-3 sectors) and the values are handed to
   // the owner lanes through a per-warp shared-memory tile.  Arithmetic and order are unchanged (bit-identical).
   // Decided once per slice by probing the column stride along the row and across the rows in the first chunk.
-  __shared__ __align__(16) int32_t ctile_all[WARPS][32 * 20];  // [row][16 cols + 4 pad]: 16-byte aligned rows
-  __shared__ __align__(16) double xtile_all[WARPS][32 * 18];   // [row][16 x + 2 pad]: odd number of 16-byte pieces
+  __shared__ __align__(16) int32_t ctile_all[WARPS][32 * CT_LD];  // [row][CH cols + 4 pad]
+  __shared__ __align__(16) double xtile_all[WARPS][32 * XT_LD];   // [row][CH x + 2 pad]
   int32_t* ctile = ctile_all[warp];
   double* xtile = xtile_all[warp];
-  const int gk = lane & 15, gr = lane >> 4;  // row-major mode: my entry / which row of the pair
+  const int gk = lane % CH, gr = lane / CH;  // row-major mode: my entry / which row of the request's group
   auto gather_lane_per_row = [&](const int32_t (&c)[CH], double (&xv)[CH]) {
 #pragma unroll
     for (int k = 0; k < CH; ++k) xv[k] = ld_gather_f64(x + c[k], pol_keep);
   };
   auto gather_row_major = [&](const int32_t (&c)[CH], double (&xv)[CH]) {
-    // publish my row's columns, then request j gathers entries 0..15 of rows 2j and 2j+1
+    // publish my row's columns, then request j gathers entries 0..CH-1 of rows RPR*j .. RPR*j + RPR-1
 #pragma unroll
     for (int q = 0; q < CH / 4; ++q)
-      *reinterpret_cast<int4*>(ctile + lane * 20 + 4 * q) = make_int4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+      *reinterpret_cast<int4*>(ctile + lane * CT_LD + 4 * q) = make_int4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < CH; ++j) xv[j] = ld_gather_f64(x + ctile[(2 * j + gr) * 20 + gk], pol_keep);
+    for (int j = 0; j < CH; ++j) xv[j] = ld_gather_f64(x + ctile[(RPR * j + gr) * CT_LD + gk], pol_keep);
     __syncwarp();
   };
   auto deliver_row_major = [&](double (&xv)[CH]) {
-    // xv[j] currently holds x for (row 2j + gr, entry gk): hand every value to the lane that owns its row
+    // xv[j] currently holds x for (row RPR*j + gr, entry gk): hand every value to the lane that owns its row
 #pragma unroll
-    for (int j = 0; j < CH; ++j) xtile[(2 * j + gr) * 18 + gk] = xv[j];
+    for (int j = 0; j < CH; ++j) xtile[(RPR * j + gr) * XT_LD + gk] = xv[j];
     __syncwarp();
-    const double2* xr = reinterpret_cast<const double2*>(xtile + lane * 18);
+    const double2* xr = reinterpret_cast<const double2*>(xtile + lane * XT_LD);
 #pragma unroll
     for (int j = 0; j < CH / 2; ++j) {
       const double2 t = xr[j];
@@ -623,23 +659,25 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
   bool row_major = false;
   if (nit > 0) {
     load_cols(0, c1);
-    load_vals(0, v0);
+    if (!GEOM) load_vals(0, v0);
     {
-      const bool ok = len >= 10;
-      const int cn = __shfl_xor_sync(0xffffffffu, c1[8], 1);
+      constexpr int PB = CH / 2;  // probe position inside the first chunk
+      const bool ok = len >= PB + 2;
+      const int cn = __shfl_xor_sync(0xffffffffu, c1[PB], 1);
       const bool okn = __shfl_xor_sync(0xffffffffu, (int)ok, 1) != 0;
-      const unsigned along = __ballot_sync(0xffffffffu, ok && (c1[9] - c1[8]) <= 2 && (c1[8] - c1[7]) <= 2);
-      const unsigned across = __ballot_sync(0xffffffffu, ok && okn && abs(c1[8] - cn) <= 6);
+      const unsigned along = __ballot_sync(0xffffffffu, ok && (c1[PB + 1] - c1[PB]) <= 2 && (c1[PB] - c1[PB - 1]) <= 2);
+      const unsigned across = __ballot_sync(0xffffffffu, ok && okn && abs(c1[PB] - cn) <= 6);
       row_major = __popc(along) > __popc(across) + 8;
       if (gather_mode == 1) row_major = false;
       if (gather_mode == 2) row_major = true;
     }
     if (row_major) gather_row_major(c1, x0);
     else gather_lane_per_row(c1, x0);
+    if (GEOM) entry_values(c1, v0);
   }
   if (nit > 1) {
     load_cols(1, c1);
-    load_vals(1, v1);
+    if (!GEOM) load_vals(1, v1);
   }
   double acc = 0.0;
   for (int it = 0; it < nit; ++it) {
@@ -658,6 +696,7 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
     if (it + 1 < nit) {
       if (row_major) gather_row_major(c1, x0);
       else gather_lane_per_row(c1, x0);
+      if (GEOM) entry_values(c1, v1);  // values of chunk it+1 while its gathers fly
     }
     // stream loads of chunk it+2
     double v2[CH];
@@ -665,13 +704,16 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
     for (int k = 0; k < CH; ++k) v2[k] = 0.0;
     if (it + 2 < nit) {
       load_cols(it + 2, c1);
-      load_vals(it + 2, v2);
+      if (!GEOM) load_vals(it + 2, v2);
     }
     // the rounding chain, in index order
 #pragma unroll
     for (int k = 0; k < CH; ++k) acc = __dadd_rn(acc, p[k]);
 #pragma unroll
-    for (int k = 0; k < CH; ++k) v0[k] = v1[k], v1[k] = v2[k];
+    for (int k = 0; k < CH; ++k) {
+      v0[k] = v1[k];
+      if (!GEOM) v1[k] = v2[k];
+    }
   }
 
   dd_t nrm = dd_zero();
@@ -923,18 +965,18 @@ static int spmv_launch(int order, int64_t m, int64_t nnz, const int64_t* rowptr,
 
 static int g_sell_warps = 4;  // tuning knob (tb200_spmv_set_variant, bits 8-9: 0/2 -> 4, 1 -> 2, 3 -> 1 warps per CTA)
 
-template <typename VT>
+template <typename VT, bool GEOM = false, int CH = 16>
 static int sell_launch(int64_t m, const int64_t* sliceptr, const int32_t* rowlen, const int32_t* col, const VT* val,
                        const double* x, double* y, double coef_host, const double* coef_dev, const double* z,
-                       double* norm_out, double* ws, cudaStream_t st) {
+                       double* norm_out, double* ws, cudaStream_t st, CtRays ct = CtRays()) {
   double* partials = norm_out ? ws : nullptr;
   const int64_t nslices = (m + 31) / 32;
   const int warps = g_sell_warps;
   const int64_t nblocks = (nslices + warps - 1) / warps;
   switch (warps) {
-    case 1: spmv_sell_kernel<VT, 1><<<(unsigned)nblocks, 32, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials, g_seq_gather_mode); break;
-    case 2: spmv_sell_kernel<VT, 2><<<(unsigned)nblocks, 64, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials, g_seq_gather_mode); break;
-    default: spmv_sell_kernel<VT, 4><<<(unsigned)nblocks, 128, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials, g_seq_gather_mode); break;
+    case 1: spmv_sell_kernel<VT, 1, GEOM, CH><<<(unsigned)nblocks, 32, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials, g_seq_gather_mode, ct); break;
+    case 2: spmv_sell_kernel<VT, 2, GEOM, CH><<<(unsigned)nblocks, 64, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials, g_seq_gather_mode, ct); break;
+    default: spmv_sell_kernel<VT, 4, GEOM, CH><<<(unsigned)nblocks, 128, 0, st>>>(m, sliceptr, rowlen, col, val, x, y, coef_host, coef_dev, z, partials, g_seq_gather_mode, ct); break;
   }
   int rc = check_launch("spmv_sell");
   if (rc) return rc;
@@ -1033,6 +1075,30 @@ int tb200_spmv_sell_f32s(int64_t m, int64_t n, const int64_t* sliceptr, const in
   if (m == 0) return 0;
   return sell_launch<float>(m, sliceptr, rowlen, colidx, vals, x, y, coef_host, coef_dev, z, norm_out, ws,
                             (cudaStream_t)stream);
+}
+
+// Parallel-beam CT forward projection y = A x - coef*z with the VALUES OF A RE-EVALUATED ON THE FLY (see CtRays above):
+// only the SELL-32-4 column indices of A are read.  geom: tb200_ct_geometry output for the n_ang angles of A's rows
+// (row = angle*n_det + detector).  Bit-identical to tb200_spmv_sell_f64 on the matrix tb200_ct_fill_rows writes.
+int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
+                         const int32_t* rowlen, const int32_t* colidx, const double* x, double* y, double coef_host,
+                         const double* coef_dev, const double* z, double* norm_out, double* ws, void* stream) {
+  TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0 && (int64_t)nx * ny < ((int64_t)1 << 31), "bad geometry");
+  const int64_t m = (int64_t)n_ang * n_det;
+  int rc = check_sell_args(m, (int64_t)nx * ny, sliceptr, rowlen, colidx, nullptr, x, y, norm_out, ws);
+  if (rc) return rc;
+  TB200_REQUIRE(geom != nullptr || m == 0, "null geometry table");
+  if (m == 0) return 0;
+  CtRays ct;
+  ct.geom = geom;
+  ct.nx = nx, ct.ny = ny, ct.n_det = n_det;
+  int sh = 0;
+  while ((2u << sh) <= (uint32_t)nx) ++sh;  // floor(log2(nx))
+  const uint64_t mg = (((uint64_t)1) << (32 + sh)) / (uint64_t)nx;
+  ct.nx_magic = (uint32_t)(mg > 0xffffffffull ? 0xffffffffull : mg);
+  ct.nx_shift = sh;
+  return sell_launch<double, true, 8>(m, sliceptr, rowlen, colidx, (const double*)nullptr, x, y, coef_host, coef_dev, z,
+                                   norm_out, ws, (cudaStream_t)stream, ct);
 }
 
 // One Golub-Kahan step (the reference's golub_kahan_update, trips/utilities/decompositions.py:230-255) on SELL-32-4

@@ -90,6 +90,14 @@ class GKState:
                            self.beta[k - 1, 1:2] if k else None, v, u, self.alpha[k], self.beta[k])
             self.U.push()
             return
+        if self.comm is None and getattr(A, "projector", None) is not None:
+            # matrix-free CT operator: the whole step behind tb200_gk_step_ct_f64
+            self.V.push()
+            u = self.U.next_col()
+            A.projector.gk_step(u_k, self.V.col(k - 1) if k else None, self.beta[k - 1, 1:2] if k else None, v, u,
+                                self.alpha[k], self.beta[k])
+            self.U.push()
+            return
         # v = A^T u_k - beta_{k-1} v_{k-1} ; alpha = ||v|| ; v /= alpha      (decompositions.py:234-239)
         if k == 0:
             apply_fused(self.A, u_k, v, adjoint=True, norm_out=self.alpha[k])

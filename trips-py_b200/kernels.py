@@ -491,6 +491,83 @@ def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False, layout="csr"):
     return CSRDevice(shape, rowptr, colidx, vals)
 
 
+class CTProjector:
+    """Parallel-beam CT operator whose matrix VALUES are never stored (csrc/ct_project.cu, spmv.cu GEOM mode):
+    forward projection streams only A's SELL-32-4 column indices (4 B per entry) and re-evaluates each entry from the
+    ray geometry; back-projection is fully matrix-free.  Bit-identical to the stored-matrix SpMVs."""
+
+    def __init__(self, nx, ny, n_det, cos_t, sin_t):
+        dev = cos_t.device
+        self.nx, self.ny, self.n_det, self.n_ang = int(nx), int(ny), int(n_det), int(cos_t.numel())
+        self.shape = (self.n_ang * self.n_det, self.nx * self.ny)
+        self.device = dev
+        self.geom = torch.zeros(max(6 * self.n_ang, 2), dtype=F64, device=dev)
+        check(lib().tb200_ct_geometry(self.n_ang, _p(cos_t), _p(sin_t), _p(self.geom), _stream()), "ct_geometry")
+        self.rowlen = torch.zeros(self.shape[0], dtype=torch.int32, device=dev)
+        check(lib().tb200_ct_count_rows(self.nx, self.ny, self.n_det, self.n_ang, _p(cos_t), _p(sin_t), _p(self.rowlen),
+                                        _stream()), "ct_count")
+        self.sliceptr = sell_slice_pointers(self.rowlen)
+        total = int(self.sliceptr[-1].item())
+        self.colidx = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)[:total]
+        check(lib().tb200_ct_fill_rows(self.nx, self.ny, self.n_det, self.n_ang, _p(cos_t), _p(sin_t), _p(self.sliceptr), 1,
+                                       _p(self.colidx), None, _stream()), "ct_fill")
+        _lib.count(3)
+        self.stored = total
+        self.nnz = int(self.rowlen.sum().item())
+
+    @property
+    def nbytes(self):
+        return 4 * self.stored + 8 * self.sliceptr.numel() + 4 * self.rowlen.numel() + 8 * self.geom.numel()
+
+    def _coef(self, coef, z):
+        if z is None:
+            return 0.0, None
+        return (0.0, coef) if isinstance(coef, torch.Tensor) else (float(coef), None)
+
+    def forward(self, x, out=None, coef=None, z=None, norm_out=None):
+        m, n = self.shape
+        _vec(x, n, "x")
+        out = torch.empty(m, dtype=F64, device=self.device) if out is None else _vec(out, m, "out")
+        if z is not None:
+            _vec(z, m, "z")
+        ch, cd = self._coef(coef, z)
+        ws = Workspace.get(self.device).spmv(m) if norm_out is not None else None
+        check(lib().tb200_ct_forward_f64(self.nx, self.ny, self.n_det, self.n_ang, _p(self.geom), _p(self.sliceptr),
+                                         _p(self.rowlen), _p(self.colidx), _p(x), _p(out), ch, _p(cd), _p(z), _p(norm_out),
+                                         _p(ws), _stream()), "ct_forward")
+        _lib.count(2 if norm_out is not None else 1)
+        return out
+
+    def backproject(self, u, out=None, coef=None, z=None, norm_out=None):
+        m, n = self.shape
+        _vec(u, m, "u")
+        out = torch.empty(n, dtype=F64, device=self.device) if out is None else _vec(out, n, "out")
+        if z is not None:
+            _vec(z, n, "z")
+        ch, cd = self._coef(coef, z)
+        ws = None
+        if norm_out is not None:
+            ws = Workspace.get(self.device).buf("ct_bp", int(lib().tb200_ct_backproject_workspace_len(self.nx, self.ny)))
+        check(lib().tb200_ct_backproject_f64(self.nx, self.ny, self.n_det, self.n_ang, _p(self.geom), _p(u), _p(out), ch,
+                                             _p(cd), _p(z), _p(norm_out), _p(ws), _stream()), "ct_backproject")
+        _lib.count(2 if norm_out is not None else 1)
+        return out
+
+
+    def gk_step(self, u_k, v_prev, beta_prev, v_out, u_out, alpha_pair, beta_pair):
+        """One Golub-Kahan step in a single C-ABI call (6 kernels); scalars stay on the device."""
+        m, _ = self.shape
+        need = max(int(lib().tb200_spmv_workspace_len(m)), int(lib().tb200_ct_backproject_workspace_len(self.nx, self.ny)))
+        ws = Workspace.get(self.device).buf("ct_gk", need)
+        ev = None
+        if GK_STEP_EVENTS is not None:
+            ev = (ctypes.c_void_p * 4)(*[e.cuda_event for e in GK_STEP_EVENTS()])
+        check(lib().tb200_gk_step_ct_f64(self.nx, self.ny, self.n_det, self.n_ang, _p(self.geom), _p(self.sliceptr),
+                                         _p(self.rowlen), _p(self.colidx), _p(u_k), _p(v_prev), _p(beta_prev), _p(v_out),
+                                         _p(u_out), _p(alpha_pair), _p(beta_pair), _p(ws), ev, _stream()), "gk_step_ct")
+        _lib.count(6)
+
+
 # ---- stencils -------------------------------------------------------------------------------------------------
 
 def correlate2d(x, W, nrow, ncol, ch, cw, mode=0, out=None):

@@ -361,7 +361,11 @@ class ParallelBeamCT(CSROperator):
 
     Geometry follows the reference's conventions (Tomography.py:53-56, io.py:392-400): `views` angles in [0, pi),
     n_det = int(sqrt(2)*nx) unit-spaced detector bins, sinogram ordered angle-major (row = angle*n_det + det),
-    image vectorised row-major.  `angle_subset` keeps only those angle indices (row sharding by projection angle)."""
+    image vectorised row-major.  `angle_subset` keeps only those angle indices (row sharding by projection angle).
+
+    layout: 'csr' / 'sell' / 'both' store A and A^T (12 B per entry each); 'implicit' stores only A's column indices
+    (4 B per entry) and re-evaluates the values in the kernels, with a fully matrix-free back-projection - the
+    reference's operator is matrix-free too (astra.OpTomo).  All layouts give bit-identical products."""
 
     def __init__(self, nx, views, ny=None, n_det=None, angles=None, angle_subset=None, device=None, layout="auto"):
         device = torch.device(device) if device is not None else default_device()
@@ -374,10 +378,19 @@ class ParallelBeamCT(CSROperator):
         cos_t = torch.from_numpy(np.cos(theta)).to(device)
         sin_t = torch.from_numpy(np.sin(theta)).to(device)
         K._lib.require_device()
-        if layout == "auto":  # SELL is the fast path; keep CSR too while it is cheap (tests, export, 'tree' order)
+        self.projector = None
+        if layout == "auto":  # SELL is the fast stored path; keep CSR too while it is cheap (tests, export, 'tree' order)
             layout = "both" if 1.3 * len(theta) * self.nx * self.ny <= 2e8 else "sell"
+        if layout == "implicit":
+            # values re-evaluated on the fly: only A's column indices are stored, A^T is matrix-free
+            self.projector = K.CTProjector(self.nx, self.ny, n_det, cos_t, sin_t)
+            LinearOperator.__init__(self, self.projector.shape, device)
+            self.A = self.AT = self.A_sell = self.AT_sell = None
+            self.order = "sequential"
+            self._explicit = None
+            return
         if layout not in ("csr", "sell", "both"):
-            raise ValueError("layout must be 'auto', 'csr', 'sell' or 'both'")
+            raise ValueError("layout must be 'auto', 'csr', 'sell', 'both' or 'implicit'")
         mats = {}
         for lay in (("csr", "sell") if layout == "both" else (layout,)):
             a = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=False, layout=lay)
@@ -387,6 +400,43 @@ class ParallelBeamCT(CSROperator):
             mats[lay] = (a, at)
         csr, sell = mats.get("csr", (None, None)), mats.get("sell", (None, None))
         super().__init__(csr[0], csr[1], "sequential", sell[0], sell[1])
+
+    # -- layout='implicit' ------------------------------------------------------------------------------------------
+    def explicit(self, layout="csr"):
+        """The same operator with stored matrices (built on first use) - export, 'tree' order, cross-checks."""
+        if self.projector is None:
+            return self
+        if self._explicit is None:
+            self._explicit = ParallelBeamCT(self.nx, len(self.theta), ny=self.ny, n_det=self.n_det, angles=self.theta,
+                                            device=self.device, layout=layout)
+        return self._explicit
+
+    @property
+    def nnz(self):
+        return self.projector.nnz if self.projector is not None else super().nnz
+
+    def _csr(self, transposed):
+        return self.explicit()._csr(transposed) if self.projector is not None else super()._csr(transposed)
+
+    def with_order(self, order):
+        return self.explicit().with_order(order) if (self.projector is not None and order != "sequential") else \
+            (self if self.projector is not None else super().with_order(order))
+
+    def with_layout(self, layout):
+        return self.explicit(layout).with_layout(layout) if self.projector is not None else super().with_layout(layout)
+
+    def with_f32_storage(self):
+        return self.explicit("sell").with_f32_storage() if self.projector is not None else super().with_f32_storage()
+
+    def apply_dev(self, x, out=None, coef=None, z=None, norm_out=None):
+        if self.projector is not None:
+            return self.projector.forward(x, out=out, coef=coef, z=z, norm_out=norm_out)
+        return super().apply_dev(x, out=out, coef=coef, z=z, norm_out=norm_out)
+
+    def adjoint_dev(self, y, out=None, coef=None, z=None, norm_out=None):
+        if self.projector is not None:
+            return self.projector.backproject(y, out=out, coef=coef, z=z, norm_out=norm_out)
+        return super().adjoint_dev(y, out=out, coef=coef, z=z, norm_out=norm_out)
 
 
 class BlockDiagCT(CSROperator):
