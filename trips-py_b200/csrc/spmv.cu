@@ -539,6 +539,7 @@ struct SellVals<float> {
 // builder writes) while the index stream - 4 bytes per entry instead of 12 - and the gathers are in flight.
 struct CtRays {
   const double* geom;  // 6 doubles per angle: c, s, d2, 1/hi, 1/(hi*lo), 0
+  const int32_t* cta_order;  // nullable: CTA b works on slice group cta_order[b] (longest first: no straggler tail)
   int nx, ny, n_det;
   uint32_t nx_magic;   // floor(2^(32+nx_shift) / nx) clipped to 2^32-1: col / nx = umulhi(col, magic) >> shift (+1 fix-up)
   int nx_shift;
@@ -560,7 +561,8 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
   const uint64_t pol_keep = policy_evict_last();
   const uint64_t pol_stream = policy_evict_first();
   const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
-  const int64_t slice = (int64_t)blockIdx.x * WARPS + warp;
+  const int64_t group = (GEOM && ct.cta_order != nullptr) ? (int64_t)ct.cta_order[blockIdx.x] : (int64_t)blockIdx.x;
+  const int64_t slice = group * WARPS + warp;
   const int64_t nslices = (m + 31) >> 5;
   const int64_t row = slice * 32 + lane;
   int64_t base = 0;
@@ -1080,9 +1082,12 @@ int tb200_spmv_sell_f32s(int64_t m, int64_t n, const int64_t* sliceptr, const in
 // Parallel-beam CT forward projection y = A x - coef*z with the VALUES OF A RE-EVALUATED ON THE FLY (see CtRays above):
 // only the SELL-32-4 column indices of A are read.  geom: tb200_ct_geometry output for the n_ang angles of A's rows
 // (row = angle*n_det + detector).  Bit-identical to tb200_spmv_sell_f64 on the matrix tb200_ct_fill_rows writes.
+// cta_order (nullable): a permutation of the ceil(ceil(m/32)/4) groups of four slices, heaviest first, so that the
+// long central rays are scheduled before the short peripheral ones.
 int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
-                         const int32_t* rowlen, const int32_t* colidx, const double* x, double* y, double coef_host,
-                         const double* coef_dev, const double* z, double* norm_out, double* ws, void* stream) {
+                         const int32_t* rowlen, const int32_t* colidx, const int32_t* cta_order, const double* x, double* y,
+                         double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
+                         void* stream) {
   TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0 && (int64_t)nx * ny < ((int64_t)1 << 31), "bad geometry");
   const int64_t m = (int64_t)n_ang * n_det;
   int rc = check_sell_args(m, (int64_t)nx * ny, sliceptr, rowlen, colidx, nullptr, x, y, norm_out, ws);
@@ -1091,6 +1096,7 @@ int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geo
   if (m == 0) return 0;
   CtRays ct;
   ct.geom = geom;
+  ct.cta_order = (g_sell_warps == 4) ? cta_order : nullptr;  // the order is a permutation of groups of FOUR slices
   ct.nx = nx, ct.ny = ny, ct.n_det = n_det;
   int sh = 0;
   while ((2u << sh) <= (uint32_t)nx) ++sh;  // floor(log2(nx))

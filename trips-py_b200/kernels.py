@@ -514,6 +514,13 @@ class CTProjector:
         _lib.count(3)
         self.stored = total
         self.nnz = int(self.rowlen.sum().item())
+        # CTA schedule of the forward projector: groups of four slices, heaviest first (central rays are ~2000 entries
+        # long, peripheral ones a handful: in launch order the last wave would be stragglers)
+        width = self.sliceptr[1:] - self.sliceptr[:-1]
+        ngroups = (width.numel() + 3) // 4
+        padded = torch.zeros(ngroups * 4, dtype=torch.int64, device=dev)
+        padded[:width.numel()] = width
+        self.cta_order = torch.argsort(padded.view(ngroups, 4).sum(dim=1), descending=True, stable=True).to(torch.int32)
 
     @property
     def nbytes(self):
@@ -533,7 +540,7 @@ class CTProjector:
         ch, cd = self._coef(coef, z)
         ws = Workspace.get(self.device).spmv(m) if norm_out is not None else None
         check(lib().tb200_ct_forward_f64(self.nx, self.ny, self.n_det, self.n_ang, _p(self.geom), _p(self.sliceptr),
-                                         _p(self.rowlen), _p(self.colidx), _p(x), _p(out), ch, _p(cd), _p(z), _p(norm_out),
+                                         _p(self.rowlen), _p(self.colidx), _p(self.cta_order), _p(x), _p(out), ch, _p(cd), _p(z), _p(norm_out),
                                          _p(ws), _stream()), "ct_forward")
         _lib.count(2 if norm_out is not None else 1)
         return out
@@ -563,7 +570,7 @@ class CTProjector:
         if GK_STEP_EVENTS is not None:
             ev = (ctypes.c_void_p * 4)(*[e.cuda_event for e in GK_STEP_EVENTS()])
         check(lib().tb200_gk_step_ct_f64(self.nx, self.ny, self.n_det, self.n_ang, _p(self.geom), _p(self.sliceptr),
-                                         _p(self.rowlen), _p(self.colidx), _p(u_k), _p(v_prev), _p(beta_prev), _p(v_out),
+                                         _p(self.rowlen), _p(self.colidx), _p(self.cta_order), _p(u_k), _p(v_prev), _p(beta_prev), _p(v_out),
                                          _p(u_out), _p(alpha_pair), _p(beta_pair), _p(ws), ev, _stream()), "gk_step_ct")
         _lib.count(6)
 
