@@ -223,32 +223,61 @@ class _HostBasis:
         return self.arr[:, :k]
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    """Side stream for host<->device copies that overlap with the operator kernels (one per device)."""
+    st = _COPY_STREAMS.get(dev)
+    if st is None:
+        st = _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return st
+
+
 def golub_kahan_update(A, U, S, V):
     """One Golub-Kahan step; same contract as trips.utilities.decompositions.golub_kahan_update (:230-255).
 
     U: m x k, S: (k x (k-1)) bidiagonal or np.empty(1) on the first call, V: n x (k-1) (ignored on the first
-    call, exactly as the reference replaces the caller's dummy).  Returns (U: m x (k+1), S: (k+1) x k, V: n x k)."""
+    call, exactly as the reference replaces the caller's dummy).  Returns (U: m x (k+1), S: (k+1) x k, V: n x k).
+
+    Host traffic per call: u_k and v_{k-1} up, the new u and v down, all through pinned buffers.  Two of the four
+    copies hide behind the kernels: v_{k-1} arrives on a side stream while A^T u_k runs (it is only needed by the
+    recurrence that follows), and the new v leaves on the side stream while A v runs."""
     A = as_operator(A)
     dev = A.device
+    main = torch.cuda.current_stream(dev)
+    side = _copy_stream(dev)
     first = (S.shape[0] == 1)
     k = 1 if first else S.shape[0]
     hu, ku = _HostBasis.adopt(U)
+    v_prev = None
+    if first:
+        hv, kv = _HostBasis.adopt(np.empty((A.shape[1], 0)))
+    else:
+        hv, kv = _HostBasis.adopt(V)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            v_prev = hv.t[kv - 1].to(dev, non_blocking=True)
     u_k = hu.t[ku - 1].to(dev, non_blocking=True)
     v = torch.empty(A.shape[1], dtype=F64, device=dev)
     pair = torch.zeros(4, dtype=F64, device=dev)
     if first:
         apply_fused(A, u_k, v, adjoint=True, norm_out=pair[0:2])
-        hv, kv = _HostBasis.adopt(np.empty((A.shape[1], 0)))
     else:
-        hv, kv = _HostBasis.adopt(V)
-        v_prev = hv.t[kv - 1].to(dev, non_blocking=True)
-        apply_fused(A, u_k, v, adjoint=True, coef=float(S[k - 1, k - 2]), z=v_prev, norm_out=pair[0:2])
+        A.adjoint_dev(u_k, out=v)  # v_{k-1} is still in flight
+        main.wait_stream(side)
+        v_prev.record_stream(main)
+        K.vec_axpy(float(S[k - 1, k - 2]), v_prev, v, out=v, norm_out=pair[0:2], sign=-1.0)
     K.vec_div(v, pair[1:2], out=v)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        hv.t[kv].copy_(v, non_blocking=True)  # overlaps with A v below
     u = torch.empty(A.shape[0], dtype=F64, device=dev)
     apply_fused(A, v, u, coef=pair[1:2], z=u_k, norm_out=pair[2:4])
     K.vec_div(u, pair[3:4], out=u)
     hu.t[ku].copy_(u, non_blocking=True)
-    hv.t[kv].copy_(v, non_blocking=True)
+    main.wait_stream(side)
+    v.record_stream(side)
     sc = pair.cpu().numpy()  # synchronises the stream: the host copies above are complete after this
     alpha, beta = sc[1], sc[3]
     if first:
