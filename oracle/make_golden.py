@@ -118,8 +118,15 @@ def main():
     Qk = Qf[:, :k]
     lam_dp_L = ref.dp.discrepancy_principle(Qk, RA, RL, bfull, delta=0.8)
     lam_gcv_L = ref.gcv.generalized_crossvalidation(Qk, RA, RL, bfull)
+    # L-curve rule (trips/utilities/reg_param/l_curve.py) on the same projected problems
+    bp = Qk.T @ bfull
+    lc_grid = np.array([1e-6, 1e-3, 0.1, 1.5])
+    lc_kappa = np.array([ref.l_curve.curvature(l, RA, RL, bp) for l in lc_grid])
+    lam_lc_L = ref.l_curve.l_curve(RA, RL, bp)
+    lam_lc_I = ref.l_curve.l_curve(np.diag(s), np.eye(k), Q.T @ bhat.reshape(-1, 1))
     np.savez_compressed(os.path.join(OUT, "regparam.npz"), B=Bm, bhat=bhat, Qf=Qf, bfull=bfull, RA=RA, RL=RL,
-                        lam_std=lam_std, lam_mod=lam_mod, lam_dp=lam_dp, lam_dp_L=lam_dp_L, lam_gcv_L=lam_gcv_L)
+                        lam_std=lam_std, lam_mod=lam_mod, lam_dp=lam_dp, lam_dp_L=lam_dp_L, lam_gcv_L=lam_gcv_L,
+                        lc_grid=lc_grid, lc_kappa=lc_kappa, lam_lc_L=lam_lc_L, lam_lc_I=lam_lc_I)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

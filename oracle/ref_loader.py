@@ -311,6 +311,7 @@ def load():
     ns.decompositions = importlib.import_module("trips.utilities.decompositions")
     ns.gcv = importlib.import_module("trips.utilities.reg_param.gcv")
     ns.dp = importlib.import_module("trips.utilities.reg_param.discrepancy_principle")
+    ns.l_curve = importlib.import_module("trips.utilities.reg_param.l_curve")
     ns.weights = importlib.import_module("trips.utilities.weights")
     ns.phantoms = importlib.import_module("trips.utilities.phantoms")
     ns.CGLS = importlib.import_module("trips.solvers.CGLS").CGLS

@@ -208,6 +208,50 @@ def generalized_crossvalidation(Q_A, R_A, R_L, b, **kwargs):
     return op.fminbound(func=f, x1=1e-09, x2=1e2, args=(), xtol=1e-12, maxfun=1000, full_output=0, disp=0)
 
 
+def _lc_x(l, C, D, B, E, b, d):
+    """l_curve.py:25-45: (C + l D) x = B^T b + l E^T d."""
+    return np.linalg.lstsq(C + l * D, B.T @ b + l * E.T @ d, rcond=None)[0]
+
+
+def _lc_dx(l, C, D, E, x_l, d):
+    """l_curve.py:47-67."""
+    return -np.linalg.lstsq(C + l * D, D @ x_l - E.T @ d, rcond=None)[0]
+
+
+def _lc_d2x(l, C, D, E, x_l, dx_l, d):
+    """l_curve.py:69-87."""
+    lhs = C + l * D
+    inv4 = np.linalg.lstsq(lhs, D @ x_l, rcond=None)[0]
+    return 2 * np.linalg.lstsq(lhs, D @ dx_l - D @ inv4, rcond=None)[0]
+
+
+def _lc_term(l, Op, A, L, b, c, d, order):
+    """First (order 1) or second (order 2) derivative of ||Op x_l - c||^2   (l_curve.py:89-131, callers :133-169)."""
+    C, D = A.T @ A, L.T @ L
+    x_l = _lc_x(l, C, D, A, L, b, d)
+    dx = _lc_dx(l, C, D, L, x_l, d)
+    f, f1 = Op @ x_l, Op @ dx
+    if order == 1:
+        return (2 * (f - c).T @ f1).item()
+    f2 = Op @ _lc_d2x(l, C, D, L, x_l, dx, d)
+    return (2 * (f1.T @ f1 + (f - c).T @ f2)).item()
+
+
+def l_curve_curvature(l, A, L, b, d=None):
+    """l_curve.py:171-188."""
+    b = np.asarray(b).reshape(-1, 1)
+    d = np.zeros((L.shape[0], 1)) if d is None else d
+    f1, f2 = _lc_term(l, A, A, L, b, b, d, 1), _lc_term(l, A, A, L, b, b, d, 2)
+    g1, g2 = _lc_term(l, L, A, L, b, d, d, 1), _lc_term(l, L, A, L, b, d, d, 2)
+    return (-g1 * f2 + f1 * g2) / (g1 ** 2 + f1 ** 2) ** 1.5
+
+
+def l_curve(A, L, b, d=None):
+    """l_curve.py:190-202."""
+    return op.fminbound(func=lambda l: -1 * l_curve_curvature(l, A, L, b, d), x1=1e-9, x2=2, xtol=1e-12, maxfun=1000,
+                        full_output=0, disp=0)
+
+
 class IdentityOp:
     """Stand-in for pylops.Identity where the reference passes one as L / R_L (Hybrid_LSQR.py:76, Hybrid_GMRES.py:56)."""
 
@@ -367,6 +411,9 @@ def Hybrid_LSQR(A, b, n_iter=100, regparam="gcv", x_true=None, **kwargs):
                                                   fullsize=A.shape[0], **kwargs)
         elif regparam == "dp":
             lambdah = discrepancy_principle(U, B, IdentityOp(k), b, **kwargs)
+        elif regparam == "l_curve":  # Hybrid_LSQR.py:94-98
+            Q_A, s, _ = la.svd(B, full_matrices=False)
+            lambdah = l_curve(np.diag(s), np.eye(k), Q_A.T @ bhat.reshape((-1, 1)))
         else:
             lambdah = regparam
         lambda_history.append(lambdah)
@@ -404,6 +451,9 @@ def Hybrid_GMRES(A, b, n_iter, regparam="gcv", x_true=None, reorth="mgs", **kwar
             lambdah = generalized_crossvalidation(Q_A, np.diag(s), IdentityOp(k), bhat, **kwargs)
         elif regparam == "dp":
             lambdah = discrepancy_principle(V, H, IdentityOp(k), b, **kwargs)
+        elif regparam == "l_curve":  # Hybrid_GMRES.py:67-71
+            Q_A, s, _ = la.svd(H, full_matrices=False)
+            lambdah = l_curve(np.diag(s), np.eye(k), Q_A.T @ bhat.reshape((-1, 1)))
         else:
             lambdah = regparam
         lambda_history.append(lambdah)
@@ -432,6 +482,8 @@ def GKS(A, b, L, projection_dim=3, n_iter=50, regparam="gcv", x_true=None, **kwa
             lambdah = generalized_crossvalidation(Q_A, R_A, R_L, b, **kwargs)
         elif regparam == "dp":
             lambdah = discrepancy_principle(Q_A, R_A, R_L, b, **kwargs)
+        elif regparam == "l_curve":  # GKS.py:67-68
+            lambdah = l_curve(R_A, R_L, Q_A.T @ b)
         else:
             lambdah = regparam
         lambda_history.append(lambdah)
@@ -496,6 +548,8 @@ def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv",
             lambdah = generalized_crossvalidation(Q_A, R_A, R_L, wf * b, **kwargs)
         elif regparam == "dp":
             lambdah = discrepancy_principle(Q_A, R_A, R_L, wf * b, **kwargs)
+        elif regparam == "l_curve":  # MMGKS.py:100-101 (unweighted b)
+            lambdah = l_curve(R_A, R_L, Q_A.T @ b)
         else:
             lambdah = regparam
         lambda_history.append(lambdah)

@@ -172,6 +172,32 @@ def test_golden_ct24_all_solvers(tb, golden_dir):
     assert rel(x, g["gks_fix_x"]) < TOL
 
 
+def test_l_curve_rule_through_all_solvers(tb):
+    """regparam='l_curve' (trips/utilities/reg_param/l_curve.py; call sites Hybrid_LSQR.py:94-98, Hybrid_GMRES.py:67-71,
+    GKS.py:67-68, MMGKS.py:100-101) against the oracle's restatement of the same rule."""
+    op, A, xt, b, delta = ct_problem(tb, 32, 24)
+    x, info = tb.Hybrid_LSQR(op, b, n_iter=10, regparam="l_curve", x_true=xt)
+    xo, io = O.Hybrid_LSQR(A, b, n_iter=10, regparam="l_curve", x_true=xt)
+    lam, lam_o = np.array(info["regParam_history"], dtype=float), np.array(io["regParam_history"], dtype=float)
+    print("l_curve Hybrid_LSQR: lambda dev", np.max(np.abs(lam - lam_o) / lam_o), "iterate dev", rel(x, xo))
+    assert np.allclose(lam, lam_o, rtol=1e-6) and rel(x, xo) < 1e-7
+    M, Mo = op.T @ op, normal_op(A)
+    rhs = A.T @ b
+    x, info = tb.Hybrid_GMRES(M, rhs, 8, regparam="l_curve")
+    xo, io = O.Hybrid_GMRES(Mo, rhs, 8, regparam="l_curve")
+    assert np.allclose(np.array(info["regParam_history"], dtype=float), np.array(io["regParam_history"], dtype=float), rtol=1e-6)
+    assert rel(x, xo) < 1e-7
+    L, Lo = tb.FirstDerivative2D(32, 32), O.first_derivative_2d(32, 32)
+    x, info = tb.GKS(op, b, L, projection_dim=3, n_iter=8, regparam="l_curve")
+    xo, io = O.GKS(A, b, Lo, projection_dim=3, n_iter=8, regparam="l_curve")
+    assert np.allclose(np.array(info["regParam_history"], dtype=float), np.array(io["regParam_history"], dtype=float), rtol=1e-6)
+    assert rel(x, xo) < 1e-7
+    x, info = tb.MMGKS(op, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=8, regparam="l_curve")
+    xo, io = O.MMGKS(A, b, Lo, pnorm=2, qnorm=1, projection_dim=3, n_iter=8, regparam="l_curve")
+    assert np.allclose(np.array(info["regParam_history"], dtype=float), np.array(io["regParam_history"], dtype=float), rtol=1e-6)
+    assert rel(x, xo) < 1e-7
+
+
 def test_golden_deblur32(tb, golden_dir):
     g = np.load(f"{golden_dir}/deblur32.npz")
     n = int(g["n"])

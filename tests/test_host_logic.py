@@ -59,6 +59,38 @@ def test_product_discrepancy_principle_matches_reference_values():
         discrepancy_principle_projected(g["RA"], g["RL"], bp, res, None)
 
 
+def test_product_l_curve_matches_reference_values():
+    """trips/utilities/reg_param/l_curve.py: curvature values and the maximiser, against numbers produced by the real
+    reference (tests/golden/regparam.npz), the oracle's restatement, and - in the build container - the live reference."""
+    from trips_b200.reg_param import l_curve
+    from trips_b200.reg_param.l_curve import l_curve_curvature
+
+    g = np.load(f"{GOLDEN}/regparam.npz")
+    RA, RL, k = g["RA"], g["RL"], g["RA"].shape[0]
+    bp = g["Qf"][:, :k].T @ g["bfull"]
+    for lam, want in zip(g["lc_grid"], g["lc_kappa"]):
+        assert l_curve_curvature(lam, RA, RL, bp) == want  # same lstsq calls on the same matrices: same bits
+        assert O.l_curve_curvature(lam, RA, RL, bp) == want
+    assert l_curve(RA, RL, bp) == float(g["lam_lc_L"]) == O.l_curve(RA, RL, bp)
+    Q, s, _ = np.linalg.svd(g["B"], full_matrices=False)
+    c = Q.T @ g["bhat"].reshape(-1, 1)
+    assert l_curve(np.diag(s), np.eye(k), c) == float(g["lam_lc_I"])
+    # Cholesky vs Householder sign conventions of the triangular factor cannot change the rule
+    sg = np.diag([1, -1, 1, -1, -1, 1.0])
+    assert l_curve(sg @ RA, RL, sg @ bp) == pytest.approx(float(g["lam_lc_L"]), rel=1e-9)
+    import ref_loader
+
+    if ref_loader.available():
+        import importlib
+
+        ref_loader.load()
+        lc = importlib.import_module("trips.utilities.reg_param.l_curve")
+        rng = np.random.default_rng(9)
+        A2, L2, b2 = np.triu(rng.standard_normal((5, 5))) + 3 * np.eye(5), np.eye(5), rng.standard_normal((5, 1))
+        assert l_curve(A2, L2, b2) == lc.l_curve(A2, L2, b2)
+        assert l_curve_curvature(0.05, A2, L2, b2) == lc.curvature(0.05, A2, L2, b2)
+
+
 def test_argument_errors_mirror_the_reference():
     """Raised before any device work (Hybrid_LSQR.py:59-61, Hybrid_GMRES.py:29-31, GKS.py:32-34)."""
     from trips_b200 import GKS, Hybrid_GMRES, Hybrid_LSQR

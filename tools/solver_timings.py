@@ -65,6 +65,23 @@ def main():
         lambda: tb.MMGKS(Ad, b, L, pnorm=2, qnorm=1, projection_dim=1, n_iter=50, regparam="dp", delta=float(delta),
                          epsilon=0.1, x_true=xt), 50)
     run("cfg5 Hybrid_LSQR gcv dynamic CT 50 it", lambda: tb.Hybrid_LSQR(Ad, b, n_iter=50, regparam="gcv", x_true=xt), 50)
+    del Ad, L
+    torch.cuda.empty_cache()
+    # configs[3] = the headline geometry, whole solvers (matrix-free layout: 15.7 GB resident)
+    nx, views = 2048, 720
+    A4 = tb.ParallelBeamCT(nx, views, layout="implicit")
+    xt = O.shepp_logan(nx).reshape(-1, 1)
+    b, delta = O.add_noise(A4 @ xt, 0.01, rng)
+    run("cfg4 Hybrid_LSQR dp  CT2048/720 50 it", lambda: tb.Hybrid_LSQR(A4, b, n_iter=50, regparam="dp", delta=float(delta), x_true=xt), 50)
+    run("cfg4 Hybrid_LSQR gcv CT2048/720 50 it", lambda: tb.Hybrid_LSQR(A4, b, n_iter=50, regparam="gcv", x_true=xt), 50)
+    run("cfg4 CGLS CT2048/720 50 it", lambda: tb.CGLS(A4, b, np.zeros((nx * nx, 1)), 50, 0.0, x_true=xt), 50)
+    M4, rhs = A4.T @ A4, A4.T @ b
+    for reorth in ("mgs", "cgs2"):
+        run(f"cfg4 Hybrid_GMRES on A^T A ({reorth}) CT2048/720 50 it",
+            lambda: tb.Hybrid_GMRES(M4, rhs, 50, regparam=1e-2, x_true=xt, b200_reorth=reorth), 50)
+    L4 = tb.FirstDerivative2D(nx, nx)
+    run("cfg4 MMGKS anisoTV CT2048/720 30 it dp",
+        lambda: tb.MMGKS(A4, b, L4, pnorm=2, qnorm=1, projection_dim=3, n_iter=30, regparam="dp", delta=float(delta), x_true=xt), 30)
 
 
 if __name__ == "__main__":

@@ -20,6 +20,7 @@ from ..decompositions import ArnoldiState
 from ..operators import as_operator, to_device_vector
 from ..reg_param.discrepancy_principle import discrepancy_principle_projected
 from ..reg_param.gcv import generalized_crossvalidation
+from ..reg_param.l_curve import l_curve
 from ._common import ErrorTracker, LazyHistory, dev_scalar, host_column, need_delta, tikhonov_projected
 
 
@@ -65,8 +66,11 @@ def Hybrid_GMRES(A, b, n_iter, regparam="gcv", x_true=None, **kwargs):
                 resid = float(res.cpu()[1])
             lambdah = discrepancy_principle_projected(H, None, h.cpu().numpy()[:k + 1], resid, delta,
                                                       rp_kwargs.get("eta", 1.01), explicit)
+        elif isinstance(regparam, str) and regparam == "l_curve":
+            Q_A, s, _ = la.svd(H, full_matrices=False)  #                                       (Hybrid_GMRES.py:67-71)
+            lambdah = l_curve(np.diag(s), eye, Q_A.T @ bhat.reshape((-1, 1)))
         elif isinstance(regparam, str):
-            raise NotImplementedError(f"regparam={regparam!r}: only 'gcv', 'dp' or a number are on the hot path")
+            raise NotImplementedError(f"regparam={regparam!r}: 'gcv', 'dp', 'l_curve' or a number")
         else:
             lambdah = regparam
         lambda_history.append(lambdah)

@@ -81,7 +81,7 @@ def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv",
         else:
             _, wr = apply_L_with_weights(L, xd, epsilon, qnorm / 2 - 1, comm=comm)  # u = L@x; wr           (:60,93)
         R_A, R_L, c_plain, c_w, resid_w = factor_pair(bases, bd, wf=wf, wr=wr)  #               (:58-59,94-95)
-        lambdah = choose_lambda(regparam, R_A, R_L, c_w, resid_w, delta, rp_kwargs)  #           (:96-103)
+        lambdah = choose_lambda(regparam, R_A, R_L, c_w, resid_w, delta, rp_kwargs, c_plain=c_plain)  # (:96-103)
         lambda_history.append(lambdah)
         y = tikhonov_projected(R_A, R_L, c_plain, lambdah)  #                                    (:106)
         yd = dev_scalar(y, dev)

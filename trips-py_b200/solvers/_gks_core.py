@@ -17,6 +17,7 @@ from ..kernels import Basis
 from ..operators import CenteredDerivative2D, SpaceTimeDerivative
 from ..reg_param.discrepancy_principle import discrepancy_principle_projected
 from ..reg_param.gcv import generalized_crossvalidation
+from ..reg_param.l_curve import l_curve
 
 
 class GKSBases:
@@ -118,15 +119,17 @@ def factor_pair(bases, bd, wf=None, wr=None):
     return R_A, R_L, c_plain, c_w, resid_w
 
 
-def choose_lambda(regparam, R_A, R_L, c_w, resid_w, delta, rp_kwargs):
+def choose_lambda(regparam, R_A, R_L, c_w, resid_w, delta, rp_kwargs, c_plain=None):
     """GKS.py:60-69 / MMGKS.py:96-103 with the long-vector products already projected."""
+    if isinstance(regparam, str) and regparam == "l_curve":  # l_curve(R_A, R_L, Q_A.T @ b): the UNWEIGHTED b (MMGKS.py:101)
+        return l_curve(R_A, R_L, c_w if c_plain is None else c_plain)
     if isinstance(regparam, str) and regparam == "gcv":
         return generalized_crossvalidation(None, R_A, R_L, c_w, **rp_kwargs)
     if isinstance(regparam, str) and regparam == "dp":
         return discrepancy_principle_projected(R_A, R_L, c_w, resid_w, delta, rp_kwargs.get("eta", 1.01),
                                                rp_kwargs.get("explicitProj", False))
     if isinstance(regparam, str):
-        raise NotImplementedError(f"regparam={regparam!r}: only 'gcv', 'dp' or a number are on the hot path")
+        raise NotImplementedError(f"regparam={regparam!r}: 'gcv', 'dp', 'l_curve' or a number")
     return regparam
 
 
