@@ -128,6 +128,19 @@ int tb200_ct_count_cols(int nx, int ny, int n_det, int n_ang, const double* cosv
 int tb200_ct_fill_cols(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
                        const int64_t* ptr, int sell, int32_t* colidx, double* vals, void* stream);
 
+/* Flat-detector fan beam, the geometry the reference requests from ASTRA ('fanflat' projection geometry with the
+ * 'line_fanflat' projector, trips/test_problems/Tomography.py:57-67): source at so*(sin, -cos), detector centre at
+ * dd*(-sin, cos), detector axis (cos, sin), bins of width dps.  Same passes, layouts and entry function (chord of the
+ * source->bin ray through the unit pixel) as the parallel-beam builder above. */
+int tb200_ctfan_count_rows(double so, double dd, double dps, int nx, int ny, int n_det, int n_ang, const double* cosv,
+                           const double* sinv, int32_t* counts, void* stream);
+int tb200_ctfan_fill_rows(double so, double dd, double dps, int nx, int ny, int n_det, int n_ang, const double* cosv,
+                          const double* sinv, const int64_t* ptr, int sell, int32_t* colidx, double* vals, void* stream);
+int tb200_ctfan_count_cols(double so, double dd, double dps, int nx, int ny, int n_det, int n_ang, const double* cosv,
+                           const double* sinv, int32_t* counts, void* stream);
+int tb200_ctfan_fill_cols(double so, double dd, double dps, int nx, int ny, int n_det, int n_ang, const double* cosv,
+                          const double* sinv, const int64_t* ptr, int sell, int32_t* colidx, double* vals, void* stream);
+
 /* ---- parallel-beam CT projectors with the matrix values re-evaluated on the fly ---------------------------
  * The reference's tomography operator is matrix-free (astra.OpTomo behind pylops.FunctionOperator,
  * trips/test_problems/Tomography.py:73-83); SURVEY.md section 8(f) item 1.  Same matrix as the builder above, same

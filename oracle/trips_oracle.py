@@ -674,43 +674,79 @@ def ct_num_detectors(nx):
     return int(np.sqrt(2) * nx)
 
 
-def ct_matrix(nx, theta, ny=None, n_det=None):
+def _ray_tables(c, s, n_det, fan):
+    """Per-detector line parameters at one angle: unit normal (cd, sd), signed offset rho, and the trapezoid constants.
+    Parallel beam: the same normal for every bin, rho = d - (n_det-1)/2.  Fan beam (so, dd, dps): ASTRA 'fanflat'
+    conventions (Tomography.py:57-67) - source so*(sin, -cos), detector centre dd*(-sin, cos), axis (cos, sin).
+    Same operations in the same order as tb200_ctgeom.cuh ray_geometry / make_geom."""
+    k = np.arange(n_det) - 0.5 * (n_det - 1)
+    if fan is None:
+        cd, sd, rho = np.full(n_det, c), np.full(n_det, s), k
+    else:
+        so, dd, dps = (np.float64(v) for v in fan)
+        sx, sy = so * s, -(so * c)
+        px = -(dd * s) + k * (c * dps)
+        py = (dd * c) + k * (s * dps)
+        ex, ey = px - sx, py - sy
+        ln = np.sqrt(ex * ex + ey * ey)
+        cd, sd = ey / ln, -(ex / ln)
+        rho = cd * sx + sd * sy
+    hi, lo = np.maximum(np.abs(cd), np.abs(sd)), np.minimum(np.abs(cd), np.abs(sd))
+    d2 = 0.5 * (hi + lo)
+    with np.errstate(divide="ignore"):
+        inv_hi, inv_hilo = 1.0 / hi, 1.0 / (hi * lo)  # lo == 0: inf, the min below returns the plateau
+    return cd, sd, rho, d2, inv_hi, inv_hilo
+
+
+def ct_matrix(nx, theta, ny=None, n_det=None, fan=None):
     """Dense-loop-free NumPy statement of the device builder (trips-py_b200/csrc/ct_builder.cu): entry = chord length
     of ray (angle a, detector d) through unit pixel (iy, ix); row = a*n_det + d, column = iy*nx + ix.
-    Every arithmetic step is a separately rounded IEEE operation in the same order as the CUDA code."""
+    Every arithmetic step is a separately rounded IEEE operation in the same order as the CUDA code.
+    fan = (source_origin, detector_origin, detector_pixel_size) selects the flat-detector fan beam."""
     ny = nx if ny is None else ny
     n_det = ct_num_detectors(nx) if n_det is None else n_det
     theta = np.asarray(theta, dtype=np.float64)
     cx = np.arange(nx) - 0.5 * (nx - 1)
     cy = np.arange(ny) - 0.5 * (ny - 1)
-    sd = np.arange(n_det) - 0.5 * (n_det - 1)
     rows, cols, vals = [], [], []
     for a, (c, s) in enumerate(zip(np.cos(theta), np.sin(theta))):
-        hi, lo = max(abs(c), abs(s)), min(abs(c), abs(s))
-        d2 = 0.5 * (hi + lo)
-        with np.errstate(divide="ignore"):
-            inv_hi, inv_hilo = 1.0 / hi, 1.0 / (hi * lo)  # lo == 0: inf, the min below returns the plateau
-        proj = (cx[None, :] * c) + (cy[:, None] * s)          # (ny, nx): cx*c + cy*s
-        # candidate detectors around each pixel's projection
-        centre = proj + 0.5 * (n_det - 1)
-        base = np.floor(centre).astype(np.int64)
-        for off in (-1, 0, 1, 2):
+        cd, sd, rho, d2, inv_hi, inv_hilo = _ray_tables(c, s, n_det, fan)
+        # candidate detectors around each pixel's projection (any estimate within a bin or two will do: the exact
+        # predicate below decides)
+        if fan is None:
+            centre = (cx[None, :] * c) + (cy[:, None] * s) + 0.5 * (n_det - 1)
+            offsets = (-1, 0, 1, 2)
+        else:
+            so, dd, dps = fan
+            qx, qy = cx[None, :] - so * s, cy[:, None] + so * c
+            depth, lateral = -qx * s + qy * c, qx * c + qy * s
+            centre = lateral * (so + dd) / (depth * dps) + 0.5 * (n_det - 1)
+            offsets = (-2, -1, 0, 1, 2, 3)
+        base = np.floor(np.clip(centre, -4, n_det + 4)).astype(np.int64)
+        for off in offsets:
             d = base + off
             ok = (d >= 0) & (d < n_det)
-            dd = np.clip(d, 0, n_det - 1)
-            t = sd[dd] - proj
+            dd_ = np.clip(d, 0, n_det - 1)
+            proj = (cx[None, :] * cd[dd_]) + (cy[:, None] * sd[dd_])      # cx*c + cy*s with the ray's own normal
+            t = rho[dd_] - proj
             at = np.abs(t)
-            hit = ok & (at < d2)
+            hit = ok & (at < d2[dd_])
             with np.errstate(invalid="ignore"):
-                w = np.minimum(inv_hi, (d2 - at) * inv_hilo)  # trapezoid: plateau 1/hi, slopes (d2-|t|)/(hi*lo)
+                w = np.minimum(inv_hi[dd_], (d2[dd_] - at) * inv_hilo[dd_])  # plateau 1/hi, slopes (d2-|t|)/(hi*lo)
             iy, ix = np.nonzero(hit)
-            rows.append(a * n_det + dd[iy, ix])
+            rows.append(a * n_det + dd_[iy, ix])
             cols.append(iy * nx + ix)
             vals.append(w[iy, ix])
     A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
                       shape=(len(theta) * n_det, nx * ny))
     A.sort_indices()
     return A
+
+
+def fan_geometry(nx):
+    """(source_origin, detector_origin, detector_pixel_size) of Tomography.define_proj_id (Tomography.py:57-59)."""
+    so, dd = 3.0 * nx, 1.0 * nx
+    return so, dd, (so + dd) / so
 
 
 def shepp_logan(n):

@@ -299,6 +299,30 @@ def test_matrix_free_golub_kahan_equals_stored_matrix_golub_kahan(tb):
     assert np.array_equal(got.U.to_numpy(), ref.U.to_numpy()) and np.array_equal(got.V.to_numpy(), ref.V.to_numpy())
 
 
+@pytest.mark.parametrize("nx,ny,views,n_det,geom", [(24, None, 16, None, None), (64, None, 45, None, None),
+                                                    (33, 20, 7, None, None), (40, 40, 9, 70, (90.0, 25.0, 1.1)),
+                                                    (48, None, 5, None, (60.0, 0.0, 1.0))])
+def test_fan_beam_builder_is_bit_identical_to_the_numpy_statement(tb, nx, ny, views, n_det, geom):
+    """Flat-detector fan beam (the reference's ASTRA geometry, Tomography.py:57-67): A in CSR and SELL-32-4 and the
+    stored transpose against the oracle's NumPy statement of the same per-ray arithmetic; SpMV = scipy bit for bit."""
+    kw = {} if geom is None else dict(source_origin=geom[0], detector_origin=geom[1], detector_pixel_size=geom[2])
+    op = tb.FanBeamCT(nx, views, ny=ny, n_det=n_det, layout="both", **kw)
+    fan = O.fan_geometry(nx) if geom is None else geom
+    assert op.fan == tuple(fan)
+    A0 = O.ct_matrix(nx, O.ct_angles(views), ny=ny, n_det=n_det, fan=fan)
+    A, AT = op.to_scipy(), op.transpose_to_scipy()
+    assert A.shape == A0.shape and A.nnz == A0.nnz
+    assert np.array_equal(A.indptr, A0.indptr) and np.array_equal(A.indices, A0.indices) and np.array_equal(A.data, A0.data)
+    T0 = A0.T.tocsr()
+    T0.sort_indices()
+    assert np.array_equal(AT.indptr, T0.indptr) and np.array_equal(AT.indices, T0.indices) and np.array_equal(AT.data, T0.data)
+    rng = np.random.default_rng(0)
+    x, u = rng.standard_normal(A.shape[1]), rng.standard_normal(A.shape[0])
+    assert np.array_equal(host(op.apply_dev(dev(x))), A0 @ x) and np.array_equal(host(op.adjoint_dev(dev(u))), A0.T @ u)
+    # physics: every ray that crosses the image centrally has a path length close to the image width / |cos| bound
+    assert 0.9 * min(nx, ny if ny else nx) < (A0 @ np.ones(A.shape[1])).max() <= np.hypot(nx, ny if ny else nx) + 1e-9
+
+
 def test_ct_builder_angle_subset_and_block_diagonal(tb):
     nx, views = 32, 12
     full = tb.ParallelBeamCT(nx, views).to_scipy()

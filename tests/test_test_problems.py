@@ -86,7 +86,7 @@ def test_tomography_demo_sequence_matches_oracle():
 
     nx = ny = 32
     views = 24
-    T = tb.Tomography(CommitCrime=False, seed=3)
+    T = tb.Tomography(CommitCrime=False, seed=3, geometry="parallel")
     x_true, _, _ = T.gen_true("smooth", nx=nx, ny=ny)
     A, b_true, p, q, AforMatrixOperation = T.gen_data(x_true, nx, ny, views)
     assert (p, q) == (views, int(np.sqrt(2) * nx)) and AforMatrixOperation is A
@@ -101,7 +101,17 @@ def test_tomography_demo_sequence_matches_oracle():
     x_gpu, _ = tb.CGLS(A, b.reshape((-1, 1)), np.zeros((nx * ny, 1)), 30, 0.0)[:2]
     assert np.linalg.norm(x_gpu - x_ref) / np.linalg.norm(x_ref) <= 1e-10
     # CommitCrime=True: two return values, data from the operator itself
-    T2 = tb.Tomography(CommitCrime=True)
+    T2 = tb.Tomography(CommitCrime=True, geometry="parallel", layout="implicit")
     ops = T2.forward_Op(nx, ny, views)
     assert len(ops) == 2
     assert np.array_equal(T2.gen_data(x_true, nx, ny, views)[1], O.ct_matrix(nx, theta) @ x_true)
+    # the reference's own geometry (default): flat-detector fan beam, source at 3 nx, detector at nx, bins 4/3 wide
+    T3 = tb.Tomography(CommitCrime=True, seed=3)
+    A3, b3, p3, q3, _ = T3.gen_data(x_true, nx, ny, views)
+    F = O.ct_matrix(nx, theta, fan=O.fan_geometry(nx))
+    assert isinstance(A3, tb.FanBeamCT) and np.array_equal(b3, F @ x_true)
+    bm, delta = T3.add_noise(b3, "Gaussian", 0.02)
+    with O.reductions("exact"):
+        x_ref, _ = O.Hybrid_LSQR(F, bm.reshape((-1, 1)), n_iter=15, regparam="dp", delta=delta)
+    x_gpu, _ = tb.Hybrid_LSQR(A3, bm.reshape((-1, 1)), n_iter=15, regparam="dp", delta=delta)
+    assert np.linalg.norm(x_gpu - x_ref) / np.linalg.norm(x_ref) <= 1e-10

@@ -26,12 +26,21 @@ def run(name, fn, iters):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     extra = f" RRE {info['relError'][-1]:.4f}" if "relError" in info else ""
+    lam = info.get("regParam")
+    lam = f"lambda {float(lam):.3e}" if np.isscalar(lam) else "lambda -"
     print(f"{name}: {dt:.2f} s total, {dt / iters * 1e3:.1f} ms/it, {(_lib.launch_count - l0) / iters:.0f} launches/it, "
-          f"lambda {float(info['regParam']):.3e}{extra}", flush=True)
+          f"{lam}{extra}", flush=True)
 
 
 def main():
     rng = np.random.default_rng(2022)
+    only_cfg4 = "--cfg4" in sys.argv
+    if not only_cfg4:
+        small_and_mid(rng)
+    cfg4(rng)
+
+
+def small_and_mid(rng):
     # configs[1]
     A = tb.ParallelBeamCT(256, 180)
     xt = O.shepp_logan(256).reshape(-1, 1)
@@ -67,6 +76,9 @@ def main():
     run("cfg5 Hybrid_LSQR gcv dynamic CT 50 it", lambda: tb.Hybrid_LSQR(Ad, b, n_iter=50, regparam="gcv", x_true=xt), 50)
     del Ad, L
     torch.cuda.empty_cache()
+
+
+def cfg4(rng):
     # configs[3] = the headline geometry, whole solvers (matrix-free layout: 15.7 GB resident)
     nx, views = 2048, 720
     A4 = tb.ParallelBeamCT(nx, views, layout="implicit")

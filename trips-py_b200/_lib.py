@@ -48,6 +48,10 @@ SIGNATURES = {
     "tb200_ct_fill_rows": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_count_cols": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_fill_cols": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
+    "tb200_ctfan_count_rows": (c_int, [c_dbl, c_dbl, c_dbl, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_ctfan_fill_rows": (c_int, [c_dbl, c_dbl, c_dbl, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
+    "tb200_ctfan_count_cols": (c_int, [c_dbl, c_dbl, c_dbl, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_ctfan_fill_cols": (c_int, [c_dbl, c_dbl, c_dbl, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_geometry": (c_int, [c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_forward_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_backproject_workspace_len": (c_i64, [c_int, c_int]),

@@ -72,6 +72,31 @@ __device__ __forceinline__ void det_range(const RayGeom& g, double cx, double cy
   while (hi >= lo && !pred(hi)) --hi;
 }
 
+// fan beam: inclusive detector range hit by pixel (cx, cy) at the angle (cosa, sina).  The estimate is the bin under
+// the perspective projection of the pixel centre; the exact per-ray predicate settles it (the shadow is an interval).
+__device__ __forceinline__ bool fan_hits(const Beam& bm, double cosa, double sina, int d, int n_det, double cx, double cy) {
+  RayGeom g;
+  double rho;
+  ray_geometry(bm, cosa, sina, d, n_det, g, rho);
+  return hits(g, ray_pixel_t(g, rho, cx, cy));
+}
+__device__ __forceinline__ void det_range_fan(const Beam& bm, double cosa, double sina, double cx, double cy, int n_det,
+                                              int& lo, int& hi) {
+  const double qx = cx - bm.so * sina, qy = cy + bm.so * cosa;       // pixel relative to the source
+  const double depth = -qx * sina + qy * cosa, lateral = qx * cosa + qy * sina;
+  double est = lateral * (bm.so + bm.dd) / (depth * bm.dps) + 0.5 * (double)(n_det - 1);
+  est = fmin(fmax(est, -2.0), (double)n_det + 1.0);
+  auto pred = [&](int d) { return fan_hits(bm, cosa, sina, d, n_det, cx, cy); };
+  lo = (int)floor(est);
+  hi = lo + 1;
+  if (lo < 0) lo = 0;
+  if (hi > n_det - 1) hi = n_det - 1;
+  while (lo > 0 && pred(lo - 1)) --lo;
+  while (hi < n_det - 1 && pred(hi + 1)) ++hi;
+  while (lo <= hi && !pred(lo)) ++lo;
+  while (hi >= lo && !pred(hi)) --hi;
+}
+
 // address of entry j of `row` in either layout (ptr = rowptr for CSR, slice pointers for SELL-32-4)
 __device__ __forceinline__ int64_t entry_addr(const int64_t* __restrict__ ptr, int sell, int64_t row, int64_t j) {
   if (!sell) return ptr[row] + j;
@@ -92,15 +117,16 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
 // ---- A: one warp per ray -------------------------------------------------------------------------------
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-ct_rows_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ cosv, const double* __restrict__ sinv,
-               int32_t* __restrict__ counts, const int64_t* __restrict__ rowptr, int sell, int32_t* __restrict__ col,
-               double* __restrict__ val) {
+ct_rows_kernel(Beam bm, int nx, int ny, int n_det, int n_ang, const double* __restrict__ cosv,
+               const double* __restrict__ sinv, int32_t* __restrict__ counts, const int64_t* __restrict__ rowptr, int sell,
+               int32_t* __restrict__ col, double* __restrict__ val) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (ray >= (int64_t)n_ang * n_det) return;
   const int a = (int)(ray / n_det), d = (int)(ray % n_det);
-  const RayGeom g = make_geom(cosv[a], sinv[a]);
-  const double sd = (double)d - 0.5 * (double)(n_det - 1);
+  RayGeom g;
+  double sd;
+  ray_geometry(bm, cosv[a], sinv[a], d, n_det, g, sd);
   const double x0 = 0.5 * (double)(nx - 1);
   int64_t base = 0;  // entries of this row written so far
   int total = 0;
@@ -134,9 +160,9 @@ ct_rows_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ 
 // ---- A^T: one warp per pixel ---------------------------------------------------------------------------
 template <bool FILL>
 __global__ void __launch_bounds__(256)
-ct_cols_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ cosv, const double* __restrict__ sinv,
-               int32_t* __restrict__ counts, const int64_t* __restrict__ rowptr, int sell, int32_t* __restrict__ col,
-               double* __restrict__ val) {
+ct_cols_kernel(Beam bm, int nx, int ny, int n_det, int n_ang, const double* __restrict__ cosv,
+               const double* __restrict__ sinv, int32_t* __restrict__ counts, const int64_t* __restrict__ rowptr, int sell,
+               int32_t* __restrict__ col, double* __restrict__ val) {
   const int lane = threadIdx.x & 31;
   const int64_t pix = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (pix >= (int64_t)nx * ny) return;
@@ -149,9 +175,15 @@ ct_cols_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ 
     const int a = a0 + lane;
     int lo = 0, hi = -1;
     RayGeom g = make_geom(1.0, 0.0);
+    double ca = 1.0, sa = 0.0;
     if (a < n_ang) {
-      g = make_geom(cosv[a], sinv[a]);
-      det_range(g, cx, cy, n_det, lo, hi);
+      ca = cosv[a], sa = sinv[a];
+      if (bm.fan) {
+        det_range_fan(bm, ca, sa, cx, cy, n_det, lo, hi);
+      } else {
+        g = make_geom(ca, sa);
+        det_range(g, cx, cy, n_det, lo, hi);
+      }
     }
     const int cnt = (hi >= lo) ? (hi - lo + 1) : 0;
     if (FILL) {
@@ -161,7 +193,9 @@ ct_cols_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ 
       for (int d = lo; d <= hi; ++d, ++j) {
         const int64_t pos = entry_addr(rowptr, sell, pix, j);
         col[pos] = a * n_det + d;
-        val[pos] = chord(g, ray_pixel_t(g, (double)d - dc, cx, cy));
+        double offs = (double)d - dc;
+        if (bm.fan) ray_geometry(bm, ca, sa, d, n_det, g, offs);  // every ray of a fan has its own normal
+        val[pos] = chord(g, ray_pixel_t(g, offs, cx, cy));
       }
       base += chunk;
     } else {
@@ -188,17 +222,64 @@ static int ct_args_ok(int nx, int ny, int n_det, int n_ang, const void* c, const
   return 0;
 }
 
-// counts[ray] = number of pixels crossed by ray (ray = angle*n_det + det), for the n_ang angles in cos/sin.
-int tb200_ct_count_rows(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
-                        void* stream) {
+static int fan_args_ok(double so, double dd, double dps, int nx, int ny) {
+  TB200_REQUIRE(so > 0.0 && dd >= 0.0 && dps > 0.0, "fan beam: source distance and bin width must be positive");
+  TB200_REQUIRE(so * so > 0.25 * ((double)nx * nx + (double)ny * ny), "fan beam: the source must lie outside the image");
+  return 0;
+}
+
+static int count_rows(Beam bm, int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
+                      void* stream) {
   int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
   if (rc) return rc;
   const int64_t rays = (int64_t)n_ang * n_det;
   if (rays == 0) return 0;
   TB200_REQUIRE(counts, "null counts");
   ct_rows_kernel<false><<<(unsigned)((rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, 0, nullptr, nullptr);
+      bm, nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, 0, nullptr, nullptr);
   return check_launch("ct_count_rows");
+}
+
+static int fill_rows(Beam bm, int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
+                     const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream) {
+  int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
+  if (rc) return rc;
+  const int64_t rays = (int64_t)n_ang * n_det;
+  if (rays == 0) return 0;
+  TB200_REQUIRE(rowptr && colidx, "null output");
+  ct_rows_kernel<true><<<(unsigned)((rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      bm, nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, sell, colidx, vals);
+  return check_launch("ct_fill_rows");
+}
+
+static int count_cols(Beam bm, int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
+                      void* stream) {
+  int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
+  if (rc) return rc;
+  TB200_REQUIRE(counts, "null counts");
+  const int64_t npix = (int64_t)nx * ny;
+  ct_cols_kernel<false><<<(unsigned)((npix * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      bm, nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, 0, nullptr, nullptr);
+  return check_launch("ct_count_cols");
+}
+
+static int fill_cols(Beam bm, int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
+                     const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream) {
+  int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
+  if (rc) return rc;
+  TB200_REQUIRE(rowptr && colidx && vals, "null output");
+  const int64_t npix = (int64_t)nx * ny;
+  ct_cols_kernel<true><<<(unsigned)((npix * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      bm, nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, sell, colidx, vals);
+  return check_launch("ct_fill_cols");
+}
+
+static const Beam PARALLEL = {0, 0.0, 0.0, 1.0};
+
+// counts[ray] = number of pixels crossed by ray (ray = angle*n_det + det), for the n_ang angles in cos/sin.
+int tb200_ct_count_rows(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
+                        void* stream) {
+  return count_rows(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, counts, stream);
 }
 
 // Fills colidx/vals of A.  sell = 0: CSR, ptr = rowptr (exclusive prefix sum of the counts).
@@ -206,38 +287,52 @@ int tb200_ct_count_rows(int nx, int ny, int n_det, int n_ang, const double* cosv
 // vals may be NULL: only the column indices are written (index-only matrix for tb200_ct_forward_f64).
 int tb200_ct_fill_rows(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
                        const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream) {
-  int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
-  if (rc) return rc;
-  const int64_t rays = (int64_t)n_ang * n_det;
-  if (rays == 0) return 0;
-  TB200_REQUIRE(rowptr && colidx, "null output");
-  ct_rows_kernel<true><<<(unsigned)((rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, sell, colidx, vals);
-  return check_launch("ct_fill_rows");
+  return fill_rows(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, rowptr, sell, colidx, vals, stream);
 }
 
 // counts[pixel] = number of rays crossing the pixel (rows of A^T).
 int tb200_ct_count_cols(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
                         void* stream) {
-  int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
-  if (rc) return rc;
-  TB200_REQUIRE(counts, "null counts");
-  const int64_t npix = (int64_t)nx * ny;
-  ct_cols_kernel<false><<<(unsigned)((npix * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, 0, nullptr, nullptr);
-  return check_launch("ct_count_cols");
+  return count_cols(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, counts, stream);
 }
 
 // Fills colidx/vals of A^T (rows = pixels; column = angle*n_det + det); layouts as for tb200_ct_fill_rows.
 int tb200_ct_fill_cols(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
                        const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream) {
-  int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
+  return fill_cols(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, rowptr, sell, colidx, vals, stream);
+}
+
+// Flat-detector fan beam (the geometry the reference asks ASTRA for: 'fanflat' + 'line_fanflat',
+// trips/test_problems/Tomography.py:57-67): source at distance so from the rotation centre, detector at distance dd
+// behind it, bins of width dps.  Same four passes, same layouts, same entry function (chord of the source->bin ray
+// through the unit pixel).
+int tb200_ctfan_count_rows(double so, double dd, double dps, int nx, int ny, int n_det, int n_ang, const double* cosv,
+                           const double* sinv, int32_t* counts, void* stream) {
+  int rc = fan_args_ok(so, dd, dps, nx, ny);
   if (rc) return rc;
-  TB200_REQUIRE(rowptr && colidx && vals, "null output");
-  const int64_t npix = (int64_t)nx * ny;
-  ct_cols_kernel<true><<<(unsigned)((npix * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, sell, colidx, vals);
-  return check_launch("ct_fill_cols");
+  const Beam bm = {1, so, dd, dps};
+  return count_rows(bm, nx, ny, n_det, n_ang, cosv, sinv, counts, stream);
+}
+int tb200_ctfan_fill_rows(double so, double dd, double dps, int nx, int ny, int n_det, int n_ang, const double* cosv,
+                          const double* sinv, const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream) {
+  int rc = fan_args_ok(so, dd, dps, nx, ny);
+  if (rc) return rc;
+  const Beam bm = {1, so, dd, dps};
+  return fill_rows(bm, nx, ny, n_det, n_ang, cosv, sinv, rowptr, sell, colidx, vals, stream);
+}
+int tb200_ctfan_count_cols(double so, double dd, double dps, int nx, int ny, int n_det, int n_ang, const double* cosv,
+                           const double* sinv, int32_t* counts, void* stream) {
+  int rc = fan_args_ok(so, dd, dps, nx, ny);
+  if (rc) return rc;
+  const Beam bm = {1, so, dd, dps};
+  return count_cols(bm, nx, ny, n_det, n_ang, cosv, sinv, counts, stream);
+}
+int tb200_ctfan_fill_cols(double so, double dd, double dps, int nx, int ny, int n_det, int n_ang, const double* cosv,
+                          const double* sinv, const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream) {
+  int rc = fan_args_ok(so, dd, dps, nx, ny);
+  if (rc) return rc;
+  const Beam bm = {1, so, dd, dps};
+  return fill_cols(bm, nx, ny, n_det, n_ang, cosv, sinv, rowptr, sell, colidx, vals, stream);
 }
 
 }  // extern "C"

@@ -45,6 +45,34 @@ __device__ __forceinline__ double chord(const RayGeom& g, double t) {
   return chord_from_margin(__dsub_rn(g.d2, fabs(t)), g.inv_hi, g.inv_hilo);
 }
 
+// Beam geometry.  fan == 0: parallel beam, ray (angle, d) has normal (cos, sin) and offset d - (n_det-1)/2.
+// fan == 1: flat-detector fan beam in the conventions of ASTRA's 'fanflat' geometry that the reference builds
+// (trips/test_problems/Tomography.py:57-67): source at so*(sin, -cos), detector centre at dd*(-sin, cos), detector
+// axis (cos, sin), bins of width dps.  The ray from the source to the centre of bin d is a line with unit normal
+// (c, s) and signed offset rho = (c, s).source; the entry is the same chord function of t = rho - (c, s).pixel.
+struct Beam {
+  int fan;
+  double so, dd, dps;
+};
+
+__device__ __forceinline__ void ray_geometry(const Beam& bm, double cosa, double sina, int d, int n_det, RayGeom& g,
+                                             double& offset) {
+  const double k = (double)d - 0.5 * (double)(n_det - 1);
+  if (!bm.fan) {
+    g = make_geom(cosa, sina);
+    offset = k;
+    return;
+  }
+  const double sx = __dmul_rn(bm.so, sina), sy = -__dmul_rn(bm.so, cosa);
+  const double px = __dadd_rn(-__dmul_rn(bm.dd, sina), __dmul_rn(k, __dmul_rn(cosa, bm.dps)));
+  const double py = __dadd_rn(__dmul_rn(bm.dd, cosa), __dmul_rn(k, __dmul_rn(sina, bm.dps)));
+  const double ex = __dsub_rn(px, sx), ey = __dsub_rn(py, sy);
+  const double len = __dsqrt_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)));
+  const double c = __ddiv_rn(ey, len), s = -__ddiv_rn(ex, len);
+  g = make_geom(c, s);
+  offset = __dadd_rn(__dmul_rn(c, sx), __dmul_rn(s, sy));
+}
+
 // k - 0.5*(n-1) for 0 <= k < 2^31, exact (both operands are multiples of 0.5 well inside 2^52): the integer is
 // dropped into the mantissa of 2^51 (ulp 0.5) and one subtraction removes the bias together with the centre offset.
 // Equal to `(double)k - 0.5*(double)(n-1)` (which is exact too) without the int->fp64 conversion.

@@ -460,16 +460,21 @@ def gram_factor(Ghi, Glo, k):
 
 # ---- CT builder ---------------------------------------------------------------------------------------------
 
-def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False, layout="csr"):
+def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False, layout="csr", fan=None):
     """Build A (rows = rays) or A^T (rows = pixels) for the angles in the device tables cos_t/sin_t, directly in the
-    requested device layout ('csr' -> CSRDevice, 'sell' -> SellDevice)."""
+    requested device layout ('csr' -> CSRDevice, 'sell' -> SellDevice).  fan = (source_origin, detector_origin,
+    detector_pixel_size) selects the flat-detector fan beam instead of the parallel beam."""
     dev = cos_t.device
     n_ang = cos_t.numel()
     rows = nx * ny if transpose else n_ang * n_det
     counts = torch.zeros(rows, dtype=torch.int32, device=dev)
-    cnt_fn = lib().tb200_ct_count_cols if transpose else lib().tb200_ct_count_rows
-    fill_fn = lib().tb200_ct_fill_cols if transpose else lib().tb200_ct_fill_rows
-    check(cnt_fn(nx, ny, n_det, n_ang, _p(cos_t), _p(sin_t), _p(counts), _stream()), "ct_count")
+    which = "cols" if transpose else "rows"
+    if fan is None:
+        pre, cnt_fn, fill_fn = (), getattr(lib(), f"tb200_ct_count_{which}"), getattr(lib(), f"tb200_ct_fill_{which}")
+    else:
+        pre = tuple(float(v) for v in fan)
+        cnt_fn, fill_fn = getattr(lib(), f"tb200_ctfan_count_{which}"), getattr(lib(), f"tb200_ctfan_fill_{which}")
+    check(cnt_fn(*pre, nx, ny, n_det, n_ang, _p(cos_t), _p(sin_t), _p(counts), _stream()), "ct_count")
     shape = (nx * ny, n_ang * n_det) if transpose else (n_ang * n_det, nx * ny)
     _lib.count(2)
     if layout == "sell":
@@ -477,7 +482,8 @@ def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False, layout="csr"):
         total = int(sliceptr[-1].item())
         colidx = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)[:total]
         vals = torch.zeros(max(total, 1), dtype=F64, device=dev)[:total]
-        check(fill_fn(nx, ny, n_det, n_ang, _p(cos_t), _p(sin_t), _p(sliceptr), 1, _p(colidx), _p(vals), _stream()), "ct_fill")
+        check(fill_fn(*pre, nx, ny, n_det, n_ang, _p(cos_t), _p(sin_t), _p(sliceptr), 1, _p(colidx), _p(vals), _stream()),
+              "ct_fill")
         return SellDevice(shape, sliceptr, counts, colidx, vals)
     if layout != "csr":
         raise ValueError("layout must be 'csr' or 'sell'")
@@ -487,7 +493,7 @@ def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False, layout="csr"):
     nnz = int(rowptr[-1].item())
     colidx = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
     vals = torch.empty(max(nnz, 1), dtype=F64, device=dev)[:nnz]
-    check(fill_fn(nx, ny, n_det, n_ang, _p(cos_t), _p(sin_t), _p(rowptr), 0, _p(colidx), _p(vals), _stream()), "ct_fill")
+    check(fill_fn(*pre, nx, ny, n_det, n_ang, _p(cos_t), _p(sin_t), _p(rowptr), 0, _p(colidx), _p(vals), _stream()), "ct_fill")
     return CSRDevice(shape, rowptr, colidx, vals)
 
 

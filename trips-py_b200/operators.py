@@ -439,6 +439,53 @@ class ParallelBeamCT(CSROperator):
         return super().adjoint_dev(y, out=out, coef=coef, z=z, norm_out=norm_out)
 
 
+def fan_geometry(nx):
+    """(source_origin, detector_origin, detector_pixel_size) = (3 nx, nx, 4/3): Tomography.define_proj_id
+    (trips/test_problems/Tomography.py:57-59)."""
+    so, dd = 3.0 * nx, 1.0 * nx
+    return so, dd, (so + dd) / so
+
+
+class FanBeamCT(CSROperator):
+    """Flat-detector fan-beam tomography matrix, line (chord-length) model - the geometry the reference's Tomography
+    class requests from ASTRA (`astra.create_proj_geom('fanflat', ...)` + `'line_fanflat'`, Tomography.py:57-67):
+    `views` angles in [0, pi), int(sqrt(2)*nx) bins of width (so+dd)/so, source at 3*nx, detector at nx.
+    A and the exact transpose are built on the device and stored (CSR and/or SELL-32-4); every ray of a fan has its own
+    direction, so the values are not re-evaluated on the fly here (layout 'implicit' is parallel-beam only).
+    ASTRA itself is not part of the reference tree: rotation sense and image-axis orientation follow ASTRA's documented
+    conventions but cannot be pinned against it."""
+
+    def __init__(self, nx, views, ny=None, n_det=None, angles=None, angle_subset=None, device=None, layout="auto",
+                 source_origin=None, detector_origin=None, detector_pixel_size=None):
+        device = torch.device(device) if device is not None else default_device()
+        ny = nx if ny is None else ny
+        n_det = ct_num_detectors(nx) if n_det is None else int(n_det)
+        theta = ct_angles(views) if angles is None else np.asarray(angles, dtype=np.float64)
+        if angle_subset is not None:
+            theta = theta[np.asarray(angle_subset)]
+        so, dd, dps = fan_geometry(nx)
+        so = float(source_origin) if source_origin is not None else so
+        dd = float(detector_origin) if detector_origin is not None else dd
+        dps = float(detector_pixel_size) if detector_pixel_size is not None else (so + dd) / so
+        self.nx, self.ny, self.n_det, self.theta, self.fan = int(nx), int(ny), n_det, theta, (so, dd, dps)
+        cos_t = torch.from_numpy(np.cos(theta)).to(device)
+        sin_t = torch.from_numpy(np.sin(theta)).to(device)
+        K._lib.require_device()
+        if layout == "auto":
+            layout = "both" if 1.5 * len(theta) * self.nx * self.ny <= 2e8 else "sell"
+        if layout not in ("csr", "sell", "both"):
+            raise ValueError("layout must be 'auto', 'csr', 'sell' or 'both'")
+        mats = {}
+        for lay in (("csr", "sell") if layout == "both" else (layout,)):
+            a = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=False, layout=lay, fan=self.fan)
+            at = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=True, layout=lay, fan=self.fan)
+            if a.nnz != at.nnz:
+                raise RuntimeError(f"fan-beam builder: nnz(A)={a.nnz} differs from nnz(A^T)={at.nnz}")
+            mats[lay] = (a, at)
+        csr, sell = mats.get("csr", (None, None)), mats.get("sell", (None, None))
+        super().__init__(csr[0], csr[1], "sequential", sell[0], sell[1])
+
+
 class BlockDiagCT(CSROperator):
     """Block-diagonal dynamic-CT operator, one parallel-beam block per time frame, stored as ONE CSR matrix
     (and one CSR transpose) so a frame-major x is applied in a single launch.  Mirrors `pylops.BlockDiag` of

@@ -6,9 +6,11 @@ Only the problem SET-UP lives here (host-side, done once); the operators it retu
 `trips_b200.operators`.
 
 Deliberate differences, all forced by the environment:
-  * Tomography is PARALLEL-BEAM with the line (chord-length) model built by this package; the reference drives ASTRA's
-    fan-beam projector (`astra.create_projector('line_fanflat', ...)`, Tomography.py:49-67), which is not part of
-    the reference tree.  Geometry conventions are the reference's (views in [0, pi), p = int(sqrt(2)*nx) bins).
+  * Tomography(geometry='fan') - the default - is the reference's geometry: flat-detector fan beam, line model, source at
+    3 nx, detector at nx, bins of width 4/3 (`astra.create_proj_geom('fanflat', ...)`, `'line_fanflat'`,
+    Tomography.py:57-67), built by this package's FanBeamCT because ASTRA is not part of the reference tree (its rotation
+    sense / axis orientation follow ASTRA's documented conventions, unpinned).  geometry='parallel' gives the
+    parallel-beam operator, whose matrix-free layout is the fast path (`layout='implicit'`).
   * `seed=` is honoured (the reference pops it and never uses it: noise there is unseeded, Tomography.py:43,206).
   * `gen_true` offers the deterministic analytic phantoms (shepp_logan, smooth) and, like the reference, images from
     `./data/image_data/<name>.mat` when that file exists; the random phantoms and downloads are not reproduced.
@@ -19,7 +21,8 @@ import numpy as np
 import torch
 
 from .kernels import F64
-from .operators import ParallelBeamCT, PSFBlur2D, ct_angles, ct_num_detectors, default_device, gauss_psf, to_device_vector
+from .operators import (FanBeamCT, ParallelBeamCT, PSFBlur2D, ct_angles, ct_num_detectors, default_device, gauss_psf,
+                        to_device_vector)
 
 
 def shepp_logan(n):
@@ -143,16 +146,28 @@ class Deblurring2D(_Problem):
 
 
 class Tomography(_Problem):
-    """trips/test_problems/Tomography.py:41-227 (forward_Op :78-88, gen_data :153-168) with this package's parallel-beam operator (see the module docstring)."""
+    """trips/test_problems/Tomography.py:41-227 (forward_Op :78-88, gen_data :153-168) on this package's CT operators
+    (geometry='fan' | 'parallel', layout= passed to the operator; see the module docstring)."""
+
+    def __init__(self, **kwargs):
+        self.geometry = kwargs.pop("geometry", "fan")
+        self.layout = kwargs.pop("layout", "auto")
+        if self.geometry not in ("fan", "parallel"):
+            raise ValueError("geometry must be 'fan' (the reference's) or 'parallel'")
+        super().__init__(**kwargs)
+
+    def _operator(self, nx, ny, views, angles):
+        cls = FanBeamCT if self.geometry == "fan" else ParallelBeamCT
+        return cls(nx, views, ny=ny, angles=angles, device=self.device, layout=self.layout)
 
     def forward_Op(self, nx, ny, views):
         self.nx, self.ny, self.views = nx, ny, views
         self.p, self.q = ct_num_detectors(nx), views
         self.theta = ct_angles(views)
-        A = ParallelBeamCT(nx, views, ny=ny, device=self.device)
+        A = self._operator(nx, ny, views, self.theta)
         self.A = A
         if self.CommitCrime is False:
-            self.A_mis = ParallelBeamCT(nx, views, ny=ny, angles=self.theta + 1e-8, device=self.device)  # :62-65,74-75
+            self.A_mis = self._operator(nx, ny, views, self.theta + 1e-8)  # :62-65,74-75
             return A, A, self.A_mis
         return A, A
 
