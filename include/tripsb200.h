@@ -150,12 +150,20 @@ int tb200_ctfan_fill_cols(double so, double dd, double dps, int nx, int ny, int 
  * geom: 6 doubles per angle (c, s, d2, 1/hi, 1/(hi*lo), 0) written by tb200_ct_geometry, 16-byte aligned.
  * coef / z / norm_out / ws as for tb200_spmv_sell_f64; back-projector ws: tb200_ct_backproject_workspace_len.
  * cta_order (nullable): int32 permutation of the groups of four 32-row slices, heaviest first (schedules the long
- * central rays before the short peripheral ones; the result does not depend on it). */
+ * central rays before the short peripheral ones; the result does not depend on it).
+ * Row-aligned index layout (optional, rowskip nullable): tb200_ct_count_rows_first also reports the first image row each
+ * ray crosses; the caller derives rowskip[r] (leading padding of row r inside its lane) so that the 32 rays of a slice
+ * walk through the same image rows at the same positions - their x-gathers then share 32-byte sectors - and
+ * tb200_ct_fill_rows_aligned writes the column indices at [rowskip[r], rowskip[r] + rowlen[r]). */
 int tb200_ct_geometry(int n_ang, const double* cosv, const double* sinv, double* geom, void* stream);
+int tb200_ct_count_rows_first(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
+                              int32_t* counts, int32_t* first_row, void* stream);
+int tb200_ct_fill_rows_aligned(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
+                               const int64_t* sliceptr, const int32_t* rowskip, int32_t* colidx, void* stream);
 int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
-                         const int32_t* rowlen, const int32_t* colidx, const int32_t* cta_order, const double* x, double* y,
-                         double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
-                         void* stream);
+                         const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
+                         const double* x, double* y, double coef_host, const double* coef_dev, const double* z,
+                         double* norm_out, double* ws, void* stream);
 int64_t tb200_ct_backproject_workspace_len(int nx, int ny);
 int tb200_ct_backproject_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* u, double* y,
                              double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
@@ -163,9 +171,9 @@ int tb200_ct_backproject_f64(int nx, int ny, int n_det, int n_ang, const double*
 /* One Golub-Kahan step (trips/utilities/decompositions.py:230-255) on the matrix-free operator, as
  * tb200_gk_step_sell_f64; ws: max(tb200_spmv_workspace_len(m), tb200_ct_backproject_workspace_len(nx, ny)). */
 int tb200_gk_step_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
-                         const int32_t* rowlen, const int32_t* colidx, const int32_t* cta_order, const double* u_k,
-                         const double* v_prev, const double* beta_prev_dev, double* v_out, double* u_out, double* alpha_pair,
-                         double* beta_pair, double* ws, void* const* events_host, void* stream);
+                         const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
+                         const double* u_k, const double* v_prev, const double* beta_prev_dev, double* v_out, double* u_out,
+                         double* alpha_pair, double* beta_pair, double* ws, void* const* events_host, void* stream);
 
 /* ---- stencils ---------------------------------------------------------------------------------------------
  * PSF blur and its reference "adjoint": trips/test_problems/Deblurring2D.py:66-73 (scipy.ndimage.convolve,

@@ -131,7 +131,7 @@ def _static_worker(rank, world, port, out_dir):
 
         xt, b, delta = _static_problem()
         comm = RowComm()
-        A, rows = sharded_ct(SNX, SVIEWS, comm)
+        A, rows = sharded_ct(SNX, SVIEWS, comm, layout="implicit")  # matrix-free shards: same bits as stored ones
         out = _run_static(tb, A, b[rows], xt, delta, comm)
         np.savez(os.path.join(out_dir, f"s{rank}.npz"), **out)
     finally:

@@ -119,7 +119,8 @@ template <bool FILL>
 __global__ void __launch_bounds__(256)
 ct_rows_kernel(Beam bm, int nx, int ny, int n_det, int n_ang, const double* __restrict__ cosv,
                const double* __restrict__ sinv, int32_t* __restrict__ counts, const int64_t* __restrict__ rowptr, int sell,
-               int32_t* __restrict__ col, double* __restrict__ val) {
+               int32_t* __restrict__ col, double* __restrict__ val, int32_t* __restrict__ first_row,
+               const int32_t* __restrict__ rowskip) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (ray >= (int64_t)n_ang * n_det) return;
@@ -128,13 +129,15 @@ ct_rows_kernel(Beam bm, int nx, int ny, int n_det, int n_ang, const double* __re
   double sd;
   ray_geometry(bm, cosv[a], sinv[a], d, n_det, g, sd);
   const double x0 = 0.5 * (double)(nx - 1);
-  int64_t base = 0;  // entries of this row written so far
+  int64_t base = (FILL && rowskip != nullptr) ? rowskip[ray] : 0;  // position of the next entry of this row
   int total = 0;
+  int first = ny;  // first image row the ray crosses
   for (int iy0 = 0; iy0 < ny; iy0 += 32) {
     const int iy = iy0 + lane;
     int lo = 0, hi = -1;
     if (iy < ny) row_range(g, sd, iy, nx, ny, lo, hi);
     const int cnt = (hi >= lo) ? (hi - lo + 1) : 0;
+    if (cnt > 0 && iy < first) first = iy;
     if (FILL) {
       int chunk;
       const int off = warp_excl_scan(cnt, lane, chunk);
@@ -152,8 +155,14 @@ ct_rows_kernel(Beam bm, int nx, int ny, int n_det, int n_ang, const double* __re
   }
   if (!FILL) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    if (lane == 0) counts[ray] = total;
+    for (int o = 16; o > 0; o >>= 1) {
+      total += __shfl_xor_sync(0xffffffffu, total, o);
+      first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    }
+    if (lane == 0) {
+      counts[ray] = total;
+      if (first_row != nullptr) first_row[ray] = first;
+    }
   }
 }
 
@@ -229,26 +238,27 @@ static int fan_args_ok(double so, double dd, double dps, int nx, int ny) {
 }
 
 static int count_rows(Beam bm, int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
-                      void* stream) {
+                      void* stream, int32_t* first_row = nullptr) {
   int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
   if (rc) return rc;
   const int64_t rays = (int64_t)n_ang * n_det;
   if (rays == 0) return 0;
   TB200_REQUIRE(counts, "null counts");
   ct_rows_kernel<false><<<(unsigned)((rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      bm, nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, 0, nullptr, nullptr);
+      bm, nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, 0, nullptr, nullptr, first_row, nullptr);
   return check_launch("ct_count_rows");
 }
 
 static int fill_rows(Beam bm, int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
-                     const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream) {
+                     const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream,
+                     const int32_t* rowskip = nullptr) {
   int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
   if (rc) return rc;
   const int64_t rays = (int64_t)n_ang * n_det;
   if (rays == 0) return 0;
   TB200_REQUIRE(rowptr && colidx, "null output");
   ct_rows_kernel<true><<<(unsigned)((rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      bm, nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, sell, colidx, vals);
+      bm, nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, sell, colidx, vals, nullptr, rowskip);
   return check_launch("ct_fill_rows");
 }
 
@@ -288,6 +298,21 @@ int tb200_ct_count_rows(int nx, int ny, int n_det, int n_ang, const double* cosv
 int tb200_ct_fill_rows(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
                        const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream) {
   return fill_rows(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, rowptr, sell, colidx, vals, stream);
+}
+
+// The index-only, ROW-ALIGNED form of A for the matrix-free forward projector (tb200_ct_forward_f64).
+// count pass: counts[ray] and first_row[ray] = first image row the ray crosses (ny for a ray that misses the image).
+// fill pass: column indices only, SELL-32-4, entry j of ray r at position rowskip[r] + j of its lane: the caller
+// chooses rowskip so that the 32 rays of a slice walk through the same image rows at the same positions (their
+// x-gathers then share sectors); skipped positions stay zero-filled and are masked by the kernel.
+int tb200_ct_count_rows_first(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
+                              int32_t* counts, int32_t* first_row, void* stream) {
+  TB200_REQUIRE(first_row != nullptr || (int64_t)n_ang * n_det == 0, "null first_row");
+  return count_rows(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, counts, stream, first_row);
+}
+int tb200_ct_fill_rows_aligned(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
+                               const int64_t* sliceptr, const int32_t* rowskip, int32_t* colidx, void* stream) {
+  return fill_rows(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, sliceptr, 1, colidx, nullptr, stream, rowskip);
 }
 
 // counts[pixel] = number of rays crossing the pixel (rows of A^T).

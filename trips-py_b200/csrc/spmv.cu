@@ -540,6 +540,7 @@ struct SellVals<float> {
 struct CtRays {
   const double* geom;  // 6 doubles per angle: c, s, d2, 1/hi, 1/(hi*lo), 0
   const int32_t* cta_order;  // nullable: CTA b works on slice group cta_order[b] (longest first: no straggler tail)
+  const int32_t* rowskip;    // nullable: row r's entries start at position rowskip[r] of its lane (row-aligned slices)
   int nx, ny, n_det;
   uint32_t nx_magic;   // floor(2^(32+nx_shift) / nx) clipped to 2^32-1: col / nx = umulhi(col, magic) >> shift (+1 fix-up)
   int nx_shift;
@@ -566,11 +567,14 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
   const int64_t nslices = (m + 31) >> 5;
   const int64_t row = slice * 32 + lane;
   int64_t base = 0;
-  int w = 0, len = 0;  // slice width (entries per row, multiple of 4), length of this lane's row
+  int w = 0, len = 0, skip = 0;  // slice width (positions per lane, multiple of 4); this lane's entries: [skip, skip+len)
   if (slice < nslices) {
     base = sliceptr[slice];
     w = (int)((sliceptr[slice + 1] - base) >> 5);
-    if (row < m) len = rowlen[row];
+    if (row < m) {
+      len = rowlen[row];
+      if (GEOM && ct.rowskip != nullptr) skip = ct.rowskip[row];
+    }
   }
   const int nit = (w + CH - 1) / CH;
   const int32_t* cp = col + base + lane * 4;
@@ -664,7 +668,7 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
     if (!GEOM) load_vals(0, v0);
     {
       constexpr int PB = CH / 2;  // probe position inside the first chunk
-      const bool ok = len >= PB + 2;
+      const bool ok = skip == 0 && len >= PB + 2;
       const int cn = __shfl_xor_sync(0xffffffffu, c1[PB], 1);
       const bool okn = __shfl_xor_sync(0xffffffffu, (int)ok, 1) != 0;
       const unsigned along = __ballot_sync(0xffffffffu, ok && (c1[PB + 1] - c1[PB]) <= 2 && (c1[PB] - c1[PB - 1]) <= 2);
@@ -684,12 +688,12 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
   double acc = 0.0;
   for (int it = 0; it < nit; ++it) {
     if (row_major) deliver_row_major(x0);
-    // products of chunk it; positions at or beyond the row's length are padding and contribute +0.0
-    const int hi = len - it * CH;
+    // products of chunk it; positions outside [skip, skip + len) are padding and contribute +0.0
+    const int lo = skip - it * CH, hi = skip + len - it * CH;
     double p[CH];
-    if (hi < CH) {
+    if (hi < CH || lo > 0) {
 #pragma unroll
-      for (int k = 0; k < CH; ++k) p[k] = (k >= hi) ? 0.0 : __dmul_rn(v0[k], x0[k]);
+      for (int k = 0; k < CH; ++k) p[k] = (k >= hi || k < lo) ? 0.0 : __dmul_rn(v0[k], x0[k]);
     } else {
 #pragma unroll
       for (int k = 0; k < CH; ++k) p[k] = __dmul_rn(v0[k], x0[k]);
@@ -1083,11 +1087,12 @@ int tb200_spmv_sell_f32s(int64_t m, int64_t n, const int64_t* sliceptr, const in
 // only the SELL-32-4 column indices of A are read.  geom: tb200_ct_geometry output for the n_ang angles of A's rows
 // (row = angle*n_det + detector).  Bit-identical to tb200_spmv_sell_f64 on the matrix tb200_ct_fill_rows writes.
 // cta_order (nullable): a permutation of the ceil(ceil(m/32)/4) groups of four slices, heaviest first, so that the
-// long central rays are scheduled before the short peripheral ones.
+// long central rays are scheduled before the short peripheral ones.  rowskip (nullable): leading padding of each row
+// inside its lane (tb200_ct_fill_rows_aligned).
 int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
-                         const int32_t* rowlen, const int32_t* colidx, const int32_t* cta_order, const double* x, double* y,
-                         double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
-                         void* stream) {
+                         const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
+                         const double* x, double* y, double coef_host, const double* coef_dev, const double* z,
+                         double* norm_out, double* ws, void* stream) {
   TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0 && (int64_t)nx * ny < ((int64_t)1 << 31), "bad geometry");
   const int64_t m = (int64_t)n_ang * n_det;
   int rc = check_sell_args(m, (int64_t)nx * ny, sliceptr, rowlen, colidx, nullptr, x, y, norm_out, ws);
@@ -1097,6 +1102,7 @@ int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geo
   CtRays ct;
   ct.geom = geom;
   ct.cta_order = (g_sell_warps == 4) ? cta_order : nullptr;  // the order is a permutation of groups of FOUR slices
+  ct.rowskip = rowskip;
   ct.nx = nx, ct.ny = ny, ct.n_det = n_det;
   int sh = 0;
   while ((2u << sh) <= (uint32_t)nx) ++sh;  // floor(log2(nx))

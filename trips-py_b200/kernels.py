@@ -502,21 +502,42 @@ class CTProjector:
     forward projection streams only A's SELL-32-4 column indices (4 B per entry) and re-evaluates each entry from the
     ray geometry; back-projection is fully matrix-free.  Bit-identical to the stored-matrix SpMVs."""
 
-    def __init__(self, nx, ny, n_det, cos_t, sin_t):
+    def __init__(self, nx, ny, n_det, cos_t, sin_t, align=True):
         dev = cos_t.device
         self.nx, self.ny, self.n_det, self.n_ang = int(nx), int(ny), int(n_det), int(cos_t.numel())
         self.shape = (self.n_ang * self.n_det, self.nx * self.ny)
         self.device = dev
+        m = self.shape[0]
         self.geom = torch.zeros(max(6 * self.n_ang, 2), dtype=F64, device=dev)
         check(lib().tb200_ct_geometry(self.n_ang, _p(cos_t), _p(sin_t), _p(self.geom), _stream()), "ct_geometry")
-        self.rowlen = torch.zeros(self.shape[0], dtype=torch.int32, device=dev)
-        check(lib().tb200_ct_count_rows(self.nx, self.ny, self.n_det, self.n_ang, _p(cos_t), _p(sin_t), _p(self.rowlen),
-                                        _stream()), "ct_count")
-        self.sliceptr = sell_slice_pointers(self.rowlen)
+        self.rowlen = torch.zeros(m, dtype=torch.int32, device=dev)
+        first = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
+        check(lib().tb200_ct_count_rows_first(self.nx, self.ny, self.n_det, self.n_ang, _p(cos_t), _p(sin_t),
+                                              _p(self.rowlen), _p(first), _stream()), "ct_count")
+        # Row alignment.  Lane = ray; the 32 rays of a slice are neighbours on the detector.  A steep ray (|cos| >= |sin|)
+        # crosses every image row in 1 + |tan| pixels on average, but rays that enter through the side of the image start
+        # at different rows, so at the same position j the lanes would sit in different rows and every x-gather would
+        # touch its own sector.  Give each ray a leading padding of (its first row - the slice's first row) * (1 + |tan|)
+        # positions: the lanes then walk through the same rows together (simulated: 0.49 -> 0.35 sectors per entry).
+        self.rowskip = None
+        span = self.rowlen
+        if align and m > 0:
+            nsl = (m + 31) // 32
+            big = torch.iinfo(torch.int32).max
+            f = torch.full((nsl * 32,), big, dtype=torch.int32, device=dev)
+            f[:m] = torch.where(self.rowlen > 0, first[:m], torch.full_like(first[:m], big))
+            fmin = f.view(nsl, 32).min(dim=1).values.repeat_interleave(32)[:m]
+            ang = torch.arange(m, device=dev, dtype=torch.int64) // self.n_det
+            ct, st = cos_t.abs()[ang], sin_t.abs()[ang]
+            rate = torch.where(ct >= st, 1.0 + st / ct.clamp_min(1e-300), torch.zeros_like(ct))  # shallow rays: no padding
+            lead = torch.where(self.rowlen > 0, (f[:m] - fmin).to(F64) * rate, torch.zeros_like(rate))
+            self.rowskip = torch.floor(lead).to(torch.int32).contiguous()
+            span = self.rowlen + self.rowskip
+        self.sliceptr = sell_slice_pointers(span)
         total = int(self.sliceptr[-1].item())
         self.colidx = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)[:total]
-        check(lib().tb200_ct_fill_rows(self.nx, self.ny, self.n_det, self.n_ang, _p(cos_t), _p(sin_t), _p(self.sliceptr), 1,
-                                       _p(self.colidx), None, _stream()), "ct_fill")
+        check(lib().tb200_ct_fill_rows_aligned(self.nx, self.ny, self.n_det, self.n_ang, _p(cos_t), _p(sin_t),
+                                               _p(self.sliceptr), _p(self.rowskip), _p(self.colidx), _stream()), "ct_fill")
         _lib.count(3)
         self.stored = total
         self.nnz = int(self.rowlen.sum().item())
@@ -546,7 +567,8 @@ class CTProjector:
         ch, cd = self._coef(coef, z)
         ws = Workspace.get(self.device).spmv(m) if norm_out is not None else None
         check(lib().tb200_ct_forward_f64(self.nx, self.ny, self.n_det, self.n_ang, _p(self.geom), _p(self.sliceptr),
-                                         _p(self.rowlen), _p(self.colidx), _p(self.cta_order), _p(x), _p(out), ch, _p(cd), _p(z), _p(norm_out),
+                                         _p(self.rowlen), _p(self.rowskip), _p(self.colidx), _p(self.cta_order), _p(x), _p(out), ch, _p(cd), _p(z),
+                                         _p(norm_out),
                                          _p(ws), _stream()), "ct_forward")
         _lib.count(2 if norm_out is not None else 1)
         return out
@@ -576,7 +598,8 @@ class CTProjector:
         if GK_STEP_EVENTS is not None:
             ev = (ctypes.c_void_p * 4)(*[e.cuda_event for e in GK_STEP_EVENTS()])
         check(lib().tb200_gk_step_ct_f64(self.nx, self.ny, self.n_det, self.n_ang, _p(self.geom), _p(self.sliceptr),
-                                         _p(self.rowlen), _p(self.colidx), _p(self.cta_order), _p(u_k), _p(v_prev), _p(beta_prev), _p(v_out),
+                                         _p(self.rowlen), _p(self.rowskip), _p(self.colidx), _p(self.cta_order), _p(u_k), _p(v_prev),
+                                         _p(beta_prev), _p(v_out),
                                          _p(u_out), _p(alpha_pair), _p(beta_pair), _p(ws), ev, _stream()), "gk_step_ct")
         _lib.count(6)
 
