@@ -37,6 +37,7 @@ def main():
     q = views // 8
     subsets = {"vertical(0-22deg)": th[:q], "diag(34-56deg)": th[3 * q // 2:5 * q // 2], "horizontal(79-101deg)": th[7 * q // 2:9 * q // 2],
                "all/4": th[::4]}
+    subsets["all/8 (one of 8 ranks)"] = th[::8]
     if a.full:
         subsets["all"] = th
     for name, sub in subsets.items():

@@ -5,6 +5,7 @@ returns without synchronising.  Vectors are 1-D float64 CUDA tensors; a Basis is
 i.e. column j of the mathematical basis is the contiguous row j.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -521,6 +522,8 @@ class CTProjector:
         # positions: the lanes then walk through the same rows together (simulated: 0.49 -> 0.35 sectors per entry).
         self.rowskip = None
         span = self.rowlen
+        if os.environ.get("TB200_CT_ALIGN", "1") == "0":  # measurement switch (tools/mf_probe.py)
+            align = False
         if align and m > 0:
             nsl = (m + 31) // 32
             big = torch.iinfo(torch.int32).max
@@ -529,7 +532,13 @@ class CTProjector:
             fmin = f.view(nsl, 32).min(dim=1).values.repeat_interleave(32)[:m]
             ang = torch.arange(m, device=dev, dtype=torch.int64) // self.n_det
             ct, st = cos_t.abs()[ang], sin_t.abs()[ang]
-            rate = torch.where(ct >= st, 1.0 + st / ct.clamp_min(1e-300), torch.zeros_like(ct))  # shallow rays: no padding
+            # measured (tools/mf_probe.py, bench.py): aligning the rays up to 45 degrees is best when the launch has many
+            # waves of CTAs (whole cfg4 problem: 6.93 vs 7.10 ms); on an angle shard (1/8 of the rows, ~3 waves) the
+            # padding of the longest, near-diagonal slices lengthens the critical path, and stopping at tan = 0.7 wins
+            # (0.99 vs 1.13 ms)
+            waves = (m / 128.0) / (4 * torch.cuda.get_device_properties(dev).multi_processor_count)
+            tan_max = float(os.environ.get("TB200_CT_ALIGN_TAN", "1.0" if waves >= 8 else "0.7"))
+            rate = torch.where(st <= tan_max * ct, 1.0 + st / ct.clamp_min(1e-300), torch.zeros_like(ct))  # others: no padding
             lead = torch.where(self.rowlen > 0, (f[:m] - fmin).to(F64) * rate, torch.zeros_like(rate))
             self.rowskip = torch.floor(lead).to(torch.int32).contiguous()
             span = self.rowlen + self.rowskip
