@@ -518,13 +518,20 @@ def smoothed_holder_weights(x, epsilon, p):
 
 
 def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv", x_true=None, **kwargs):
-    """MMGKS.py:37-137, default (anisotropic) weights; isoTV via kwargs isoTV='isoTV', Ls=<2N x N gradient>."""
+    """MMGKS.py:37-137, default (anisotropic) weights; isoTV via kwargs isoTV='isoTV', Ls=<2N x N gradient>;
+    group sparsity via GS='GS', prob_dims=(nx, ny, nt) (:45-52, 79-91: L is REPLACED by kron(I_nt, old 2-D differences))."""
     epsilon = kwargs["epsilon"] if ("epsilon" in kwargs) else 0.1
     iso_L = kwargs.pop("iso_Ls", None)
+    gs = kwargs.pop("GS", False) in ["GS", "gs", "Gs"]
+    prob_dims = kwargs.pop("prob_dims", False)
     (U, B, V) = golub_kahan(A, b, projection_dim)
     x_history, lambda_history, residual_history = [], [], []
     x = A.T @ b
     AV = A @ V
+    if gs:
+        nx, ny, nt = prob_dims
+        Ls = first_derivative_old_2d(nx, ny)
+        L = sp.kron(sp.identity(nt), Ls).tocsr()
     LV = L @ V
     for ii in range(n_iter):
         v = A @ x - b
@@ -540,6 +547,13 @@ def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv",
             weightx = np.concatenate((weightx.flatten(), weightx.flatten()))
             weightt = (u[2 * spacen:] ** 2 + epsilon ** 2) ** ((qnorm - 2) / 4)
             wr = np.concatenate((weightx.reshape(-1, 1), weightt))
+        elif gs:  # MMGKS.py:79-91 (C-order reshape of the frame-major x, exp(2) as the smoothing constant: as written)
+            nt_ = int(x.reshape((-1, 1)).shape[0] / (nx * ny))
+            Dutemp = Ls.dot(np.reshape(x, (nx * ny, nt_)))
+            wr = np.exp(2) * np.ones((2 * nx * (ny - 1), 1))
+            for i in range(2 * nx * (ny - 1)):
+                wr[i] = (np.linalg.norm(Dutemp[i, :]) ** 2 + wr[i]) ** (qnorm / 2 - 1)
+            wr = np.kron(np.ones((nt_, 1)), wr)
         else:
             wr = smoothed_holder_weights(u, epsilon=epsilon, p=qnorm).reshape((-1, 1))
         LL = LV * wr
@@ -593,6 +607,20 @@ def first_derivative_2d(nx, ny):
     """operators.py:30-36."""
     IDx = sp.kron(sp.identity(nx), first_derivative_1d(nx))
     DyI = sp.kron(first_derivative_1d(ny), sp.identity(ny))
+    return sp.vstack((IDx, DyI)).tocsr()
+
+
+def first_derivative_old_1d(n):
+    """operators_old.py:66-72 (generate_first_derivative_operator_matrix): rows 0..n-2 of I - subdiag(1), i.e. row 0 is
+    x_0 and row i is x_i - x_{i-1}.  (.tocsr(): the dia_matrix of the reference is not subscriptable under scipy 1.18.)"""
+    D = sp.spdiags(data=np.ones(n - 1), diags=-1, m=n, n=n)
+    return (sp.identity(n, format="csr") - D).tocsr()[0:-1, :]
+
+
+def first_derivative_old_2d(nx, ny):
+    """operators_old.py:75-85 (generate_first_derivative_operator_2d_matrix)."""
+    IDx = sp.kron(sp.identity(nx), first_derivative_old_1d(nx))
+    DyI = sp.kron(first_derivative_old_1d(ny), sp.identity(ny))
     return sp.vstack((IDx, DyI)).tocsr()
 
 

@@ -198,6 +198,33 @@ def test_l_curve_rule_through_all_solvers(tb):
     assert rel(x, xo) < 1e-7
 
 
+def test_mmgks_group_sparsity_weights(tb):
+    """GS='GS' (MMGKS.py:45-52,79-91): L replaced by kron(I_nt, old 2-D differences), group weights over the frames
+    with exp(2) as smoothing constant - against the oracle's statement of the same lines, one frame and two frames."""
+    nx = 24
+    op, A, xt, b, delta = ct_problem(tb, nx, 16)
+    x, info = tb.MMGKS(op, b, None, pnorm=2, qnorm=1, projection_dim=3, n_iter=10, regparam="dp", delta=delta, x_true=xt,
+                       GS="GS", prob_dims=(nx, nx, 1))
+    xo, io = O.MMGKS(A, b, None, pnorm=2, qnorm=1, projection_dim=3, n_iter=10, regparam="dp", delta=delta, x_true=xt,
+                     GS="GS", prob_dims=(nx, nx, 1))
+    print("MMGKS GS nt=1: iterate dev", rel(x, xo))
+    assert rel(x, xo) < 1e-9
+    assert np.allclose(np.array(info["regParam_history"], dtype=float), np.array(io["regParam_history"], dtype=float), rtol=1e-7)
+    with pytest.raises(TypeError, match="Group Sparsity"):
+        tb.MMGKS(op, b, None, GS="GS")
+    # two frames: block-diagonal operator, frame-major x
+    th = O.ct_angles(16)
+    frames = [th[0::2], th[1::2]]
+    op2 = tb.BlockDiagCT(nx, frames)
+    A2 = op2.to_scipy()
+    xt2 = np.concatenate([xt.ravel(), 1.2 * xt.ravel()]).reshape(-1, 1)
+    b2, d2 = O.add_noise(A2 @ xt2, 0.01, np.random.default_rng(4))
+    x, info = tb.MMGKS(op2, b2, None, pnorm=2, qnorm=1, projection_dim=2, n_iter=8, regparam=0.05, GS="GS", prob_dims=(nx, nx, 2))
+    xo, io = O.MMGKS(A2, b2, None, pnorm=2, qnorm=1, projection_dim=2, n_iter=8, regparam=0.05, GS="GS", prob_dims=(nx, nx, 2))
+    print("MMGKS GS nt=2: iterate dev", rel(x, xo))
+    assert rel(x, xo) < 1e-9
+
+
 def test_golden_deblur32(tb, golden_dir):
     g = np.load(f"{golden_dir}/deblur32.npz")
     n = int(g["n"])

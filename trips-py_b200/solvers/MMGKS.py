@@ -15,14 +15,46 @@ The weights follow the CODE, not the paper: both `AV*wf` and `LV*wr` use the ful
 (p/2-1), (q/2-1) (:57,93), except the isoTV branch which uses (q-2)/4 (:75-77).
 isoTV: the reference builds its own spatial gradient with pylops' float32 centred differences
 (operators_old.py:35-45); here the gradient is the fp64 statement of the same centred stencil and `L`
-must be that operator (`CenteredDerivative2D`), single frame.  GS (group sparsity) is not provided.
+must be that operator (`CenteredDerivative2D`), single frame.
+GS (group sparsity, :45-52,79-91): as in the reference the caller's L is replaced by kron(I_nt, Ls) with Ls the 2-D
+differences of operators_old.py:75-85 (applied through the CSR kernels), and the weights are
+(||(Ls X)_{i,:}||^2 + e^2)^(q/2-1) with X the C-order reshape of x - both exactly as written there.
 """
+import numpy as np
 import torch
+from scipy import sparse
 
 from .. import kernels as K
 from ..operators import as_operator, to_device_vector
 from ._common import ErrorTracker, LazyHistory, dev_scalar, host_column, need_delta, tikhonov_projected
 from ._gks_core import GKSBases, adjoint_L_weighted, apply_L_with_weights, choose_lambda, expand, factor_pair
+
+
+def _old_first_derivative_1d(n):
+    """Rows 0..n-2 of I - subdiag(1): (L x)_0 = x_0, (L x)_i = x_i - x_{i-1}   (operators_old.py:66-72)."""
+    D = sparse.spdiags(data=np.ones(n - 1), diags=-1, m=n, n=n)
+    return (sparse.identity(n, format="csr") - D).tocsr()[0:-1, :]
+
+
+def _old_first_derivative_2d(nx, ny):
+    """operators_old.py:75-85."""
+    return sparse.vstack((sparse.kron(sparse.identity(nx), _old_first_derivative_1d(nx)),
+                          sparse.kron(_old_first_derivative_1d(ny), sparse.identity(ny)))).tocsr()
+
+
+def _group_sparsity_weights(Ls, xd, n_space, qnorm):
+    """wr_i = (||(Ls X)_{i,:}||^2 + e^2)^(q/2-1), X = x reshaped (n_space, nt) in C order, repeated for every frame
+    (MMGKS.py:79-91, as written: C-order reshape of the frame-major x and exp(2) as the smoothing constant)."""
+    nt = xd.numel() // n_space
+    acc = None
+    for t in range(nt):
+        col = xd if nt == 1 else xd[t::nt].contiguous()
+        d = Ls.apply_dev(col)
+        sq = K.vec_mul(d, d)
+        acc = sq if acc is None else K.vec_add(acc, sq, out=acc)
+    # (v^2 + eps^2)^expo with v = sqrt(acc) (the reference takes the norm, then squares it) and eps = e
+    wr = K.irls_weights(torch.sqrt(acc), float(np.exp(1.0)), qnorm / 2 - 1)
+    return wr if nt == 1 else wr.repeat(nt)
 
 
 def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv", x_true=None, **kwargs):
@@ -37,12 +69,21 @@ def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv",
     epsilon = kwargs["epsilon"] if ("epsilon" in kwargs) else 0.1
     prob_dims = kwargs["prob_dims"] if ("prob_dims" in kwargs) else False
     iso = isoTV_option in ["isoTV", "ISOTV", "IsoTV"]
-    if GS_option in ["GS", "gs", "Gs"]:
-        raise NotImplementedError("the group-sparsity (GS) weights of MMGKS.py:79-91 are outside this build's hot path")
+    gs = GS_option in ["GS", "gs", "Gs"]
+    if gs and prob_dims is False:
+        raise TypeError("For Isotropic Group Sparsity you must enter the dimension of the dynamic problem. (x_mmgks, info_mmgks) = MMGKS(A, data_vec, L, pnorm=2, qnorm=1, projection_dim=2, n_iter =3, regparam = 'gcv', x_true = None, GS = 'GS', prob_dims = (nx,ny, nt))")
     if iso and prob_dims is False:
         raise TypeError("For Isotropic TV you must enter the dimension of the dynamic problem! Example: (x_mmgks, info_mmgks) = MMGKS(A, data_vec, L, pnorm=2, qnorm=1, projection_dim=2, n_iter =3, regparam = 'gcv', x_true = None, isoTV = 'isoTV', prob_dims = (nx,ny, nt))")
 
     A = as_operator(A)
+    Ls = None
+    if gs:
+        # the reference REPLACES the caller's L by kron(I_nt, Ls), Ls = the 2-D differences of operators_old.py:75-85
+        # (row 0 of each 1-D block is x_0, row i is x_i - x_{i-1})                                   (MMGKS.py:45-52)
+        gnx, gny, gnt = (int(v) for v in prob_dims)
+        Ls_host = _old_first_derivative_2d(gnx, gny)
+        Ls = as_operator(Ls_host, A.device)
+        L = Ls if gnt == 1 else sparse.kron(sparse.identity(gnt), Ls_host).tocsr()
     L = as_operator(L, A.device)
     dev = A.device
     m, n = A.shape
@@ -78,6 +119,8 @@ def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv",
             wf = K.irls_weights(tm, epsilon, pnorm / 2 - 1)  #                                   (:57)
         if iso:
             wr = L.iso_weights(xd, epsilon, (qnorm - 2) / 4)  #                                  (:64-78)
+        elif gs:
+            wr = _group_sparsity_weights(Ls, xd, gnx * gny, qnorm)  #                            (:79-91)
         else:
             _, wr = apply_L_with_weights(L, xd, epsilon, qnorm / 2 - 1, comm=comm)  # u = L@x; wr           (:60,93)
         R_A, R_L, c_plain, c_w, resid_w = factor_pair(bases, bd, wf=wf, wr=wr)  #               (:58-59,94-95)
