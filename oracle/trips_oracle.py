@@ -624,6 +624,43 @@ def first_derivative_old_2d(nx, ny):
     return sp.vstack((IDx, DyI)).tocsr()
 
 
+def framelet_filters(l, n):
+    """operators.py:50-83 (construct_H)."""
+    e = np.ones((n,))
+    H_0 = (sp.spdiags(e, -l, n, n) + sp.spdiags(2 * e, 0, n, n) + sp.spdiags(e, l, n, n)).tolil()
+    H_1 = (sp.spdiags(-e, -l, n, n) + sp.spdiags(e, l, n, n)).tolil()
+    H_2 = (sp.spdiags(-e, -l, n, n) + sp.spdiags(2 * e, 0, n, n) + sp.spdiags(-e, l, n, n)).tolil()
+    for jj in range(0, l):
+        H_0[jj, l - jj - 1] += 1
+        H_0[-jj - 1, -l + jj] += 1
+        H_1[jj, l - jj - 1] -= 1
+        H_1[-jj - 1, -l + jj] += 1
+        H_2[jj, l - jj - 1] -= 1
+        H_2[-jj - 1, -l + jj] -= 1
+    return (H_0.tocsr() / 4).tocsr(), (H_1.tocsr() * (np.sqrt(2) / 4)).tocsr(), (H_2.tocsr() / 4).tocsr()
+
+
+def framelet_analysis(n, l):
+    """operators.py:86-101 (create_analysis_operator_rec / create_analysis_operator)."""
+    def rec(level, w):
+        if level == l:
+            return sp.vstack(framelet_filters(level, n))
+        (H_0, H_1, H_2) = framelet_filters(level, n)
+        W_1 = rec(level + 1, H_0)
+        return sp.vstack((W_1, H_1, H_2)) * w
+    return sp.csr_matrix(rec(1, 1))
+
+
+def framelet_operator(n, m, l):
+    """operators.py:104-113 (create_framelet_operator; `.H` of a real sparse matrix written as `.T`, which is what
+    scipy >= 1.14 still offers)."""
+    W_n, W_m = framelet_analysis(n, l), framelet_analysis(m, l)
+    k = 2 * l + 1
+    fwd = lambda x: (W_n @ (np.asarray(x).reshape(n, m, order="F") @ W_m.T)).reshape(-1, 1, order="F")  # noqa: E731
+    bwd = lambda x: (W_n.T @ (np.asarray(x).reshape(n * k, m * k, order="F") @ W_m)).reshape(-1, 1, order="F")  # noqa: E731
+    return FunctionOp(fwd, bwd, (n * k * m * k, n * m))
+
+
 def spacetime_derivative(nx, ny, nt):
     """operators.py:39-45."""
     ITLs = sp.kron(sp.identity(nt), first_derivative_2d(nx, ny))

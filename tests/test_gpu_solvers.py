@@ -203,9 +203,9 @@ def test_mmgks_group_sparsity_weights(tb):
     with exp(2) as smoothing constant - against the oracle's statement of the same lines, one frame and two frames."""
     nx = 24
     op, A, xt, b, delta = ct_problem(tb, nx, 16)
-    x, info = tb.MMGKS(op, b, None, pnorm=2, qnorm=1, projection_dim=3, n_iter=10, regparam="dp", delta=delta, x_true=xt,
+    x, info = tb.MMGKS(op, b, None, pnorm=2, qnorm=1, projection_dim=3, n_iter=10, regparam=0.3, x_true=xt,
                        GS="GS", prob_dims=(nx, nx, 1))
-    xo, io = O.MMGKS(A, b, None, pnorm=2, qnorm=1, projection_dim=3, n_iter=10, regparam="dp", delta=delta, x_true=xt,
+    xo, io = O.MMGKS(A, b, None, pnorm=2, qnorm=1, projection_dim=3, n_iter=10, regparam=0.3, x_true=xt,
                      GS="GS", prob_dims=(nx, nx, 1))
     print("MMGKS GS nt=1: iterate dev", rel(x, xo))
     assert rel(x, xo) < 1e-9
@@ -223,6 +223,30 @@ def test_mmgks_group_sparsity_weights(tb):
     xo, io = O.MMGKS(A2, b2, None, pnorm=2, qnorm=1, projection_dim=2, n_iter=8, regparam=0.05, GS="GS", prob_dims=(nx, nx, 2))
     print("MMGKS GS nt=2: iterate dev", rel(x, xo))
     assert rel(x, xo) < 1e-9
+
+
+def test_framelet_operator_and_mmgks_with_framelet_regulariser(tb):
+    """create_framelet_operator (trips/utilities/operators.py:104-113) as one Kronecker CSR matrix on the GPU against the
+    oracle's two-sided statement, and as the regularisation operator of MMGKS / GKS."""
+    import warnings
+
+    n = m = 24
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        W, Wo = tb.FrameletOperator(n, m, 2), O.framelet_operator(n, m, 2)
+    assert W.shape == Wo.shape == (25 * n * m, n * m)
+    rng = np.random.default_rng(0)
+    x, r = rng.standard_normal((n * m, 1)), rng.standard_normal((25 * n * m, 1))
+    assert rel(W @ x, Wo @ x) < 1e-15 and rel(W.T @ r, Wo.T @ r) < 1e-15
+    op, A, xt, b, delta = ct_problem(tb, n, 16)
+    # (fixed lambda: on this small problem the discrepancy principle returns 0 and the regulariser would drop out)
+    xg, ig = tb.MMGKS(op, b, W, pnorm=2, qnorm=1, projection_dim=3, n_iter=10, regparam=0.2, x_true=xt)
+    xo, io = O.MMGKS(A, b, Wo, pnorm=2, qnorm=1, projection_dim=3, n_iter=10, regparam=0.2, x_true=xt)
+    print("MMGKS with framelet L: iterate dev", rel(xg, xo))
+    assert rel(xg, xo) < 1e-9
+    xg, _ = tb.GKS(op, b, W, projection_dim=3, n_iter=8, regparam=0.1)
+    xo, _ = O.GKS(A, b, Wo, projection_dim=3, n_iter=8, regparam=0.1)
+    assert rel(xg, xo) < 1e-9
 
 
 def test_golden_deblur32(tb, golden_dir):

@@ -91,6 +91,39 @@ def test_product_l_curve_matches_reference_values():
         assert l_curve_curvature(0.05, A2, L2, b2) == lc.curvature(0.05, A2, L2, b2)
 
 
+def test_framelet_analysis_matrices_match_oracle_and_reference():
+    """trips/utilities/operators.py:50-101: the product's and the oracle's analysis matrices are the same matrix, equal -
+    in the build container - to the reference's create_analysis_operator entry for entry; level 1 is a tight frame."""
+    import warnings
+
+    import scipy.sparse as sp
+    from trips_b200.operators import framelet_analysis
+
+    def canon(M):
+        M = sp.csr_matrix(M)
+        M.sort_indices()
+        M.eliminate_zeros()
+        return M
+
+    import ref_loader
+
+    ref_ops = None
+    if ref_loader.available():
+        import importlib
+
+        ref_loader.load()
+        ref_ops = importlib.import_module("trips.utilities.operators")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for n, levels in ((8, 1), (9, 2), (16, 3), (7, 2)):
+            P, Q = canon(framelet_analysis(n, levels)), canon(O.framelet_analysis(n, levels))
+            assert P.shape == ((2 * levels + 1) * n, n) and abs(P - Q).max() == 0
+            if ref_ops is not None:
+                assert abs(P - canon(ref_ops.create_analysis_operator(n, levels))).max() == 0
+    W1 = framelet_analysis(12, 1)
+    assert abs(W1.T @ W1 - sp.identity(12)).max() < 1e-15
+
+
 def test_argument_errors_mirror_the_reference():
     """Raised before any device work (Hybrid_LSQR.py:59-61, Hybrid_GMRES.py:29-31, GKS.py:32-34)."""
     from trips_b200 import GKS, Hybrid_GMRES, Hybrid_LSQR

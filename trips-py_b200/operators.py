@@ -628,6 +628,66 @@ class CenteredDerivative2D(LinearOperator):
         return out
 
 
+# ---- framelet analysis operator -------------------------------------------------------------------------------------
+
+def framelet_filters(level, n):
+    """The three n x n filter matrices (low pass, two high passes) of the piecewise-linear B-spline framelet at one level,
+    reflective boundaries - trips/utilities/operators.py:50-83 (construct_H): stencils [1 2 1]/4, sqrt(2)/4 [-1 0 1],
+    [-1 2 -1]/4 with the two outer taps `level` samples away from the centre."""
+    import scipy.sparse as sp
+
+    ones = np.ones(n)
+    rows = np.arange(level)
+    lo_r, lo_c = rows, level - rows - 1                # taps falling off the left edge fold back onto these columns
+    hi_r, hi_c = n - 1 - rows, n - level + rows        # ... and off the right edge
+    out = []
+    for centre, left, right, fold_l, fold_r, scale in ((2.0, 1.0, 1.0, 1.0, 1.0, 0.25),
+                                                       (0.0, -1.0, 1.0, -1.0, 1.0, np.sqrt(2) / 4),
+                                                       (2.0, -1.0, -1.0, -1.0, -1.0, 0.25)):
+        H = sp.spdiags(left * ones, -level, n, n) + sp.spdiags(right * ones, level, n, n)
+        if centre:
+            H = H + sp.spdiags(centre * ones, 0, n, n)
+        H = H.tolil()
+        for r, c in zip(lo_r, lo_c):
+            H[r, c] += fold_l
+        for r, c in zip(hi_r, hi_c):
+            H[r, c] += fold_r
+        out.append((H.tocsr() * scale).tocsr())
+    return tuple(out)
+
+
+def framelet_analysis(n, levels):
+    """(2*levels+1) n x n analysis matrix, assembled exactly as the reference does (operators.py:86-101,
+    create_analysis_operator): the deepest level contributes its three filters as they are; every shallower level stacks
+    its two high passes under what came from below and multiplies the stack by the low pass handed down from above."""
+    import scipy.sparse as sp
+
+    def build(level, carry):
+        H0, H1, H2 = framelet_filters(level, n)
+        if level == levels:
+            return sp.vstack((H0, H1, H2)).tocsr()
+        below = build(level + 1, H0)
+        stack = sp.vstack((below, H1, H2)).tocsr()
+        return stack if carry is None else (stack @ carry).tocsr()
+
+    return build(1, None)
+
+
+class FrameletOperator(CSROperator):
+    """Two-dimensional framelet analysis operator W x = vec_F(W_n X W_m^T), X = x reshaped (n, m) in Fortran order -
+    `create_framelet_operator(n, m, l)` of the reference (trips/utilities/operators.py:104-113), used as the
+    regularisation operator L of GKS / MMGKS.  Applied as ONE sparse matrix, kron(W_m, W_n), through the CSR kernels
+    (the reference's two sparse-dense products sum in a different order: agreement to rounding, not bitwise)."""
+
+    def __init__(self, n, m, levels, device=None):
+        import scipy.sparse as sp
+
+        self.n, self.m, self.levels = int(n), int(m), int(levels)
+        Wn, Wm = framelet_analysis(self.n, self.levels), framelet_analysis(self.m, self.levels)
+        op = CSROperator.from_scipy(sp.kron(Wm, Wn, format="csr"), device)
+        super().__init__(op.A, op.AT, "sequential", op.A_sell, op.AT_sell)
+
+
 def as_operator(A, device=None):
     """Accept what the reference accepts for A / L and return a GPU operator: our operators pass through;
     scipy.sparse matrices and (small) dense arrays are uploaded as CSR with an explicit transpose."""
