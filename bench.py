@@ -277,7 +277,10 @@ def main():
     KM.spmv = timed_spmv
     KM.GK_STEP_EVENTS = step_events
     if proj is not None and world > 1:  # (single GPU: tb200_gk_step_ct_f64 records the events itself)
-        proj.forward, proj.backproject = timed(orig_proj[0]), timed(orig_proj[1])
+        # sharded: the back-projection runs in bands with the all-reduce of each band under the next band's kernel
+        # (dist.adjoint_allreduce), so its event pair covers kernels + the exposed tail of the reduction
+        proj.forward = timed(orig_proj[0])
+        st.be.adjoint_allreduce = timed(st.be.adjoint_allreduce)
     sampler.mark_begin()
     launches0 = _lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

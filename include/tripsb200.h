@@ -168,6 +168,11 @@ int64_t tb200_ct_backproject_workspace_len(int nx, int ny);
 int tb200_ct_backproject_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* u, double* y,
                              double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
                              void* stream);
+/* Image rows [iy_begin, iy_end) only (y, z indexed by the global pixel number): a row-sharded caller back-projects the
+ * image in bands and all-reduces each band while the next one is computed (trips-py_b200/dist.py). */
+int tb200_ct_backproject_rows_f64(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* geom,
+                                  const double* u, double* y, double coef_host, const double* coef_dev, const double* z,
+                                  double* norm_out, double* ws, void* stream);
 /* One Golub-Kahan step (trips/utilities/decompositions.py:230-255) on the matrix-free operator, as
  * tb200_gk_step_sell_f64; ws: max(tb200_spmv_workspace_len(m), tb200_ct_backproject_workspace_len(nx, ny)). */
 int tb200_gk_step_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,

@@ -58,6 +58,7 @@ SIGNATURES = {
     "tb200_ct_forward_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_backproject_workspace_len": (c_i64, [c_int, c_int]),
     "tb200_ct_backproject_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_ct_backproject_rows_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_gk_step_ct_f64": (c_int, [c_int, c_int, c_int, c_int] + [c_ptr] * 16),
     "tb200_correlate2d_f64": (c_int, [c_int, c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "tb200_fd_rows": (c_i64, [c_int, c_int, c_int, c_int]),

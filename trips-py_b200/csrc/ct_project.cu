@@ -86,15 +86,15 @@ __device__ __forceinline__ double bp_tile(double acc, const double* __restrict__
 
 template <int UNROLL>
 __global__ void __launch_bounds__(128, 8)
-ct_backproject_kernel(int nx, int ny, int n_det, int n_ang, const double* __restrict__ geom, const double* __restrict__ u,
-                      double* __restrict__ y, double coef_host, const double* __restrict__ coef_dev,
-                      const double* __restrict__ z, double* __restrict__ partials) {
+ct_backproject_kernel(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* __restrict__ geom,
+                      const double* __restrict__ u, double* __restrict__ y, double coef_host,
+                      const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials) {
   __shared__ __align__(16) double gtab[BP_TA * 6];
   __shared__ double red[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ix = blockIdx.x * 32 + warp * 8 + (lane & 7);
-  const int iy = blockIdx.y * 4 + (lane >> 3);
-  const bool valid = ix < nx && iy < ny;
+  const int iy = iy_begin + blockIdx.y * 4 + (lane >> 3);
+  const bool valid = ix < nx && iy < iy_end;
   const uint64_t pol_keep = policy_evict_last();
   const double cx = (double)ix - 0.5 * (double)(nx - 1), cy = (double)iy - 0.5 * (double)(ny - 1);
   const double dc = 0.5 * (double)(n_det - 1);
@@ -156,18 +156,33 @@ int64_t tb200_ct_backproject_workspace_len(int nx, int ny) {
 // y = A^T u - coef*z (z nullable; coef from coef_dev if non-null), optional norm_out = (||y||^2, ||y||), for the
 // parallel-beam matrix of n_ang angles (geom from tb200_ct_geometry), u angle-major (angle*n_det + detector),
 // y row-major (iy*nx + ix).  No matrix is read.  Same bits as tb200_spmv_sell_f64 on tb200_ct_fill_cols' matrix.
+// The _rows form computes only image rows [iy_begin, iy_end) (y, z still indexed by the global pixel number; the norm
+// covers those rows): a sharded caller back-projects the image in bands and all-reduces each band while the next
+// one is being computed.
+int tb200_ct_backproject_rows_f64(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* geom,
+                                  const double* u, double* y, double coef_host, const double* coef_dev, const double* z,
+                                  double* norm_out, double* ws, void* stream);
+
 int tb200_ct_backproject_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* u, double* y,
                              double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
                              void* stream) {
+  return tb200_ct_backproject_rows_f64(nx, ny, 0, ny, n_det, n_ang, geom, u, y, coef_host, coef_dev, z, norm_out, ws, stream);
+}
+
+int tb200_ct_backproject_rows_f64(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* geom,
+                                  const double* u, double* y, double coef_host, const double* coef_dev, const double* z,
+                                  double* norm_out, double* ws, void* stream) {
   TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0, "bad geometry");
+  TB200_REQUIRE(0 <= iy_begin && iy_begin <= iy_end && iy_end <= ny, "bad row band");
+  if (iy_begin == iy_end) return 0;
   TB200_REQUIRE((int64_t)nx * ny < ((int64_t)1 << 31) && (int64_t)n_ang * n_det < ((int64_t)1 << 31), "index space exceeds int32");
   TB200_REQUIRE(y && (n_ang == 0 || (geom && u)), "null pointer");
   TB200_REQUIRE(((uintptr_t)geom % 16) == 0, "geom must be 16-byte aligned");
   TB200_REQUIRE(norm_out == nullptr || ws != nullptr, "norm_out requires a workspace");
   cudaStream_t st = (cudaStream_t)stream;
-  const dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((ny + 3) / 4));
+  const dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((iy_end - iy_begin + 3) / 4));
   TB200_REQUIRE(grid.y <= 65535u, "ny too large for this launch shape");
-  ct_backproject_kernel<4><<<grid, 128, 0, st>>>(nx, ny, n_det, n_ang, geom, u, y, coef_host, coef_dev, z,
+  ct_backproject_kernel<4><<<grid, 128, 0, st>>>(nx, ny, iy_begin, iy_end, n_det, n_ang, geom, u, y, coef_host, coef_dev, z,
                                                  norm_out ? ws : nullptr);
   int rc = check_launch("ct_backproject");
   if (rc) return rc;

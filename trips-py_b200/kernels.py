@@ -582,6 +582,17 @@ class CTProjector:
         _lib.count(2 if norm_out is not None else 1)
         return out
 
+    def backproject_rows(self, u, out, iy_begin, iy_end):
+        """Image rows [iy_begin, iy_end) of A^T u into out (full-length vector): bands for comm/compute overlap."""
+        m, n = self.shape
+        _vec(u, m, "u")
+        _vec(out, n, "out")
+        check(lib().tb200_ct_backproject_rows_f64(self.nx, self.ny, int(iy_begin), int(iy_end), self.n_det, self.n_ang,
+                                                  _p(self.geom), _p(u), _p(out), 0.0, None, None, None, None, _stream()),
+              "ct_backproject_rows")
+        _lib.count(1)
+        return out
+
     def backproject(self, u, out=None, coef=None, z=None, norm_out=None):
         m, n = self.shape
         _vec(u, m, "u")
