@@ -277,10 +277,15 @@ def main():
     KM.spmv = timed_spmv
     KM.GK_STEP_EVENTS = step_events
     if proj is not None and world > 1:  # (single GPU: tb200_gk_step_ct_f64 records the events itself)
-        # sharded: the back-projection runs in bands with the all-reduce of each band under the next band's kernel
-        # (dist.adjoint_allreduce), so its event pair covers kernels + the exposed tail of the reduction
+        # sharded, TB200_ADJOINT_BANDS > 1: the back-projection runs in bands with the all-reduce of each band under the
+        # next band's kernel (dist.adjoint_allreduce), so its event pair covers kernels + the exposed tail of the reduction
+        from trips_b200 import dist as tbdist
+
         proj.forward = timed(orig_proj[0])
-        st.be.adjoint_allreduce = timed(st.be.adjoint_allreduce)
+        if tbdist.ADJOINT_BANDS > 1:
+            st.be.adjoint_allreduce = timed(st.be.adjoint_allreduce)
+        else:
+            proj.backproject = timed(orig_proj[1])  # kernel only; the all-reduce follows it
     sampler.mark_begin()
     launches0 = _lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
