@@ -5,17 +5,20 @@
 
 One "step" = one Golub-Kahan iteration (the reference's golub_kahan_update, trips/utilities/decompositions.py:230-255):
 v = A^T u - beta v_prev, alpha = ||v||, v /= alpha, u = A v - alpha u_prev, beta = ||u||, u /= beta, with U and V retained.
-Workload at N = 1: configs[3]'s geometry (2048^2 pixels, 720 angles, 2896 detector bins; A and the explicit A^T in
-CSR, fp64 values, int32 column indices, int64 row pointers: ~92 GB) - it fits one 180 GB B200.  For N > 1 the rows
-are sharded by projection angle (strong scaling: the problem is fixed), one all-reduce of an n-vector and one
-scalar all-reduce per iteration over NCCL.
+Workload at N = 1: configs[3]'s geometry (2048^2 pixels, 720 angles, 2896 detector bins, nnz 3.85e9).  Default layout
+'implicit': the matrix VALUES are re-evaluated inside the kernels (forward projection streams A's column indices only,
+15.7 GB; back-projection is matrix-free) - bit-identical to the stored layouts '--layout sell' / '--layout csr' (A and
+the explicit A^T, fp64 values, int32 column indices, int64 row pointers: ~92 GB, which also fits one 180 GB B200).
+For N > 1 the rows are sharded by projection angle (strong scaling: the problem is fixed), one all-reduce of an
+n-vector and one scalar all-reduce per iteration over NCCL.
 
 JSON keys beyond the base contract:
   value      it/s with every input resident in HBM (CUDA events around exactly K steps, max over ranks)
   e2e        it/s through the reference-signature call golub_kahan_update(A, U, S, V) with HOST (NumPy) U, S, V:
              every step copies u_k and v_{k-1} host->device and the new u, v device->host inside the timed region
-  roofline   dominant kernel (CSR SpMV): algorithmic bytes per launch / mean launch duration measured with CUDA
-             events inside the timed region, against MEASURED_PEAKS.json's HBM copy bandwidth
+  roofline   dominant kernel (the forward projection; `back_projection` holds the other launch): SURVEY 8(d)'s
+             algorithmic bytes per launch / launch duration measured with CUDA events inside the timed region, against
+             MEASURED_PEAKS.json's HBM copy bandwidth; `traffic` = DRAM bytes the kernel really moves (ncu)
   cpu_baseline  the oracle's golub_kahan_update (NumPy + scipy.sparse, the reference's arithmetic) on a bounded sample
 --impl reference times that CPU path as its own arm (rank 0 only).
 """
