@@ -154,16 +154,22 @@ int tb200_ctfan_fill_cols(double so, double dd, double dps, int nx, int ny, int 
  * Row-aligned index layout (optional, rowskip nullable): tb200_ct_count_rows_first also reports the first image row each
  * ray crosses; the caller derives rowskip[r] (leading padding of row r inside its lane) so that the 32 rays of a slice
  * walk through the same image rows at the same positions - their x-gathers then share 32-byte sectors - and
- * tb200_ct_fill_rows_aligned writes the column indices at [rowskip[r], rowskip[r] + rowlen[r]). */
+ * tb200_ct_fill_rows_aligned writes the column indices at [rowskip[r], rowskip[r] + rowlen[r]).
+ * Shallow rays (|sin| > |cos|) run along the image rows: neighbouring rays then sit in DIFFERENT rows and their gathers
+ * share nothing.  With transpose_shallow != 0 their indices address the transposed image (ix*ny + iy), which
+ * tb200_ct_forward_f64 forms in xT_scratch (nx*ny doubles) before the product: they then behave like steep rays.
+ * first_run (nullable output of the count pass) is their alignment key: distance along x, from the side the ray comes
+ * from, at which it enters its first row.  The order in which a row's entries are added never changes. */
 int tb200_ct_geometry(int n_ang, const double* cosv, const double* sinv, double* geom, void* stream);
 int tb200_ct_count_rows_first(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
-                              int32_t* counts, int32_t* first_row, void* stream);
+                              int32_t* counts, int32_t* first_row, int32_t* first_run, void* stream);
 int tb200_ct_fill_rows_aligned(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
-                               const int64_t* sliceptr, const int32_t* rowskip, int32_t* colidx, void* stream);
+                               const int64_t* sliceptr, const int32_t* rowskip, int transpose_shallow, int32_t* colidx,
+                               void* stream);
 int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
                          const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
-                         const double* x, double* y, double coef_host, const double* coef_dev, const double* z,
-                         double* norm_out, double* ws, void* stream);
+                         double* xT_scratch, const double* x, double* y, double coef_host, const double* coef_dev,
+                         const double* z, double* norm_out, double* ws, void* stream);
 int64_t tb200_ct_backproject_workspace_len(int nx, int ny);
 int tb200_ct_backproject_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* u, double* y,
                              double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
@@ -177,8 +183,9 @@ int tb200_ct_backproject_rows_f64(int nx, int ny, int iy_begin, int iy_end, int 
  * tb200_gk_step_sell_f64; ws: max(tb200_spmv_workspace_len(m), tb200_ct_backproject_workspace_len(nx, ny)). */
 int tb200_gk_step_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
                          const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
-                         const double* u_k, const double* v_prev, const double* beta_prev_dev, double* v_out, double* u_out,
-                         double* alpha_pair, double* beta_pair, double* ws, void* const* events_host, void* stream);
+                         double* xT_scratch, const double* u_k, const double* v_prev, const double* beta_prev_dev,
+                         double* v_out, double* u_out, double* alpha_pair, double* beta_pair, double* ws,
+                         void* const* events_host, void* stream);
 
 /* ---- stencils ---------------------------------------------------------------------------------------------
  * PSF blur and its reference "adjoint": trips/test_problems/Deblurring2D.py:66-73 (scipy.ndimage.convolve,

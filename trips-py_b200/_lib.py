@@ -53,13 +53,13 @@ SIGNATURES = {
     "tb200_ctfan_count_cols": (c_int, [c_dbl, c_dbl, c_dbl, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ctfan_fill_cols": (c_int, [c_dbl, c_dbl, c_dbl, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_geometry": (c_int, [c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "tb200_ct_count_rows_first": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "tb200_ct_fill_rows_aligned": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "tb200_ct_forward_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_ct_count_rows_first": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_ct_fill_rows_aligned": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr]),
+    "tb200_ct_forward_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_backproject_workspace_len": (c_i64, [c_int, c_int]),
     "tb200_ct_backproject_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_backproject_rows_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "tb200_gk_step_ct_f64": (c_int, [c_int, c_int, c_int, c_int] + [c_ptr] * 16),
+    "tb200_gk_step_ct_f64": (c_int, [c_int, c_int, c_int, c_int] + [c_ptr] * 17),
     "tb200_correlate2d_f64": (c_int, [c_int, c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "tb200_fd_rows": (c_i64, [c_int, c_int, c_int, c_int]),
     "tb200_fd_apply": (c_int, [c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_dbl, c_ptr]),

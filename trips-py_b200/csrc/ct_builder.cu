@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256)
 ct_rows_kernel(Beam bm, int nx, int ny, int n_det, int n_ang, const double* __restrict__ cosv,
                const double* __restrict__ sinv, int32_t* __restrict__ counts, const int64_t* __restrict__ rowptr, int sell,
                int32_t* __restrict__ col, double* __restrict__ val, int32_t* __restrict__ first_row,
-               const int32_t* __restrict__ rowskip) {
+               const int32_t* __restrict__ rowskip, int32_t* __restrict__ first_run, int tshallow) {
   const int lane = threadIdx.x & 31;
   const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (ray >= (int64_t)n_ang * n_det) return;
@@ -132,12 +132,15 @@ ct_rows_kernel(Beam bm, int nx, int ny, int n_det, int n_ang, const double* __re
   int64_t base = (FILL && rowskip != nullptr) ? rowskip[ray] : 0;  // position of the next entry of this row
   int total = 0;
   int first = ny;  // first image row the ray crosses
+  int first_lo = 0, first_hi = 0;  // ... and the run of pixels it crosses there
+  // index-only layouts can address a shallow ray's pixels in the TRANSPOSED image (ix*ny + iy): see spmv.cu, CtRays::xT
+  const bool tmode = tshallow && fabs(g.s) > fabs(g.c);
   for (int iy0 = 0; iy0 < ny; iy0 += 32) {
     const int iy = iy0 + lane;
     int lo = 0, hi = -1;
     if (iy < ny) row_range(g, sd, iy, nx, ny, lo, hi);
     const int cnt = (hi >= lo) ? (hi - lo + 1) : 0;
-    if (cnt > 0 && iy < first) first = iy;
+    if (cnt > 0 && iy < first) first = iy, first_lo = lo, first_hi = hi;
     if (FILL) {
       int chunk;
       const int off = warp_excl_scan(cnt, lane, chunk);
@@ -145,7 +148,7 @@ ct_rows_kernel(Beam bm, int nx, int ny, int n_det, int n_ang, const double* __re
       int64_t j = base + off;
       for (int ix = lo; ix <= hi; ++ix, ++j) {
         const int64_t pos = entry_addr(rowptr, sell, ray, j);
-        col[pos] = iy * nx + ix;
+        col[pos] = tmode ? ix * ny + iy : iy * nx + ix;
         if (val != nullptr) val[pos] = chord(g, ray_pixel_t(g, sd, (double)ix - x0, cy));
       }
       base += chunk;
@@ -154,6 +157,7 @@ ct_rows_kernel(Beam bm, int nx, int ny, int n_det, int n_ang, const double* __re
     }
   }
   if (!FILL) {
+    const int mine = first;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       total += __shfl_xor_sync(0xffffffffu, total, o);
@@ -162,6 +166,12 @@ ct_rows_kernel(Beam bm, int nx, int ny, int n_det, int n_ang, const double* __re
     if (lane == 0) {
       counts[ray] = total;
       if (first_row != nullptr) first_row[ray] = first;
+    }
+    // the lane that saw the first row reports where the ray enters it, as a distance travelled along x: the ray moves
+    // towards +x with increasing row index when s/c < 0, towards -x otherwise
+    if (first_run != nullptr && first < ny && mine == first) {
+      const bool rightwards = (g.s < 0.0) != (g.c < 0.0);
+      first_run[ray] = rightwards ? first_lo : (nx - 1 - first_hi);
     }
   }
 }
@@ -238,27 +248,27 @@ static int fan_args_ok(double so, double dd, double dps, int nx, int ny) {
 }
 
 static int count_rows(Beam bm, int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv, int32_t* counts,
-                      void* stream, int32_t* first_row = nullptr) {
+                      void* stream, int32_t* first_row = nullptr, int32_t* first_run = nullptr) {
   int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
   if (rc) return rc;
   const int64_t rays = (int64_t)n_ang * n_det;
   if (rays == 0) return 0;
   TB200_REQUIRE(counts, "null counts");
   ct_rows_kernel<false><<<(unsigned)((rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      bm, nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, 0, nullptr, nullptr, first_row, nullptr);
+      bm, nx, ny, n_det, n_ang, cosv, sinv, counts, nullptr, 0, nullptr, nullptr, first_row, nullptr, first_run, 0);
   return check_launch("ct_count_rows");
 }
 
 static int fill_rows(Beam bm, int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
                      const int64_t* rowptr, int sell, int32_t* colidx, double* vals, void* stream,
-                     const int32_t* rowskip = nullptr) {
+                     const int32_t* rowskip = nullptr, int tshallow = 0) {
   int rc = ct_args_ok(nx, ny, n_det, n_ang, cosv, sinv);
   if (rc) return rc;
   const int64_t rays = (int64_t)n_ang * n_det;
   if (rays == 0) return 0;
   TB200_REQUIRE(rowptr && colidx, "null output");
   ct_rows_kernel<true><<<(unsigned)((rays * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      bm, nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, sell, colidx, vals, nullptr, rowskip);
+      bm, nx, ny, n_det, n_ang, cosv, sinv, nullptr, rowptr, sell, colidx, vals, nullptr, rowskip, nullptr, tshallow);
   return check_launch("ct_fill_rows");
 }
 
@@ -305,14 +315,20 @@ int tb200_ct_fill_rows(int nx, int ny, int n_det, int n_ang, const double* cosv,
 // fill pass: column indices only, SELL-32-4, entry j of ray r at position rowskip[r] + j of its lane: the caller
 // chooses rowskip so that the 32 rays of a slice walk through the same image rows at the same positions (their
 // x-gathers then share sectors); skipped positions stay zero-filled and are masked by the kernel.
+// first_run[ray] (nullable): how far along x, measured from the side it comes from, the ray enters its first row - the
+// alignment key of shallow rays.  transpose_shallow != 0: rays with |sin| > |cos| get the column index ix*ny + iy (their
+// pixels addressed in the transposed image, which tb200_ct_forward_f64 forms in its xT scratch): neighbouring shallow
+// rays then gather neighbouring addresses, exactly as steep rays do in the image itself.
 int tb200_ct_count_rows_first(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
-                              int32_t* counts, int32_t* first_row, void* stream) {
+                              int32_t* counts, int32_t* first_row, int32_t* first_run, void* stream) {
   TB200_REQUIRE(first_row != nullptr || (int64_t)n_ang * n_det == 0, "null first_row");
-  return count_rows(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, counts, stream, first_row);
+  return count_rows(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, counts, stream, first_row, first_run);
 }
 int tb200_ct_fill_rows_aligned(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
-                               const int64_t* sliceptr, const int32_t* rowskip, int32_t* colidx, void* stream) {
-  return fill_rows(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, sliceptr, 1, colidx, nullptr, stream, rowskip);
+                               const int64_t* sliceptr, const int32_t* rowskip, int transpose_shallow, int32_t* colidx,
+                               void* stream) {
+  return fill_rows(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, sliceptr, 1, colidx, nullptr, stream, rowskip,
+                   transpose_shallow);
 }
 
 // counts[pixel] = number of rays crossing the pixel (rows of A^T).

@@ -201,13 +201,14 @@ int tb200_ct_backproject_rows_f64(int nx, int ny, int iy_begin, int iy_end, int 
 int tb200_vec_div(int64_t n, const double* x, double d_host, const double* d_dev, double* out, void* stream);
 int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
                          const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
-                         const double* x, double* y, double coef_host, const double* coef_dev, const double* z,
-                         double* norm_out, double* ws, void* stream);
+                         double* xT_scratch, const double* x, double* y, double coef_host, const double* coef_dev,
+                         const double* z, double* norm_out, double* ws, void* stream);
 
 int tb200_gk_step_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
                          const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
-                         const double* u_k, const double* v_prev, const double* beta_prev_dev, double* v_out, double* u_out,
-                         double* alpha_pair, double* beta_pair, double* ws, void* const* events_host, void* stream) {
+                         double* xT_scratch, const double* u_k, const double* v_prev, const double* beta_prev_dev,
+                         double* v_out, double* u_out, double* alpha_pair, double* beta_pair, double* ws,
+                         void* const* events_host, void* stream) {
   TB200_REQUIRE(u_k && v_out && u_out && alpha_pair && beta_pair && ws, "null pointer");
   TB200_REQUIRE((v_prev == nullptr) == (beta_prev_dev == nullptr), "v_prev and beta_prev_dev go together");
   cudaStream_t st = (cudaStream_t)stream;
@@ -222,7 +223,7 @@ int tb200_gk_step_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geo
   rc = tb200_vec_div(n, v_out, 0.0, alpha_pair + 1, v_out, stream);
   if (rc) return rc;
   mark(2);
-  rc = tb200_ct_forward_f64(nx, ny, n_det, n_ang, geom, sliceptr, rowlen, rowskip, colidx, cta_order, v_out, u_out, 0.0,
+  rc = tb200_ct_forward_f64(nx, ny, n_det, n_ang, geom, sliceptr, rowlen, rowskip, colidx, cta_order, xT_scratch, v_out, u_out, 0.0,
                             alpha_pair + 1, u_k, beta_pair, ws, stream);
   mark(3);
   if (rc) return rc;

@@ -537,10 +537,29 @@ struct SellVals<float> {
 // GEOM = true: the matrix is the parallel-beam CT matrix A (rows = rays) and its VALUES ARE NOT STORED: an entry is
 // re-evaluated from its column index and the ray's geometry (tb200_ctgeom.cuh, ~9 fp64 instructions, same bits as the
 // builder writes) while the index stream - 4 bytes per entry instead of 12 - and the gathers are in flight.
+// out[c*rows + r] = in[r*cols + c] (rows x cols, row-major), 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+transpose_f64_kernel(int rows, int cols, const double* __restrict__ in, double* __restrict__ out) {
+  __shared__ double tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = in[(int64_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(int64_t)c * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
 struct CtRays {
   const double* geom;  // 6 doubles per angle: c, s, d2, 1/hi, 1/(hi*lo), 0
   const int32_t* cta_order;  // nullable: CTA b works on slice group cta_order[b] (longest first: no straggler tail)
   const int32_t* rowskip;    // nullable: row r's entries start at position rowskip[r] of its lane (row-aligned slices)
+  const double* xT;          // nullable: the transposed image; rays with |sin| > |cos| then carry indices ix*ny + iy
+  uint32_t ny_magic;         // as nx_magic, for the division by ny of those indices
+  int ny_shift;
   int nx, ny, n_det;
   uint32_t nx_magic;   // floor(2^(32+nx_shift) / nx) clipped to 2^32-1: col / nx = umulhi(col, magic) >> shift (+1 fix-up)
   int nx_shift;
@@ -580,24 +599,35 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
   const int32_t* cp = col + base + lane * 4;
   const VT* vp = val + base + lane * 4;
 
-  // GEOM: this lane's ray
+  // GEOM: this lane's ray.  An index is q*div + r: (q, r) = (iy, ix) in the image, or (ix, iy) for a shallow ray that
+  // addresses the transposed image.  proj = cx*c + cy*s is formed as r-term + q-term either way (a + b == b + a).
   RayGeom g = {1.0, 0.0, 0.5, 1.0, 1.0};
-  double sd = 0.0, bx = 0.0, by = 0.0;
+  double sd = 0.0, bias_q = 0.0, bias_r = 0.0, coef_q = 0.0, coef_r = 0.0;
+  uint32_t dmagic = ct.nx_magic;
+  int dshift = ct.nx_shift, ddiv = ct.nx;
+  const double* xb = x;  // where this lane's indices point
   if (GEOM) {
     const int64_t r = (row < m) ? row : 0;
     const int a = (int)(r / ct.n_det), d = (int)(r - (int64_t)a * ct.n_det);
     const double* gp = ct.geom + 6 * (int64_t)a;
     g.c = gp[0], g.s = gp[1], g.d2 = gp[2], g.inv_hi = gp[3], g.inv_hilo = gp[4];
     sd = (double)d - 0.5 * (double)(ct.n_det - 1);
-    bx = centred_bias(ct.nx), by = centred_bias(ct.ny);
+    const bool tmode = ct.xT != nullptr && fabs(g.s) > fabs(g.c);
+    if (tmode) {
+      xb = ct.xT, dmagic = ct.ny_magic, dshift = ct.ny_shift, ddiv = ct.ny;
+      bias_q = centred_bias(ct.nx), coef_q = g.c, bias_r = centred_bias(ct.ny), coef_r = g.s;
+    } else {
+      bias_q = centred_bias(ct.ny), coef_q = g.s, bias_r = centred_bias(ct.nx), coef_r = g.c;
+    }
   }
   auto entry_values = [&](const int32_t (&c)[CH], double (&v)[CH]) {
 #pragma unroll
     for (int k = 0; k < CH; ++k) {
-      int iy = (int)(__umulhi((uint32_t)c[k], ct.nx_magic) >> ct.nx_shift);
-      int ix = c[k] - iy * ct.nx;
-      if (ix >= ct.nx) ix -= ct.nx, ++iy;
-      v[k] = chord(g, ray_pixel_t(g, sd, centred_coord(ix, bx), centred_coord(iy, by)));
+      int q = (int)(__umulhi((uint32_t)c[k], dmagic) >> dshift);
+      int r = c[k] - q * ddiv;
+      if (r >= ddiv) r -= ddiv, ++q;
+      const double proj = __dadd_rn(__dmul_rn(centred_coord(r, bias_r), coef_r), __dmul_rn(centred_coord(q, bias_q), coef_q));
+      v[k] = chord(g, __dsub_rn(sd, proj));
     }
   };
 
@@ -631,7 +661,7 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
   const int gk = lane % CH, gr = lane / CH;  // row-major mode: my entry / which row of the request's group
   auto gather_lane_per_row = [&](const int32_t (&c)[CH], double (&xv)[CH]) {
 #pragma unroll
-    for (int k = 0; k < CH; ++k) xv[k] = ld_gather_f64(x + c[k], pol_keep);
+    for (int k = 0; k < CH; ++k) xv[k] = ld_gather_f64(xb + c[k], pol_keep);
   };
   auto gather_row_major = [&](const int32_t (&c)[CH], double (&xv)[CH]) {
     // publish my row's columns, then request j gathers entries 0..CH-1 of rows RPR*j .. RPR*j + RPR-1
@@ -674,7 +704,7 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
       const unsigned along = __ballot_sync(0xffffffffu, ok && (c1[PB + 1] - c1[PB]) <= 2 && (c1[PB] - c1[PB - 1]) <= 2);
       const unsigned across = __ballot_sync(0xffffffffu, ok && okn && abs(c1[PB] - cn) <= 6);
       row_major = __popc(along) > __popc(across) + 8;
-      if (gather_mode == 1) row_major = false;
+      if (gather_mode == 1 || (GEOM && ct.xT != nullptr)) row_major = false;  // shallow rays read the transposed image
       if (gather_mode == 2) row_major = true;
     }
     if (row_major) gather_row_major(c1, x0);
@@ -1088,11 +1118,12 @@ int tb200_spmv_sell_f32s(int64_t m, int64_t n, const int64_t* sliceptr, const in
 // (row = angle*n_det + detector).  Bit-identical to tb200_spmv_sell_f64 on the matrix tb200_ct_fill_rows writes.
 // cta_order (nullable): a permutation of the ceil(ceil(m/32)/4) groups of four slices, heaviest first, so that the
 // long central rays are scheduled before the short peripheral ones.  rowskip (nullable): leading padding of each row
-// inside its lane (tb200_ct_fill_rows_aligned).
+// inside its lane (tb200_ct_fill_rows_aligned).  xT_scratch: nx*ny doubles, REQUIRED iff the indices were filled with
+// transpose_shallow != 0 (the image is transposed into it first), NULL otherwise.
 int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
                          const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
-                         const double* x, double* y, double coef_host, const double* coef_dev, const double* z,
-                         double* norm_out, double* ws, void* stream) {
+                         double* xT_scratch, const double* x, double* y, double coef_host, const double* coef_dev,
+                         const double* z, double* norm_out, double* ws, void* stream) {
   TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0 && (int64_t)nx * ny < ((int64_t)1 << 31), "bad geometry");
   const int64_t m = (int64_t)n_ang * n_det;
   int rc = check_sell_args(m, (int64_t)nx * ny, sliceptr, rowlen, colidx, nullptr, x, y, norm_out, ws);
@@ -1103,6 +1134,18 @@ int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geo
   ct.geom = geom;
   ct.cta_order = (g_sell_warps == 4) ? cta_order : nullptr;  // the order is a permutation of groups of FOUR slices
   ct.rowskip = rowskip;
+  ct.xT = xT_scratch;
+  int shy = 0;
+  while ((2u << shy) <= (uint32_t)ny) ++shy;
+  const uint64_t mgy = (((uint64_t)1) << (32 + shy)) / (uint64_t)ny;
+  ct.ny_magic = (uint32_t)(mgy > 0xffffffffull ? 0xffffffffull : mgy);
+  ct.ny_shift = shy;
+  if (xT_scratch != nullptr) {  // xT[ix*ny + iy] = x[iy*nx + ix]
+    const dim3 tg((unsigned)((nx + 31) / 32), (unsigned)((ny + 31) / 32));
+    transpose_f64_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(ny, nx, x, xT_scratch);
+    rc = check_launch("ct_forward transpose");
+    if (rc) return rc;
+  }
   ct.nx = nx, ct.ny = ny, ct.n_det = n_det;
   int sh = 0;
   while ((2u << sh) <= (uint32_t)nx) ++sh;  // floor(log2(nx))

@@ -513,13 +513,20 @@ class CTProjector:
         check(lib().tb200_ct_geometry(self.n_ang, _p(cos_t), _p(sin_t), _p(self.geom), _stream()), "ct_geometry")
         self.rowlen = torch.zeros(m, dtype=torch.int32, device=dev)
         first = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
+        run0 = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
         check(lib().tb200_ct_count_rows_first(self.nx, self.ny, self.n_det, self.n_ang, _p(cos_t), _p(sin_t),
-                                              _p(self.rowlen), _p(first), _stream()), "ct_count")
-        # Row alignment.  Lane = ray; the 32 rays of a slice are neighbours on the detector.  A steep ray (|cos| >= |sin|)
-        # crosses every image row in 1 + |tan| pixels on average, but rays that enter through the side of the image start
-        # at different rows, so at the same position j the lanes would sit in different rows and every x-gather would
-        # touch its own sector.  Give each ray a leading padding of (its first row - the slice's first row) * (1 + |tan|)
-        # positions: the lanes then walk through the same rows together (simulated: 0.49 -> 0.35 sectors per entry).
+                                              _p(self.rowlen), _p(first), _p(run0), _stream()), "ct_count")
+        # Shallow rays (|sin| > |cos|) run along the image rows: neighbouring rays sit in different rows, so in the image
+        # their gathers share nothing.  Their indices therefore address the TRANSPOSED image (formed per product in a
+        # scratch vector), where they behave exactly like steep rays do in the image itself.
+        self.tshallow = os.environ.get("TB200_CT_TRANSPOSE", "1") != "0"
+        self.xT = torch.empty(self.shape[1], dtype=F64, device=dev) if self.tshallow else None
+        # Alignment.  Lane = ray; the 32 rays of a slice are neighbours on the detector.  A steep ray crosses every image
+        # row in 1 + |tan| pixels on average, but rays that enter through the side of the image start at different rows,
+        # so at the same position j the lanes would sit in different rows and every x-gather would touch its own
+        # sector.  Give each ray a leading padding of (its first row - the slice's first row) * (1 + |tan|) positions:
+        # the lanes then walk through the same rows together (simulated: 0.49 -> 0.35 sectors per entry).  Shallow rays
+        # in the transposed image: the same with rows and columns exchanged (key: where the ray enters its first row).
         self.rowskip = None
         span = self.rowlen
         if os.environ.get("TB200_CT_ALIGN", "1") == "0":  # measurement switch (tools/mf_probe.py)
@@ -527,26 +534,35 @@ class CTProjector:
         if align and m > 0:
             nsl = (m + 31) // 32
             big = torch.iinfo(torch.int32).max
-            f = torch.full((nsl * 32,), big, dtype=torch.int32, device=dev)
-            f[:m] = torch.where(self.rowlen > 0, first[:m], torch.full_like(first[:m], big))
-            fmin = f.view(nsl, 32).min(dim=1).values.repeat_interleave(32)[:m]
             ang = torch.arange(m, device=dev, dtype=torch.int64) // self.n_det
             ct, st = cos_t.abs()[ang], sin_t.abs()[ang]
+            steep = ct >= st
+            live = self.rowlen > 0
+
+            def lead_of(key, mask, rate):
+                """rate * (key - min of key over the slice's rows selected by mask), 0 elsewhere"""
+                f = torch.full((nsl * 32,), big, dtype=torch.int32, device=dev)
+                f[:m] = torch.where(mask, key[:m], torch.full_like(key[:m], big))
+                fmin = f.view(nsl, 32).min(dim=1).values.repeat_interleave(32)[:m]
+                return torch.where(mask, (f[:m] - fmin).to(F64) * rate, torch.zeros_like(rate))
+
             # measured (tools/mf_probe.py, bench.py): aligning the rays up to 45 degrees is best when the launch has many
             # waves of CTAs (whole cfg4 problem: 6.93 vs 7.10 ms); on an angle shard (1/8 of the rows, ~3 waves) the
             # padding of the longest, near-diagonal slices lengthens the critical path, and stopping at tan = 0.7 wins
             # (0.99 vs 1.13 ms)
             waves = (m / 128.0) / (4 * torch.cuda.get_device_properties(dev).multi_processor_count)
             tan_max = float(os.environ.get("TB200_CT_ALIGN_TAN", "1.0" if waves >= 8 else "0.7"))
-            rate = torch.where(st <= tan_max * ct, 1.0 + st / ct.clamp_min(1e-300), torch.zeros_like(ct))  # others: no padding
-            lead = torch.where(self.rowlen > 0, (f[:m] - fmin).to(F64) * rate, torch.zeros_like(rate))
+            lead = lead_of(first, live & steep & (st <= tan_max * ct), 1.0 + st / ct.clamp_min(1e-300))
+            if self.tshallow:
+                lead = lead + lead_of(run0, live & ~steep & (ct <= tan_max * st), 1.0 + ct / st.clamp_min(1e-300))
             self.rowskip = torch.floor(lead).to(torch.int32).contiguous()
             span = self.rowlen + self.rowskip
         self.sliceptr = sell_slice_pointers(span)
         total = int(self.sliceptr[-1].item())
         self.colidx = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)[:total]
         check(lib().tb200_ct_fill_rows_aligned(self.nx, self.ny, self.n_det, self.n_ang, _p(cos_t), _p(sin_t),
-                                               _p(self.sliceptr), _p(self.rowskip), _p(self.colidx), _stream()), "ct_fill")
+                                               _p(self.sliceptr), _p(self.rowskip), int(self.tshallow), _p(self.colidx),
+                                               _stream()), "ct_fill")
         _lib.count(3)
         self.stored = total
         self.nnz = int(self.rowlen.sum().item())
@@ -560,7 +576,8 @@ class CTProjector:
 
     @property
     def nbytes(self):
-        return 4 * self.stored + 8 * self.sliceptr.numel() + 4 * self.rowlen.numel() + 8 * self.geom.numel()
+        return (4 * self.stored + 8 * self.sliceptr.numel() + 4 * self.rowlen.numel() + 8 * self.geom.numel()
+                + (8 * self.xT.numel() if self.xT is not None else 0))
 
     def _coef(self, coef, z):
         if z is None:
@@ -576,7 +593,8 @@ class CTProjector:
         ch, cd = self._coef(coef, z)
         ws = Workspace.get(self.device).spmv(m) if norm_out is not None else None
         check(lib().tb200_ct_forward_f64(self.nx, self.ny, self.n_det, self.n_ang, _p(self.geom), _p(self.sliceptr),
-                                         _p(self.rowlen), _p(self.rowskip), _p(self.colidx), _p(self.cta_order), _p(x), _p(out), ch, _p(cd), _p(z),
+                                         _p(self.rowlen), _p(self.rowskip), _p(self.colidx), _p(self.cta_order), _p(self.xT), _p(x), _p(out), ch,
+                                         _p(cd), _p(z),
                                          _p(norm_out),
                                          _p(ws), _stream()), "ct_forward")
         _lib.count(2 if norm_out is not None else 1)
@@ -618,7 +636,7 @@ class CTProjector:
         if GK_STEP_EVENTS is not None:
             ev = (ctypes.c_void_p * 4)(*[e.cuda_event for e in GK_STEP_EVENTS()])
         check(lib().tb200_gk_step_ct_f64(self.nx, self.ny, self.n_det, self.n_ang, _p(self.geom), _p(self.sliceptr),
-                                         _p(self.rowlen), _p(self.rowskip), _p(self.colidx), _p(self.cta_order), _p(u_k), _p(v_prev),
+                                         _p(self.rowlen), _p(self.rowskip), _p(self.colidx), _p(self.cta_order), _p(self.xT), _p(u_k), _p(v_prev),
                                          _p(beta_prev), _p(v_out),
                                          _p(u_out), _p(alpha_pair), _p(beta_pair), _p(ws), ev, _stream()), "gk_step_ct")
         _lib.count(6)
