@@ -194,7 +194,7 @@ int tb200_ct_backproject_rows_f64(int nx, int ny, int iy_begin, int iy_end, int 
 }
 
 // One Golub-Kahan step (the reference's golub_kahan_update, trips/utilities/decompositions.py:230-255) on the
-// matrix-free CT operator, enqueued as 6 kernels on `stream` with every scalar kept on the device:
+// matrix-free CT operator, enqueued as 6 kernels (7 with the image transpose) on `stream`, every scalar on the device:
 //   v = A^T u_k - beta_prev * v_prev ; alpha = ||v|| ; v /= alpha ; u = A v - alpha * u_k ; beta = ||u|| ; u /= beta
 // Arguments as tb200_gk_step_sell_f64, the operator as tb200_ct_forward_f64 / tb200_ct_backproject_f64.
 // ws: max(tb200_spmv_workspace_len(n_ang*n_det), tb200_ct_backproject_workspace_len(nx, ny)) doubles.

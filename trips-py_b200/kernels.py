@@ -597,7 +597,7 @@ class CTProjector:
                                          _p(cd), _p(z),
                                          _p(norm_out),
                                          _p(ws), _stream()), "ct_forward")
-        _lib.count(2 if norm_out is not None else 1)
+        _lib.count((2 if norm_out is not None else 1) + (1 if self.xT is not None else 0))  # + the image transpose
         return out
 
     def backproject_rows(self, u, out, iy_begin, iy_end):
@@ -628,7 +628,7 @@ class CTProjector:
 
 
     def gk_step(self, u_k, v_prev, beta_prev, v_out, u_out, alpha_pair, beta_pair):
-        """One Golub-Kahan step in a single C-ABI call (6 kernels); scalars stay on the device."""
+        """One Golub-Kahan step in a single C-ABI call (6 kernels + the image transpose); scalars stay on the device."""
         m, _ = self.shape
         need = max(int(lib().tb200_spmv_workspace_len(m)), int(lib().tb200_ct_backproject_workspace_len(self.nx, self.ny)))
         ws = Workspace.get(self.device).buf("ct_gk", need)
@@ -639,7 +639,7 @@ class CTProjector:
                                          _p(self.rowlen), _p(self.rowskip), _p(self.colidx), _p(self.cta_order), _p(self.xT), _p(u_k), _p(v_prev),
                                          _p(beta_prev), _p(v_out),
                                          _p(u_out), _p(alpha_pair), _p(beta_pair), _p(ws), ev, _stream()), "gk_step_ct")
-        _lib.count(6)
+        _lib.count(7 if self.xT is not None else 6)
 
 
 # ---- stencils -------------------------------------------------------------------------------------------------
