@@ -392,15 +392,19 @@ def main():
     else:
         # sharded e2e: each rank feeds its host slice of b; the timed region includes that H2D and the D2H of the factors
         b_host = b.cpu().pin_memory()
-        barrier()
-        t0 = time.perf_counter()
-        bd = b_host.to(dev, non_blocking=True)
-        st2 = DistGKState(A, bd, args.e2e_steps)
-        for _ in range(args.e2e_steps):
-            st2.step()
-        _ = st2.B_host()
-        barrier()
-        dt = time.perf_counter() - t0
+        del st  # its bases are not needed any more: the e2e state below re-uses their memory
+        for attempt in range(2):  # the first pass warms the caching allocator for the new state (untimed)
+            barrier()
+            t0 = time.perf_counter()
+            bd = b_host.to(dev, non_blocking=True)
+            st2 = DistGKState(A, bd, args.e2e_steps)
+            for _ in range(args.e2e_steps):
+                st2.step()
+            _ = st2.B_host()
+            barrier()
+            dt = time.perf_counter() - t0
+            if attempt == 0:
+                del st2, bd
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item()) / args.e2e_steps
