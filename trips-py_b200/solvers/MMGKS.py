@@ -26,7 +26,7 @@ from scipy import sparse
 
 from .. import kernels as K
 from ..operators import as_operator, to_device_vector
-from ._common import ErrorTracker, LazyHistory, dev_scalar, host_column, need_delta, tikhonov_projected
+from ._common import ErrorTracker, LazyHistory, dev_scalar, host_column, tikhonov_projected
 from ._gks_core import GKSBases, adjoint_L_weighted, apply_L_with_weights, choose_lambda, expand, factor_pair
 
 

@@ -3,7 +3,6 @@ import numpy as np
 import torch
 
 from .. import kernels as K
-from ..kernels import F64
 
 
 class LazyHistory:
