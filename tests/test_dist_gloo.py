@@ -195,3 +195,66 @@ def test_row_comm_sums_only_the_sharded_space_world2_gloo(tmp_path):
         assert np.array_equal(p["row_model"], alone) and np.array_equal(p["row_reg"], alone)
         for space in ("data", "model", "reg"):
             assert np.array_equal(p[f"frame_{space}"], summed)
+
+
+class _FakeProjector:
+    """CPU stand-in with the interface dist.adjoint_allreduce uses: row bands of a 'back-projection' (here: a dense
+    matrix-vector product restricted to the pixels of the band)."""
+
+    def __init__(self, At, nx, ny):
+        self.At, self.nx, self.ny = At, nx, ny
+        self.calls = []
+
+    def backproject_rows(self, u, out, r0, r1):
+        self.calls.append((r0, r1))
+        out[r0 * self.nx:r1 * self.nx] = self.At[r0 * self.nx:r1 * self.nx] @ u
+        return out
+
+
+class _FakeOp:
+    def __init__(self, proj):
+        self.projector = proj
+
+    def adjoint_dev(self, u, out=None):
+        out[:] = self.projector.At @ u
+        return out
+
+
+def _bands_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from trips_b200.dist import adjoint_allreduce
+
+        nx, ny, m = 5, 22, 7
+        g = torch.Generator().manual_seed(100 + rank)
+        At = torch.randn(nx * ny, m, dtype=torch.float64, generator=g)
+        u = torch.randn(m, dtype=torch.float64, generator=g)
+        res = {}
+        for bands in (1, 4, 6):
+            proj = _FakeProjector(At, nx, ny)
+            out = torch.zeros(nx * ny, dtype=torch.float64)
+            adjoint_allreduce(_FakeOp(proj), u, out, None, bands=bands)
+            res[f"out{bands}"] = out.numpy()
+            res[f"calls{bands}"] = np.array(proj.calls, dtype=np.int64).reshape(-1, 2)
+        np.savez(os.path.join(out_dir, f"bands{rank}.npz"), part=(At @ u).numpy(), **res)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_banded_adjoint_allreduce_world2_gloo(tmp_path):
+    """dist.adjoint_allreduce: back-projection in row bands with one asynchronous all-reduce per band gives the same
+    sum as one product + one all-reduce; the bands tile the image rows exactly, on multiples of four rows."""
+    world = 2
+    mp.spawn(_bands_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / f"bands{r}.npz") for r in range(world)]
+    want = parts[0]["part"] + parts[1]["part"]
+    for p in parts:
+        for bands in (1, 4, 6):
+            assert np.array_equal(p[f"out{bands}"], want), bands
+        assert p["calls1"].size == 0  # one band = the plain path (operator's own adjoint)
+        calls = p["calls4"]
+        assert calls[0, 0] == 0 and calls[-1, 1] == 22 and np.array_equal(calls[1:, 0], calls[:-1, 1])
+        assert all(c % 4 == 0 for c in calls[:, 0])
+        assert p["calls6"].size == 0  # fewer than four rows per band: falls back to the plain path
