@@ -179,3 +179,41 @@ def test_oracle_is_bit_identical_to_the_reference():
     Ls = pl.VStack((pl.Kronecker(pl.Identity(6), Dx), pl.Kronecker(Dx, pl.Identity(6))))
     w = rng.standard_normal(36)
     assert np.allclose(Lc @ w, Ls.matvec(w), atol=1e-15) and np.allclose(Lc.T @ np.r_[w, w], Ls.rmatvec(np.r_[w, w]), atol=1e-15)
+
+
+def _clip_length(c, s, rho, half_w, half_h):
+    """Length of the line {p : (c, s).p = rho} inside the rectangle [-half_w, half_w] x [-half_h, half_h]
+    (Liang-Barsky on the parametrisation p = rho*(c, s) + tau*(-s, c)): an independent, closed-form answer."""
+    px, py, ex, ey = rho * c, rho * s, -s, c
+    lo, hi = -np.inf, np.inf
+    for p0, e, h in ((px, ex, half_w), (py, ey, half_h)):
+        if abs(e) < 1e-300:
+            if abs(p0) >= h:
+                return 0.0
+            continue
+        t0, t1 = (-h - p0) / e, (h - p0) / e
+        lo, hi = max(lo, min(t0, t1)), min(hi, max(t0, t1))
+    return max(hi - lo, 0.0)
+
+
+@pytest.mark.parametrize("fan", [None, "reference", (40.0, 0.0, 0.8)])
+def test_ct_matrix_rows_sum_to_the_ray_length_inside_the_image(fan):
+    """Physics check of the system matrix that does not depend on any implementation of it: the chord lengths of one
+    ray through all unit pixels add up to the length of the ray inside the image rectangle.  Holds for the parallel beam
+    and for the fan beam (every ray with its own normal and offset: ASTRA 'fanflat' conventions, Tomography.py:57-67),
+    on a non-square image, including rays that clip corners and rays that miss the image."""
+    nx, ny, views = 20, 14, 11
+    theta = np.linspace(0, np.pi, views, endpoint=False) + 0.013
+    n_det = 41
+    geom = O.fan_geometry(nx) if fan == "reference" else fan
+    A = O.ct_matrix(nx, theta, ny=ny, n_det=n_det, fan=geom)
+    got = np.asarray(A @ np.ones(nx * ny)).ravel()
+    want = np.empty_like(got)
+    for a, th in enumerate(theta):
+        cd, sd, rho, *_ = O._ray_tables(np.cos(th), np.sin(th), n_det, geom)
+        for d in range(n_det):
+            want[a * n_det + d] = _clip_length(cd[d], sd[d], rho[d], nx / 2, ny / 2)
+    assert np.allclose(got, want, rtol=0, atol=1e-11)
+    assert (want == 0).any() and want.max() > min(nx, ny)  # the fixture has missing rays and long central ones
+    # and every entry is a genuine chord: positive, at most sqrt(2)
+    assert A.data.min() > 0 and A.data.max() <= np.sqrt(2) + 1e-15
