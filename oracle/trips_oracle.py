@@ -2,7 +2,7 @@
 
 A NumPy/SciPy restatement of the reference's algorithms, written so that every floating-point operation happens
 in the same order as in the reference: on identical inputs it reproduces the reference BIT FOR BIT (pinned by
-tests/test_oracle_pinned.py against the real reference in the build container, and by the golden vectors under
+tests/test_oracle.py::test_oracle_is_bit_identical_to_the_reference against the real reference in the build container, and by the golden vectors under
 tests/golden/ everywhere else).  It exists because /root/reference cannot travel to the GPU box and because
 the reference needs pylops/astra/matplotlib to import.
 
