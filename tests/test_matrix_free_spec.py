@@ -67,3 +67,93 @@ def test_integer_to_double_by_mantissa_insertion_is_exact():
         bits = (np.int64(0x43200000) << 32) | (k << 1)
         built = bits.view(np.float64) if bits.ndim else bits
         assert np.array_equal(built - (2251799813685248.0 + 0.5 * (n - 1)), k - 0.5 * (n - 1))
+
+
+def _magic(d):
+    """The host-side constants of tb200_ct_forward_f64 (spmv.cu): shift = floor(log2 d), magic = floor(2^(32+shift)/d)
+    clipped to 2^32 - 1."""
+    sh = 0
+    while (2 << sh) <= d:
+        sh += 1
+    mg = (1 << (32 + sh)) // d
+    return min(mg, 0xFFFFFFFF), sh
+
+
+def test_index_division_by_multiply_high_with_one_fixup_is_exact():
+    """The forward projector splits a column index into (row, column) of the image - or of the transposed image for
+    shallow rays - with q = umulhi(c, magic) >> shift, r = c - q*d and ONE conditional correction.  Exact for every
+    divisor and every index below 2^31 (checked on edge values and a seeded sample)."""
+    rng = np.random.default_rng(0)
+    divisors = [1, 2, 3, 5, 7, 24, 255, 256, 257, 724, 1448, 2047, 2048, 2049, 2896, 4096, 5792, 46340, 65535, 65536]
+    for d in divisors:
+        mg, sh = _magic(d)
+        top = min((1 << 31) - 1, d * 65536 - 1)
+        c = np.unique(np.concatenate((np.arange(0, min(4 * d, top) + 1), rng.integers(0, top + 1, 20000),
+                                      [top, top - 1, top - d, (top // d) * d, (top // d) * d - 1]))).astype(np.uint64)
+        q = ((c * np.uint64(mg)) >> np.uint64(32)) >> np.uint64(sh)
+        r = c.astype(np.int64) - q.astype(np.int64) * d
+        fix = r >= d
+        q, r = q.astype(np.int64) + fix, r - fix * d
+        assert np.array_equal(q, c.astype(np.int64) // d) and np.array_equal(r, c.astype(np.int64) % d), d
+        assert fix.sum() <= c.size  # (the correction is needed at all only for some divisors)
+
+
+def _sectors_per_entry(rows_cols, skips):
+    """Lane-per-ray gathers: at every position j the 32 rays of a slice request one element each; count the distinct
+    32-byte sectors (4 doubles) per request, summed over the slice, per stored entry."""
+    sectors = entries = 0
+    for s0 in range(0, len(rows_cols), 32):
+        grp, sk = rows_cols[s0:s0 + 32], skips[s0:s0 + 32]
+        width = max((len(c) + k for c, k in zip(grp, sk)), default=0)
+        M = np.full((len(grp), width), -1, dtype=np.int64)
+        for i, (c, k) in enumerate(zip(grp, sk)):
+            M[i, k:k + len(c)] = c
+        for j in range(width):
+            col = M[:, j]
+            col = col[col >= 0]
+            if col.size:
+                sectors += np.unique(col // 4).size
+        entries += sum(len(c) for c in grp)
+    return sectors / max(entries, 1)
+
+
+def test_alignment_and_transposed_addressing_reduce_gather_sectors():
+    """Why the index layout of the forward projector looks the way it does (kernels.py CTProjector, NumPy transcription
+    of its formulas): leading padding (first row - slice's first row)*(1 + |tan|) for steep rays, and for shallow rays
+    addresses in the TRANSPOSED image with the same alignment on the column where the ray enters its first row."""
+    nx = ny = 192
+    n_det = O.ct_num_detectors(nx)
+
+    def layout(theta, transposed):
+        c, s = np.cos(theta), np.sin(theta)
+        A = O.ct_matrix(nx, np.array([theta]))
+        rows = [A.indices[A.indptr[r]:A.indptr[r + 1]].astype(np.int64) for r in range(n_det)]
+        key = []
+        for cols in rows:
+            if cols.size == 0:
+                key.append(None)
+                continue
+            iy0 = cols[0] // nx
+            run = cols[cols // nx == iy0] % nx
+            rightwards = (s < 0) != (c < 0)
+            key.append(iy0 if not transposed else (run.min() if rightwards else nx - 1 - run.max()))
+        if transposed:
+            rows = [(cols % nx) * ny + cols // nx for cols in rows]
+        rate = 1 + (abs(s / c) if not transposed else abs(c / s))
+        skips = []
+        for s0 in range(0, n_det, 32):
+            ks = [k for k in key[s0:s0 + 32] if k is not None]
+            kmin = min(ks) if ks else 0
+            skips += [0 if k is None else int(np.floor(rate * (k - kmin))) for k in key[s0:s0 + 32]]
+        return rows, skips
+
+    for deg in (20.0, 40.0):  # steep rays: alignment alone
+        rows, skips = layout(np.radians(deg), transposed=False)
+        plain, aligned = _sectors_per_entry(rows, [0] * n_det), _sectors_per_entry(rows, skips)
+        assert aligned < 0.85 * plain, (deg, plain, aligned)
+    for deg in (70.0, 110.0):  # shallow rays: in the image every lane sits in its own row; transposed they share sectors
+        rows_img, _ = layout(np.radians(deg), transposed=False)
+        rows_t, skips_t = layout(np.radians(deg), transposed=True)
+        plain, fixed = _sectors_per_entry(rows_img, [0] * n_det), _sectors_per_entry(rows_t, skips_t)
+        # (not as low as a steep ray's 0.35: the entries keep their (iy, ix) order, a sawtooth in the transposed image)
+        assert plain > 0.75 and fixed < 0.65 * plain, (deg, plain, fixed)
