@@ -157,3 +157,61 @@ def test_alignment_and_transposed_addressing_reduce_gather_sectors():
         plain, fixed = _sectors_per_entry(rows_img, [0] * n_det), _sectors_per_entry(rows_t, skips_t)
         # (not as low as a steep ray's 0.35: the entries keep their (iy, ix) order, a sawtooth in the transposed image)
         assert plain > 0.75 and fixed < 0.65 * plain, (deg, plain, fixed)
+
+
+def forward_reevaluated(nx, ny, n_det, theta, x, transpose_shallow=True):
+    """NumPy transcription of spmv_sell_kernel<GEOM> + the index-only builder (one ray at a time, entries vectorised):
+    the ray's pixels come from the stored pattern (the index stream), their VALUES are re-evaluated from the geometry;
+    shallow rays carry indices into the transposed image and gather from it."""
+    A = O.ct_matrix(nx, theta, ny=ny, n_det=n_det)
+    xT = x.reshape(ny, nx).T.copy().reshape(-1)  # xT[ix*ny + iy] = x[iy*nx + ix]
+    bias_x, bias_y = 2251799813685248.0 + 0.5 * (nx - 1), 2251799813685248.0 + 0.5 * (ny - 1)
+
+    def insert(k, bias):  # centred_coord: integer into the mantissa of 2^51, one exact subtraction
+        return (((np.int64(0x43200000) << 32) | (k.astype(np.int64) << 1)).view(np.float64)) - bias
+
+    y = np.zeros(A.shape[0])
+    for a, th in enumerate(theta):
+        c, s = np.cos(th), np.sin(th)
+        hi, lo = max(abs(c), abs(s)), min(abs(c), abs(s))
+        d2 = 0.5 * (hi + lo)
+        with np.errstate(divide="ignore"):
+            inv_hi, inv_hilo = 1.0 / hi, 1.0 / (hi * lo)
+        tmode = transpose_shallow and abs(s) > abs(c)
+        for d in range(n_det):
+            row = a * n_det + d
+            cols = A.indices[A.indptr[row]:A.indptr[row + 1]].astype(np.int64)
+            iy, ix = cols // nx, cols % nx
+            stored = ix * ny + iy if tmode else cols  # what tb200_ct_fill_rows_aligned writes
+            div = ny if tmode else nx
+            mg, sh = _magic(div)
+            q = ((stored.astype(np.uint64) * np.uint64(mg)) >> np.uint64(32)) >> np.uint64(sh)
+            q = q.astype(np.int64)
+            r = stored - q * div
+            fix = r >= div
+            q, r = q + fix, r - fix * div
+            if tmode:   # (q, r) = (ix, iy): proj = r-term + q-term = cy*s + cx*c
+                proj = insert(r, bias_y) * s + insert(q, bias_x) * c
+                xs = xT[stored]
+            else:       # (q, r) = (iy, ix): proj = cx*c + cy*s
+                proj = insert(r, bias_x) * c + insert(q, bias_y) * s
+                xs = x[stored]
+            sd = d - 0.5 * (n_det - 1)
+            slope = (d2 - np.abs(sd - proj)) * inv_hilo
+            val = np.where(slope < inv_hi, slope, inv_hi)
+            acc = 0.0
+            for p in val * xs:  # the rounding chain, in index order
+                acc = acc + p
+            y[row] = acc
+    return y, A
+
+
+@pytest.mark.parametrize("nx,ny,views,n_det", [(16, 16, 10, None), (21, 13, 7, None), (12, 28, 9, 25)])
+def test_reevaluated_forward_projection_equals_the_stored_product_bitwise(nx, ny, views, n_det):
+    rng = np.random.default_rng(nx + 7 * views)
+    n_det = O.ct_num_detectors(nx) if n_det is None else n_det
+    theta = np.concatenate((O.ct_angles(views), [np.pi / 4, 3 * np.pi / 4, np.pi / 2 + 1e-9]))
+    x = rng.standard_normal(nx * ny)
+    for transpose_shallow in (False, True):
+        y, A = forward_reevaluated(nx, ny, n_det, theta, x, transpose_shallow)
+        assert np.array_equal(y, A @ x), transpose_shallow
