@@ -127,6 +127,23 @@ def main():
     np.savez_compressed(os.path.join(OUT, "regparam.npz"), B=Bm, bhat=bhat, Qf=Qf, bfull=bfull, RA=RA, RL=RL,
                         lam_std=lam_std, lam_mod=lam_mod, lam_dp=lam_dp, lam_dp_L=lam_dp_L, lam_gcv_L=lam_gcv_L,
                         lc_grid=lc_grid, lc_kappa=lc_kappa, lam_lc_L=lam_lc_L, lam_lc_I=lam_lc_I)
+    # ---- fan-beam CT 20 x 20, 12 views (the reference's own ASTRA geometry) + the L-curve rule inside the solvers ---
+    nxf, vf = 20, 12
+    Af = O.ct_matrix(nxf, O.ct_angles(vf), fan=O.fan_geometry(nxf))
+    xf = O.shepp_logan(nxf).reshape((-1, 1))
+    bf, deltaf = O.add_noise(Af @ xf, 0.01, rng)
+    outf = dict(nx=nxf, views=vf, x_true=xf, b=bf, delta=deltaf, **csr_fields(Af, "A"))
+    x, info = ref.CGLS(Af, bf, np.zeros((Af.shape[1], 1)), 15, 0, x_true=xf)
+    outf.update(cgls_x=x, cgls_relerr=np.array(info["relError"]))
+    x, info = ref.Hybrid_LSQR(Af, bf, n_iter=12, regparam="l_curve", x_true=xf)
+    outf.update(hlsqr_lc_x=x, hlsqr_lc_lam=np.array(info["regParam_history"], dtype=float))
+    Lf = O.first_derivative_2d(nxf, nxf)
+    x, info = ref.GKS(Af, bf, Lf, projection_dim=3, n_iter=8, regparam="l_curve")
+    outf.update(gks_lc_x=x, gks_lc_lam=np.array(info["regParam_history"], dtype=float))
+    x, info = ref.MMGKS(Af, bf, Lf, pnorm=2, qnorm=1, projection_dim=3, n_iter=8, regparam="l_curve")
+    outf.update(mmgks_lc_x=x, mmgks_lc_lam=np.array(info["regParam_history"], dtype=float))
+    np.savez_compressed(os.path.join(OUT, "ctfan20.npz"), **outf)
+
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -217,3 +217,23 @@ def test_ct_matrix_rows_sum_to_the_ray_length_inside_the_image(fan):
     assert (want == 0).any() and want.max() > min(nx, ny)  # the fixture has missing rays and long central ones
     # and every entry is a genuine chord: positive, at most sqrt(2)
     assert A.data.min() > 0 and A.data.max() <= np.sqrt(2) + 1e-15
+
+
+def test_golden_fan_beam_and_l_curve_inside_the_solvers():
+    """Outputs of the REAL reference's solvers on the fan-beam matrix (its own ASTRA geometry, built by O.ct_matrix) with
+    regparam='l_curve' (trips/utilities/reg_param/l_curve.py through Hybrid_LSQR.py:94-98, GKS.py:67-68,
+    MMGKS.py:100-101): the oracle reproduces them bit for bit, and the matrix in the fixture is the oracle's."""
+    g = load("ctfan20")
+    A, b, xt = csr(g), g["b"], g["x_true"]
+    nx, views = int(g["nx"]), int(g["views"])
+    A0 = O.ct_matrix(nx, O.ct_angles(views), fan=O.fan_geometry(nx))
+    assert np.array_equal(A0.indptr, A.indptr) and np.array_equal(A0.indices, A.indices) and np.array_equal(A0.data, A.data)
+    x, info = O.CGLS(A, b, np.zeros((A.shape[1], 1)), 15, 0, x_true=xt)
+    assert np.array_equal(x, g["cgls_x"]) and np.array_equal(info["relError"], g["cgls_relerr"])
+    x, info = O.Hybrid_LSQR(A, b, n_iter=12, regparam="l_curve", x_true=xt)
+    assert np.array_equal(np.array(info["regParam_history"], dtype=float), g["hlsqr_lc_lam"]) and np.array_equal(x, g["hlsqr_lc_x"])
+    L = O.first_derivative_2d(nx, nx)
+    x, info = O.GKS(A, b, L, projection_dim=3, n_iter=8, regparam="l_curve")
+    assert np.array_equal(np.array(info["regParam_history"], dtype=float), g["gks_lc_lam"]) and np.array_equal(x, g["gks_lc_x"])
+    x, info = O.MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=8, regparam="l_curve")
+    assert np.array_equal(np.array(info["regParam_history"], dtype=float), g["mmgks_lc_lam"]) and np.array_equal(x, g["mmgks_lc_x"])
