@@ -33,6 +33,12 @@ const char* tb200_last_error(void);
 int tb200_version(void);
 int tb200_device_info(int* sm_count, int64_t* l2_bytes, int64_t* mem_bytes, int* cc);
 int tb200_require_sm100(void);
+/* Measured fp64 instruction-issue peak (the roofline denominator of the matrix-free CT projectors, which read almost
+ * no DRAM): one launch of a DFMA-chain microbenchmark (8 independent chains per thread, 8 CTAs x 256 threads per SM, no
+ * memory traffic) executing tb200_fp64_peak_instructions(iters) thread-level fp64 instructions.  The caller times it
+ * with CUDA events (bench.py).  No reference counterpart: measurement support. */
+int64_t tb200_fp64_peak_instructions(int iters);
+int tb200_fp64_peak_run(int iters, double* sink, void* stream);
 
 /* ---- CSR SpMV: y = A x - coef * z, optional fused ||y||^2 ---------------------------------------------
  * Replaces `A @ v` and (on the explicitly stored transpose) `A.T @ u`:

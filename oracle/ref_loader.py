@@ -1,8 +1,11 @@
-"""TEST INFRASTRUCTURE - loads the REAL reference (mpasha3/trips-py) read-only from /root/reference.
+"""TEST INFRASTRUCTURE - loads the REAL, unmodified reference (mpasha3/trips-py).
 
-Only usable in the build container (the GPU box has no /root/reference).  It is used to
-  (1) pin oracle/trips_oracle.py bit for bit against the reference's own functions (tests/test_oracle_pinned.py),
-  (2) generate the golden vectors committed under tests/golden/ (oracle/make_golden.py).
+Search order: $TRIPS_REFERENCE_ROOT, then oracle/_ref/ (the git-ignored pip install made by oracle/make_ref.sh; it
+travels to the GPU box), then /root/reference (build container only).  It is used to
+  (1) pin oracle/trips_oracle.py bit for bit against the reference's own functions (tests/test_oracle.py),
+  (2) generate the golden vectors committed under tests/golden/ (oracle/make_golden.py),
+  (3) run the reference's own solver loops on trips_b200 operators (the drop-in claim, tests/test_gpu_dropin.py),
+  (4) time the reference's golub_kahan_update on the host cores (bench.py --impl reference, cpu_baseline).
 Nothing under trips-py_b200/ imports this file.
 
 The reference imports pylops, astra, matplotlib, h5py, resizeimage, PIL, requests at module level; none of the
@@ -20,7 +23,18 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("TRIPS_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    env = os.environ.get("TRIPS_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + [os.path.join(_HERE, "_ref"), "/root/reference"]:
+        if os.path.isdir(os.path.join(cand, "trips")):
+            return cand
+    return env or os.path.join(_HERE, "_ref")
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():

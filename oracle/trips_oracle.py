@@ -113,8 +113,11 @@ def golub_kahan_update(A, U, S, V):
     return (U, S, V)
 
 
-def golub_kahan(A, b, n_iter):
-    """decompositions.py:118-205 with dp_stop=False."""
+def golub_kahan(A, b, n_iter, dp_stop=False, **kwargs):
+    """decompositions.py:118-205."""
+    eta = kwargs["gk_eta"] if ("gk_eta" in kwargs) else 1.001
+    delta = kwargs["gk_delta"] if ("gk_delta" in kwargs) else 0.001
+    res_norm = np.inf
     rows, cols = A.shape
     betas = np.zeros(1)
     alphas = np.zeros(1)
@@ -122,6 +125,8 @@ def golub_kahan(A, b, n_iter):
     V = np.zeros((cols, 1))
     U[:, 0] = (b / _norm(b)).flatten()
     for it in range(n_iter):
+        if (dp_stop == True) and (res_norm <= eta * delta):  # noqa: E712                         (:166-168)
+            break
         if it != 0:
             U = np.pad(U, ((0, 0), (0, 1)))
             V = np.pad(V, ((0, 0), (0, 1)))
@@ -133,6 +138,12 @@ def golub_kahan(A, b, n_iter):
         U[:, it + 1] = A @ V[:, it] - alphas[it] * U[:, it]
         betas[it] = _norm(U[:, it + 1])
         U[:, it + 1] = U[:, it + 1] / betas[it]
+        if dp_stop == True:  # noqa: E712                                                          (:185-195)
+            S = np.pad(np.diag(alphas), ((0, 1), (0, 0))) + np.pad(np.diag(betas), ((1, 0), (0, 0)))
+            bhat = U.T @ b
+            y = np.linalg.lstsq(S, bhat, rcond=None)[0]
+            x = V @ y
+            res_norm = _norm(A @ x - b)
     k = alphas.shape[0]
     S = np.zeros((k + 1, k))
     S[range(0, k), range(0, k)] = alphas
@@ -471,7 +482,8 @@ def Hybrid_GMRES(A, b, n_iter, regparam="gcv", x_true=None, reorth="mgs", **kwar
 
 def GKS(A, b, L, projection_dim=3, n_iter=50, regparam="gcv", x_true=None, **kwargs):
     """GKS.py:36-105, QR branch (L not the identity)."""
-    (U, B, V) = golub_kahan(A, b, projection_dim)
+    dp_stop = kwargs["dp_stop"] if ("dp_stop" in kwargs) else False
+    (U, B, V) = golub_kahan(A, b, projection_dim, dp_stop, **kwargs)  # TypeError when dp_stop is in kwargs, as the reference
     AV = A @ V
     LV = L @ V
     x_history, lambda_history, residual_history = [], [], []
@@ -524,7 +536,8 @@ def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv",
     iso_L = kwargs.pop("iso_Ls", None)
     gs = kwargs.pop("GS", False) in ["GS", "gs", "Gs"]
     prob_dims = kwargs.pop("prob_dims", False)
-    (U, B, V) = golub_kahan(A, b, projection_dim)
+    dp_stop = kwargs["dp_stop"] if ("dp_stop" in kwargs) else False
+    (U, B, V) = golub_kahan(A, b, projection_dim, dp_stop, **kwargs)  # TypeError when dp_stop is in kwargs, as the reference
     x_history, lambda_history, residual_history = [], [], []
     x = A.T @ b
     AV = A @ V

@@ -204,3 +204,35 @@ def test_parameter_rules_agree_with_the_oracle_on_random_projected_problems():
         assert l_curve(RA, RL, c) == O.l_curve(RA, RL, c), (trial, "l_curve")
         checked += 1
     assert checked == 12
+
+
+def test_host_basis_appends_in_place_only_behind_the_newest_view():
+    """golub_kahan_update / arnoldi_update grow the caller's basis inside a capacity buffer.  Writing column
+    k in place is only allowed when the array handed in is the newest view (k == high-water mark); an older or
+    truncated view gets a fresh copy, so arrays already returned are never mutated (the reference returns fresh arrays
+    from np.hstack, decompositions.py:243-247)."""
+    from trips_b200.decompositions import _HostBasis, release_host_buffers
+
+    release_host_buffers()
+    U0 = np.arange(6.0).reshape(6, 1)
+    hb, k = _HostBasis.adopt(U0)
+    assert k == 1 and np.array_equal(hb.arr[:, :1], U0)
+    hb.arr[:, 1] = 10.0
+    U1 = hb.view(2)
+    hb2, k2 = _HostBasis.adopt(U1)          # newest view: same buffer, append in place
+    assert hb2 is hb and k2 == 2
+    hb.arr[:, 2] = 20.0
+    U2 = hb.view(3)
+    hb3, k3 = _HostBasis.adopt(U1)          # an OLDER view (restart / branch): must not overwrite U2's column 2
+    assert hb3 is not hb and k3 == 2
+    hb3.arr[:, 2] = -1.0
+    assert np.array_equal(U2[:, 2], np.full(6, 20.0))
+    hb4, _ = _HostBasis.adopt(U2[:, :2])    # a truncated view shares the data pointer: also copied
+    assert hb4 is not hb
+    # eviction: the registry never pins more than MAX_LIVE buffers, and release drops them all
+    for i in range(8):
+        _HostBasis.adopt(np.full((3, 1), float(i)))
+    assert len(_HostBasis.registry) <= _HostBasis.MAX_LIVE
+    release_host_buffers()
+    assert not _HostBasis.registry
+    assert np.array_equal(U2[:, 2], np.full(6, 20.0))  # returned arrays stay valid

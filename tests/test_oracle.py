@@ -237,3 +237,26 @@ def test_golden_fan_beam_and_l_curve_inside_the_solvers():
     assert np.array_equal(np.array(info["regParam_history"], dtype=float), g["gks_lc_lam"]) and np.array_equal(x, g["gks_lc_x"])
     x, info = O.MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=8, regparam="l_curve")
     assert np.array_equal(np.array(info["regParam_history"], dtype=float), g["mmgks_lc_lam"]) and np.array_equal(x, g["mmgks_lc_x"])
+
+
+def test_oracle_golub_kahan_dp_stop_is_bit_identical_to_the_reference():
+    """decompositions.py:164-195 (discrepancy-principle stop inside golub_kahan): same stopping step, same factors; and
+    the reference's GKS forwards dp_stop twice (GKS.py:36) - a TypeError the oracle reproduces."""
+    import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference not available (neither oracle/_ref nor /root/reference)")
+    R = ref_loader.load()
+    A = O.ct_matrix(24, O.ct_angles(20))
+    x = O.shepp_logan(24).reshape(-1, 1)
+    b, delta = O.add_noise(A @ x, 0.01, np.random.default_rng(1))
+    for gd in (0.001, 2.0):
+        Ur, Sr, Vr = R.decompositions.golub_kahan(A, b, 30, dp_stop=True, gk_delta=gd)
+        Uo, So, Vo = O.golub_kahan(A, b, 30, True, gk_delta=gd)
+        assert Sr.shape == So.shape
+        assert np.array_equal(Ur, Uo) and np.array_equal(Sr, So) and np.array_equal(Vr, Vo)
+    assert So.shape[1] < 30
+    L = O.first_derivative_2d(24, 24)
+    for fn in (R.GKS, O.GKS, R.MMGKS, O.MMGKS):
+        with pytest.raises(TypeError, match="multiple values"):
+            fn(A, b, L, projection_dim=3, n_iter=2, regparam=0.01, dp_stop=True, delta=float(delta))

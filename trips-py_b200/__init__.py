@@ -6,7 +6,7 @@ there is no CPU fallback.
 """
 from . import kernels, operators, decompositions, reg_param, solvers  # noqa: F401
 from .decompositions import (ArnoldiState, GKState, arnoldi_update, golub_kahan, golub_kahan_device,  # noqa: F401
-                             golub_kahan_update)
+                             golub_kahan_update, release_host_buffers)
 from .operators import (BlockDiagCT, CenteredDerivative2D, CSROperator, FanBeamCT, FirstDerivative1D, FrameletOperator,  # noqa: F401
                         FirstDerivative2D, Identity, LinearOperator, ParallelBeamCT, PSFBlur2D, SpaceTimeDerivative,
                         as_operator, gauss_psf)

@@ -21,6 +21,8 @@ SIGNATURES = {
     "tb200_version": (c_int, []),
     "tb200_device_info": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_require_sm100": (c_int, []),
+    "tb200_fp64_peak_instructions": (c_i64, [c_int]),
+    "tb200_fp64_peak_run": (c_int, [c_int, c_ptr, c_ptr]),
     "tb200_spmv_workspace_len": (c_i64, [c_i64]),
     "tb200_spmv_launches": (c_int, [c_int]),
     "tb200_spmv_set_variant": (c_int, [c_int]),

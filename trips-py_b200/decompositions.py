@@ -190,37 +190,62 @@ class ArnoldiState:
 # ---- reference-signature functions (NumPy in / NumPy out, arithmetic on the GPU) -------------------------------
 
 class _HostBasis:
-    """Pinned, column-contiguous host buffer; views of its leading columns are what the callers hold."""
+    """Pinned, column-contiguous host capacity buffer behind the arrays golub_kahan_update / arnoldi_update return.
 
-    registry = {}
+    The reference returns FRESH arrays from np.hstack at every call (decompositions.py:243-247).  Here the returned
+    array is a view of the first k columns of a buffer, and the next call appends column k in place instead of
+    re-copying - but ONLY when that is indistinguishable from the reference's behaviour: the array handed back by the
+    caller must be the buffer's newest view (k == high-water mark `self.k`).  A call with an older / truncated view
+    (restart, branching, two solves sharing a prefix) would otherwise overwrite a column of an array some caller still
+    holds; such a call gets a fresh buffer and a copy, exactly like the reference.  Buffers are found again through the
+    data pointer of the array passed in; the registry keeps the `MAX_LIVE` most recently used ones (each pins up to GBs
+    of host memory) and `release_host_buffers()` drops them all at the end of a run."""
+
+    registry = {}  # data pointer -> _HostBasis, in least-recently-used order
+    MAX_LIVE = 4
 
     def __init__(self, rows, cap):
         self.t = torch.empty((cap, rows), dtype=F64)
         if torch.cuda.is_available():
             self.t = self.t.pin_memory()
         self.cap, self.rows = cap, rows
+        self.k = 0  # high-water mark: columns [0, k) have been handed out
         self.arr = self.t.numpy().T  # (rows, cap), Fortran order: column j contiguous
-        _HostBasis.registry[self.arr.__array_interface__["data"][0]] = self
-        if len(_HostBasis.registry) > 4:  # each entry pins up to GBs of host memory: keep only the live pair(s)
+        self.key = self.arr.__array_interface__["data"][0]
+        _HostBasis.registry[self.key] = self
+        while len(_HostBasis.registry) > _HostBasis.MAX_LIVE:
             _HostBasis.registry.pop(next(iter(_HostBasis.registry)))
 
     @classmethod
     def adopt(cls, M, extra=1):
-        """Return (buffer, k) such that buffer.arr[:, :k] holds M and has room for `extra` more columns."""
+        """Return (buffer, k) such that buffer.arr[:, :k] holds M and columns k .. k+extra-1 may be written."""
         M = np.asarray(M)
         if M.ndim == 1:
             M = M.reshape(-1, 1)
         rows, k = M.shape
-        hb = cls.registry.get(M.__array_interface__["data"][0])
-        if hb is not None and hb.rows == rows and M.strides == (8, 8 * rows) and k + extra <= hb.cap:
+        key = M.__array_interface__["data"][0] if k else None
+        hb = cls.registry.get(key)
+        if hb is not None and hb.rows == rows and M.strides == (8, 8 * rows) and k == hb.k and k + extra <= hb.cap:
+            cls.registry[key] = cls.registry.pop(key)  # most recently used
             return hb, k
+        # not the newest view of a live buffer (or no room left): copy, as the reference's np.hstack does.
         # pinning is expensive (page-locking): start with room for a typical run and double from there
-        hb = cls(rows, max(2 * (k + extra), 64 if rows * 64 * 8 <= (4 << 30) else 16))
-        hb.arr[:, :k] = M
-        return hb, k
+        new = cls(rows, max(2 * (k + extra), 64 if rows * 64 * 8 <= (4 << 30) else 16))
+        new.arr[:, :k] = M
+        new.k = k
+        if hb is not None and hb.rows == rows and k == hb.k:
+            cls.registry.pop(key, None)  # outgrown: its contents moved to `new`
+        return new, k
 
     def view(self, k):
+        self.k = max(self.k, k)
         return self.arr[:, :k]
+
+
+def release_host_buffers():
+    """Drop the pinned host capacity buffers of golub_kahan_update / arnoldi_update (arrays already returned stay
+    valid: they keep their buffer alive; later calls with them copy into a fresh buffer)."""
+    _HostBasis.registry.clear()
 
 
 _COPY_STREAMS = {}
@@ -234,8 +259,10 @@ def _copy_stream(dev):
     return st
 
 
-def golub_kahan_update(A, U, S, V):
+def golub_kahan_update(A, U, S, V, b200_comm=None):
     """One Golub-Kahan step; same contract as trips.utilities.decompositions.golub_kahan_update (:230-255).
+    (b200_comm: a dist.RowComm when A is a row-sharded operator and U holds this rank's rows - the squared norm of the
+    new u is then summed over the ranks; everything else is as on one GPU.)
 
     U: m x k, S: (k x (k-1)) bidiagonal or np.empty(1) on the first call, V: n x (k-1) (ignored on the first
     call, exactly as the reference replaces the caller's dummy).  Returns (U: m x (k+1), S: (k+1) x k, V: n x k).
@@ -274,6 +301,8 @@ def golub_kahan_update(A, U, S, V):
         hv.t[kv].copy_(v, non_blocking=True)  # overlaps with A v below
     u = torch.empty(A.shape[0], dtype=F64, device=dev)
     apply_fused(A, v, u, coef=pair[1:2], z=u_k, norm_out=pair[2:4])
+    if b200_comm is not None:
+        b200_comm.sync_norm_(pair[2:4], "data")
     K.vec_div(u, pair[3:4], out=u)
     hu.t[ku].copy_(u, non_blocking=True)
     main.wait_stream(side)
@@ -292,20 +321,47 @@ def golub_kahan_update(A, U, S, V):
 
 def golub_kahan(A, b, n_iter, dp_stop=False, **kwargs):
     """Batch Golub-Kahan, contract of trips.utilities.decompositions.golub_kahan (:118-205): returns NumPy
-    (U: m x (n_iter+1), S: (n_iter+1) x n_iter, V: n x n_iter).  The basis stays on the device while it is built."""
-    if dp_stop:
-        raise NotImplementedError("golub_kahan(dp_stop=True) is not provided (the reference path solves a host "
-                                  "least-squares problem per step; use Hybrid_LSQR with regparam='dp')")
-    st = golub_kahan_device(A, b, n_iter)
+    (U: m x (k+1), S: (k+1) x k, V: n x k) with k = n_iter, or fewer when `dp_stop=True` halts the factorisation by the
+    discrepancy principle (kwargs gk_eta = 1.001, gk_delta = 0.001 as in the reference, :148-149).  The basis stays on
+    the device while it is built."""
+    st = golub_kahan_device(A, b, n_iter, dp_stop=dp_stop, gk_eta=kwargs.get("gk_eta", 1.001),
+                            gk_delta=kwargs.get("gk_delta", 0.001))
     return st.U.to_numpy(), st.B_host(), st.V.to_numpy()
 
 
-def golub_kahan_device(A, b, n_iter, kmax=None):
-    """GKState after n_iter steps (device-resident result of golub_kahan)."""
+def golub_kahan_device(A, b, n_iter, kmax=None, dp_stop=False, gk_eta=1.001, gk_delta=0.001, comm=None):
+    """GKState after n_iter steps (device-resident result of golub_kahan).
+
+    dp_stop=True follows decompositions.py:164-195: after every step solve min ||S y - U^T b|| on the host (k+1 x k),
+    lift x = V y on the device, and stop before the next step once ||A x - b|| <= gk_eta * gk_delta.  Per step this
+    costs one extra product with A and two basis passes; only the k+1 coefficients and the residual norm cross PCIe."""
     A = as_operator(A)
-    st = GKState(A, to_device_vector(b, A.device), max(kmax or n_iter, n_iter))
+    bd = to_device_vector(b, A.device)
+    st = GKState(A, bd, max(kmax or n_iter, n_iter), comm=comm)
+    if dp_stop != True:  # noqa: E712  (the reference tests `dp_stop == True`, :166,185)
+        for _ in range(n_iter):
+            st.step()
+        return st
+    res_norm = np.inf
+    m, n = A.shape
+    xd = torch.empty(n, dtype=F64, device=A.device)
+    rd = torch.empty(m, dtype=F64, device=A.device)
+    pair = K.new_pair(A.device)
     for _ in range(n_iter):
+        if res_norm <= gk_eta * gk_delta:  #                                                       (:166-168)
+            break
         st.step()
+        k = st.k
+        bhat = K.basis_dots(st.U, k + 1, bd)  # U.T @ b                                            (:189)
+        if comm is not None:
+            comm.sum_(bhat, "data")
+        y = np.linalg.lstsq(st.B_host(), bhat[:k + 1].cpu().numpy(), rcond=None)[0]  #             (:191)
+        K.basis_combine(st.V, k, torch.from_numpy(np.ascontiguousarray(y)).to(A.device), out=xd)  # x = V @ y   (:193)
+        A.apply_dev(xd, out=rd)
+        K.vec_diffnorm2(rd, bd, out=pair)  # ||A x - b||                                           (:195)
+        if comm is not None:
+            comm.sync_norm_(pair, "data")
+        res_norm = float(pair[1])
     return st
 
 

@@ -215,7 +215,9 @@ class DistGKState:
     """Golub-Kahan bidiagonalisation with rows sharded by angle.  `A_local` is this rank's CSROperator, `b_local`
     its part of the right-hand side.  With world_size == 1 (or no process group) it degenerates to GKState."""
 
-    def __init__(self, A_local, b_local, kmax, backend=None, group=None):
+    exchange_name = "nccl all-reduce of the partial back-projections"
+
+    def __init__(self, A_local, b_local, kmax, backend=None, group=None, exchange=None):
         self.A, self.be = A_local, backend or CudaBackend()
         self.group = group
         self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -259,6 +261,20 @@ class DistGKState:
         self._allreduce_sq(self.beta[k])
         be.div(u, self.beta[k][1:2], u)
         self.k += 1
+
+    def bench_hooks(self, timed):
+        """bench.py: wrap (timed = a decorator) or restore (None) the two operator launches of a step."""
+        proj = getattr(self.A, "projector", None)
+        if timed is None:
+            for obj, name in getattr(self, "_hooked", []):
+                delattr(obj, name)  # instance attribute shadows the class method
+            self._hooked = []
+            return
+        self._hooked = []
+        if proj is not None:  # A^T first (adjoint), then A: the order of the events list
+            proj.backproject = timed(proj.backproject)
+            proj.forward = timed(proj.forward)
+            self._hooked = [(proj, "backproject"), (proj, "forward")]
 
     def scalars_host(self):
         k = self.k
@@ -313,3 +329,35 @@ def sharded_ct(nx, views, comm, **kwargs):
     op = ParallelBeamCT(nx, views, angle_subset=mine, **kwargs)
     rows = (mine[:, None] * op.n_det + np.arange(op.n_det)[None, :]).reshape(-1)
     return ShardedRowsOperator(op, comm), rows
+
+
+def sharded_parity_check(st, nx, views, layout, b_local, steps=10):
+    """bench.py, N > 1, outside the timed region: the first `steps` (alpha, beta) of the sharded state `st` against the
+    SAME problem on ONE GPU (rank 0 rebuilds the whole operator, gathers the right-hand side in angle-major order and
+    repeats the steps).  Returns the maximal relative deviation (rank 0; None elsewhere)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = b_local.device
+    _, al, be = st.scalars_host()
+    n_det = b_local.numel() // len(shard_angles(views, world, rank))
+    parts = [torch.empty(len(shard_angles(views, world, r)) * n_det, dtype=F64, device=dev) for r in range(world)]
+    dist.all_gather(parts, b_local.contiguous())
+    out = None
+    if rank == 0:
+        order = torch.from_numpy(gather_sinogram_order(views, world, n_det)).to(dev)
+        b_full = torch.cat(parts)[order]
+        del parts
+        from .decompositions import GKState
+
+        A1 = ParallelBeamCT(nx, views, device=dev, layout=layout)
+        s1 = GKState(A1, b_full, steps)
+        for _ in range(steps):
+            s1.step()
+        _, al1, be1 = s1.scalars_host()
+        k = min(steps, len(al))
+        d = float(max(np.max(np.abs(al[:k] - al1[:k]) / al1[:k]), np.max(np.abs(be[:k] - be1[:k]) / be1[:k])))
+        out = {"what": f"first {k} (alpha, beta) of the {world}-GPU run vs the same problem on one GPU",
+               "alpha_beta_max_rel_dev_vs_1gpu": d, "bitwise": bool(d == 0.0), "ok": bool(d < 1e-9)}
+        del A1, s1
+        torch.cuda.empty_cache()
+    dist.barrier()
+    return out

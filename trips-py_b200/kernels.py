@@ -24,9 +24,19 @@ def _stream():
     return c_ptr(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_current_device(t, name):
+    """Kernels are enqueued on the CURRENT device's current stream: a tensor of another GPU would be dereferenced by
+    the wrong device (illegal address or silent peer reads).  Refuse instead of guessing."""
+    cur = torch.cuda.current_device()
+    if t.device.index != cur:
+        raise RuntimeError(f"{name} lives on {t.device} but the current CUDA device is cuda:{cur}; run the call under "
+                           f"`with torch.cuda.device({t.device.index}):` (one process per GPU sets it once)")
+
+
 def _vec(t, n=None, name="vector"):
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == F64 and t.dim() == 1 and t.is_contiguous()):
         raise TypeError(f"{name} must be a contiguous 1-D float64 CUDA tensor")
+    _on_current_device(t, name)
     if n is not None and t.numel() != n:
         raise ValueError(f"{name} has {t.numel()} elements, expected {n}")
     return t
@@ -48,6 +58,9 @@ class Workspace:
         device = torch.device(device)
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
+        if device.index != torch.cuda.current_device():
+            raise RuntimeError(f"operator / workspace device {device} is not the current CUDA device "
+                               f"cuda:{torch.cuda.current_device()}; run the call under `with torch.cuda.device(...)`")
         ws = cls._cache.get(device)
         if ws is None:
             _lib.require_device()
@@ -584,6 +597,19 @@ class CTProjector:
             return 0.0, None
         return (0.0, coef) if isinstance(coef, torch.Tensor) else (float(coef), None)
 
+    def fp64_instruction_counts(self):
+        """Thread-level fp64 instructions one launch of each projector executes (bench.py's fp64-issue roofline).
+        Per-unit figures are read off the SASS of the main loops and cross-checked against ncu's
+        smsp__inst_executed_pipe_fp64 (profiles/):
+          forward (index stream): 12 per stored position (3 index->coordinate, 3 projection, 1 t, 1 margin, 1 slope,
+                  1 compare, 1 product, 1 add), padding included because it is executed;
+          back-projection: 19 per pixel and angle (see ct_project.cu) + 12 per pixel of epilogue (recurrence, dd norm)."""
+        npix = self.nx * self.ny
+        return {"forward": 12 * self.stored + 14 * self.shape[0],
+                "forward_kernel": "spmv_sell_kernel<double,4,GEOM,8> (forward projection A v: index stream, values re-evaluated)",
+                "backproject": 19 * npix * self.n_ang + 12 * npix,
+                "backproject_kernel": "ct_backproject_kernel<4> (matrix-free back-projection A^T u)"}
+
     def forward(self, x, out=None, coef=None, z=None, norm_out=None):
         m, n = self.shape
         _vec(x, n, "x")
@@ -678,6 +704,10 @@ def fd_adjoint(r, nt, nrow, ncol, has_next=False, w=None, rt_prev=None, wt_prev=
         _vec(w, rows, "w")
     if out is None:
         out = torch.empty(nt * nrow * ncol, dtype=F64, device=r.device)
+    _vec(out, nt * nrow * ncol, "out")
+    for name, h in (("rt_prev", rt_prev), ("wt_prev", wt_prev)):
+        if h is not None:
+            _vec(h, nrow * ncol, name)
     check(lib().tb200_fd_adjoint(nt, nrow, ncol, int(has_next), _p(r), _p(w), _p(rt_prev), _p(wt_prev), _p(out), _stream()),
           "fd_adjoint")
     _lib.count()
@@ -712,18 +742,20 @@ def cd2d_adjoint(r, nrow, ncol, w=None, out=None):
 
 
 def fd1d_apply(x, out=None):
-    n = x.numel()
+    n = _vec(x, name="x").numel()
     if out is None:
         out = torch.empty(max(n - 1, 0), dtype=F64, device=x.device)
+    _vec(out, max(n - 1, 0), "out")
     check(lib().tb200_fd1d_apply(n, _p(x), _p(out), _stream()), "fd1d_apply")
     _lib.count()
     return out
 
 
 def fd1d_adjoint(r, out=None):
-    n = r.numel() + 1
+    n = _vec(r, name="r").numel() + 1
     if out is None:
         out = torch.empty(n, dtype=F64, device=r.device)
+    _vec(out, n, "out")
     check(lib().tb200_fd1d_adjoint(n, _p(r), _p(out), _stream()), "fd1d_adjoint")
     _lib.count()
     return out

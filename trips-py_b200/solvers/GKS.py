@@ -20,8 +20,8 @@ from ._gks_core import GKSBases, adjoint_L_weighted, choose_lambda, expand, fact
 
 def GKS(A, b, L, projection_dim=3, n_iter=50, regparam="gcv", x_true=None, **kwargs):
     delta, dp_stop = need_delta(regparam, kwargs, "gcv or a different stopping criterion.")
-    if dp_stop is not False:
-        raise NotImplementedError("dp_stop=True (early stop inside golub_kahan) is not supported")
+    if "dp_stop" in kwargs:  # the reference forwards it twice: golub_kahan(A, b, projection_dim, dp_stop, **kwargs) (:36)
+        raise TypeError("golub_kahan() got multiple values for argument 'dp_stop'")
     A = as_operator(A)
     L = as_operator(L, A.device)
     dev = A.device

@@ -61,9 +61,8 @@ def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv",
     # unlike the other drivers the reference does not validate delta up front (:30-36); the discrepancy-principle
     # routine raises the same Exception when it is missing (discrepancy_principle.py:21-23)
     delta = kwargs["delta"] if ("delta" in kwargs) else None
-    dp_stop = kwargs["dp_stop"] if ("dp_stop" in kwargs) else False
-    if dp_stop is not False:
-        raise NotImplementedError("dp_stop=True (early stop inside golub_kahan) is not supported")
+    if "dp_stop" in kwargs:  # the reference forwards it twice: golub_kahan(A, b, projection_dim, dp_stop, **kwargs) (:37)
+        raise TypeError("golub_kahan() got multiple values for argument 'dp_stop'")
     isoTV_option = kwargs["isoTV"] if ("isoTV" in kwargs) else False
     GS_option = kwargs["GS"] if ("GS" in kwargs) else False
     epsilon = kwargs["epsilon"] if ("epsilon" in kwargs) else 0.1

@@ -12,7 +12,7 @@ regularisation-parameter rules nor y = argmin ||R_A y - Q_A^T b||^2 + lam ||R_L 
 import numpy as np
 
 from .. import kernels as K
-from ..decompositions import GKState
+from ..decompositions import golub_kahan_device
 from ..kernels import Basis
 from ..operators import CenteredDerivative2D, SpaceTimeDerivative
 from ..reg_param.discrepancy_principle import discrepancy_principle_projected
@@ -21,13 +21,15 @@ from ..reg_param.l_curve import l_curve
 
 
 class GKSBases:
-    def __init__(self, A, L, bd, projection_dim, n_iter, comm=None):
+    def __init__(self, A, L, bd, projection_dim, n_iter, comm=None, dp_stop=False, gk_kwargs=None):
         self.A, self.L, self.comm = A, L, comm
         dev = bd.device
         kmax = projection_dim + n_iter + 1
-        st = GKState(A, bd, projection_dim, comm=comm)  # golub_kahan(A, b, projection_dim) (GKS.py:36, MMGKS.py:37)
-        for _ in range(projection_dim):
-            st.step()
+        gk_kwargs = gk_kwargs or {}
+        # golub_kahan(A, b, projection_dim, dp_stop, **kwargs)   (GKS.py:36, MMGKS.py:37); dp_stop may return fewer columns
+        st = golub_kahan_device(A, bd, projection_dim, dp_stop=dp_stop, gk_eta=gk_kwargs.get("gk_eta", 1.001),
+                                gk_delta=gk_kwargs.get("gk_delta", 0.001), comm=comm)
+        projection_dim = st.k
         self.V = Basis(A.shape[1], kmax, dev)
         self.AV = Basis(A.shape[0], kmax, dev)
         self.LV = Basis(L.shape[0], kmax, dev)
