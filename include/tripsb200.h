@@ -176,6 +176,15 @@ int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geo
                          const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
                          double* xT_scratch, const double* x, double* y, double coef_host, const double* coef_dev,
                          const double* z, double* norm_out, double* ws, void* stream);
+/* Ray-driven forward projection with NO index array (csrc/ct_forward.cu): the pixels of a ray are enumerated row by row
+ * from the ray equation (candidate bracket + the builder's exact predicate), summed in ascending column index: same
+ * bits as tb200_ct_forward_f64 / tb200_spmv_sell_f64 on the stored matrix and as scipy's A @ x.  Replaces `A @ v`
+ * (trips/utilities/decompositions.py:240; astra.OpTomo's forward projection, trips/test_problems/Tomography.py:73-83).
+ * ws: tb200_ct_forward_rays_workspace_len(n_det, n_ang) doubles iff norm_out != NULL. */
+int64_t tb200_ct_forward_rays_workspace_len(int n_det, int n_ang);
+int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
+                              double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
+                              void* stream);
 int64_t tb200_ct_backproject_workspace_len(int nx, int ny);
 int tb200_ct_backproject_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* u, double* y,
                              double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
@@ -186,7 +195,9 @@ int tb200_ct_backproject_rows_f64(int nx, int ny, int iy_begin, int iy_end, int 
                                   const double* u, double* y, double coef_host, const double* coef_dev, const double* z,
                                   double* norm_out, double* ws, void* stream);
 /* One Golub-Kahan step (trips/utilities/decompositions.py:230-255) on the matrix-free operator, as
- * tb200_gk_step_sell_f64; ws: max(tb200_spmv_workspace_len(m), tb200_ct_backproject_workspace_len(nx, ny)). */
+ * tb200_gk_step_sell_f64; ws: max(tb200_spmv_workspace_len(m), tb200_ct_backproject_workspace_len(nx, ny),
+ * tb200_ct_forward_rays_workspace_len(n_det, n_ang)).  colidx == NULL: fully matrix-free (ray-driven forward
+ * projector; sliceptr .. xT_scratch are ignored and may be NULL). */
 int tb200_gk_step_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
                          const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
                          double* xT_scratch, const double* u_k, const double* v_prev, const double* beta_prev_dev,

@@ -257,19 +257,31 @@ def test_ct_builder_is_bit_identical_to_the_numpy_statement(tb, nx, views):
     assert abs(lhs - rhs) < 1e-12 * abs(lhs)
 
 
+AWKWARD = sorted(set(t + d for t in (0.0, np.pi / 2, np.pi / 4, 3 * np.pi / 4, np.arctan(3.0), np.pi - np.arctan(3.0),
+                                      np.arctan(1.0 / 3.0), np.pi / 3, np.pi / 6)
+                     for d in (0.0, 1e-7, -1e-7, 3e-6, -3e-6, 1e-12) if 0 <= t + d < np.pi))
+
+
+@pytest.mark.parametrize("forward", ["rays", "index"])
 @pytest.mark.parametrize("nx,ny,views,n_det,angles", [
     (24, None, 16, None, None), (64, None, 90, None, None), (33, 20, 7, None, None), (40, 56, 9, 70, None),
-    (48, None, 5, None, [0.0, np.pi / 2, np.pi / 4, 3 * np.pi / 4, 3.0]), (37, None, 11, 30, None), (128, None, 13, None, None)])
-def test_matrix_free_projectors_are_bit_identical_to_the_stored_matrix(tb, nx, ny, views, n_det, angles):
-    """layout='implicit': forward projection re-evaluates A's values from the column indices, back-projection is
-    matrix-free.  Both must give the SAME BITS as scipy on the stored matrix (same entries, same summation order),
-    including the fused recurrence / norm epilogue.  Covers non-square images, detectors narrower than the image
-    (clipped footprints), axis-aligned and 45-degree angles (degenerate trapezoids)."""
+    (48, None, 5, None, [0.0, np.pi / 2, np.pi / 4, 3 * np.pi / 4, 3.0]), (37, None, 11, 30, None), (128, None, 13, None, None),
+    (20, None, len(AWKWARD), 29, AWKWARD), (130, 70, 40, None, None), (96, 200, 24, 333, None),
+    (8, 7000, 5, 40, None), (8, 13000, 5, 40, None)])  # tall images: > 48 KB / no shared-memory row table
+def test_matrix_free_projectors_are_bit_identical_to_the_stored_matrix(tb, nx, ny, views, n_det, angles, forward):
+    """layout='implicit': the ray-driven forward projector enumerates each ray's pixels (forward='rays'; 'index' is round
+    1's, which streams A's column indices), back-projection is pixel-driven.  Both must give the SAME BITS as scipy on
+    the stored matrix (same entries, same summation order), including the fused recurrence / norm epilogue.  Covers
+    non-square images, detectors narrower / wider than the image (clipped footprints), axis-aligned, 30 / 45 / 60-degree
+    angles (degenerate trapezoids, rays through pixel corners) and angles a hair off the kernel's class boundaries."""
     kw = dict(ny=ny, n_det=n_det, angles=None if angles is None else np.array(angles))
-    mf = tb.ParallelBeamCT(nx, views, layout="implicit", **kw)
+    mf = tb.ParallelBeamCT(nx, views, layout="implicit", forward=forward, **kw)
     A0 = tb.ParallelBeamCT(nx, views, layout="csr", **kw).to_scipy()
     assert mf.shape == A0.shape and mf.nnz == A0.nnz
-    assert mf.projector.nbytes < 0.3 * 24 * A0.nnz + 65536  # A's column indices only, against 24 B/entry for the stored pair
+    if forward == "rays":
+        assert mf.projector.nbytes <= 64 * len(mf.theta) + 16  # a per-angle table and nothing else
+    else:
+        assert mf.projector.nbytes < 0.3 * 24 * A0.nnz + 65536  # A's column indices only, against 24 B/entry for the stored pair
     rng = np.random.default_rng(3)
     for trial in range(2):
         x, u = rng.standard_normal(A0.shape[1]), rng.standard_normal(A0.shape[0])
@@ -290,11 +302,12 @@ def test_matrix_free_projectors_are_bit_identical_to_the_stored_matrix(tb, nx, n
     assert (mf.to_scipy() != A0).nnz == 0  # explicit() materialises the same matrix on demand
 
 
-def test_matrix_free_golub_kahan_equals_stored_matrix_golub_kahan(tb):
+@pytest.mark.parametrize("forward", ["rays", "index"])
+def test_matrix_free_golub_kahan_equals_stored_matrix_golub_kahan(tb, forward):
     nx, views, steps = 48, 36, 12
     b = np.random.default_rng(1).standard_normal(views * O.ct_num_detectors(nx))
     ref = tb.golub_kahan_device(tb.ParallelBeamCT(nx, views, layout="sell"), b, steps)
-    got = tb.golub_kahan_device(tb.ParallelBeamCT(nx, views, layout="implicit"), b, steps)
+    got = tb.golub_kahan_device(tb.ParallelBeamCT(nx, views, layout="implicit", forward=forward), b, steps)
     assert np.array_equal(got.B_host(), ref.B_host())
     assert np.array_equal(got.U.to_numpy(), ref.U.to_numpy()) and np.array_equal(got.V.to_numpy(), ref.V.to_numpy())
 

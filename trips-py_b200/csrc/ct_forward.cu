@@ -1,0 +1,329 @@
+// Matrix-free (ray-driven) parallel-beam forward projection  y = A x - coef*z  for the CT matrix of ct_builder.cu,
+// bit-identical to the sequential-order SpMV on the stored matrix (and so to scipy's A @ x on the same matrix).
+//
+// Role in the reference: A @ v inside golub_kahan_update / CGLS / GKS / MMGKS (trips/utilities/decompositions.py:240,
+// trips/solvers/CGLS.py:60, GKS.py:92, MMGKS.py:124); the reference's own tomography operator is matrix-free
+// (astra.OpTomo behind a pylops FunctionOperator, trips/test_problems/Tomography.py:73-83).  SURVEY.md 8(f) item 1.
+//
+// Round 1 re-evaluated the VALUES but still streamed A's column indices (4 B per entry, 15.7 GB at 2048^2 x 720) only to
+// learn which pixels a ray meets, in index order.  This kernel enumerates them instead.  Nothing is read but x.
+//
+// The row of ray (angle a, detector d) must be summed over its pixels in ascending column index iy*nx + ix, every
+// product and every addition separately rounded (scipy's csr_matvec).  In image row iy the pixels the ray meets are
+// those with |t| < d2, t = sd - (cx*c + cy*s): an interval of ix around xi = ((sd - cy*s)/c) + x0 of half-width
+// h = d2/|c| = (1 + |s/c|)/2.  So: walk the rows upwards, and in each row test LMAX = ceil(2h + slack) consecutive
+// candidates starting at the first integer above xi - h - eta, with the SAME predicate on the SAME separately rounded
+// t as the builder: a superset of candidates + the exact predicate = the stored pattern, in the stored order.
+//   * lane = ray; the 32 lanes of a warp are neighbouring detectors of one angle and walk the rows in lockstep, so at
+//     every step their gathers fall into 32/|c| consecutive pixels of ONE image row (3-4 cache lines for steep rays).
+//   * the bracket position is a DDA: e += slope per row, converted with the 1.5*2^52 trick; its rounding drift
+//     (< 1e-9 pixels over 16k rows) is covered by the slack eta = 1e-6.
+//   * rows where every lane's candidates are inside the image run without bounds tests.
+//   * per-row term cy*s: a shared-memory table per CTA (one angle per CTA), one broadcast LDS per row.
+// Rays with |s/c| > 3 (within 18.4 degrees of the image rows: few rows, long runs) take the run form: lane = ray, each
+// lane walks the runs of its own rows with 256-bit loads of four consecutive pixels.
+// fp64 instructions per candidate: 9 (coordinate, cx*c, +cy*s, sd-, margin, slope, compare, product, add) + 2 per row.
+#include "tb200_common.cuh"
+#include "tb200_ctgeom.cuh"
+#include "tb200_dd.cuh"
+
+namespace tb200 {
+
+constexpr double FW_ETA = 1e-6;    // slack of the candidate bracket, in pixels
+constexpr int FW_WARPS = 4;        // 128 rays of one angle per CTA
+constexpr double FW_RUN_TAN = 3.0; // |s/c| above this: run form
+
+__device__ __forceinline__ double fw_add_if_positive(double acc, double p, int flag) {
+  asm("{\n\t.reg .pred q;\n\tsetp.gt.s32 q, %2, 0;\n\t@q add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(p), "r"(flag));
+  return acc;
+}
+
+struct FwRay {
+  double sd, c, d2, inv_hi, inv_hilo, biasx;
+};
+
+// one candidate pixel (ix in [0, nx) guaranteed by the caller): acc += chord * x when the ray meets the pixel
+__device__ __forceinline__ double fw_candidate(double acc, const FwRay& r, double Q, int ix, double xv) {
+  const double cx = centred_coord(ix, r.biasx);
+  const double t = __dsub_rn(r.sd, __dadd_rn(__dmul_rn(cx, r.c), Q));
+  const double e = __dsub_rn(r.d2, fabs(t));  // > 0 inside the footprint (never denormal: |t|, d2 = O(1))
+  const double w = chord_from_margin(e, r.inv_hi, r.inv_hilo);
+  return fw_add_if_positive(acc, __dmul_rn(w, xv), __double2hiint(e));
+}
+
+// rows [r0, r1) of the lockstep walk; CHECKED: candidates may fall outside [0, nx)
+template <int LMAX, bool CHECKED, bool QTAB>
+__device__ __forceinline__ void fw_rows(double& acc, double& e1, int r0, int r1, const FwRay& r, double slope, double s,
+                                        double biasy, const double* __restrict__ qtab, const double* __restrict__ x, int nx,
+                                        uint64_t pol) {
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+  const double* xr = x + (int64_t)r0 * nx;
+#pragma unroll 2
+  for (int iy = r0; iy < r1; ++iy, xr += nx) {
+    const double Q = QTAB ? qtab[iy] : __dmul_rn(centred_coord(iy, biasy), s);
+    const int i0 = __double2loint(__dadd_rn(e1, MAGIC)) + 1;  // first integer above the bracket's left end (or one below)
+    e1 = __dadd_rn(e1, slope);
+    if (CHECKED) {
+#pragma unroll
+      for (int k = 0; k < LMAX; ++k) {
+        const int ix = i0 + k;
+        if ((unsigned)ix < (unsigned)nx) acc = fw_candidate(acc, r, Q, ix, ld_gather_f64(xr + ix, pol));
+      }
+    } else {
+      double xv[LMAX];
+#pragma unroll
+      for (int k = 0; k < LMAX; ++k) xv[k] = ld_gather_f64(xr + (i0 + k), pol);
+#pragma unroll
+      for (int k = 0; k < LMAX; ++k) acc = fw_candidate(acc, r, Q, i0 + k, xv[k]);
+    }
+  }
+}
+
+// rows of [0, ny) on which lo <= E0 + iy*slope <= hi  ->  [a, b) (empty: a >= b)
+__device__ __forceinline__ void fw_row_window(double E0, double slope, double lo, double hi, int ny, int& a, int& b) {
+  if (slope == 0.0) {
+    const bool in = (E0 >= lo) && (E0 <= hi);
+    a = 0;
+    b = in ? ny : 0;
+    return;
+  }
+  double ta = (lo - E0) / slope, tb = (hi - E0) / slope;
+  if (ta > tb) {
+    const double tmp = ta;
+    ta = tb;
+    tb = tmp;
+  }
+  ta = fmin(fmax(ta, -1.0), (double)ny + 1.0);
+  tb = fmin(fmax(tb, -1.0), (double)ny + 1.0);
+  a = max((int)ceil(ta), 0);
+  b = min((int)floor(tb) + 1, ny);
+}
+
+template <int LMAX, bool QTAB>
+__device__ __forceinline__ double fw_lockstep(const FwRay& r, double s, bool live, int nx, int ny, double biasy,
+                                              const double* __restrict__ qtab, const double* __restrict__ x, uint64_t pol) {
+  // bracket of row iy: candidates i0 .. i0 + LMAX - 1, i0 = rn(e1) + 1, e1 = xi - h - eta - 1/2 (see the header)
+  const double inv_c = 1.0 / r.c;
+  const double h = r.d2 * fabs(inv_c);
+  const double x0 = 0.5 * (double)(nx - 1), y0 = 0.5 * (double)(ny - 1);
+  const double slope = -s * inv_c;
+  const double E0 = (r.sd + y0 * s) * inv_c + x0 - h - FW_ETA - 0.5;
+  // rows on which some candidate can be inside the image, and rows on which all of them surely are
+  int a0 = 0, a1 = 0, i0r = 0, i1r = 0;
+  if (live) {
+    fw_row_window(E0, slope, -(double)(LMAX + 1), (double)nx, ny, a0, a1);
+    fw_row_window(E0, slope, 0.0, (double)(nx - LMAX) - 1.5, ny, i0r, i1r);
+  }
+  const bool has = live && a0 < a1;
+  const unsigned FULL = 0xffffffffu;
+  int wa0 = has ? a0 : ny, wa1 = has ? a1 : 0;
+  int wi0 = has ? i0r : 0, wi1 = has ? i1r : ny;  // lanes without rows do not constrain the interior (they are masked below)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wa0 = min(wa0, __shfl_xor_sync(FULL, wa0, o));
+    wa1 = max(wa1, __shfl_xor_sync(FULL, wa1, o));
+    wi0 = max(wi0, __shfl_xor_sync(FULL, wi0, o));
+    wi1 = min(wi1, __shfl_xor_sync(FULL, wi1, o));
+  }
+  if (wa0 >= wa1) return 0.0;
+  if (!__all_sync(FULL, has)) wi0 = wi1 = wa0;  // a lane without rows would gather out of bounds in the unchecked loop
+  wi0 = min(max(wi0, wa0), wa1);
+  wi1 = min(max(wi1, wi0), wa1);
+  double acc = 0.0;
+  double e1 = __fma_rn((double)wa0, slope, E0);
+  if (has) {
+    fw_rows<LMAX, true, QTAB>(acc, e1, wa0, wi0, r, slope, s, biasy, qtab, x, nx, pol);
+    fw_rows<LMAX, false, QTAB>(acc, e1, wi0, wi1, r, slope, s, biasy, qtab, x, nx, pol);
+    fw_rows<LMAX, true, QTAB>(acc, e1, wi1, wa1, r, slope, s, biasy, qtab, x, nx, pol);
+  }
+  return acc;
+}
+
+// Run form: few rows per ray, long runs of consecutive pixels in each.  Every lane walks its own rows; the warp keeps
+// common trip counts (rows: max over lanes; groups of four pixels per row: max over lanes).
+__device__ __forceinline__ double fw_runs(const FwRay& r, double s, bool live, int nx, int ny, double biasy,
+                                          const double* __restrict__ x, int64_t n, bool vec4, uint64_t pol) {
+  const unsigned FULL = 0xffffffffu;
+  const double x0 = 0.5 * (double)(nx - 1), y0 = 0.5 * (double)(ny - 1);
+  const double ac = fabs(r.c), as = fabs(s);
+  const double inv_c = (r.c != 0.0) ? 1.0 / r.c : 0.0;  // estimates only
+  // rows the ray can meet: |cy - (sd - cx*c)/s| < d2/|s| for some |cx| <= x0 + 1/2
+  int ra = 0, rb = 0;
+  if (live) {
+    const double reach = (ac * (x0 + 1.0) + r.d2) / as + 1e-6;
+    const double yc = r.sd / s;
+    ra = max((int)ceil(yc - reach + y0), 0);
+    rb = min((int)floor(yc + reach + y0) + 1, ny);
+  }
+  int nrows = max(rb - ra, 0);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nrows = max(nrows, __shfl_xor_sync(FULL, nrows, o));
+  double acc = 0.0;
+  for (int t = 0; t < nrows; ++t) {
+    const int iy = ra + t;
+    int lo = 0, hi = -1;
+    double Q = 0.0;
+    if (iy < rb) {
+      const double cy = centred_coord(iy, biasy);
+      Q = __dmul_rn(cy, s);
+      const double q = r.sd - cy * s;                 // estimate only
+      const double half = r.d2 + 1e-6;
+      if (ac * (x0 + 1.0) < 1e-7) {                   // (numerically) parallel to the rows: all of the row or none
+        if (fabs(q) < half + 1e-6) lo = 0, hi = nx - 1;
+      } else {
+        const double ea = (q - half) * inv_c + x0, eb = (q + half) * inv_c + x0;
+        const double el = fmin(fmax(fmin(ea, eb), -2.0), (double)nx + 1.0);
+        const double eh = fmin(fmax(fmax(ea, eb), -2.0), (double)nx + 1.0);
+        lo = max((int)floor(el), 0);
+        hi = min((int)ceil(eh), nx - 1);
+      }
+    }
+    const int64_t rowbase = (int64_t)iy * nx;
+    // groups of four consecutive pixels, aligned in the flat index (so the 256-bit loads are aligned)
+    const int64_t g0 = (hi >= lo) ? ((rowbase + lo) & ~(int64_t)3) : 0;
+    int ng = (hi >= lo) ? (int)(((rowbase + hi) >> 2) - (g0 >> 2) + 1) : 0;
+    int ngw = ng;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ngw = max(ngw, __shfl_xor_sync(FULL, ngw, o));
+    for (int q4 = 0; q4 < ngw; ++q4) {
+      if (q4 < ng) {
+        const int64_t g = g0 + 4 * (int64_t)q4;
+        double xv[4];
+        if (vec4 && g + 3 < n) {
+          asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                       : "=d"(xv[0]), "=d"(xv[1]), "=d"(xv[2]), "=d"(xv[3])
+                       : "l"(x + g), "l"(pol));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) xv[k] = (g + k < n) ? ld_gather_f64(x + g + k, pol) : 0.0;
+        }
+        const int ixb = (int)(g - rowbase);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int ix = ixb + k;
+          if (ix >= lo && ix <= hi) acc = fw_candidate(acc, r, Q, ix, xv[k]);
+        }
+      }
+    }
+  }
+  return acc;
+}
+
+template <bool QTAB>
+__global__ void __launch_bounds__(FW_WARPS * 32, 4)
+ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const double* __restrict__ geom,
+                       const double* __restrict__ x, double* __restrict__ y, double coef_host,
+                       const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials,
+                       int vec4) {
+  extern __shared__ __align__(16) double qtab[];  // QTAB: cy*s for every image row of this CTA's angle
+  __shared__ double red[64];
+  const int lane = threadIdx.x & 31;
+  // CTA -> (angle, block of 128 detectors), blocks from the detector centre outwards: the long central rays of every
+  // angle are scheduled first, the short peripheral ones fill the tail
+  const int a = blockIdx.x % n_ang;
+  const int rank = blockIdx.x / n_ang;
+  const int mid = nblk >> 1;
+  const int blk = (rank & 1) ? mid + ((rank + 1) >> 1) : mid - (rank >> 1);
+  const bool blk_ok = blk >= 0 && blk < nblk;  // (nblk even: one rank of the sequence falls outside)
+  const int d = blk * (FW_WARPS * 32) + threadIdx.x;
+  const bool live = blk_ok && d < n_det;
+  const double* gp = geom + 6 * (int64_t)a;
+  const double c = gp[0], s = gp[1];
+  FwRay r;
+  r.c = c, r.d2 = gp[2], r.inv_hi = gp[3], r.inv_hilo = gp[4];
+  r.sd = (double)d - 0.5 * (double)(n_det - 1);
+  r.biasx = centred_bias(nx);
+  const double biasy = centred_bias(ny);
+  const uint64_t pol = policy_evict_last();
+  const double ac = fabs(c), as = fabs(s);
+  const bool runs = as > FW_RUN_TAN * ac;  // also c == 0
+  if (QTAB && !runs) {
+    for (int i = threadIdx.x; i < ny; i += FW_WARPS * 32) qtab[i] = __dmul_rn(centred_coord(i, biasy), s);
+    __syncthreads();
+  }
+  double acc;
+  if (runs) {
+    acc = fw_runs(r, s, live, nx, ny, biasy, x, (int64_t)nx * ny, vec4 != 0, pol);
+  } else {
+    // candidates per row: all integers of an open interval of length 2h + 2 eta (+ DDA drift): ceil of it
+    const double width = (ac + as) / ac + 2.0 * FW_ETA + 1e-7;
+    if (width <= 2.0) acc = fw_lockstep<2, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
+    else if (width <= 3.0) acc = fw_lockstep<3, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
+    else if (width <= 4.0) acc = fw_lockstep<4, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
+    else acc = fw_lockstep<5, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
+  }
+  const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
+  dd_t nrm = dd_zero();
+  if (live) {
+    const int64_t row = (int64_t)a * n_det + d;
+    if (z != nullptr) acc = __dsub_rn(acc, __dmul_rn(coef, z[row]));
+    y[row] = acc;
+    nrm = dd_fma(nrm, acc, acc);
+  }
+  if (partials != nullptr) {
+    const dd_t tot2 = dd_block_sum(nrm, red);
+    if (threadIdx.x == 0) {
+      partials[2 * (int64_t)blockIdx.x] = tot2.hi;
+      partials[2 * (int64_t)blockIdx.x + 1] = tot2.lo;
+    }
+  }
+}
+
+}  // namespace tb200
+
+using namespace tb200;
+
+extern "C" {
+
+// Doubles of workspace tb200_ct_forward_rays_f64 needs for its fused norm (one double-double partial per CTA).
+int64_t tb200_ct_forward_rays_workspace_len(int n_det, int n_ang) {
+  const int64_t nblk = (n_det + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
+  return 2 * ((nblk + 1) * (int64_t)n_ang + 8);
+}
+
+// y = A x - coef*z (z nullable; coef from coef_dev if non-null), optional norm_out = (||y||^2, ||y||), for the
+// parallel-beam matrix of n_ang angles (geom from tb200_ct_geometry): x row-major (iy*nx + ix), y angle-major
+// (angle*n_det + detector).  No matrix and no index array is read.  Same bits as tb200_spmv_sell_f64 on
+// tb200_ct_fill_rows' matrix.  ws: tb200_ct_forward_rays_workspace_len(n_det, n_ang) doubles iff norm_out != NULL.
+int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
+                              double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
+                              void* stream) {
+  TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0, "bad geometry");
+  TB200_REQUIRE((int64_t)nx * ny < ((int64_t)1 << 31) && (int64_t)n_ang * n_det < ((int64_t)1 << 31), "index space exceeds int32");
+  if (n_ang == 0) return 0;
+  TB200_REQUIRE(geom && x && y, "null pointer");
+  TB200_REQUIRE(norm_out == nullptr || ws != nullptr, "norm_out requires a workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = (n_det + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
+  const int ranks = nblk + ((nblk & 1) ? 0 : 1);  // centre-out sequence mid, mid+1, mid-1, ...: covers [0, nblk) in `ranks` steps
+  const int64_t nctas = (int64_t)ranks * n_ang;
+  TB200_REQUIRE(nctas < ((int64_t)1 << 31), "too many CTAs");
+  const int vec4 = ((uintptr_t)x % 32) == 0;
+  const size_t qbytes = (size_t)ny * sizeof(double);
+  int rc;
+  if (qbytes <= 96 * 1024) {
+    if (qbytes > 48 * 1024) {
+      static thread_local int configured_dev = -1;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev != configured_dev) {
+        cudaFuncSetAttribute(ct_forward_rays_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        configured_dev = dev;
+      }
+    }
+    ct_forward_rays_kernel<true><<<(unsigned)nctas, FW_WARPS * 32, qbytes, st>>>(nx, ny, n_det, n_ang, nblk, geom, x, y, coef_host,
+                                                                                   coef_dev, z, norm_out ? ws : nullptr, vec4);
+  } else {
+    ct_forward_rays_kernel<false><<<(unsigned)nctas, FW_WARPS * 32, 0, st>>>(nx, ny, n_det, n_ang, nblk, geom, x, y, coef_host,
+                                                                              coef_dev, z, norm_out ? ws : nullptr, vec4);
+  }
+  rc = check_launch("ct_forward_rays");
+  if (rc) return rc;
+  if (norm_out) {
+    finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, nctas, norm_out);
+    rc = check_launch("ct_forward_rays finalize");
+  }
+  return rc;
+}
+
+}  // extern "C"

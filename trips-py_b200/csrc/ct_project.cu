@@ -197,12 +197,18 @@ int tb200_ct_backproject_rows_f64(int nx, int ny, int iy_begin, int iy_end, int 
 // matrix-free CT operator, enqueued as 6 kernels (7 with the image transpose) on `stream`, every scalar on the device:
 //   v = A^T u_k - beta_prev * v_prev ; alpha = ||v|| ; v /= alpha ; u = A v - alpha * u_k ; beta = ||u|| ; u /= beta
 // Arguments as tb200_gk_step_sell_f64, the operator as tb200_ct_forward_f64 / tb200_ct_backproject_f64.
-// ws: max(tb200_spmv_workspace_len(n_ang*n_det), tb200_ct_backproject_workspace_len(nx, ny)) doubles.
+// colidx == NULL selects the ray-driven forward projector (tb200_ct_forward_rays_f64): sliceptr .. xT_scratch unused.
+// ws: max(tb200_spmv_workspace_len(n_ang*n_det), tb200_ct_backproject_workspace_len(nx, ny),
+//         tb200_ct_forward_rays_workspace_len(n_det, n_ang)) doubles.
 int tb200_vec_div(int64_t n, const double* x, double d_host, const double* d_dev, double* out, void* stream);
 int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
                          const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
                          double* xT_scratch, const double* x, double* y, double coef_host, const double* coef_dev,
                          const double* z, double* norm_out, double* ws, void* stream);
+
+int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
+                              double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
+                              void* stream);
 
 int tb200_gk_step_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
                          const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
@@ -223,8 +229,11 @@ int tb200_gk_step_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geo
   rc = tb200_vec_div(n, v_out, 0.0, alpha_pair + 1, v_out, stream);
   if (rc) return rc;
   mark(2);
-  rc = tb200_ct_forward_f64(nx, ny, n_det, n_ang, geom, sliceptr, rowlen, rowskip, colidx, cta_order, xT_scratch, v_out, u_out, 0.0,
-                            alpha_pair + 1, u_k, beta_pair, ws, stream);
+  if (colidx == nullptr)  // fully matrix-free: the ray-driven forward projector (ct_forward.cu), no index arrays
+    rc = tb200_ct_forward_rays_f64(nx, ny, n_det, n_ang, geom, v_out, u_out, 0.0, alpha_pair + 1, u_k, beta_pair, ws, stream);
+  else
+    rc = tb200_ct_forward_f64(nx, ny, n_det, n_ang, geom, sliceptr, rowlen, rowskip, colidx, cta_order, xT_scratch, v_out, u_out, 0.0,
+                              alpha_pair + 1, u_k, beta_pair, ws, stream);
   mark(3);
   if (rc) return rc;
   return tb200_vec_div(m, u_out, 0.0, beta_pair + 1, u_out, stream);

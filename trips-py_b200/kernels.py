@@ -512,18 +512,45 @@ def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False, layout="csr", fan=Non
 
 
 class CTProjector:
-    """Parallel-beam CT operator whose matrix VALUES are never stored (csrc/ct_project.cu, spmv.cu GEOM mode):
-    forward projection streams only A's SELL-32-4 column indices (4 B per entry) and re-evaluates each entry from the
-    ray geometry; back-projection is fully matrix-free.  Bit-identical to the stored-matrix SpMVs."""
+    """Matrix-free parallel-beam CT operator (csrc/ct_forward.cu, ct_project.cu): neither values nor indices are stored.
+    forward='rays' (default): the ray-driven forward projector enumerates each ray's pixels on the fly; back-projection
+    is pixel-driven.  forward='index' is round 1's projector, which streams A's SELL-32-4 column indices (4 B per entry)
+    and re-evaluates only the values - kept for A/B measurements (TB200_CT_FORWARD=index).  All bit-identical to the
+    stored-matrix SpMVs."""
 
-    def __init__(self, nx, ny, n_det, cos_t, sin_t, align=True):
+    def __init__(self, nx, ny, n_det, cos_t, sin_t, align=True, forward=None):
         dev = cos_t.device
         self.nx, self.ny, self.n_det, self.n_ang = int(nx), int(ny), int(n_det), int(cos_t.numel())
         self.shape = (self.n_ang * self.n_det, self.nx * self.ny)
         self.device = dev
         m = self.shape[0]
+        self.cos_t, self.sin_t = cos_t, sin_t
         self.geom = torch.zeros(max(6 * self.n_ang, 2), dtype=F64, device=dev)
         check(lib().tb200_ct_geometry(self.n_ang, _p(cos_t), _p(sin_t), _p(self.geom), _stream()), "ct_geometry")
+        _lib.count(1)
+        self.forward_mode = forward or os.environ.get("TB200_CT_FORWARD", "rays")
+        if self.forward_mode not in ("rays", "index"):
+            raise ValueError("forward must be 'rays' or 'index'")
+        self._nnz = None
+        self.sliceptr = self.rowlen = self.rowskip = self.colidx = self.cta_order = self.xT = None
+        self.stored = 0
+        if self.forward_mode == "index":
+            self._build_index(align)
+
+    @property
+    def nnz(self):
+        """Entries of the (never stored) matrix: one counting pass of the builder, on first use."""
+        if self._nnz is None:
+            counts = torch.zeros(max(self.shape[0], 1), dtype=torch.int32, device=self.device)
+            check(lib().tb200_ct_count_rows(self.nx, self.ny, self.n_det, self.n_ang, _p(self.cos_t), _p(self.sin_t),
+                                            _p(counts), _stream()), "ct_count")
+            _lib.count(1)
+            self._nnz = int(counts.to(torch.int64).sum().item())
+        return self._nnz
+
+    def _build_index(self, align):
+        dev, m = self.device, self.shape[0]
+        cos_t, sin_t = self.cos_t, self.sin_t
         self.rowlen = torch.zeros(m, dtype=torch.int32, device=dev)
         first = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
         run0 = torch.zeros(max(m, 1), dtype=torch.int32, device=dev)
@@ -540,7 +567,6 @@ class CTProjector:
         # sector.  Give each ray a leading padding of (its first row - the slice's first row) * (1 + |tan|) positions:
         # the lanes then walk through the same rows together (simulated: 0.49 -> 0.35 sectors per entry).  Shallow rays
         # in the transposed image: the same with rows and columns exchanged (key: where the ray enters its first row).
-        self.rowskip = None
         span = self.rowlen
         if os.environ.get("TB200_CT_ALIGN", "1") == "0":  # measurement switch (tools/mf_probe.py)
             align = False
@@ -578,7 +604,7 @@ class CTProjector:
                                                _stream()), "ct_fill")
         _lib.count(3)
         self.stored = total
-        self.nnz = int(self.rowlen.sum().item())
+        self._nnz = int(self.rowlen.sum().item())
         # CTA schedule of the forward projector: groups of four slices, heaviest first (central rays are ~2000 entries
         # long, peripheral ones a handful: in launch order the last wave would be stragglers)
         width = self.sliceptr[1:] - self.sliceptr[:-1]
@@ -589,6 +615,8 @@ class CTProjector:
 
     @property
     def nbytes(self):
+        if self.forward_mode == "rays":
+            return 8 * self.geom.numel() + 16 * self.n_ang
         return (4 * self.stored + 8 * self.sliceptr.numel() + 4 * self.rowlen.numel() + 8 * self.geom.numel()
                 + (8 * self.xT.numel() if self.xT is not None else 0))
 
@@ -605,10 +633,30 @@ class CTProjector:
                   1 compare, 1 product, 1 add), padding included because it is executed;
           back-projection: 19 per pixel and angle (see ct_project.cu) + 12 per pixel of epilogue (recurrence, dd norm)."""
         npix = self.nx * self.ny
-        return {"forward": 12 * self.stored + 14 * self.shape[0],
-                "forward_kernel": "spmv_sell_kernel<double,4,GEOM,8> (forward projection A v: index stream, values re-evaluated)",
+        if self.forward_mode == "rays":
+            fwd, fwd_name = self._rays_fp64_count(), "ct_forward_rays_kernel (ray-driven forward projection A v, matrix-free)"
+        else:  # ncu: 11.09 per stored position (profiles/r2_fp64_instr_counts_r1_kernels.csv)
+            fwd = int(11.09 * self.stored) + 14 * self.shape[0]
+            fwd_name = "spmv_sell_kernel<double,4,GEOM,8> (forward projection A v: index stream, values re-evaluated)"
+        return {"forward": fwd, "forward_kernel": fwd_name,
                 "backproject": 19 * npix * self.n_ang + 12 * npix,
                 "backproject_kernel": "ct_backproject_kernel<4> (matrix-free back-projection A^T u)"}
+
+    def _rays_fp64_count(self):
+        """fp64 instructions of one ct_forward_rays launch: 9 per candidate + 2 per (ray, row) step of the lockstep form
+        (9 per candidate of the run form), counted from the geometry: an angle with |s/c| <= 3 walks n*|c| (ray, row)
+        pairs with LMAX candidates each; the run form evaluates aligned groups of four pixels over each run."""
+        c, s = self.cos_t.abs().cpu().numpy(), self.sin_t.abs().cpu().numpy()
+        npix = float(self.nx * self.ny)
+        total = 0.0
+        for ci, si in zip(c, s):
+            if si > 3.0 * ci:  # run form: runs of 1 + si/ci pixels rounded out to groups of four, npix*ci runs
+                run = 1.0 + (si / ci if ci > 0 else self.nx)
+                total += 9.0 * npix * max(ci, 1.0 / self.nx) * (min(run, self.nx) + 3.0)
+            else:
+                lmax = int(np.ceil((ci + si) / ci + 2.1e-6))
+                total += npix * ci * (9.0 * lmax + 2.0)
+        return int(total) + 14 * self.shape[0]
 
     def forward(self, x, out=None, coef=None, z=None, norm_out=None):
         m, n = self.shape
@@ -617,6 +665,14 @@ class CTProjector:
         if z is not None:
             _vec(z, m, "z")
         ch, cd = self._coef(coef, z)
+        if self.forward_mode == "rays":
+            ws = None
+            if norm_out is not None:
+                ws = Workspace.get(self.device).buf("ct_fw", int(lib().tb200_ct_forward_rays_workspace_len(self.n_det, self.n_ang)))
+            check(lib().tb200_ct_forward_rays_f64(self.nx, self.ny, self.n_det, self.n_ang, _p(self.geom), _p(x), _p(out), ch,
+                                                  _p(cd), _p(z), _p(norm_out), _p(ws), _stream()), "ct_forward_rays")
+            _lib.count(2 if norm_out is not None else 1)
+            return out
         ws = Workspace.get(self.device).spmv(m) if norm_out is not None else None
         check(lib().tb200_ct_forward_f64(self.nx, self.ny, self.n_det, self.n_ang, _p(self.geom), _p(self.sliceptr),
                                          _p(self.rowlen), _p(self.rowskip), _p(self.colidx), _p(self.cta_order), _p(self.xT), _p(x), _p(out), ch,
@@ -656,7 +712,8 @@ class CTProjector:
     def gk_step(self, u_k, v_prev, beta_prev, v_out, u_out, alpha_pair, beta_pair):
         """One Golub-Kahan step in a single C-ABI call (6 kernels + the image transpose); scalars stay on the device."""
         m, _ = self.shape
-        need = max(int(lib().tb200_spmv_workspace_len(m)), int(lib().tb200_ct_backproject_workspace_len(self.nx, self.ny)))
+        need = max(int(lib().tb200_spmv_workspace_len(m)), int(lib().tb200_ct_backproject_workspace_len(self.nx, self.ny)),
+                   int(lib().tb200_ct_forward_rays_workspace_len(self.n_det, self.n_ang)))
         ws = Workspace.get(self.device).buf("ct_gk", need)
         ev = None
         if GK_STEP_EVENTS is not None:
@@ -665,7 +722,7 @@ class CTProjector:
                                          _p(self.rowlen), _p(self.rowskip), _p(self.colidx), _p(self.cta_order), _p(self.xT), _p(u_k), _p(v_prev),
                                          _p(beta_prev), _p(v_out),
                                          _p(u_out), _p(alpha_pair), _p(beta_pair), _p(ws), ev, _stream()), "gk_step_ct")
-        _lib.count(7 if self.xT is not None else 6)
+        _lib.count(7 if self.xT is not None else 6)  # 6 kernels (+ the image transpose of the index form)
 
 
 # ---- stencils -------------------------------------------------------------------------------------------------

@@ -363,11 +363,12 @@ class ParallelBeamCT(CSROperator):
     n_det = int(sqrt(2)*nx) unit-spaced detector bins, sinogram ordered angle-major (row = angle*n_det + det),
     image vectorised row-major.  `angle_subset` keeps only those angle indices (row sharding by projection angle).
 
-    layout: 'csr' / 'sell' / 'both' store A and A^T (12 B per entry each); 'implicit' stores only A's column indices
-    (4 B per entry) and re-evaluates the values in the kernels, with a fully matrix-free back-projection - the
-    reference's operator is matrix-free too (astra.OpTomo).  All layouts give bit-identical products."""
+    layout: 'csr' / 'sell' / 'both' store A and A^T (12 B per entry each); 'implicit' stores nothing: every entry is
+    re-evaluated in the kernels (ray-driven forward projection, pixel-driven back-projection) - the reference's operator
+    is matrix-free too (astra.OpTomo).  All layouts give bit-identical products."""
 
-    def __init__(self, nx, views, ny=None, n_det=None, angles=None, angle_subset=None, device=None, layout="auto"):
+    def __init__(self, nx, views, ny=None, n_det=None, angles=None, angle_subset=None, device=None, layout="auto",
+                 forward=None):
         device = torch.device(device) if device is not None else default_device()
         ny = nx if ny is None else ny
         n_det = ct_num_detectors(nx) if n_det is None else int(n_det)
@@ -382,8 +383,9 @@ class ParallelBeamCT(CSROperator):
         if layout == "auto":  # SELL is the fast stored path; keep CSR too while it is cheap (tests, export, 'tree' order)
             layout = "both" if 1.3 * len(theta) * self.nx * self.ny <= 2e8 else "sell"
         if layout == "implicit":
-            # values re-evaluated on the fly: only A's column indices are stored, A^T is matrix-free
-            self.projector = K.CTProjector(self.nx, self.ny, n_det, cos_t, sin_t)
+            # nothing stored: ray-driven forward projector, pixel-driven back-projector (forward='index': round 1's
+            # forward projector, which streams A's column indices)
+            self.projector = K.CTProjector(self.nx, self.ny, n_det, cos_t, sin_t, forward=forward)
             LinearOperator.__init__(self, self.projector.shape, device)
             self.A = self.AT = self.A_sell = self.AT_sell = None
             self.order = "sequential"
