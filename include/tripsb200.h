@@ -182,6 +182,7 @@ int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geo
  * (trips/utilities/decompositions.py:240; astra.OpTomo's forward projection, trips/test_problems/Tomography.py:73-83).
  * ws: tb200_ct_forward_rays_workspace_len(n_det, n_ang) doubles iff norm_out != NULL. */
 int64_t tb200_ct_forward_rays_workspace_len(int n_det, int n_ang);
+int tb200_ct_forward_set_tuning(double run_tan, int min_ctas); /* tuning knobs; results never depend on them */
 int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
                               double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
                               void* stream);

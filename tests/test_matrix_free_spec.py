@@ -219,10 +219,10 @@ def test_reevaluated_forward_projection_equals_the_stored_product_bitwise(nx, ny
 
 # ---- ray-driven forward projector (csrc/ct_forward.cu) -----------------------------------------------------------------
 
-FW_ETA, FW_RUN_TAN = 1e-6, 3.0
+FW_ETA = 1e-6
 
 
-def forward_rays_spec(nx, ny, n_det, theta, x):
+def forward_rays_spec(nx, ny, n_det, theta, x, run_tan=3.0):
     """NumPy transcription of ct_forward_rays_kernel, vectorised over the detectors of an angle: the lockstep form
     (candidate bracket per image row from the DDA estimate, LMAX = ceil(1 + |s/c| + slack) candidates, exact predicate,
     ascending order) and the run form (|s/c| > 3: per row the pixels lo..hi of an over-estimated run).  Returns
@@ -251,32 +251,32 @@ def forward_rays_spec(nx, ny, n_det, theta, x):
             hit = ok & (e > 0)
             return hit, w
 
-        if as_ > FW_RUN_TAN * ac:  # run form
-            inv_c = 1.0 / c if c != 0.0 else 0.0
+        if as_ > run_tan * ac:  # run form
+            flat = (ac + as_) >= 0.5 * nx * ac
+            inv_c = 0.0 if flat else 1.0 / c
+            h = d2 * abs(inv_c)
+            slope = -s * inv_c
+            E0 = (sd + y0 * s) * inv_c + x0 - h - FW_ETA - 0.5
+            width = 2.0 * h + 2.0 * FW_ETA + 1e-7
+            wlen = float(nx) if flat else np.ceil(width)
             reach = (ac * (x0 + 1.0) + d2) / as_ + 1e-6
             yc = sd / s
             ra = np.maximum(np.ceil(yc - reach + y0), 0).astype(np.int64)
             rb = np.minimum(np.floor(yc + reach + y0) + 1, ny).astype(np.int64)
             for iy in range(ny):
                 rowok = (iy >= ra) & (iy < rb)
-                cy = iy - y0
-                Q = cy * s
-                q = sd - cy * s
-                half = d2 + 1e-6
-                if ac * (x0 + 1.0) < 1e-7:
-                    full = np.abs(q) < half + 1e-6
-                    lo_i = np.where(full, 0, 0)
-                    hi_i = np.where(full, nx - 1, -1)
+                Q = (iy - y0) * s
+                if flat:
+                    lo_i, hi_i = np.zeros(n_det, dtype=np.int64), np.full(n_det, nx - 1, dtype=np.int64)
                 else:
-                    ea, eb = (q - half) * inv_c + x0, (q + half) * inv_c + x0
-                    el = np.clip(np.minimum(ea, eb), -2.0, nx + 1.0)
-                    eh = np.clip(np.maximum(ea, eb), -2.0, nx + 1.0)
-                    lo_i = np.maximum(np.floor(el), 0).astype(np.int64)
-                    hi_i = np.minimum(np.ceil(eh), nx - 1).astype(np.int64)
+                    e1 = np.clip(E0 + iy * slope, -1073741824.0, 1073741824.0)  # the kernel's DDA, restarted per lane at ra
+                    i0 = ((e1 + MAGIC) - MAGIC).astype(np.int64) + 1
+                    lo_i, hi_i = np.maximum(i0, 0), np.minimum(i0 + wlen - 1.0, nx - 1.0).astype(np.int64)
                 hi_i = np.where(rowok, hi_i, -1)
-                if not (hi_i >= lo_i).any():
+                live_rows = hi_i >= lo_i
+                if not live_rows.any():
                     continue
-                for ix in range(int(lo_i[hi_i >= lo_i].min()), int(hi_i.max()) + 1):
+                for ix in range(int(lo_i[live_rows].min()), int(hi_i.max()) + 1):
                     ok = (ix >= lo_i) & (ix <= hi_i)
                     hit, w = candidate(acc, np.full(n_det, ix), Q, ok)
                     acc = np.where(hit, acc + w * X[iy, ix], acc)
@@ -284,7 +284,7 @@ def forward_rays_spec(nx, ny, n_det, theta, x):
                     cands += int(ok.sum())
         else:  # lockstep form
             width = (ac + as_) / ac + 2.0 * FW_ETA + 1e-7
-            lmax = 2 if width <= 2.0 else 3 if width <= 3.0 else 4 if width <= 4.0 else 5
+            lmax = min(max(int(np.ceil(width)), 2), 9)
             inv_c = 1.0 / c
             h = d2 * abs(inv_c)
             slope = -s * inv_c
@@ -309,8 +309,9 @@ FORWARD_GEOMETRIES = [(16, 16, 12, None), (21, 13, 9, None), (24, 24, 8, 20), (1
                       (48, 48, 40, None), (33, 47, 36, 71), (40, 28, 24, 57)]
 
 
+@pytest.mark.parametrize("run_tan", [3.0, 0.5, 7.9])
 @pytest.mark.parametrize("nx,ny,views,n_det", FORWARD_GEOMETRIES)
-def test_ray_driven_forward_projection_equals_the_stored_product_bitwise(nx, ny, views, n_det):
+def test_ray_driven_forward_projection_equals_the_stored_product_bitwise(nx, ny, views, n_det, run_tan):
     """Same pattern (number of entries that pass the predicate == nnz), same values, same order: A @ x bit for bit,
     including axis-aligned angles, 45 / 135 degrees, 30 / 60 degrees (rays through pixel corners), odd and even sizes,
     clipped and over-wide detectors."""
@@ -318,7 +319,7 @@ def test_ray_driven_forward_projection_equals_the_stored_product_bitwise(nx, ny,
     theta = O.ct_angles(views)
     A = O.ct_matrix(nx, theta, ny=ny, n_det=n_det)
     x = np.random.default_rng(nx * 1000 + ny).standard_normal(nx * ny)
-    y, hits, cands = forward_rays_spec(nx, ny, n_det, theta, x)
+    y, hits, cands = forward_rays_spec(nx, ny, n_det, theta, x, run_tan)
     assert hits == A.nnz
     assert np.array_equal(y, A @ x)
     assert cands < 2.6 * A.nnz  # the brackets stay tight: < 2.6 candidates per stored entry on these small images

@@ -31,7 +31,11 @@ namespace tb200 {
 
 constexpr double FW_ETA = 1e-6;    // slack of the candidate bracket, in pixels
 constexpr int FW_WARPS = 4;        // 128 rays of one angle per CTA
-constexpr double FW_RUN_TAN = 3.0; // |s/c| above this: run form
+constexpr double FW_RUN_TAN_MAX = 7.9;  // lockstep form is instantiated for up to 9 candidates per row
+// measured at 2048^2 x 720 (tools/fw_tune.py, profiles/): run_tan 3 / 5 / 7.9 -> 4.87 / 4.50 / 4.37 ms with 64 registers
+// (8 CTAs per SM), 5.47 / 4.89 / 4.70 ms with 90 registers (5 CTAs per SM)
+static double g_fw_run_tan = 7.9;       // |s/c| above this: run form (tuning knob, tb200_ct_forward_set_tuning)
+static int g_fw_minb = 8;               // resident CTAs per SM the compiler must allow for (register cap 128 / 64)
 
 __device__ __forceinline__ double fw_add_if_positive(double acc, double p, int flag) {
   asm("{\n\t.reg .pred q;\n\tsetp.gt.s32 q, %2, 0;\n\t@q add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(p), "r"(flag));
@@ -43,6 +47,12 @@ struct FwRay {
 };
 
 // one candidate pixel (ix in [0, nx) guaranteed by the caller): acc += chord * x when the ray meets the pixel
+__device__ __forceinline__ double fw_candidate_cx(double acc, const FwRay& r, double Q, double cx, double xv) {
+  const double t = __dsub_rn(r.sd, __dadd_rn(__dmul_rn(cx, r.c), Q));
+  const double e = __dsub_rn(r.d2, fabs(t));  // > 0 inside the footprint (never denormal: |t|, d2 = O(1))
+  const double w = chord_from_margin(e, r.inv_hi, r.inv_hilo);
+  return fw_add_if_positive(acc, __dmul_rn(w, xv), __double2hiint(e));
+}
 __device__ __forceinline__ double fw_candidate(double acc, const FwRay& r, double Q, int ix, double xv) {
   const double cx = centred_coord(ix, r.biasx);
   const double t = __dsub_rn(r.sd, __dadd_rn(__dmul_rn(cx, r.c), Q));
@@ -73,8 +83,14 @@ __device__ __forceinline__ void fw_rows(double& acc, double& e1, int r0, int r1,
       double xv[LMAX];
 #pragma unroll
       for (int k = 0; k < LMAX; ++k) xv[k] = ld_gather_f64(xr + (i0 + k), pol);
+      // coordinates of consecutive pixels differ by exactly 1 (half-integers far below 2^52: the additions are exact),
+      // so cx of candidate k is the same double as centred_coord(i0 + k)
+      double cx = centred_coord(i0, r.biasx);
 #pragma unroll
-      for (int k = 0; k < LMAX; ++k) acc = fw_candidate(acc, r, Q, i0 + k, xv[k]);
+      for (int k = 0; k < LMAX; ++k) {
+        acc = fw_candidate_cx(acc, r, Q, cx, xv[k]);
+        if (k + 1 < LMAX) cx = __dadd_rn(cx, 1.0);
+      }
     }
   }
 }
@@ -139,14 +155,27 @@ __device__ __forceinline__ double fw_lockstep(const FwRay& r, double s, bool liv
   return acc;
 }
 
-// Run form: few rows per ray, long runs of consecutive pixels in each.  Every lane walks its own rows; the warp keeps
-// common trip counts (rows: max over lanes; groups of four pixels per row: max over lanes).
+// Run form: few rows per ray, long runs of consecutive pixels in each.  Every lane walks its OWN rows (row t of the
+// walk is image row ra + t of that lane); the run of a row is bracketed by the same DDA as above, LRUN = ceil(2h + slack)
+// pixels from the first integer above the bracket's left end, and read as aligned groups of four pixels (one 256-bit
+// load each).  Trip counts are uniform over the warp (rows: max over lanes; groups per row: a constant of the angle).
 __device__ __forceinline__ double fw_runs(const FwRay& r, double s, bool live, int nx, int ny, double biasy,
                                           const double* __restrict__ x, int64_t n, bool vec4, uint64_t pol) {
   const unsigned FULL = 0xffffffffu;
+  const double MAGIC = 6755399441055744.0;
   const double x0 = 0.5 * (double)(nx - 1), y0 = 0.5 * (double)(ny - 1);
   const double ac = fabs(r.c), as = fabs(s);
-  const double inv_c = (r.c != 0.0) ? 1.0 / r.c : 0.0;  // estimates only
+  // runs of at least half a row (incl. c == 0): every pixel of the rows in reach is a candidate - always a superset, and
+  // it keeps the DDA's magnitudes (~ |s/c| * n_det) far below the 2^30 clamp and its rounding far below eta
+  const bool flat = (ac + as) >= 0.5 * (double)nx * ac;
+  const double inv_c = flat ? 0.0 : 1.0 / r.c;
+  const double h = r.d2 * fabs(inv_c);
+  const double slope = -s * inv_c;
+  const double E0 = (r.sd + y0 * s) * inv_c + x0 - h - FW_ETA - 0.5;
+  const double width = 2.0 * h + 2.0 * FW_ETA + 1e-7;
+  const double wlen = flat ? (double)nx : ceil(width);        // pixels per run (before clipping to the image: may be huge)
+  const int lrun = (int)fmin(wlen, (double)nx);               // ... of which at most nx are inside
+  const int ngroups = (lrun + 2) / 4 + 1;  // aligned groups of four that a run of lrun pixels can touch
   // rows the ray can meet: |cy - (sd - cx*c)/s| < d2/|s| for some |cx| <= x0 + 1/2
   int ra = 0, rb = 0;
   if (live) {
@@ -159,35 +188,25 @@ __device__ __forceinline__ double fw_runs(const FwRay& r, double s, bool live, i
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nrows = max(nrows, __shfl_xor_sync(FULL, nrows, o));
   double acc = 0.0;
+  double e1 = __fma_rn((double)ra, slope, E0);
   for (int t = 0; t < nrows; ++t) {
     const int iy = ra + t;
-    int lo = 0, hi = -1;
-    double Q = 0.0;
-    if (iy < rb) {
-      const double cy = centred_coord(iy, biasy);
-      Q = __dmul_rn(cy, s);
-      const double q = r.sd - cy * s;                 // estimate only
-      const double half = r.d2 + 1e-6;
-      if (ac * (x0 + 1.0) < 1e-7) {                   // (numerically) parallel to the rows: all of the row or none
-        if (fabs(q) < half + 1e-6) lo = 0, hi = nx - 1;
-      } else {
-        const double ea = (q - half) * inv_c + x0, eb = (q + half) * inv_c + x0;
-        const double el = fmin(fmax(fmin(ea, eb), -2.0), (double)nx + 1.0);
-        const double eh = fmin(fmax(fmax(ea, eb), -2.0), (double)nx + 1.0);
-        lo = max((int)floor(el), 0);
-        hi = min((int)ceil(eh), nx - 1);
-      }
+    const double Q = __dmul_rn(centred_coord(iy, biasy), s);
+    int lo = 0, hi = nx - 1;
+    if (!flat) {
+      const double ec = fmin(fmax(e1, -1073741824.0), 1073741824.0);
+      const int i0 = __double2loint(__dadd_rn(ec, MAGIC)) + 1;
+      e1 = __dadd_rn(e1, slope);
+      lo = max(i0, 0);
+      hi = (int)fmin((double)i0 + wlen - 1.0, (double)(nx - 1));  // may be < lo: the run lies outside the image
     }
+    if (iy >= rb) hi = -1, lo = 0;
     const int64_t rowbase = (int64_t)iy * nx;
-    // groups of four consecutive pixels, aligned in the flat index (so the 256-bit loads are aligned)
-    const int64_t g0 = (hi >= lo) ? ((rowbase + lo) & ~(int64_t)3) : 0;
-    int ng = (hi >= lo) ? (int)(((rowbase + hi) >> 2) - (g0 >> 2) + 1) : 0;
-    int ngw = ng;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ngw = max(ngw, __shfl_xor_sync(FULL, ngw, o));
-    for (int q4 = 0; q4 < ngw; ++q4) {
-      if (q4 < ng) {
-        const int64_t g = g0 + 4 * (int64_t)q4;
+    const int64_t g0 = (rowbase + lo) & ~(int64_t)3;
+    const int64_t last = rowbase + hi;
+    for (int q4 = 0; q4 < ngroups; ++q4) {
+      const int64_t g = g0 + 4 * (int64_t)q4;
+      if (hi >= lo && g <= last) {
         double xv[4];
         if (vec4 && g + 3 < n) {
           asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
@@ -209,14 +228,13 @@ __device__ __forceinline__ double fw_runs(const FwRay& r, double s, bool live, i
   return acc;
 }
 
-template <bool QTAB>
-__global__ void __launch_bounds__(FW_WARPS * 32, 4)
+template <bool QTAB, int MINB>
+__global__ void __launch_bounds__(FW_WARPS * 32, MINB)
 ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const double* __restrict__ geom,
                        const double* __restrict__ x, double* __restrict__ y, double coef_host,
                        const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials,
-                       int vec4) {
+                       int vec4, double run_tan) {
   extern __shared__ __align__(16) double qtab[];  // QTAB: cy*s for every image row of this CTA's angle
-  __shared__ double red[64];
   const int lane = threadIdx.x & 31;
   // CTA -> (angle, block of 128 detectors), blocks from the detector centre outwards: the long central rays of every
   // angle are scheduled first, the short peripheral ones fill the tail
@@ -236,7 +254,7 @@ ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const dou
   const double biasy = centred_bias(ny);
   const uint64_t pol = policy_evict_last();
   const double ac = fabs(c), as = fabs(s);
-  const bool runs = as > FW_RUN_TAN * ac;  // also c == 0
+  const bool runs = as > run_tan * ac;  // also c == 0
   if (QTAB && !runs) {
     for (int i = threadIdx.x; i < ny; i += FW_WARPS * 32) qtab[i] = __dmul_rn(centred_coord(i, biasy), s);
     __syncthreads();
@@ -250,7 +268,11 @@ ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const dou
     if (width <= 2.0) acc = fw_lockstep<2, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
     else if (width <= 3.0) acc = fw_lockstep<3, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
     else if (width <= 4.0) acc = fw_lockstep<4, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
-    else acc = fw_lockstep<5, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
+    else if (width <= 5.0) acc = fw_lockstep<5, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
+    else if (width <= 6.0) acc = fw_lockstep<6, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
+    else if (width <= 7.0) acc = fw_lockstep<7, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
+    else if (width <= 8.0) acc = fw_lockstep<8, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
+    else acc = fw_lockstep<9, QTAB>(r, s, live, nx, ny, biasy, qtab, x, pol);
   }
   const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
   dd_t nrm = dd_zero();
@@ -261,10 +283,12 @@ ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const dou
     nrm = dd_fma(nrm, acc, acc);
   }
   if (partials != nullptr) {
-    const dd_t tot2 = dd_block_sum(nrm, red);
-    if (threadIdx.x == 0) {
-      partials[2 * (int64_t)blockIdx.x] = tot2.hi;
-      partials[2 * (int64_t)blockIdx.x + 1] = tot2.lo;
+    // one double-double partial per WARP (no CTA-wide barrier: the warps of a CTA finish at very different times)
+    const dd_t tot2 = dd_warp_sum(nrm);
+    if (lane == 0) {
+      const int64_t w = (int64_t)blockIdx.x * FW_WARPS + (threadIdx.x >> 5);
+      partials[2 * w] = tot2.hi;
+      partials[2 * w + 1] = tot2.lo;
     }
   }
 }
@@ -278,7 +302,17 @@ extern "C" {
 // Doubles of workspace tb200_ct_forward_rays_f64 needs for its fused norm (one double-double partial per CTA).
 int64_t tb200_ct_forward_rays_workspace_len(int n_det, int n_ang) {
   const int64_t nblk = (n_det + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
-  return 2 * ((nblk + 1) * (int64_t)n_ang + 8);
+  return 2 * ((nblk + 1) * (int64_t)n_ang * FW_WARPS + 8);
+}
+
+// Tuning knobs of the ray-driven forward projector (results never depend on them): run_tan = |s/c| above which an angle
+// takes the run form (0 < run_tan <= 7.9); min_ctas = 4 or 8 resident CTAs per SM to compile for (<= 128 / 64 registers).
+int tb200_ct_forward_set_tuning(double run_tan, int min_ctas) {
+  TB200_REQUIRE(run_tan > 0.0 && run_tan <= FW_RUN_TAN_MAX, "run_tan out of range");
+  TB200_REQUIRE(min_ctas == 4 || min_ctas == 8, "min_ctas must be 4 or 8");
+  g_fw_run_tan = run_tan;
+  g_fw_minb = min_ctas;
+  return 0;
 }
 
 // y = A x - coef*z (z nullable; coef from coef_dev if non-null), optional norm_out = (||y||^2, ||y||), for the
@@ -301,26 +335,33 @@ int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double
   const int vec4 = ((uintptr_t)x % 32) == 0;
   const size_t qbytes = (size_t)ny * sizeof(double);
   int rc;
+  const double run_tan = g_fw_run_tan;
+  auto part = norm_out ? ws : nullptr;
+#define FW_LAUNCH(QT, MB, SMEM)                                                                                          \
+  ct_forward_rays_kernel<QT, MB><<<(unsigned)nctas, FW_WARPS * 32, SMEM, st>>>(nx, ny, n_det, n_ang, nblk, geom, x, y, coef_host, \
+                                                                               coef_dev, z, part, vec4, run_tan)
   if (qbytes <= 96 * 1024) {
     if (qbytes > 48 * 1024) {
       static thread_local int configured_dev = -1;
       int dev = 0;
       cudaGetDevice(&dev);
       if (dev != configured_dev) {
-        cudaFuncSetAttribute(ct_forward_rays_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(ct_forward_rays_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(ct_forward_rays_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         configured_dev = dev;
       }
     }
-    ct_forward_rays_kernel<true><<<(unsigned)nctas, FW_WARPS * 32, qbytes, st>>>(nx, ny, n_det, n_ang, nblk, geom, x, y, coef_host,
-                                                                                   coef_dev, z, norm_out ? ws : nullptr, vec4);
+    if (g_fw_minb == 8) FW_LAUNCH(true, 8, qbytes);
+    else FW_LAUNCH(true, 4, qbytes);
   } else {
-    ct_forward_rays_kernel<false><<<(unsigned)nctas, FW_WARPS * 32, 0, st>>>(nx, ny, n_det, n_ang, nblk, geom, x, y, coef_host,
-                                                                              coef_dev, z, norm_out ? ws : nullptr, vec4);
+    if (g_fw_minb == 8) FW_LAUNCH(false, 8, 0);
+    else FW_LAUNCH(false, 4, 0);
   }
+#undef FW_LAUNCH
   rc = check_launch("ct_forward_rays");
   if (rc) return rc;
   if (norm_out) {
-    finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, nctas, norm_out);
+    finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, nctas * FW_WARPS, norm_out);
     rc = check_launch("ct_forward_rays finalize");
   }
   return rc;
