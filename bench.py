@@ -449,10 +449,19 @@ def main():
     del noise, x_true
 
     K, W = args.steps, args.warmup
-    exchange = None
+    exchange, exchange_fallback = None, None
     if world > 1:
-        st = tbdist.DistGKState(A, b, K + W, exchange=args.exchange)
-        exchange = getattr(st, "exchange_name", "nccl all-reduce")
+        st = None
+        if layout == "implicit" and args.exchange != "nccl":
+            try:
+                st = tbdist.ShardedGKState(nx, views, b, K + W)
+            except Exception as exc:  # noqa: BLE001  (CUDA IPC unavailable in this container: use the NCCL transport)
+                if args.exchange == "p2p":
+                    raise
+                exchange_fallback = f"{type(exc).__name__}: {exc}"[:300]
+        if st is None:
+            st = tbdist.DistGKState(A, b, K + W)
+        exchange = st.exchange_name
     else:
         st = tb.GKState(A, b, K + W)
     proj = getattr(A, "projector", None)
@@ -540,36 +549,64 @@ def main():
             parity = tbdist.sharded_parity_check(st, nx, views, layout, b, steps=min(10, K + W))
 
     # ------------------------------------------------------------------ e2e: reference-signature call, host buffers
+    e2e = None
+    if world > 1 and isinstance(st, tbdist.ShardedGKState):
+        # every rank holds ITS rows of U and ITS band of V in pinned host memory; each step uploads u_k and v_{k-1},
+        # runs the sharded step and downloads the new u, v and (alpha, beta)
+        hu = torch.empty((args.e2e_steps + 3, st.m_loc), dtype=torch.float64).pin_memory()
+        hv = torch.empty((args.e2e_steps + 3, st.n_band), dtype=torch.float64).pin_memory()
+        hu[0].copy_(st.U.data[0])
+        torch.cuda.synchronize()
+        beta_prev = 0.0
+        dt = 0.0
+        for i in range(args.e2e_steps + 2):
+            if i == 2:
+                dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            al_i, be_i = st.host_step(hu[i], hv[i - 1] if i else None, beta_prev, hu[i + 1], hv[i])
+            beta_prev = be_i
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item()) / args.e2e_steps
+        e2e = {"value": 1.0 / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * (st.m_loc + st.n_band),
+               "d2h_bytes_per_step": 8 * (st.m_loc + st.n_band) + 16, "ms_per_step": dt * 1e3,
+               "api": f"one golub_kahan_update per step with HOST (pinned) bases, sharded: per rank its rows of U and its band "
+                      f"of V (ShardedGKState.host_step; bytes are per rank, x{world} ranks)"}
+        st.close()
     del st
     torch.cuda.empty_cache()
     comm = tbdist.RowComm() if world > 1 else None
-    A_call = A if world == 1 else tbdist.ShardedRowsOperator(A, comm)
-    b_host = b.cpu().numpy().reshape(-1, 1)
-    bn = float(np.sqrt(comm.allreduce_(torch.tensor([float(b_host.T @ b_host)], dtype=torch.float64, device=dev)).item())) \
-        if world > 1 else float(np.linalg.norm(b_host))
-    U = b_host / bn
-    S, V = np.empty(1), np.empty((n, 1))
-    for _ in range(2):
-        U, S, V = tb.golub_kahan_update(A_call, U, S, V, b200_comm=comm)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        U, S, V = tb.golub_kahan_update(A_call, U, S, V, b200_comm=comm)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-    dt /= args.e2e_steps
-    e2e = {"value": 1.0 / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * (m_loc + n), "d2h_bytes_per_step": 8 * (m_loc + n) + 32,
-           "ms_per_step": dt * 1e3,
-           "api": "trips_b200.golub_kahan_update(A, U, S, V) with NumPy U, S, V (pinned host bases)"
-                  + ("" if world == 1 else f"; per rank: its rows of U and the whole V (bytes are per rank, x{world} ranks)")}
-    del U, V
-    tb.release_host_buffers()
+    if e2e is None:
+        A_call = A if world == 1 else tbdist.ShardedRowsOperator(A, comm)
+        b_host = b.cpu().numpy().reshape(-1, 1)
+        bn = float(np.sqrt(comm.allreduce_(torch.tensor([float(b_host.T @ b_host)], dtype=torch.float64, device=dev)).item())) \
+            if world > 1 else float(np.linalg.norm(b_host))
+        U = b_host / bn
+        S, V = np.empty(1), np.empty((n, 1))
+        for _ in range(2):
+            U, S, V = tb.golub_kahan_update(A_call, U, S, V, b200_comm=comm)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            U, S, V = tb.golub_kahan_update(A_call, U, S, V, b200_comm=comm)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        dt /= args.e2e_steps
+        e2e = {"value": 1.0 / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * (m_loc + n), "d2h_bytes_per_step": 8 * (m_loc + n) + 32,
+               "ms_per_step": dt * 1e3,
+               "api": "trips_b200.golub_kahan_update(A, U, S, V) with NumPy U, S, V (pinned host bases)"
+                      + ("" if world == 1 else f"; per rank: its rows of U and the whole V (bytes are per rank, x{world} ranks)")}
+        del U, V
+        tb.release_host_buffers()
 
     # ------------------------------------------------------------------ secondary records (N = 1): the stored SpMV
     secondary = None

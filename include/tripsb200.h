@@ -91,6 +91,8 @@ int64_t tb200_reduce_workspace_len(void);
 int tb200_vec_div(int64_t n, const double* x, double d_host, const double* d_dev, double* out, void* stream);
 int tb200_vec_axpy(int64_t n, double a_host, const double* a_dev, double sign, const double* x, const double* y,
                    double* out, double* norm_out, double* ws, void* stream); /* out = y + sign*(a*x), sign = +-1 */
+/* The (hi, lo) partials of x.y (y == NULL: sum x^2) without the final reduction, for tb200_comm_allreduce_dd. */
+int tb200_vec_dot_partials(int64_t n, const double* x, const double* y, double* ws, int64_t* n_partials_out, void* stream);
 int tb200_vec_norm2(int64_t n, const double* x, double* out, double* ws, void* stream);
 int tb200_vec_dot(int64_t n, const double* x, const double* y, double* out, double* ws, void* stream);
 int tb200_vec_diffnorm2(int64_t n, const double* x, const double* y, double* out, double* ws, void* stream);
@@ -195,6 +197,22 @@ int tb200_ct_backproject_f64(int nx, int ny, int n_det, int n_ang, const double*
 int tb200_ct_backproject_rows_f64(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* geom,
                                   const double* u, double* y, double coef_host, const double* coef_dev, const double* z,
                                   double* norm_out, double* ws, void* stream);
+/* Sharded forms of the two projectors (one process per GPU, trips-py_b200/dist.py; the reference has no parallelism:
+ * SURVEY.md 2.2, 8e).  The sinogram is split by projection angle, the image by row band; each projector reads a WHOLE
+ * vector (this rank's copy) and produces this rank's part of the other one, which its epilogue stores into every rank's
+ * copy over NVLink peer memory (peers_host: n_peers <= 15 device pointers into the other ranks' arenas, see
+ * tb200_comm_*), then fences at system scope.  Norm partials are left in `partials` for tb200_comm_allreduce_dd.
+ * Back-projection: image rows [iy_begin, iy_end) from all n_ang angles; geom[6a+5] holds, as an int64 bit pattern, the
+ * row of u at which global angle a starts (angles grouped by owner); z (nullable) = this rank's slice of the previous
+ * basis vector, z[pix - iy_begin*nx].  Forward: this rank's n_ang angles (its own geom table) from the whole image.
+ * Both sum in the single-GPU order: results are bit-identical to one GPU. */
+int tb200_ct_backproject_sharded_f64(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* geom,
+                                     const double* u, double* y, double* const* peers_host, int n_peers, double coef_host,
+                                     const double* coef_dev, const double* z, double* partials, int64_t* n_partials_out,
+                                     void* stream);
+int tb200_ct_forward_rays_sharded_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
+                                      double* const* peers_host, int n_peers, double coef_host, const double* coef_dev,
+                                      const double* z, double* partials, int64_t* n_partials_out, void* stream);
 /* One Golub-Kahan step (trips/utilities/decompositions.py:230-255) on the matrix-free operator, as
  * tb200_gk_step_sell_f64; ws: max(tb200_spmv_workspace_len(m), tb200_ct_backproject_workspace_len(nx, ny),
  * tb200_ct_forward_rays_workspace_len(n_det, n_ang)).  colidx == NULL: fully matrix-free (ray-driven forward
@@ -226,6 +244,37 @@ int tb200_cd2d_apply(int nrow, int ncol, const double* x, double* u, double* wou
 int tb200_cd2d_adjoint(int nrow, int ncol, const double* r, const double* w, double* out, void* stream);
 int tb200_fd1d_apply(int64_t n, const double* x, double* u, void* stream);
 int tb200_fd1d_adjoint(int64_t n, const double* r, double* out, void* stream);
+
+/* ---- intra-node communication over NVLink peer memory (csrc/comm.cu) -----------------------
+ * No reference counterpart (the reference is single-process).  Every rank allocates one arena and publishes its CUDA IPC
+ * handle; tb200_comm_connect maps all peers' arenas.  The first tb200_comm_mailbox_bytes() bytes of an arena are the
+ * mailboxes of tb200_comm_allreduce_dd; the caller lays out the rest.
+ *   tb200_comm_init       arena_bytes of zero-filled device memory + its handle (tb200_comm_handle_bytes() bytes)
+ *   tb200_comm_connect    all_handles = nranks handles in rank order (exchanged by the caller out of band)
+ *   tb200_comm_arena      device address, valid in this process, of rank `peer`'s arena
+ *   tb200_comm_allreduce_dd  sum over the ranks of nval (<= 64) double-double values, each given as npart local (hi, lo)
+ *                         partials; out[2j] = total, out[2j+1] = sqrt(total); summed in rank order => bit-identical on
+ *                         every rank and equal to the single-GPU value; also the barrier that makes earlier pushes /
+ *                         projector peer stores visible.  box in [0, 8), epoch strictly increasing per box.
+ *   tb200_comm_push       src[0:n) -> offset_bytes of the arena of every rank in rank_mask
+ *   tb200_halo_exchange   one-frame halos with rank-1 / rank+1 for the temporal difference operator of frame-sharded
+ *                         dynamic CT (replaces the halo of trips-py_b200/dist.py FrameComm; operators.py:39-45)
+ *   tb200_comm_scale      out = x / d over a gathered vector, own slice copied into the basis column in the same pass
+ *                         (v / alpha, u / beta of decompositions.py:239,242) */
+int64_t tb200_comm_mailbox_bytes(void);
+int tb200_comm_handle_bytes(void);
+int tb200_comm_max_ranks(void);
+int tb200_comm_init(int rank, int nranks, int64_t arena_bytes, void** comm_out, unsigned char* handle_out);
+int tb200_comm_connect(void* comm, const unsigned char* all_handles);
+void* tb200_comm_arena(void* comm, int peer);
+int tb200_comm_destroy(void* comm);
+int tb200_comm_allreduce_dd(void* comm, int box, int64_t epoch, const double* partials, int64_t npart, int nval, double* out,
+                            void* stream);
+int tb200_comm_push(void* comm, unsigned rank_mask, int64_t offset_bytes, const double* src, int64_t n, void* stream);
+int tb200_halo_exchange(void* comm, int box, int64_t epoch, int64_t offset_bytes, const double* send_prev, const double* send_next,
+                        int64_t n, double* recv_prev, double* recv_next, double* scratch_pair, void* stream);
+int tb200_comm_scale(int64_t n, const double* x, const double* d_dev, double* out, int64_t keep_begin, int64_t keep_n,
+                     double* keep, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,7 @@ SIGNATURES = {
     "tb200_reduce_workspace_len": (c_i64, []),
     "tb200_vec_div": (c_int, [c_i64, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr]),
     "tb200_vec_axpy": (c_int, [c_i64, c_dbl, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_vec_dot_partials": (c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_vec_norm2": (c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_vec_dot": (c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_vec_diffnorm2": (c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
@@ -64,6 +65,21 @@ SIGNATURES = {
     "tb200_ct_backproject_workspace_len": (c_i64, [c_int, c_int]),
     "tb200_ct_backproject_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_backproject_rows_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_ct_backproject_sharded_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_dbl,
+                                                 c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_ct_forward_rays_sharded_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_dbl, c_ptr, c_ptr,
+                                                  c_ptr, c_ptr, c_ptr]),
+    "tb200_comm_mailbox_bytes": (c_i64, []),
+    "tb200_comm_handle_bytes": (c_int, []),
+    "tb200_comm_max_ranks": (c_int, []),
+    "tb200_comm_init": (c_int, [c_int, c_int, c_i64, c_ptr, c_ptr]),
+    "tb200_comm_connect": (c_int, [c_ptr, c_ptr]),
+    "tb200_comm_arena": (c_ptr, [c_ptr, c_int]),
+    "tb200_comm_destroy": (c_int, [c_ptr]),
+    "tb200_comm_allreduce_dd": (c_int, [c_ptr, c_int, c_i64, c_ptr, c_i64, c_int, c_ptr, c_ptr]),
+    "tb200_comm_push": (c_int, [c_ptr, ctypes.c_uint, c_i64, c_ptr, c_i64, c_ptr]),
+    "tb200_halo_exchange": (c_int, [c_ptr, c_int, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_comm_scale": (c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "tb200_gk_step_ct_f64": (c_int, [c_int, c_int, c_int, c_int] + [c_ptr] * 17),
     "tb200_correlate2d_f64": (c_int, [c_int, c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "tb200_fd_rows": (c_i64, [c_int, c_int, c_int, c_int]),

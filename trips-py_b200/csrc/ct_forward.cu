@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, MINB)
 ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const double* __restrict__ geom,
                        const double* __restrict__ x, double* __restrict__ y, double coef_host,
                        const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials,
-                       int vec4, double run_tan) {
+                       int vec4, double run_tan, PeerOut po) {
   extern __shared__ __align__(16) double qtab[];  // QTAB: cy*s for every image row of this CTA's angle
   const int lane = threadIdx.x & 31;
   // CTA -> (angle, block of 128 detectors), blocks from the detector centre outwards: the long central rays of every
@@ -280,8 +280,12 @@ ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const dou
     const int64_t row = (int64_t)a * n_det + d;
     if (z != nullptr) acc = __dsub_rn(acc, __dmul_rn(coef, z[row]));
     y[row] = acc;
+#pragma unroll
+    for (int p = 0; p < 15; ++p)  // the other GPUs' copies of the vector, over NVLink (unrolled: parameters stay in the constant bank)
+      if (p < po.n) po.p[p][row] = acc;
     nrm = dd_fma(nrm, acc, acc);
   }
+  if (po.n > 0) __threadfence_system();
   if (partials != nullptr) {
     // one double-double partial per WARP (no CTA-wide barrier: the warps of a CTA finish at very different times)
     const dd_t tot2 = dd_warp_sum(nrm);
@@ -319,27 +323,24 @@ int tb200_ct_forward_set_tuning(double run_tan, int min_ctas) {
 // parallel-beam matrix of n_ang angles (geom from tb200_ct_geometry): x row-major (iy*nx + ix), y angle-major
 // (angle*n_det + detector).  No matrix and no index array is read.  Same bits as tb200_spmv_sell_f64 on
 // tb200_ct_fill_rows' matrix.  ws: tb200_ct_forward_rays_workspace_len(n_det, n_ang) doubles iff norm_out != NULL.
-int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
-                              double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
-                              void* stream) {
+static int forward_rays_launch(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
+                               double coef_host, const double* coef_dev, const double* z, double* part, const PeerOut& po,
+                               cudaStream_t st, int64_t& nparts) {
   TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0, "bad geometry");
   TB200_REQUIRE((int64_t)nx * ny < ((int64_t)1 << 31) && (int64_t)n_ang * n_det < ((int64_t)1 << 31), "index space exceeds int32");
+  nparts = 0;
   if (n_ang == 0) return 0;
   TB200_REQUIRE(geom && x && y, "null pointer");
-  TB200_REQUIRE(norm_out == nullptr || ws != nullptr, "norm_out requires a workspace");
-  cudaStream_t st = (cudaStream_t)stream;
   const int nblk = (n_det + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
   const int ranks = nblk + ((nblk & 1) ? 0 : 1);  // centre-out sequence mid, mid+1, mid-1, ...: covers [0, nblk) in `ranks` steps
   const int64_t nctas = (int64_t)ranks * n_ang;
   TB200_REQUIRE(nctas < ((int64_t)1 << 31), "too many CTAs");
   const int vec4 = ((uintptr_t)x % 32) == 0;
   const size_t qbytes = (size_t)ny * sizeof(double);
-  int rc;
   const double run_tan = g_fw_run_tan;
-  auto part = norm_out ? ws : nullptr;
 #define FW_LAUNCH(QT, MB, SMEM)                                                                                          \
   ct_forward_rays_kernel<QT, MB><<<(unsigned)nctas, FW_WARPS * 32, SMEM, st>>>(nx, ny, n_det, n_ang, nblk, geom, x, y, coef_host, \
-                                                                               coef_dev, z, part, vec4, run_tan)
+                                                                               coef_dev, z, part, vec4, run_tan, po)
   if (qbytes <= 96 * 1024) {
     if (qbytes > 48 * 1024) {
       static thread_local int configured_dev = -1;
@@ -358,13 +359,41 @@ int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double
     else FW_LAUNCH(false, 4, 0);
   }
 #undef FW_LAUNCH
-  rc = check_launch("ct_forward_rays");
+  nparts = nctas * FW_WARPS;
+  return check_launch("ct_forward_rays");
+}
+
+int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
+                              double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
+                              void* stream) {
+  TB200_REQUIRE(norm_out == nullptr || ws != nullptr, "norm_out requires a workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  PeerOut po;
+  po.n = 0;
+  int64_t nparts = 0;
+  int rc = forward_rays_launch(nx, ny, n_det, n_ang, geom, x, y, coef_host, coef_dev, z, norm_out ? ws : nullptr, po, st, nparts);
   if (rc) return rc;
-  if (norm_out) {
-    finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, nctas * FW_WARPS, norm_out);
+  if (norm_out && nparts > 0) {
+    finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, nparts, norm_out);
     rc = check_launch("ct_forward_rays finalize");
   }
   return rc;
+}
+
+// Sharded form (trips-py_b200/dist.py): this rank projects ITS angles (geom: its n_ang angles) from the whole image x.
+// y (the rank's chunk of its own copy of the gathered sinogram) receives the rows; the same values are stored into
+// peers[0 .. n_peers) (the same chunk of the other ranks' copies) from the epilogue, followed by a system-scope fence.
+// partials: tb200_ct_forward_rays_workspace_len doubles, to be summed over the ranks by tb200_comm_allreduce_dd.
+int tb200_ct_forward_rays_sharded_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
+                                      double* const* peers_host, int n_peers, double coef_host, const double* coef_dev,
+                                      const double* z, double* partials, int64_t* n_partials_out, void* stream) {
+  TB200_REQUIRE(partials && n_partials_out, "null pointer");
+  TB200_REQUIRE(n_peers >= 0 && n_peers <= 15 && (n_peers == 0 || peers_host), "bad peer list");
+  PeerOut po;
+  po.n = n_peers;
+  for (int i = 0; i < n_peers; ++i) po.p[i] = peers_host[i];
+  return forward_rays_launch(nx, ny, n_det, n_ang, geom, x, y, coef_host, coef_dev, z, partials, po, (cudaStream_t)stream,
+                             *n_partials_out);
 }
 
 }  // extern "C"

@@ -44,7 +44,9 @@ __device__ __forceinline__ double add_if_positive(double acc, double p, int flag
 
 // One tile of angles for one pixel.  CHECKED = false is the path of warps whose pixels project at least two bins
 // inside the detector at every angle (all but the image corners): no bounds tests, unconditional gathers.
-template <bool CHECKED, int UNROLL>
+// OFFS: the sinogram rows of angle j start at the int64 stored (bit pattern) in gtab[6j + 5] instead of at
+// (a0 + j) * n_det - the sharded layout, where the angles of a gathered sinogram are grouped by owner rank.
+template <bool CHECKED, int UNROLL, bool OFFS>
 __device__ __forceinline__ double bp_tile(double acc, const double* __restrict__ gtab, int na, const double* __restrict__ u, int row0,
                                           int n_det, double cx, double cy, double dcm, double sbias, uint64_t pol_keep) {
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (v + MAGIC) - MAGIC = v rounded to an integer
@@ -64,8 +66,9 @@ __device__ __forceinline__ double bp_tile(double acc, const double* __restrict__
     const double e0 = __dsub_rn(dh.x, fabs(__dsub_rn(sd0, proj)));  // d2 - |t|: positive inside the footprint
     const double e1 = __dsub_rn(dh.x, fabs(__dsub_rn(sd1, proj)));
     // e > 0 (never denormal here: |t| and d2 are O(1)) <=> the high word, read as an int, is positive
+    const int rowj = OFFS ? (int)__double_as_longlong(gtab[6 * j + 5]) : row0 + j * n_det;
     if (CHECKED) {
-      const double* up = u + ((int64_t)row0 + (int64_t)j * n_det + d0);
+      const double* up = u + ((int64_t)rowj + d0);
       const bool in0 = (unsigned)d0 < und, in1 = (unsigned)(d0 + 1) < und;
       const double u0 = in0 ? ld_gather_f64(up, pol_keep) : 0.0;
       const double u1 = in1 ? ld_gather_f64(up + 1, pol_keep) : 0.0;
@@ -74,7 +77,7 @@ __device__ __forceinline__ double bp_tile(double acc, const double* __restrict__
       if (in0 && __double2hiint(e0) > 0) acc = __dadd_rn(acc, p0);
       if (in1 && __double2hiint(e1) > 0) acc = __dadd_rn(acc, p1);
     } else {
-      const double* up = u + (unsigned)(row0 + j * n_det + d0);  // n_ang * n_det < 2^31 is checked at launch
+      const double* up = u + (unsigned)(rowj + d0);  // n_ang * n_det < 2^31 is checked at launch
       const double p0 = __dmul_rn(chord_from_margin(e0, dh.y, inv_hilo), ld_gather_f64(up, pol_keep));
       const double p1 = __dmul_rn(chord_from_margin(e1, dh.y, inv_hilo), ld_gather_f64(up + 1, pol_keep));
       acc = add_if_positive(acc, p0, __double2hiint(e0));
@@ -84,11 +87,12 @@ __device__ __forceinline__ double bp_tile(double acc, const double* __restrict__
   return acc;
 }
 
-template <int UNROLL>
+template <int UNROLL, bool OFFS>
 __global__ void __launch_bounds__(128, 8)
 ct_backproject_kernel(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* __restrict__ geom,
                       const double* __restrict__ u, double* __restrict__ y, double coef_host,
-                      const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials) {
+                      const double* __restrict__ coef_dev, const double* __restrict__ z, int64_t z_offset,
+                      double* __restrict__ partials, PeerOut po) {
   __shared__ __align__(16) double gtab[BP_TA * 6];
   __shared__ double red[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -110,18 +114,22 @@ ct_backproject_kernel(int nx, int ny, int iy_begin, int iy_end, int n_det, int n
     for (int i = threadIdx.x; i < na * 3; i += 128)
       reinterpret_cast<double2*>(gtab)[i] = reinterpret_cast<const double2*>(geom + 6 * (int64_t)a0)[i];
     __syncthreads();
-    if (interior) acc = bp_tile<false, UNROLL>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dcm, sbias, pol_keep);
-    else acc = bp_tile<true, UNROLL>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dcm, sbias, pol_keep);
+    if (interior) acc = bp_tile<false, UNROLL, OFFS>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dcm, sbias, pol_keep);
+    else acc = bp_tile<true, UNROLL, OFFS>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dcm, sbias, pol_keep);
   }
 
   const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
   dd_t nrm = dd_zero();
   if (valid) {
     const int64_t pix = (int64_t)iy * nx + ix;
-    if (z != nullptr) acc = __dsub_rn(acc, __dmul_rn(coef, z[pix]));
+    if (z != nullptr) acc = __dsub_rn(acc, __dmul_rn(coef, z[pix - z_offset]));
     y[pix] = acc;
+#pragma unroll
+    for (int p = 0; p < 15; ++p)  // the other GPUs' copies of the vector, over NVLink (unrolled: parameters stay in the constant bank)
+      if (p < po.n) po.p[p][pix] = acc;
     nrm = dd_fma(nrm, acc, acc);
   }
+  if (po.n > 0) __threadfence_system();
   if (partials != nullptr) {
     const dd_t tot2 = dd_block_sum(nrm, red);
     if (threadIdx.x == 0) {
@@ -169,27 +177,67 @@ int tb200_ct_backproject_f64(int nx, int ny, int n_det, int n_ang, const double*
   return tb200_ct_backproject_rows_f64(nx, ny, 0, ny, n_det, n_ang, geom, u, y, coef_host, coef_dev, z, norm_out, ws, stream);
 }
 
-int tb200_ct_backproject_rows_f64(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* geom,
-                                  const double* u, double* y, double coef_host, const double* coef_dev, const double* z,
-                                  double* norm_out, double* ws, void* stream) {
+static int backproject_launch(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* geom, const double* u,
+                              double* y, double coef_host, const double* coef_dev, const double* z, int64_t z_offset,
+                              double* partials, bool offsets, const PeerOut& po, cudaStream_t st, dim3& grid) {
   TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0, "bad geometry");
   TB200_REQUIRE(0 <= iy_begin && iy_begin <= iy_end && iy_end <= ny, "bad row band");
-  if (iy_begin == iy_end) return 0;
   TB200_REQUIRE((int64_t)nx * ny < ((int64_t)1 << 31) && (int64_t)n_ang * n_det < ((int64_t)1 << 31), "index space exceeds int32");
   TB200_REQUIRE(y && (n_ang == 0 || (geom && u)), "null pointer");
   TB200_REQUIRE(((uintptr_t)geom % 16) == 0, "geom must be 16-byte aligned");
-  TB200_REQUIRE(norm_out == nullptr || ws != nullptr, "norm_out requires a workspace");
-  cudaStream_t st = (cudaStream_t)stream;
-  const dim3 grid((unsigned)((nx + 31) / 32), (unsigned)((iy_end - iy_begin + 3) / 4));
+  grid = dim3((unsigned)((nx + 31) / 32), (unsigned)((iy_end - iy_begin + 3) / 4));
   TB200_REQUIRE(grid.y <= 65535u, "ny too large for this launch shape");
-  ct_backproject_kernel<4><<<grid, 128, 0, st>>>(nx, ny, iy_begin, iy_end, n_det, n_ang, geom, u, y, coef_host, coef_dev, z,
-                                                 norm_out ? ws : nullptr);
-  int rc = check_launch("ct_backproject");
+  if (offsets)
+    ct_backproject_kernel<4, true><<<grid, 128, 0, st>>>(nx, ny, iy_begin, iy_end, n_det, n_ang, geom, u, y, coef_host, coef_dev, z,
+                                                         z_offset, partials, po);
+  else
+    ct_backproject_kernel<4, false><<<grid, 128, 0, st>>>(nx, ny, iy_begin, iy_end, n_det, n_ang, geom, u, y, coef_host, coef_dev, z,
+                                                          z_offset, partials, po);
+  return check_launch("ct_backproject");
+}
+
+int tb200_ct_backproject_rows_f64(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* geom,
+                                  const double* u, double* y, double coef_host, const double* coef_dev, const double* z,
+                                  double* norm_out, double* ws, void* stream) {
+  TB200_REQUIRE(norm_out == nullptr || ws != nullptr, "norm_out requires a workspace");
+  if (iy_begin == iy_end) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid;
+  PeerOut po;
+  po.n = 0;
+  int rc = backproject_launch(nx, ny, iy_begin, iy_end, n_det, n_ang, geom, u, y, coef_host, coef_dev, z, 0, norm_out ? ws : nullptr,
+                              false, po, st, grid);
   if (rc) return rc;
   if (norm_out) {
     finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, (int64_t)grid.x * grid.y, norm_out);
     rc = check_launch("ct_backproject finalize");
   }
+  return rc;
+}
+
+// Sharded form (trips-py_b200/dist.py): this rank back-projects image rows [iy_begin, iy_end) from the WHOLE sinogram.
+//  * u holds all ranks' angles grouped by owner; geom[6a + 5] carries (as an int64 bit pattern) the row at which global
+//    angle a starts in u, so the pixel sums still run over the angles in global order: same bits as one GPU.
+//  * y is indexed by the global pixel number (the rank's copy of the full-length vector); the same values are stored
+//    into peers[0 .. n_peers) (the other ranks' copies) from the epilogue, followed by a system-scope fence.
+//  * z (nullable) is the rank's slice of the previous basis vector: z[pix - iy_begin*nx].
+//  * partials: 2 doubles per CTA (tb200_ct_backproject_workspace_len), to be summed over the ranks by
+//    tb200_comm_allreduce_dd; *n_partials_out receives their number.
+int tb200_ct_backproject_sharded_f64(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* geom,
+                                     const double* u, double* y, double* const* peers_host, int n_peers, double coef_host,
+                                     const double* coef_dev, const double* z, double* partials, int64_t* n_partials_out,
+                                     void* stream) {
+  TB200_REQUIRE(partials && n_partials_out, "null pointer");
+  TB200_REQUIRE(n_peers >= 0 && n_peers <= 15 && (n_peers == 0 || peers_host), "bad peer list");
+  PeerOut po;
+  po.n = n_peers;
+  for (int i = 0; i < n_peers; ++i) po.p[i] = peers_host[i];
+  dim3 grid(0, 0);
+  *n_partials_out = 0;
+  if (iy_begin == iy_end) return 0;
+  int rc = backproject_launch(nx, ny, iy_begin, iy_end, n_det, n_ang, geom, u, y, coef_host, coef_dev, z, (int64_t)iy_begin * nx,
+                              partials, true, po, (cudaStream_t)stream, grid);
+  *n_partials_out = (int64_t)grid.x * grid.y;
   return rc;
 }
 

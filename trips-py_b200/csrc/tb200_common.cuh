@@ -105,6 +105,13 @@ inline int grid_for(int64_t n, int per_block, int max_blocks) {
 
 int sm_count();
 
+// Extra destinations of a kernel's output vector: the same element is also stored at p[i][index] for i < n - device
+// pointers into the arenas of other GPUs (csrc/comm.cu), written over NVLink from the kernel epilogue.
+struct PeerOut {
+  int n;
+  double* p[15];
+};
+
 }  // namespace tb200
 
 #define TB200_REQUIRE(cond, msg)                               \

@@ -141,6 +141,17 @@ static int reduce_common(int mode, int64_t n, const double* x, const double* y, 
   return check_launch("vec_reduce finalize");
 }
 
+// The double-double partials of sum x*y (y == NULL: sum x^2) WITHOUT the final reduction: ws receives *n_partials_out
+// (hi, lo) pairs, to be summed over the ranks by tb200_comm_allreduce_dd (a vector split over several GPUs).
+int tb200_vec_dot_partials(int64_t n, const double* x, const double* y, double* ws, int64_t* n_partials_out, void* stream) {
+  TB200_REQUIRE(n >= 0 && ws && n_partials_out && (n == 0 || x), "bad argument");
+  const int g = red_grid(n);
+  if (y == nullptr) vec_reduce_kernel<0><<<g, kVecThreads, 0, (cudaStream_t)stream>>>(n, x, y, ws);
+  else vec_reduce_kernel<1><<<g, kVecThreads, 0, (cudaStream_t)stream>>>(n, x, y, ws);
+  *n_partials_out = g;
+  return check_launch("vec_dot_partials");
+}
+
 // out[0] = sum x^2, out[1] = ||x||
 int tb200_vec_norm2(int64_t n, const double* x, double* out, double* ws, void* stream) {
   return reduce_common(0, n, x, nullptr, out, ws, stream);

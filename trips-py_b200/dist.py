@@ -331,6 +331,291 @@ def sharded_ct(nx, views, comm, **kwargs):
     return ShardedRowsOperator(op, comm), rows
 
 
+# ---- NVLink peer-memory exchange (csrc/comm.cu): no NCCL on the data path --------------------------------------------
+
+import ctypes  # noqa: E402
+
+from . import _lib  # noqa: E402
+from ._lib import c_ptr, check, lib  # noqa: E402
+
+
+class _DeviceMemory:
+    """Zero-copy torch view of raw device memory (the arena is cudaMalloc'ed by libtripsb200, not by torch)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class PeerComm:
+    """One CUDA-IPC arena per rank, mapped into every other rank (tb200_comm_*).  `regions` maps a name to a length in
+    doubles; every rank must pass the same dict: the layout is the same everywhere, so `peer_ptr(name, r)` is where rank
+    r keeps that region.  torch.distributed (any backend) is used ONCE, to exchange the 64-byte IPC handles."""
+
+    BOX_ALPHA, BOX_BETA, BOX_MISC, BOX_HALO = 0, 1, 2, 3
+
+    def __init__(self, regions, group=None, device=None):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        L = lib()
+        if self.world > int(L.tb200_comm_max_ranks()):
+            raise ValueError(f"PeerComm supports up to {L.tb200_comm_max_ranks()} ranks")
+        off = int(L.tb200_comm_mailbox_bytes())
+        self.offsets, self.counts = {}, {}
+        for name, count in regions.items():
+            self.offsets[name], self.counts[name] = off, int(count)
+            off += (8 * int(count) + 255) // 256 * 256
+        self.bytes = off
+        hb = int(L.tb200_comm_handle_bytes())
+        handle = (ctypes.c_ubyte * hb)()
+        comm = ctypes.c_void_p()
+        check(L.tb200_comm_init(self.rank, self.world, self.bytes, ctypes.byref(comm), handle), "comm_init")
+        self._comm = comm
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        blob = (ctypes.c_ubyte * (hb * self.world)).from_buffer_copy(b"".join(handles))
+        check(L.tb200_comm_connect(self._comm, blob), "comm_connect")
+        self.base = [int(L.tb200_comm_arena(self._comm, r)) for r in range(self.world)]
+        self._epoch = {}
+        self._scratch = torch.zeros(2, dtype=F64, device=self.device)
+        self.barrier()  # every arena is mapped everywhere before anyone stores into a peer
+
+    def local(self, name):
+        return torch.as_tensor(_DeviceMemory(self.base[self.rank] + self.offsets[name], self.counts[name]), device=self.device)
+
+    def peer_ptr(self, name, r, offset_doubles=0):
+        return self.base[r] + self.offsets[name] + 8 * int(offset_doubles)
+
+    def peers_of(self, name, offset_doubles=0):
+        """ctypes array of the device pointers of `name` (+ offset) in every OTHER rank's arena."""
+        ptrs = [self.peer_ptr(name, r, offset_doubles) for r in range(self.world) if r != self.rank]
+        return (ctypes.c_void_p * max(len(ptrs), 1))(*ptrs), len(ptrs)
+
+    def _next_epoch(self, box):
+        e = self._epoch.get(box, 0) + 1
+        self._epoch[box] = e
+        return e
+
+    def allreduce_dd(self, box, partials, npart, out, nval=1):
+        """out[2j] = sum over ranks and partials of value j (double-double, rank order), out[2j+1] = its square root."""
+        check(lib().tb200_comm_allreduce_dd(self._comm, int(box), self._next_epoch(box), K._p(partials), int(npart), int(nval),
+                                            K._p(out), K._stream()), "comm_allreduce_dd")
+        _lib.count(1)
+        return out
+
+    def barrier(self):
+        self.allreduce_dd(self.BOX_MISC, None, 0, self._scratch)
+
+    def push(self, name, src, offset_doubles=0, ranks=None):
+        mask = sum(1 << r for r in (range(self.world) if ranks is None else ranks))
+        check(lib().tb200_comm_push(self._comm, mask, self.offsets[name] + 8 * int(offset_doubles), K._p(src), src.numel(),
+                                    K._stream()), "comm_push")
+        _lib.count(1)
+
+    def destroy(self):
+        if self._comm is not None:
+            torch.cuda.synchronize(self.device)
+            lib().tb200_comm_destroy(self._comm)
+            self._comm = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def band_rows(ny, world, rank):
+    """Image rows [lo, hi) owned by `rank`: equal bands, boundaries on multiples of 4 (the back-projector's CTA tile)."""
+    edge = lambda r: ny if r >= world else (ny * r // world) // 4 * 4  # noqa: E731
+    return edge(rank), edge(rank + 1)
+
+
+class ShardedGKState:
+    """Golub-Kahan bidiagonalisation of the matrix-free parallel-beam operator over G GPUs.
+
+    u-space (sinogram) is split by projection angle (round robin), v-space (image) by row band, and so are the retained
+    bases U and V.  The two projectors are matrix-free, so each can be restricted to ANY subset of its outputs:
+      back-projection:  rank g computes ITS BAND of A^T u from the whole u   (every pixel sums over all angles in order)
+      forward:          rank g computes ITS ANGLES of A v from the whole v
+    No partial sums ever cross GPUs - there is no floating-point reduction of vectors, so the factors are the same bits as
+    on one GPU.  What a step exchanges is the two vectors themselves: each projector's epilogue stores its part of the
+    result straight into every rank's copy over NVLink peer memory while the rest of its grid is still computing
+    (tb200_ct_*_sharded_f64), and the squared norms travel as double-double partials through the mailboxes of
+    tb200_comm_allreduce_dd, which is also the barrier that publishes the stores.  Per step and rank: 6 kernels, no NCCL.
+        K1 back-project band (+ peer stores)   K2 alpha = all-reduce(dd)   K3 v = vt / alpha (own band -> V)
+        K4 forward own angles (+ peer stores)  K5 beta  = all-reduce(dd)   K6 u = ut / beta  (own rows -> U)"""
+
+    exchange_name = "peer-to-peer stores from the projector epilogues + mailbox all-reduce (NVLink, no NCCL on the data path)"
+
+    def __init__(self, nx, views, b_local, kmax, ny=None, n_det=None, group=None, angles=None):
+        from .operators import ct_angles, ct_num_detectors
+
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        G, r = self.world, self.rank
+        dev = b_local.device
+        self.nx, self.ny = int(nx), int(nx if ny is None else ny)
+        self.n_det = ct_num_detectors(nx) if n_det is None else int(n_det)
+        theta = ct_angles(views) if angles is None else np.asarray(angles, dtype=np.float64)
+        self.views = len(theta)
+        mine = shard_angles(self.views, G, r)
+        self.L = -(-self.views // G)  # angles per rank, padded
+        self.n_loc_ang = len(mine)
+        self.m_loc = self.n_loc_ang * self.n_det
+        self.n = self.nx * self.ny
+        self.m_pad = G * self.L * self.n_det
+        self.row_lo, self.row_hi = band_rows(self.ny, G, r)
+        self.n_band = (self.row_hi - self.row_lo) * self.nx
+        if b_local.numel() != self.m_loc:
+            raise ValueError(f"rank {r} owns {self.n_loc_ang} angles: b_local must have {self.m_loc} entries")
+        K._lib.require_device()
+        # geometry: all angles (back-projection; slot 5 = first row of the angle in the gathered sinogram) and mine (forward)
+        cos_t, sin_t = torch.from_numpy(np.cos(theta)).to(dev), torch.from_numpy(np.sin(theta)).to(dev)
+        self.geom_all = torch.zeros(6 * self.views, dtype=F64, device=dev)
+        check(lib().tb200_ct_geometry(self.views, K._p(cos_t), K._p(sin_t), K._p(self.geom_all), K._stream()), "ct_geometry")
+        a = np.arange(self.views)
+        offs = torch.from_numpy((((a % G) * self.L + a // G) * self.n_det).astype(np.int64)).to(dev)
+        self.geom_all.view(torch.int64).view(self.views, 6)[:, 5] = offs
+        self.geom_loc = torch.zeros(max(6 * self.n_loc_ang, 2), dtype=F64, device=dev)
+        cm, sm = cos_t[torch.from_numpy(mine).to(dev)].contiguous(), sin_t[torch.from_numpy(mine).to(dev)].contiguous()
+        check(lib().tb200_ct_geometry(self.n_loc_ang, K._p(cm), K._p(sm), K._p(self.geom_loc), K._stream()), "ct_geometry")
+        # exchanged (unnormalised) vectors live in the arena; their normalised copies and the bases are ordinary tensors
+        self.comm = PeerComm({"vt": self.n, "ut": self.m_pad}, group=group, device=dev)
+        self.vt, self.ut = self.comm.local("vt"), self.comm.local("ut")
+        self.v_full = torch.empty(self.n, dtype=F64, device=dev)
+        self.u_full = torch.zeros(self.m_pad, dtype=F64, device=dev)
+        self.U = K.Basis(self.m_loc, kmax + 1, dev)
+        self.V = K.Basis(self.n_band, max(kmax, 1), dev)
+        self.alpha = torch.zeros((kmax + 1, 2), dtype=F64, device=dev)
+        self.beta = torch.zeros((kmax + 1, 2), dtype=F64, device=dev)
+        self.beta0 = torch.zeros(2, dtype=F64, device=dev)
+        nws = max(int(lib().tb200_ct_backproject_workspace_len(self.nx, self.ny)),
+                  int(lib().tb200_ct_forward_rays_workspace_len(self.n_det, max(self.n_loc_ang, 1))),
+                  int(lib().tb200_reduce_workspace_len()))
+        self.ws = torch.zeros(nws, dtype=F64, device=dev)
+        self.my_chunk = r * self.L * self.n_det  # where my angles sit in a gathered sinogram
+        self._vt_peers = self.comm.peers_of("vt")
+        self._ut_peers = self.comm.peers_of("ut", self.my_chunk)
+        self._npart = ctypes.c_int64(0)
+        # u_1 = b / ||b||: the norm through the mailboxes, my rows pushed to every rank's copy
+        check(lib().tb200_vec_dot_partials(self.m_loc, K._p(b_local), None, K._p(self.ws), ctypes.byref(self._npart), K._stream()),
+              "vec_dot_partials")
+        self.comm.allreduce_dd(PeerComm.BOX_BETA, self.ws, self._npart.value, self.beta0)
+        self.ut.zero_()
+        self.comm.barrier()  # nobody pushes into a copy that is still being cleared
+        self.comm.push("ut", b_local.contiguous(), self.my_chunk)
+        self.comm.barrier()
+        self._scale_u(self.beta0)
+        _lib.count(3)
+
+    @property
+    def k(self):
+        return self.V.k
+
+    def _scale_u(self, pair):
+        check(lib().tb200_comm_scale(self.m_pad, K._p(self.ut), K._p(pair[1:2]), K._p(self.u_full), self.my_chunk, self.m_loc,
+                                     K._p(self.U.next_col()), K._stream()), "comm_scale")
+        self.U.push()
+        _lib.count(1)
+
+    def backproject(self, k):
+        """K1: my band of vt = A^T u_full - beta_{k-1} v_{k-1}, stored into every rank's vt; partial norms -> ws."""
+        peers, npeers = self._vt_peers
+        check(lib().tb200_ct_backproject_sharded_f64(
+            self.nx, self.ny, self.row_lo, self.row_hi, self.n_det, self.views, K._p(self.geom_all), K._p(self.u_full),
+            K._p(self.vt), peers, npeers, 0.0, K._p(self.beta[k - 1, 1:2]) if k else None, K._p(self.V.col(k - 1)) if k else None,
+            K._p(self.ws), ctypes.byref(self._npart), K._stream()), "ct_backproject_sharded")
+        _lib.count(1)
+
+    def forward(self, k):
+        """K4: my angles of ut = A v_full - alpha_k u_k, stored into every rank's ut; partial norms -> ws."""
+        peers, npeers = self._ut_peers
+        check(lib().tb200_ct_forward_rays_sharded_f64(
+            self.nx, self.ny, self.n_det, self.n_loc_ang, K._p(self.geom_loc), K._p(self.v_full), K._p(self.ut[self.my_chunk:]),
+            peers, npeers, 0.0, K._p(self.alpha[k, 1:2]), K._p(self.U.col(k)), K._p(self.ws), ctypes.byref(self._npart),
+            K._stream()), "ct_forward_rays_sharded")
+        _lib.count(1)
+
+    def step(self):
+        k = self.V.k
+        if k + 1 >= self.alpha.shape[0]:
+            raise RuntimeError("ShardedGKState capacity exceeded")
+        self.backproject(k)
+        self.comm.allreduce_dd(PeerComm.BOX_ALPHA, self.ws, self._npart.value, self.alpha[k])
+        check(lib().tb200_comm_scale(self.n, K._p(self.vt), K._p(self.alpha[k, 1:2]), K._p(self.v_full), self.row_lo * self.nx,
+                                     self.n_band, K._p(self.V.next_col()), K._stream()), "comm_scale")
+        self.V.push()
+        _lib.count(1)
+        self.forward(k)
+        self.comm.allreduce_dd(PeerComm.BOX_BETA, self.ws, self._npart.value, self.beta[k])
+        self._scale_u(self.beta[k])
+
+    def bench_hooks(self, timed):
+        """bench.py: wrap (timed = a decorator) or restore (None) the two projector launches of a step."""
+        if timed is None:
+            for name in ("backproject", "forward"):
+                self.__dict__.pop(name, None)
+            return
+        self.backproject = timed(self.backproject)  # A^T first, then A: the order of bench.py's event list
+        self.forward = timed(self.forward)
+
+    def host_step(self, hu_k, hv_prev, beta_prev, hu_out, hv_out):
+        """One golub_kahan_update (decompositions.py:230-255) with HOST bases, this rank's part of it: hu_k = my rows of
+        u_k, hv_prev = my band of v_{k-1} (None at the first step), beta_prev = S[k-1, k-2]; the new v band / u rows are
+        written to the pinned host tensors hv_out / hu_out.  Returns (alpha, beta).  Per call: H2D of u_k and v_{k-1}, the
+        rows of u_k pushed to every rank over NVLink, K1..K6 as in step(), D2H of v, u and the two scalars."""
+        dev = self.v_full.device
+        u_k = self.U.data[0]
+        u_k.copy_(hu_k, non_blocking=True)
+        self.comm.push("ut", u_k, self.my_chunk)
+        self.comm.barrier()
+        peers, npeers = self._vt_peers
+        zb = None
+        if hv_prev is not None:
+            zb = self.V.data[0]
+            zb.copy_(hv_prev, non_blocking=True)
+            self.beta[0, 1:2].fill_(float(beta_prev))
+        check(lib().tb200_ct_backproject_sharded_f64(
+            self.nx, self.ny, self.row_lo, self.row_hi, self.n_det, self.views, K._p(self.geom_all), K._p(self.ut), K._p(self.vt),
+            peers, npeers, 0.0, K._p(self.beta[0, 1:2]) if zb is not None else None, K._p(zb), K._p(self.ws),
+            ctypes.byref(self._npart), K._stream()), "ct_backproject_sharded")
+        self.comm.allreduce_dd(PeerComm.BOX_ALPHA, self.ws, self._npart.value, self.alpha[0])
+        vb = self.V.data[1] if self.V.kmax > 1 else self.V.data[0]
+        check(lib().tb200_comm_scale(self.n, K._p(self.vt), K._p(self.alpha[0, 1:2]), K._p(self.v_full), self.row_lo * self.nx,
+                                     self.n_band, K._p(vb), K._stream()), "comm_scale")
+        hv_out.copy_(vb, non_blocking=True)
+        peers, npeers = self._ut_peers
+        check(lib().tb200_ct_forward_rays_sharded_f64(
+            self.nx, self.ny, self.n_det, self.n_loc_ang, K._p(self.geom_loc), K._p(self.v_full), K._p(self.ut[self.my_chunk:]),
+            peers, npeers, 0.0, K._p(self.alpha[0, 1:2]), K._p(u_k), K._p(self.ws), ctypes.byref(self._npart), K._stream()),
+            "ct_forward_rays_sharded")
+        self.comm.allreduce_dd(PeerComm.BOX_BETA, self.ws, self._npart.value, self.beta[1])
+        ub = self.U.data[1]
+        check(lib().tb200_comm_scale(self.m_pad, K._p(self.ut), K._p(self.beta[1, 1:2]), K._p(self.u_full), self.my_chunk,
+                                     self.m_loc, K._p(ub), K._stream()), "comm_scale")
+        hu_out.copy_(ub, non_blocking=True)
+        _lib.count(8)
+        sc = torch.stack((self.alpha[0, 1], self.beta[1, 1])).cpu().numpy()  # synchronises: the host copies are complete
+        return float(sc[0]), float(sc[1])
+
+    def scalars_host(self):
+        k = self.V.k
+        packed = torch.cat((self.beta0[1:2], self.alpha[:k, 1], self.beta[:k, 1])).cpu().numpy()
+        return packed[0], packed[1:1 + k], packed[1 + k:]
+
+    def B_host(self):
+        _, al, be = self.scalars_host()
+        k = al.size
+        B = np.zeros((k + 1, k))
+        B[np.arange(k), np.arange(k)] = al
+        B[np.arange(1, k + 1), np.arange(k)] = be
+        return B
+
+    def close(self):
+        self.comm.destroy()
+
+
 def sharded_parity_check(st, nx, views, layout, b_local, steps=10):
     """bench.py, N > 1, outside the timed region: the first `steps` (alpha, beta) of the sharded state `st` against the
     SAME problem on ONE GPU (rank 0 rebuilds the whole operator, gathers the right-hand side in angle-major order and
