@@ -29,10 +29,11 @@ def backproject_bracket(nx, ny, n_det, theta, u):
         with np.errstate(divide="ignore"):
             inv_hi, inv_hilo = 1.0 / hi, 1.0 / (hi * lo)
         proj = CX * c + CY * s
-        w = (proj + dcm) + MAGIC
+        # even detector counts: dc - 1/2 is an integer, MAGIC + (dc - 1/2) is exact and the kernel folds the two additions
+        w = proj + (MAGIC + dcm) if n_det % 2 == 0 else (proj + dcm) + MAGIC
         d0 = (w - MAGIC).astype(np.int64)  # the kernel reads the low word of w; same integer
-        for cand in (d0, d0 + 1):  # ascending detector order
-            sd = cand - dc
+        sd0 = (w - MAGIC) - dc             # the kernel's (d - dc): exact
+        for cand, sd in ((d0, sd0), (d0 + 1, sd0 + 1.0)):  # ascending detector order
             e = d2 - np.abs(sd - proj)
             inside = (cand >= 0) & (cand < n_det)
             hit = inside & (e > 0)

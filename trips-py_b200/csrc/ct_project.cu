@@ -48,8 +48,9 @@ __device__ __forceinline__ double add_if_positive(double acc, double p, int flag
 // (a0 + j) * n_det - the sharded layout, where the angles of a gathered sinogram are grouped by owner rank.
 template <bool CHECKED, int UNROLL, bool OFFS>
 __device__ __forceinline__ double bp_tile(double acc, const double* __restrict__ gtab, int na, const double* __restrict__ u, int row0,
-                                          int n_det, double cx, double cy, double dcm, double sbias, uint64_t pol_keep) {
+                                          int n_det, double cx, double cy, double dc, double kmagic, bool fold, uint64_t pol_keep) {
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (v + MAGIC) - MAGIC = v rounded to an integer
+  const double dcm = dc - 0.5;               // exact: multiples of 0.5
   const unsigned und = (unsigned)n_det;
 #pragma unroll UNROLL
   for (int j = 0; j < na; ++j) {
@@ -57,12 +58,15 @@ __device__ __forceinline__ double bp_tile(double acc, const double* __restrict__
     const double2 dh = reinterpret_cast<const double2*>(gtab)[3 * j + 1];  // d2, 1/hi
     const double inv_hilo = gtab[6 * j + 4];
     const double proj = __dadd_rn(__dmul_rn(cx, cs.x), __dmul_rn(cy, cs.y));
-    const double w = __dadd_rn(__dadd_rn(proj, dcm), MAGIC);
+    // d0 = round(proj + dc - 1/2) = floor(proj + dc) up to ties, as MAGIC + d0 in one double.  Even detector counts:
+    // dc - 1/2 is an integer, MAGIC + (dc - 1/2) is exact and the two additions fold into one (the sum
+    // proj + (MAGIC + dcm) rounds to the same integer as (proj + dcm) + MAGIC except on ties of the first rounding,
+    // where either neighbour is a valid bracket origin - see the header).
+    const double w = fold ? __dadd_rn(proj, kmagic) : __dadd_rn(__dadd_rn(proj, dcm), MAGIC);
     const int d0 = __double2loint(w);  // low word of MAGIC is 0: the integer, in two's complement
-    // (d - dc) for d0 and d0 + 1: the integer goes into the mantissa of 2^51 (ulp 0.5), one exact subtraction
-    // removes the bias and the detector centre; wrong only for d < 0, where CHECKED masks the candidate anyway
-    const double sd0 = __dsub_rn(__hiloint2double(0x43200000, d0 << 1), sbias);
-    const double sd1 = __dsub_rn(__hiloint2double(0x43200000, (d0 + 1) << 1), sbias);
+    // (d - dc) for d0 and d0 + 1: w - MAGIC is the integer d0 as a double (exact), minus the half-integer dc (exact)
+    const double sd0 = __dsub_rn(__dsub_rn(w, MAGIC), dc);
+    const double sd1 = __dadd_rn(sd0, 1.0);
     const double e0 = __dsub_rn(dh.x, fabs(__dsub_rn(sd0, proj)));  // d2 - |t|: positive inside the footprint
     const double e1 = __dsub_rn(dh.x, fabs(__dsub_rn(sd1, proj)));
     // e > 0 (never denormal here: |t| and d2 are O(1)) <=> the high word, read as an int, is positive
@@ -102,8 +106,8 @@ ct_backproject_kernel(int nx, int ny, int iy_begin, int iy_end, int n_det, int n
   const uint64_t pol_keep = policy_evict_last();
   const double cx = (double)ix - 0.5 * (double)(nx - 1), cy = (double)iy - 0.5 * (double)(ny - 1);
   const double dc = 0.5 * (double)(n_det - 1);
-  const double dcm = dc - 0.5;                      // exact: multiples of 0.5
-  const double sbias = 2251799813685248.0 + dc;     // 2^51 + dc, exact
+  const bool fold = (n_det & 1) == 0;               // dc - 1/2 is an integer: MAGIC + (dc - 1/2) is exact
+  const double kmagic = 6755399441055744.0 + (dc - 0.5);
   // |proj| <= |(cx, cy)|: with two bins of slack every candidate of every angle is a valid detector index
   const bool interior = __all_sync(0xffffffffu, sqrt(cx * cx + cy * cy) + 2.5 <= dc);
   double acc = 0.0;
@@ -114,8 +118,8 @@ ct_backproject_kernel(int nx, int ny, int iy_begin, int iy_end, int n_det, int n
     for (int i = threadIdx.x; i < na * 3; i += 128)
       reinterpret_cast<double2*>(gtab)[i] = reinterpret_cast<const double2*>(geom + 6 * (int64_t)a0)[i];
     __syncthreads();
-    if (interior) acc = bp_tile<false, UNROLL, OFFS>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dcm, sbias, pol_keep);
-    else acc = bp_tile<true, UNROLL, OFFS>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dcm, sbias, pol_keep);
+    if (interior) acc = bp_tile<false, UNROLL, OFFS>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dc, kmagic, fold, pol_keep);
+    else acc = bp_tile<true, UNROLL, OFFS>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dc, kmagic, fold, pol_keep);
   }
 
   const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
