@@ -32,8 +32,6 @@ __global__ void ct_geometry_kernel(int n_ang, const double* __restrict__ cosv, c
   o[0] = g.c, o[1] = g.s, o[2] = g.d2, o[3] = g.inv_hi, o[4] = g.inv_hilo, o[5] = 0.0;
 }
 
-// CTA = 4 warps side by side, each warp an 8 x 4 pixel tile (32 x 4 pixels per CTA): a compact tile keeps the two
-// gather requests of an angle within 2-3 sectors whatever the angle.
 constexpr int BP_TA = 256;  // angles per shared-memory tile of the geometry table (12 KB)
 
 // acc + p when flag > 0, else acc: one predicated DADD (the C form compiles to an add and two selects)
@@ -42,13 +40,18 @@ __device__ __forceinline__ double add_if_positive(double acc, double p, int flag
   return acc;
 }
 
-// One tile of angles for one pixel.  CHECKED = false is the path of warps whose pixels project at least two bins
-// inside the detector at every angle (all but the image corners): no bounds tests, unconditional gathers.
+// One tile of angles for the two pixels of a thread ((ix, iy) and (ix, iy + 4): they share cx*c, the geometry loads and
+// the loop overhead).  CHECKED = false is the path of warps whose pixels project at least two bins inside the detector at
+// every angle (all but the image corners): no bounds tests, unconditional gathers.
 // OFFS: the sinogram rows of angle j start at the int64 stored (bit pattern) in gtab[6j + 5] instead of at
 // (a0 + j) * n_det - the sharded layout, where the angles of a gathered sinogram are grouped by owner rank.
-template <bool CHECKED, int UNROLL, bool OFFS>
-__device__ __forceinline__ double bp_tile(double acc, const double* __restrict__ gtab, int na, const double* __restrict__ u, int row0,
-                                          int n_det, double cx, double cy, double dc, double kmagic, bool fold, uint64_t pol_keep) {
+// FOLD (even detector counts): dc - 1/2 is an integer, MAGIC + (dc - 1/2) is exact and the two additions that round
+// proj + dc - 1/2 to an integer fold into one (same integer except on ties of the first rounding, where either neighbour
+// is a valid bracket origin - see the header).
+template <bool CHECKED, int UNROLL, bool OFFS, bool FOLD>
+__device__ __forceinline__ void bp_tile(double (&acc)[2], const double* __restrict__ gtab, int na, const double* __restrict__ u,
+                                        int row0, int n_det, double cx, const double (&cy)[2], double dc, double kmagic,
+                                        uint64_t pol_keep) {
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: (v + MAGIC) - MAGIC = v rounded to an integer
   const double dcm = dc - 0.5;               // exact: multiples of 0.5
   const unsigned und = (unsigned)n_det;
@@ -57,42 +60,46 @@ __device__ __forceinline__ double bp_tile(double acc, const double* __restrict__
     const double2 cs = reinterpret_cast<const double2*>(gtab)[3 * j];      // c, s
     const double2 dh = reinterpret_cast<const double2*>(gtab)[3 * j + 1];  // d2, 1/hi
     const double inv_hilo = gtab[6 * j + 4];
-    const double proj = __dadd_rn(__dmul_rn(cx, cs.x), __dmul_rn(cy, cs.y));
-    // d0 = round(proj + dc - 1/2) = floor(proj + dc) up to ties, as MAGIC + d0 in one double.  Even detector counts:
-    // dc - 1/2 is an integer, MAGIC + (dc - 1/2) is exact and the two additions fold into one (the sum
-    // proj + (MAGIC + dcm) rounds to the same integer as (proj + dcm) + MAGIC except on ties of the first rounding,
-    // where either neighbour is a valid bracket origin - see the header).
-    const double w = fold ? __dadd_rn(proj, kmagic) : __dadd_rn(__dadd_rn(proj, dcm), MAGIC);
-    const int d0 = __double2loint(w);  // low word of MAGIC is 0: the integer, in two's complement
-    // (d - dc) for d0 and d0 + 1: w - MAGIC is the integer d0 as a double (exact), minus the half-integer dc (exact)
-    const double sd0 = __dsub_rn(__dsub_rn(w, MAGIC), dc);
-    const double sd1 = __dadd_rn(sd0, 1.0);
-    const double e0 = __dsub_rn(dh.x, fabs(__dsub_rn(sd0, proj)));  // d2 - |t|: positive inside the footprint
-    const double e1 = __dsub_rn(dh.x, fabs(__dsub_rn(sd1, proj)));
-    // e > 0 (never denormal here: |t| and d2 are O(1)) <=> the high word, read as an int, is positive
     const int rowj = OFFS ? (int)__double_as_longlong(gtab[6 * j + 5]) : row0 + j * n_det;
-    if (CHECKED) {
-      const double* up = u + ((int64_t)rowj + d0);
-      const bool in0 = (unsigned)d0 < und, in1 = (unsigned)(d0 + 1) < und;
-      const double u0 = in0 ? ld_gather_f64(up, pol_keep) : 0.0;
-      const double u1 = in1 ? ld_gather_f64(up + 1, pol_keep) : 0.0;
-      const double p0 = __dmul_rn(chord_from_margin(e0, dh.y, inv_hilo), u0);
-      const double p1 = __dmul_rn(chord_from_margin(e1, dh.y, inv_hilo), u1);
-      if (in0 && __double2hiint(e0) > 0) acc = __dadd_rn(acc, p0);
-      if (in1 && __double2hiint(e1) > 0) acc = __dadd_rn(acc, p1);
-    } else {
-      const double* up = u + (unsigned)(rowj + d0);  // n_ang * n_det < 2^31 is checked at launch
-      const double p0 = __dmul_rn(chord_from_margin(e0, dh.y, inv_hilo), ld_gather_f64(up, pol_keep));
-      const double p1 = __dmul_rn(chord_from_margin(e1, dh.y, inv_hilo), ld_gather_f64(up + 1, pol_keep));
-      acc = add_if_positive(acc, p0, __double2hiint(e0));
-      acc = add_if_positive(acc, p1, __double2hiint(e1));
+    const double pc = __dmul_rn(cx, cs.x);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const double proj = __dadd_rn(pc, __dmul_rn(cy[q], cs.y));
+      // d0 = round(proj + dc - 1/2) = floor(proj + dc) up to ties, as MAGIC + d0 in one double
+      const double w = FOLD ? __dadd_rn(proj, kmagic) : __dadd_rn(__dadd_rn(proj, dcm), MAGIC);
+      const int d0 = __double2loint(w);  // low word of MAGIC is 0: the integer, in two's complement
+      // (d - dc) for d0 and d0 + 1: w - MAGIC is the integer d0 as a double (exact), minus the half-integer dc (exact)
+      const double sd0 = __dsub_rn(__dsub_rn(w, MAGIC), dc);
+      const double sd1 = __dadd_rn(sd0, 1.0);
+      const double e0 = __dsub_rn(dh.x, fabs(__dsub_rn(sd0, proj)));  // d2 - |t|: positive inside the footprint
+      const double e1 = __dsub_rn(dh.x, fabs(__dsub_rn(sd1, proj)));
+      // e > 0 (never denormal here: |t| and d2 are O(1)) <=> the high word, read as an int, is positive
+      if (CHECKED) {
+        const double* up = u + ((int64_t)rowj + d0);
+        const bool in0 = (unsigned)d0 < und, in1 = (unsigned)(d0 + 1) < und;
+        const double u0 = in0 ? ld_gather_f64(up, pol_keep) : 0.0;
+        const double u1 = in1 ? ld_gather_f64(up + 1, pol_keep) : 0.0;
+        const double p0 = __dmul_rn(chord_from_margin(e0, dh.y, inv_hilo), u0);
+        const double p1 = __dmul_rn(chord_from_margin(e1, dh.y, inv_hilo), u1);
+        if (in0 && __double2hiint(e0) > 0) acc[q] = __dadd_rn(acc[q], p0);
+        if (in1 && __double2hiint(e1) > 0) acc[q] = __dadd_rn(acc[q], p1);
+      } else {
+        const double* up = u + (unsigned)(rowj + d0);  // n_ang * n_det < 2^31 is checked at launch
+        const double p0 = __dmul_rn(chord_from_margin(e0, dh.y, inv_hilo), ld_gather_f64(up, pol_keep));
+        const double p1 = __dmul_rn(chord_from_margin(e1, dh.y, inv_hilo), ld_gather_f64(up + 1, pol_keep));
+        acc[q] = add_if_positive(acc[q], p0, __double2hiint(e0));
+        acc[q] = add_if_positive(acc[q], p1, __double2hiint(e1));
+      }
     }
   }
-  return acc;
 }
 
-template <int UNROLL, bool OFFS>
-__global__ void __launch_bounds__(128, 8)
+// CTA = 4 warps side by side, each warp two 8 x 4 pixel tiles one above the other (32 x 8 pixels per CTA, two pixels per
+// thread): a compact tile keeps the two gather requests of an angle within 2-3 sectors whatever the angle.
+constexpr int BP_ROWS = 8;  // image rows per CTA
+
+template <int UNROLL, bool OFFS, bool FOLD>
+__global__ void __launch_bounds__(128, 6)
 ct_backproject_kernel(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* __restrict__ geom,
                       const double* __restrict__ u, double* __restrict__ y, double coef_host,
                       const double* __restrict__ coef_dev, const double* __restrict__ z, int64_t z_offset,
@@ -101,16 +108,16 @@ ct_backproject_kernel(int nx, int ny, int iy_begin, int iy_end, int n_det, int n
   __shared__ double red[64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ix = blockIdx.x * 32 + warp * 8 + (lane & 7);
-  const int iy = iy_begin + blockIdx.y * 4 + (lane >> 3);
-  const bool valid = ix < nx && iy < iy_end;
+  const int iy0 = iy_begin + blockIdx.y * BP_ROWS + (lane >> 3);
   const uint64_t pol_keep = policy_evict_last();
-  const double cx = (double)ix - 0.5 * (double)(nx - 1), cy = (double)iy - 0.5 * (double)(ny - 1);
+  const double cx = (double)ix - 0.5 * (double)(nx - 1);
+  const double cy[2] = {(double)iy0 - 0.5 * (double)(ny - 1), (double)(iy0 + 4) - 0.5 * (double)(ny - 1)};
   const double dc = 0.5 * (double)(n_det - 1);
-  const bool fold = (n_det & 1) == 0;               // dc - 1/2 is an integer: MAGIC + (dc - 1/2) is exact
-  const double kmagic = 6755399441055744.0 + (dc - 0.5);
+  const double kmagic = 6755399441055744.0 + (dc - 0.5);  // FOLD (even n_det): dc - 1/2 is an integer, the sum is exact
   // |proj| <= |(cx, cy)|: with two bins of slack every candidate of every angle is a valid detector index
-  const bool interior = __all_sync(0xffffffffu, sqrt(cx * cx + cy * cy) + 2.5 <= dc);
-  double acc = 0.0;
+  const double cymax = fmax(fabs(cy[0]), fabs(cy[1]));
+  const bool interior = __all_sync(0xffffffffu, sqrt(cx * cx + cymax * cymax) + 2.5 <= dc);
+  double acc[2] = {0.0, 0.0};
 
   for (int a0 = 0; a0 < n_ang; a0 += BP_TA) {
     const int na = min(BP_TA, n_ang - a0);
@@ -118,20 +125,25 @@ ct_backproject_kernel(int nx, int ny, int iy_begin, int iy_end, int n_det, int n
     for (int i = threadIdx.x; i < na * 3; i += 128)
       reinterpret_cast<double2*>(gtab)[i] = reinterpret_cast<const double2*>(geom + 6 * (int64_t)a0)[i];
     __syncthreads();
-    if (interior) acc = bp_tile<false, UNROLL, OFFS>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dc, kmagic, fold, pol_keep);
-    else acc = bp_tile<true, UNROLL, OFFS>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dc, kmagic, fold, pol_keep);
+    if (interior) bp_tile<false, UNROLL, OFFS, FOLD>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dc, kmagic, pol_keep);
+    else bp_tile<true, UNROLL, OFFS, FOLD>(acc, gtab, na, u, a0 * n_det, n_det, cx, cy, dc, kmagic, pol_keep);
   }
 
   const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
   dd_t nrm = dd_zero();
-  if (valid) {
-    const int64_t pix = (int64_t)iy * nx + ix;
-    if (z != nullptr) acc = __dsub_rn(acc, __dmul_rn(coef, z[pix - z_offset]));
-    y[pix] = acc;
 #pragma unroll
-    for (int p = 0; p < 15; ++p)  // the other GPUs' copies of the vector, over NVLink (unrolled: parameters stay in the constant bank)
-      if (p < po.n) po.p[p][pix] = acc;
-    nrm = dd_fma(nrm, acc, acc);
+  for (int q = 0; q < 2; ++q) {
+    const int iy = iy0 + 4 * q;
+    if (ix < nx && iy < iy_end) {
+      const int64_t pix = (int64_t)iy * nx + ix;
+      double v = acc[q];
+      if (z != nullptr) v = __dsub_rn(v, __dmul_rn(coef, z[pix - z_offset]));
+      y[pix] = v;
+#pragma unroll
+      for (int p = 0; p < 15; ++p)  // the other GPUs' copies of the vector, over NVLink (unrolled: parameters stay in the constant bank)
+        if (p < po.n) po.p[p][pix] = v;
+      nrm = dd_fma(nrm, v, v);
+    }
   }
   if (po.n > 0) __threadfence_system();
   if (partials != nullptr) {
@@ -189,14 +201,20 @@ static int backproject_launch(int nx, int ny, int iy_begin, int iy_end, int n_de
   TB200_REQUIRE((int64_t)nx * ny < ((int64_t)1 << 31) && (int64_t)n_ang * n_det < ((int64_t)1 << 31), "index space exceeds int32");
   TB200_REQUIRE(y && (n_ang == 0 || (geom && u)), "null pointer");
   TB200_REQUIRE(((uintptr_t)geom % 16) == 0, "geom must be 16-byte aligned");
-  grid = dim3((unsigned)((nx + 31) / 32), (unsigned)((iy_end - iy_begin + 3) / 4));
+  grid = dim3((unsigned)((nx + 31) / 32), (unsigned)((iy_end - iy_begin + BP_ROWS - 1) / BP_ROWS));
   TB200_REQUIRE(grid.y <= 65535u, "ny too large for this launch shape");
-  if (offsets)
-    ct_backproject_kernel<4, true><<<grid, 128, 0, st>>>(nx, ny, iy_begin, iy_end, n_det, n_ang, geom, u, y, coef_host, coef_dev, z,
-                                                         z_offset, partials, po);
-  else
-    ct_backproject_kernel<4, false><<<grid, 128, 0, st>>>(nx, ny, iy_begin, iy_end, n_det, n_ang, geom, u, y, coef_host, coef_dev, z,
-                                                          z_offset, partials, po);
+#define BP_LAUNCH(OFFS, FOLD)                                                                                             \
+  ct_backproject_kernel<4, OFFS, FOLD><<<grid, 128, 0, st>>>(nx, ny, iy_begin, iy_end, n_det, n_ang, geom, u, y, coef_host, coef_dev, \
+                                                             z, z_offset, partials, po)
+  const bool fold = (n_det & 1) == 0;
+  if (offsets) {
+    if (fold) BP_LAUNCH(true, true);
+    else BP_LAUNCH(true, false);
+  } else {
+    if (fold) BP_LAUNCH(false, true);
+    else BP_LAUNCH(false, false);
+  }
+#undef BP_LAUNCH
   return check_launch("ct_backproject");
 }
 
