@@ -454,7 +454,7 @@ def main():
         st = None
         if layout == "implicit" and args.exchange != "nccl":
             try:
-                st = tbdist.ShardedGKState(nx, views, b, K + W)
+                st = tbdist.BandShardedCT(nx, views, device=dev).gk_state(b, K + W)
             except Exception as exc:  # noqa: BLE001  (CUDA IPC unavailable in this container: use the NCCL transport)
                 if args.exchange == "p2p":
                     raise
@@ -669,7 +669,7 @@ def main():
         config = dict(base_config)
         config.update({"nnz": nnz, "parallelism": (f"u-space by angle, v-space by image band x{world}; exchange: {exchange}"
                                                    if world > 1 else "single GPU"),
-                       "spmv_order": args.order, "spmv_variant": args.variant, "layout": layout,
+                       "exchange_fallback": exchange_fallback, "spmv_order": args.order, "spmv_variant": args.variant, "layout": layout,
                        "matrix_bytes": (A.projector.nbytes if layout == "implicit" else 2 * (val_bytes + 4) * nnz),
                        "l2_note": (("matrix-free: per step the kernels read the image and the sinogram (L2 resident by "
                                     "design) and write them once; nothing else is streamed, so there is no cold input to "

@@ -184,16 +184,27 @@ def _p2p_worker(rank, world, port, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        from trips_b200.dist import ShardedGKState, band_rows, shard_angles
+        import trips_b200 as tb
+        from trips_b200.dist import BandComm, BandShardedCT, band_rows
 
         n_det = O.ct_num_detectors(PNX)
         b = np.random.default_rng(11).standard_normal(PVIEWS * n_det)
-        mine = shard_angles(PVIEWS, world, rank)
-        rows = (mine[:, None] * n_det + np.arange(n_det)[None, :]).reshape(-1)
-        st = ShardedGKState(PNX, PVIEWS, torch.from_numpy(b[rows]).cuda(), PSTEPS, ny=PNY)
+        op = BandShardedCT(PNX, PVIEWS, ny=PNY)
+        rows = op.rows
+        lo, hi = band_rows(PNY, world, rank)
+        assert op.band == (lo * PNX, hi * PNX)
+        # operator level first (gather by peer pushes + local projector) and two solvers on top of it
+        rng = np.random.default_rng(3)
+        xf, uf = rng.standard_normal(PNX * PNY), rng.standard_normal(PVIEWS * n_det)
+        y_rows = op.apply_dev(torch.from_numpy(xf[lo * PNX:hi * PNX]).cuda()).cpu().numpy()
+        z_band = op.adjoint_dev(torch.from_numpy(uf[rows]).cuda()).cpu().numpy()
+        comm = BandComm()
+        xt = O.shepp_logan(max(PNX, PNY))[:PNY, :PNX].reshape(-1, 1)
+        x_l, i_l = tb.Hybrid_LSQR(op, b[rows], n_iter=10, regparam=1e-2, x_true=xt[lo * PNX:hi * PNX], b200_comm=comm)
+        x_c, i_c = tb.CGLS(op, b[rows], np.zeros((op.shape[1], 1)), 8, 0.0, b200_comm=comm)
+        st = op.gk_state(torch.from_numpy(b[rows]).cuda(), PSTEPS)
         for _ in range(PSTEPS):
             st.step()
-        lo, hi = band_rows(PNY, world, rank)
         # host-buffer step on top of the finished state (the e2e path of bench.py): repeat step 1 from host arrays
         hu = torch.empty((2, st.m_loc), dtype=torch.float64).pin_memory()
         hv = torch.empty((1, st.n_band), dtype=torch.float64).pin_memory()
@@ -201,7 +212,8 @@ def _p2p_worker(rank, world, port, out_dir):
         hu[0].copy_(torch.from_numpy(U[:, 0]))
         al, be = st.host_step(hu[0], None, 0.0, hu[1], hv[0])
         np.savez(os.path.join(out_dir, f"p{rank}.npz"), U=U, V=V, B=B, rows=rows, band=np.array([lo, hi]),
-                 host=np.array([al, be]), hu1=hu[1].numpy(), hv0=hv[0].numpy())
+                 host=np.array([al, be]), hu1=hu[1].numpy(), hv0=hv[0].numpy(), y_rows=y_rows, z_band=z_band,
+                 x_lsqr=x_l, rre_lsqr=np.array(i_l["relError"]), x_cgls=x_c)
         st.close()
     finally:
         dist.destroy_process_group()
@@ -225,9 +237,23 @@ def test_band_sharded_matrix_free_golub_kahan_is_bit_identical_to_one_gpu(tmp_pa
     parts = [np.load(tmp_path / f"p{r}.npz") for r in range(world)]
     n_det = O.ct_num_detectors(PNX)
     b = np.random.default_rng(11).standard_normal(PVIEWS * n_det)
-    one = tb.golub_kahan_device(tb.ParallelBeamCT(PNX, PVIEWS, ny=PNY, layout="implicit"), b, PSTEPS)
+    A1 = tb.ParallelBeamCT(PNX, PVIEWS, ny=PNY, layout="implicit")
+    one = tb.golub_kahan_device(A1, b, PSTEPS)
     U1, V1, B1 = one.U.to_numpy(), one.V.to_numpy(), one.B_host()
+    rng = np.random.default_rng(3)
+    xf, uf = rng.standard_normal(PNX * PNY), rng.standard_normal(PVIEWS * n_det)
+    y1, z1 = A1 @ xf, A1.T @ uf
+    xt = O.shepp_logan(max(PNX, PNY))[:PNY, :PNX].reshape(-1, 1)
+    xl1, il1 = tb.Hybrid_LSQR(A1, b, n_iter=10, regparam=1e-2, x_true=xt)
+    xc1, _ = tb.CGLS(A1, b, np.zeros((PNX * PNY, 1)), 8, 0.0)
+    rel = lambda a, c: np.linalg.norm(a - c) / np.linalg.norm(c)  # noqa: E731
     for p in parts:
+        lo, hi = p["band"]
+        assert np.array_equal(p["y_rows"], y1[p["rows"]]) and np.array_equal(p["z_band"], z1[lo * PNX:hi * PNX])
+        # Hybrid_LSQR runs the fused recurrence (bit-identical factors); CGLS sums its norms through torch.distributed
+        assert np.array_equal(p["x_lsqr"], xl1[lo * PNX:hi * PNX])
+        assert np.allclose(p["rre_lsqr"], il1["relError"], rtol=1e-12)
+        assert rel(p["x_cgls"], xc1[lo * PNX:hi * PNX]) < 1e-9
         assert np.array_equal(p["B"], B1)
         assert np.array_equal(p["U"], U1[p["rows"]])
         lo, hi = p["band"]

@@ -432,6 +432,149 @@ def band_rows(ny, world, rank):
     return edge(rank), edge(rank + 1)
 
 
+class BandComm(_Comm):
+    """Communicator of the solvers on a BandShardedCT operator: data space split by angle, model space by image band;
+    scalar reductions (norms, dots, k-vectors) over either are summed through torch.distributed."""
+
+    SHARDED = ("data", "model")
+
+
+class BandShardedCT(LinearOperator):
+    """The matrix-free parallel-beam operator split over the G GPUs of a node: THIS RANK'S ANGLES x THIS
+    RANK'S IMAGE BAND.  shape = (m_loc, n_band): apply_dev maps the rank's band of x to the rank's rows of A x,
+    adjoint_dev the rank's rows of u to the rank's band of A^T u; the other ranks' parts travel over NVLink peer memory
+    (PeerComm), never through NCCL.  Because the projectors are matrix-free, each output element is computed on ONE rank
+    from the whole input in the single-GPU order: products are bit-identical to ParallelBeamCT's.
+    `rows` / `band` say which entries of a full sinogram / image are this rank's.  `gk_state(b_local, kmax)` is the fused
+    Golub-Kahan recurrence (ShardedGKState); the solvers take `b200_comm=BandComm()` next to this operator."""
+
+    fused = True
+
+    def __init__(self, nx, views, ny=None, n_det=None, angles=None, group=None, device=None):
+        from .operators import ct_angles, ct_num_detectors, default_device
+
+        dev = torch.device(device) if device is not None else default_device()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        G, r = self.world, self.rank
+        self.nx, self.ny = int(nx), int(nx if ny is None else ny)
+        self.n_det = ct_num_detectors(nx) if n_det is None else int(n_det)
+        theta = ct_angles(views) if angles is None else np.asarray(angles, dtype=np.float64)
+        self.theta = theta
+        self.views = len(theta)
+        self.mine = shard_angles(self.views, G, r)
+        self.L = -(-self.views // G)  # angles per rank, padded
+        self.n_loc_ang = len(self.mine)
+        self.m_loc = self.n_loc_ang * self.n_det
+        self.n = self.nx * self.ny
+        self.m_pad = G * self.L * self.n_det
+        self.row_lo, self.row_hi = band_rows(self.ny, G, r)
+        self.n_band = (self.row_hi - self.row_lo) * self.nx
+        super().__init__((self.m_loc, self.n_band), dev)
+        K._lib.require_device()
+        # geometry: all angles (back-projection; slot 5 = first row of the angle in the gathered sinogram) and mine (forward)
+        cos_t, sin_t = torch.from_numpy(np.cos(theta)).to(dev), torch.from_numpy(np.sin(theta)).to(dev)
+        self.geom_all = torch.zeros(max(6 * self.views, 2), dtype=F64, device=dev)
+        check(lib().tb200_ct_geometry(self.views, K._p(cos_t), K._p(sin_t), K._p(self.geom_all), K._stream()), "ct_geometry")
+        a = np.arange(self.views)
+        offs = torch.from_numpy((((a % G) * self.L + a // G) * self.n_det).astype(np.int64)).to(dev)
+        self.geom_all.view(torch.int64)[:6 * self.views].view(self.views, 6)[:, 5] = offs
+        self.geom_loc = torch.zeros(max(6 * self.n_loc_ang, 2), dtype=F64, device=dev)
+        idx = torch.from_numpy(self.mine).to(dev)
+        cm, sm = cos_t[idx].contiguous(), sin_t[idx].contiguous()
+        check(lib().tb200_ct_geometry(self.n_loc_ang, K._p(cm), K._p(sm), K._p(self.geom_loc), K._stream()), "ct_geometry")
+        _lib.count(2)
+        # every rank's copies of a gathered image ("vt") and a gathered sinogram ("ut") live in the peer-mapped arena
+        self.comm = PeerComm({"vt": self.n, "ut": self.m_pad}, group=group, device=dev)
+        self.vt, self.ut = self.comm.local("vt"), self.comm.local("ut")
+        self.ut.zero_()  # padding rows of ranks with fewer angles stay zero
+        self.comm.barrier()
+        nws = max(int(lib().tb200_ct_backproject_workspace_len(self.nx, self.ny)),
+                  int(lib().tb200_ct_forward_rays_workspace_len(self.n_det, max(self.n_loc_ang, 1))),
+                  int(lib().tb200_reduce_workspace_len()))
+        self.ws = torch.zeros(nws, dtype=F64, device=dev)
+        self.my_chunk = r * self.L * self.n_det  # where my angles sit in a gathered sinogram
+        self.vt_peers = self.comm.peers_of("vt")
+        self.ut_peers = self.comm.peers_of("ut", self.my_chunk)
+        self.npart = ctypes.c_int64(0)
+
+    @property
+    def rows(self):
+        """Indices of this rank's entries in a full angle-major sinogram: b_local = b_full[rows]."""
+        return (self.mine[:, None] * self.n_det + np.arange(self.n_det)[None, :]).reshape(-1)
+
+    @property
+    def band(self):
+        """(lo, hi): this rank's entries of a full row-major image are x_full[lo:hi]."""
+        return self.row_lo * self.nx, self.row_hi * self.nx
+
+    @property
+    def nnz(self):
+        return None
+
+    def gk_state(self, b_local, kmax):
+        return ShardedGKState(self, b_local, kmax)
+
+    # -- the two sharded projector launches --------------------------------------------------------------------------
+    def launch_backproject(self, u_full, out_full, peers, coef_dev, z_band, coef_host=0.0):
+        ptrs, n = peers if peers is not None else (None, 0)
+        check(lib().tb200_ct_backproject_sharded_f64(
+            self.nx, self.ny, self.row_lo, self.row_hi, self.n_det, self.views, K._p(self.geom_all), K._p(u_full), K._p(out_full),
+            ptrs, n, float(coef_host), K._p(coef_dev), K._p(z_band), K._p(self.ws), ctypes.byref(self.npart), K._stream()),
+            "ct_backproject_sharded")
+        _lib.count(1)
+
+    def launch_forward(self, x_full, out_rows, peers, coef_dev, z_rows, coef_host=0.0):
+        ptrs, n = peers if peers is not None else (None, 0)
+        check(lib().tb200_ct_forward_rays_sharded_f64(
+            self.nx, self.ny, self.n_det, self.n_loc_ang, K._p(self.geom_loc), K._p(x_full), K._p(out_rows), ptrs, n,
+            float(coef_host), K._p(coef_dev), K._p(z_rows), K._p(self.ws), ctypes.byref(self.npart), K._stream()),
+            "ct_forward_rays_sharded")
+        _lib.count(1)
+
+    def _finish(self, norm_out):
+        if norm_out is not None:  # LOCAL sum of squares; the solver's communicator sums it over the ranks
+            check(lib().tb200_reduce_finalize(K._p(self.ws), self.npart.value, K._p(norm_out), K._stream()), "reduce_finalize")
+            _lib.count(1)
+
+    def _coef(self, coef, z):
+        if z is None:
+            return 0.0, None
+        return (0.0, coef) if isinstance(coef, torch.Tensor) else (float(coef), None)
+
+    # -- operator interface (solver level): gather by peer pushes, then the local projector -----------------------------
+    def apply_dev(self, x, out=None, coef=None, z=None, norm_out=None):
+        """rows_g(A x) from the band x: every rank pushes its band into all ranks' copy of the image first."""
+        K._vec(x, self.n_band, "x (this rank's image band)")
+        out = torch.empty(self.m_loc, dtype=F64, device=self.device) if out is None else K._vec(out, self.m_loc, "out")
+        self.comm.barrier()  # every rank is done reading the previous gathered image
+        self.comm.push("vt", x, self.row_lo * self.nx)
+        self.comm.barrier()
+        ch, cd = self._coef(coef, z)
+        self.launch_forward(self.vt, out, None, cd, z, ch)
+        self._finish(norm_out)
+        return out
+
+    def adjoint_dev(self, u, out=None, coef=None, z=None, norm_out=None):
+        """band_g(A^T u) from the rank's rows of u: every rank pushes its rows into all ranks' copy of the sinogram first."""
+        K._vec(u, self.m_loc, "u (this rank's sinogram rows)")
+        self.comm.barrier()
+        self.comm.push("ut", u, self.my_chunk)
+        self.comm.barrier()
+        ch, cd = self._coef(coef, z)
+        full = torch.empty(self.n, dtype=F64, device=self.device)  # the kernel addresses by global pixel number
+        self.launch_backproject(self.ut, full, None, cd, z, ch)
+        self._finish(norm_out)
+        band = full[self.row_lo * self.nx:self.row_hi * self.nx]
+        if out is None:
+            return band.clone()
+        K._vec(out, self.n_band, "out").copy_(band)
+        return out
+
+    def close(self):
+        self.comm.destroy()
+
+
 class ShardedGKState:
     """Golub-Kahan bidiagonalisation of the matrix-free parallel-beam operator over G GPUs.
 
@@ -449,40 +592,17 @@ class ShardedGKState:
 
     exchange_name = "peer-to-peer stores from the projector epilogues + mailbox all-reduce (NVLink, no NCCL on the data path)"
 
-    def __init__(self, nx, views, b_local, kmax, ny=None, n_det=None, group=None, angles=None):
-        from .operators import ct_angles, ct_num_detectors
+    def __init__(self, op, b_local, kmax):
+        if not isinstance(b_local, torch.Tensor):
+            from .operators import to_device_vector
 
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        G, r = self.world, self.rank
-        dev = b_local.device
-        self.nx, self.ny = int(nx), int(nx if ny is None else ny)
-        self.n_det = ct_num_detectors(nx) if n_det is None else int(n_det)
-        theta = ct_angles(views) if angles is None else np.asarray(angles, dtype=np.float64)
-        self.views = len(theta)
-        mine = shard_angles(self.views, G, r)
-        self.L = -(-self.views // G)  # angles per rank, padded
-        self.n_loc_ang = len(mine)
-        self.m_loc = self.n_loc_ang * self.n_det
-        self.n = self.nx * self.ny
-        self.m_pad = G * self.L * self.n_det
-        self.row_lo, self.row_hi = band_rows(self.ny, G, r)
-        self.n_band = (self.row_hi - self.row_lo) * self.nx
+            b_local = to_device_vector(b_local, op.device)
+        self.op, self.comm = op, op.comm
+        dev = op.device
+        for name in ("nx", "ny", "n_det", "views", "n", "m_loc", "m_pad", "n_band", "row_lo", "row_hi", "my_chunk", "vt", "ut", "ws"):
+            setattr(self, name, getattr(op, name))
         if b_local.numel() != self.m_loc:
-            raise ValueError(f"rank {r} owns {self.n_loc_ang} angles: b_local must have {self.m_loc} entries")
-        K._lib.require_device()
-        # geometry: all angles (back-projection; slot 5 = first row of the angle in the gathered sinogram) and mine (forward)
-        cos_t, sin_t = torch.from_numpy(np.cos(theta)).to(dev), torch.from_numpy(np.sin(theta)).to(dev)
-        self.geom_all = torch.zeros(6 * self.views, dtype=F64, device=dev)
-        check(lib().tb200_ct_geometry(self.views, K._p(cos_t), K._p(sin_t), K._p(self.geom_all), K._stream()), "ct_geometry")
-        a = np.arange(self.views)
-        offs = torch.from_numpy((((a % G) * self.L + a // G) * self.n_det).astype(np.int64)).to(dev)
-        self.geom_all.view(torch.int64).view(self.views, 6)[:, 5] = offs
-        self.geom_loc = torch.zeros(max(6 * self.n_loc_ang, 2), dtype=F64, device=dev)
-        cm, sm = cos_t[torch.from_numpy(mine).to(dev)].contiguous(), sin_t[torch.from_numpy(mine).to(dev)].contiguous()
-        check(lib().tb200_ct_geometry(self.n_loc_ang, K._p(cm), K._p(sm), K._p(self.geom_loc), K._stream()), "ct_geometry")
-        # exchanged (unnormalised) vectors live in the arena; their normalised copies and the bases are ordinary tensors
-        self.comm = PeerComm({"vt": self.n, "ut": self.m_pad}, group=group, device=dev)
-        self.vt, self.ut = self.comm.local("vt"), self.comm.local("ut")
+            raise ValueError(f"rank {op.rank} owns {op.n_loc_ang} angles: b_local must have {self.m_loc} entries")
         self.v_full = torch.empty(self.n, dtype=F64, device=dev)
         self.u_full = torch.zeros(self.m_pad, dtype=F64, device=dev)
         self.U = K.Basis(self.m_loc, kmax + 1, dev)
@@ -490,24 +610,16 @@ class ShardedGKState:
         self.alpha = torch.zeros((kmax + 1, 2), dtype=F64, device=dev)
         self.beta = torch.zeros((kmax + 1, 2), dtype=F64, device=dev)
         self.beta0 = torch.zeros(2, dtype=F64, device=dev)
-        nws = max(int(lib().tb200_ct_backproject_workspace_len(self.nx, self.ny)),
-                  int(lib().tb200_ct_forward_rays_workspace_len(self.n_det, max(self.n_loc_ang, 1))),
-                  int(lib().tb200_reduce_workspace_len()))
-        self.ws = torch.zeros(nws, dtype=F64, device=dev)
-        self.my_chunk = r * self.L * self.n_det  # where my angles sit in a gathered sinogram
-        self._vt_peers = self.comm.peers_of("vt")
-        self._ut_peers = self.comm.peers_of("ut", self.my_chunk)
-        self._npart = ctypes.c_int64(0)
+        self._npart = op.npart
         # u_1 = b / ||b||: the norm through the mailboxes, my rows pushed to every rank's copy
         check(lib().tb200_vec_dot_partials(self.m_loc, K._p(b_local), None, K._p(self.ws), ctypes.byref(self._npart), K._stream()),
               "vec_dot_partials")
         self.comm.allreduce_dd(PeerComm.BOX_BETA, self.ws, self._npart.value, self.beta0)
-        self.ut.zero_()
-        self.comm.barrier()  # nobody pushes into a copy that is still being cleared
+        self.comm.barrier()  # every rank is done with whatever used the gathered sinogram before
         self.comm.push("ut", b_local.contiguous(), self.my_chunk)
         self.comm.barrier()
         self._scale_u(self.beta0)
-        _lib.count(3)
+        _lib.count(1)
 
     @property
     def k(self):
@@ -521,21 +633,12 @@ class ShardedGKState:
 
     def backproject(self, k):
         """K1: my band of vt = A^T u_full - beta_{k-1} v_{k-1}, stored into every rank's vt; partial norms -> ws."""
-        peers, npeers = self._vt_peers
-        check(lib().tb200_ct_backproject_sharded_f64(
-            self.nx, self.ny, self.row_lo, self.row_hi, self.n_det, self.views, K._p(self.geom_all), K._p(self.u_full),
-            K._p(self.vt), peers, npeers, 0.0, K._p(self.beta[k - 1, 1:2]) if k else None, K._p(self.V.col(k - 1)) if k else None,
-            K._p(self.ws), ctypes.byref(self._npart), K._stream()), "ct_backproject_sharded")
-        _lib.count(1)
+        self.op.launch_backproject(self.u_full, self.vt, self.op.vt_peers, self.beta[k - 1, 1:2] if k else None,
+                                   self.V.col(k - 1) if k else None)
 
     def forward(self, k):
         """K4: my angles of ut = A v_full - alpha_k u_k, stored into every rank's ut; partial norms -> ws."""
-        peers, npeers = self._ut_peers
-        check(lib().tb200_ct_forward_rays_sharded_f64(
-            self.nx, self.ny, self.n_det, self.n_loc_ang, K._p(self.geom_loc), K._p(self.v_full), K._p(self.ut[self.my_chunk:]),
-            peers, npeers, 0.0, K._p(self.alpha[k, 1:2]), K._p(self.U.col(k)), K._p(self.ws), ctypes.byref(self._npart),
-            K._stream()), "ct_forward_rays_sharded")
-        _lib.count(1)
+        self.op.launch_forward(self.v_full, self.ut[self.my_chunk:], self.op.ut_peers, self.alpha[k, 1:2], self.U.col(k))
 
     def step(self):
         k = self.V.k
@@ -565,37 +668,29 @@ class ShardedGKState:
         u_k, hv_prev = my band of v_{k-1} (None at the first step), beta_prev = S[k-1, k-2]; the new v band / u rows are
         written to the pinned host tensors hv_out / hu_out.  Returns (alpha, beta).  Per call: H2D of u_k and v_{k-1}, the
         rows of u_k pushed to every rank over NVLink, K1..K6 as in step(), D2H of v, u and the two scalars."""
-        dev = self.v_full.device
         u_k = self.U.data[0]
         u_k.copy_(hu_k, non_blocking=True)
+        self.comm.barrier()  # every rank is done reading the gathered sinogram of the previous call
         self.comm.push("ut", u_k, self.my_chunk)
         self.comm.barrier()
-        peers, npeers = self._vt_peers
         zb = None
         if hv_prev is not None:
             zb = self.V.data[0]
             zb.copy_(hv_prev, non_blocking=True)
             self.beta[0, 1:2].fill_(float(beta_prev))
-        check(lib().tb200_ct_backproject_sharded_f64(
-            self.nx, self.ny, self.row_lo, self.row_hi, self.n_det, self.views, K._p(self.geom_all), K._p(self.ut), K._p(self.vt),
-            peers, npeers, 0.0, K._p(self.beta[0, 1:2]) if zb is not None else None, K._p(zb), K._p(self.ws),
-            ctypes.byref(self._npart), K._stream()), "ct_backproject_sharded")
+        self.op.launch_backproject(self.ut, self.vt, self.op.vt_peers, self.beta[0, 1:2] if zb is not None else None, zb)
         self.comm.allreduce_dd(PeerComm.BOX_ALPHA, self.ws, self._npart.value, self.alpha[0])
         vb = self.V.data[1] if self.V.kmax > 1 else self.V.data[0]
         check(lib().tb200_comm_scale(self.n, K._p(self.vt), K._p(self.alpha[0, 1:2]), K._p(self.v_full), self.row_lo * self.nx,
                                      self.n_band, K._p(vb), K._stream()), "comm_scale")
         hv_out.copy_(vb, non_blocking=True)
-        peers, npeers = self._ut_peers
-        check(lib().tb200_ct_forward_rays_sharded_f64(
-            self.nx, self.ny, self.n_det, self.n_loc_ang, K._p(self.geom_loc), K._p(self.v_full), K._p(self.ut[self.my_chunk:]),
-            peers, npeers, 0.0, K._p(self.alpha[0, 1:2]), K._p(u_k), K._p(self.ws), ctypes.byref(self._npart), K._stream()),
-            "ct_forward_rays_sharded")
+        self.op.launch_forward(self.v_full, self.ut[self.my_chunk:], self.op.ut_peers, self.alpha[0, 1:2], u_k)
         self.comm.allreduce_dd(PeerComm.BOX_BETA, self.ws, self._npart.value, self.beta[1])
         ub = self.U.data[1]
         check(lib().tb200_comm_scale(self.m_pad, K._p(self.ut), K._p(self.beta[1, 1:2]), K._p(self.u_full), self.my_chunk,
                                      self.m_loc, K._p(ub), K._stream()), "comm_scale")
         hu_out.copy_(ub, non_blocking=True)
-        _lib.count(8)
+        _lib.count(4)
         sc = torch.stack((self.alpha[0, 1], self.beta[1, 1])).cpu().numpy()  # synchronises: the host copies are complete
         return float(sc[0]), float(sc[1])
 
@@ -613,7 +708,7 @@ class ShardedGKState:
         return B
 
     def close(self):
-        self.comm.destroy()
+        self.op.close()
 
 
 def sharded_parity_check(st, nx, views, layout, b_local, steps=10):

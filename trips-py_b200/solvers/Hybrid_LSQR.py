@@ -32,7 +32,8 @@ def Hybrid_LSQR(A, b, n_iter=100, regparam="gcv", x_true=None, **kwargs):
     bd = to_device_vector(b, dev)
     comm = kwargs.get("b200_comm")  # dist.RowComm (static CT, rows by angle) or dist.FrameComm (block-diagonal A)
     m_total = m if comm is None else comm.total(m, "data")
-    st = GKState(A, bd, n_iter, comm=comm)
+    # (a band-sharded matrix-free operator brings its own fused recurrence: dist.ShardedGKState)
+    st = A.gk_state(bd, n_iter) if hasattr(A, "gk_state") else GKState(A, bd, n_iter, comm=comm)
     x_history = LazyHistory()
     lambda_history, residual_history = [], []
     err = ErrorTracker(x_true, dev, comm=comm)
