@@ -258,3 +258,85 @@ def test_banded_adjoint_allreduce_world2_gloo(tmp_path):
         assert calls[0, 0] == 0 and calls[-1, 1] == 22 and np.array_equal(calls[1:, 0], calls[:-1, 1])
         assert all(c % 4 == 0 for c in calls[:, 0])
         assert p["calls6"].size == 0  # fewer than four rows per band: falls back to the plain path
+
+
+# ---- band-sharded layout (dist.BandShardedCT / ShardedGKState): the partition algebra on CPU ---------------------------
+
+def _band_worker(rank, world, port, nx, ny, views, steps, out_dir):
+    """NumPy statement of ShardedGKState's data movement: u split by angle (round robin), v by image band, the gathered
+    sinogram grouped by owner rank with padded chunks and addressed through per-angle row offsets (geom slot 5), the
+    gathered image addressed by global pixel; every output element computed by ONE rank from the whole input."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from trips_b200.dist import band_rows, shard_angles
+
+        n_det = O.ct_num_detectors(nx)
+        theta = O.ct_angles(views)
+        A = O.ct_matrix(nx, theta, ny=ny)  # every rank can evaluate any row / column: the operator is matrix-free
+        AT = A.T.tocsr()
+        mine = shard_angles(views, world, rank)
+        L = -(-views // world)
+        rows = (mine[:, None] * n_det + np.arange(n_det)[None, :]).reshape(-1)
+        lo, hi = band_rows(ny, world, rank)
+        b = np.random.default_rng(5).standard_normal(views * n_det)
+        offs = ((np.arange(views) % world) * L + np.arange(views) // world) * n_det  # first row of angle a, gathered layout
+        gathered_index = (offs[:, None] + np.arange(n_det)[None, :]).reshape(-1)    # angle-major order -> gathered layout
+
+        def gather_u(u_loc):  # what the peer stores of the forward projector's epilogue assemble on every rank
+            chunk = torch.zeros(L * n_det, dtype=torch.float64)
+            chunk[:u_loc.size] = torch.from_numpy(u_loc)
+            parts = [torch.empty_like(chunk) for _ in range(world)]
+            dist.all_gather(parts, chunk)
+            return torch.cat(parts).numpy()[gathered_index]  # the back-projector reads angle a at offs[a]
+
+        def gather_v(v_band):  # ... and of the back-projector's epilogue (bands are unequal: pad to the largest)
+            sizes = [(band_rows(ny, world, r)[1] - band_rows(ny, world, r)[0]) * nx for r in range(world)]
+            buf = torch.zeros(max(sizes), dtype=torch.float64)
+            buf[:v_band.size] = torch.from_numpy(v_band)
+            parts = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(parts, buf)
+            return np.concatenate([p.numpy()[:s] for p, s in zip(parts, sizes)])
+
+        with O.reductions("exact"):
+            u_full = gather_u(b[rows])
+            beta0 = O._norm(u_full)
+            u_full = u_full / beta0
+            U, V, al, be = [u_full[rows]], [], [], []
+            v_prev, beta_prev = None, 0.0
+            for _ in range(steps):
+                vt = (AT[lo * nx:hi * nx] @ u_full)  # my band of A^T u: each pixel sums over ALL angles in order
+                if v_prev is not None:
+                    vt = vt - beta_prev * v_prev
+                vt_full = gather_v(vt)
+                alpha = O._norm(vt_full)  # the mailbox all-reduce returns the correctly rounded exact total
+                v_full = vt_full / alpha
+                v_prev = v_full[lo * nx:hi * nx]
+                ut = A[rows] @ v_full - alpha * U[-1]  # my angles of A v
+                ut_full = gather_u(ut)
+                beta_prev = O._norm(ut_full)
+                u_full = ut_full / beta_prev
+                U.append(u_full[rows])
+                V.append(v_prev)
+                al.append(alpha)
+                be.append(beta_prev)
+        np.savez(os.path.join(out_dir, f"b{rank}.npz"), U=np.array(U).T, V=np.array(V).T, al=np.array(al), be=np.array(be),
+                 rows=rows, band=np.array([lo * nx, hi * nx]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_band_sharded_partition_reproduces_single_process_golub_kahan_bitwise(tmp_path):
+    nx, ny, views, steps, world = 20, 14, 9, 6, 2  # odd view count (padded chunk), band edge off a multiple of 4
+    mp.spawn(_band_worker, args=(world, _free_port(), nx, ny, views, steps, str(tmp_path)), nprocs=world, join=True)
+    n_det = O.ct_num_detectors(nx)
+    A = O.ct_matrix(nx, O.ct_angles(views), ny=ny)
+    b = np.random.default_rng(5).standard_normal(views * n_det)
+    with O.reductions("exact"):
+        U1, S1, V1 = O.golub_kahan(A, b, steps)
+    for r in range(world):
+        p = np.load(tmp_path / f"b{r}.npz")
+        lo, hi = p["band"]
+        assert np.array_equal(p["al"], np.diag(S1)) and np.array_equal(p["be"], np.diag(S1, -1))
+        assert np.array_equal(p["U"], U1[p["rows"]]) and np.array_equal(p["V"], V1[lo:hi])
