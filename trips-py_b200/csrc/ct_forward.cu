@@ -30,12 +30,13 @@
 namespace tb200 {
 
 constexpr double FW_ETA = 1e-6;    // slack of the candidate bracket, in pixels
-constexpr int FW_WARPS = 4;        // 128 rays of one angle per CTA
+constexpr int FW_WARPS = 4;        // 128 rays of one angle per CTA (64 when the launch has few CTAs: angle shards)
 constexpr double FW_RUN_TAN_MAX = 7.9;  // lockstep form is instantiated for up to 9 candidates per row
 // measured at 2048^2 x 720 (tools/fw_tune.py, profiles/): run_tan 3 / 5 / 7.9 -> 4.87 / 4.50 / 4.37 ms with 64 registers
 // (8 CTAs per SM), 5.47 / 4.89 / 4.70 ms with 90 registers (5 CTAs per SM)
 static double g_fw_run_tan = 7.9;       // |s/c| above this: run form (tuning knob, tb200_ct_forward_set_tuning)
-static int g_fw_minb = 8;               // resident CTAs per SM the compiler must allow for (register cap 128 / 64)
+static int g_fw_minb = 8;               // resident CTAs (of 128 threads) per SM the compiler must allow for (register cap 128 / 64)
+static int g_fw_warps_override = 0;     // 0 = choose 4 or 2 warps per CTA from the launch size
 
 __device__ __forceinline__ double fw_add_if_positive(double acc, double p, int flag) {
   asm("{\n\t.reg .pred q;\n\tsetp.gt.s32 q, %2, 0;\n\t@q add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(p), "r"(flag));
@@ -228,8 +229,8 @@ __device__ __forceinline__ double fw_runs(const FwRay& r, double s, bool live, i
   return acc;
 }
 
-template <bool QTAB, int MINB>
-__global__ void __launch_bounds__(FW_WARPS * 32, MINB)
+template <bool QTAB, int MINB, int W>
+__global__ void __launch_bounds__(W * 32, MINB * 4 / W)
 ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const double* __restrict__ geom,
                        const double* __restrict__ x, double* __restrict__ y, double coef_host,
                        const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials,
@@ -243,7 +244,7 @@ ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const dou
   const int mid = nblk >> 1;
   const int blk = (rank & 1) ? mid + ((rank + 1) >> 1) : mid - (rank >> 1);
   const bool blk_ok = blk >= 0 && blk < nblk;  // (nblk even: one rank of the sequence falls outside)
-  const int d = blk * (FW_WARPS * 32) + threadIdx.x;
+  const int d = blk * (W * 32) + threadIdx.x;
   const bool live = blk_ok && d < n_det;
   const double* gp = geom + 6 * (int64_t)a;
   const double c = gp[0], s = gp[1];
@@ -256,7 +257,7 @@ ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const dou
   const double ac = fabs(c), as = fabs(s);
   const bool runs = as > run_tan * ac;  // also c == 0
   if (QTAB && !runs) {
-    for (int i = threadIdx.x; i < ny; i += FW_WARPS * 32) qtab[i] = __dmul_rn(centred_coord(i, biasy), s);
+    for (int i = threadIdx.x; i < ny; i += W * 32) qtab[i] = __dmul_rn(centred_coord(i, biasy), s);
     __syncthreads();
   }
   double acc;
@@ -290,7 +291,7 @@ ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const dou
     // one double-double partial per WARP (no CTA-wide barrier: the warps of a CTA finish at very different times)
     const dd_t tot2 = dd_warp_sum(nrm);
     if (lane == 0) {
-      const int64_t w = (int64_t)blockIdx.x * FW_WARPS + (threadIdx.x >> 5);
+      const int64_t w = (int64_t)blockIdx.x * W + (threadIdx.x >> 5);
       partials[2 * w] = tot2.hi;
       partials[2 * w + 1] = tot2.lo;
     }
@@ -305,17 +306,19 @@ extern "C" {
 
 // Doubles of workspace tb200_ct_forward_rays_f64 needs for its fused norm (one double-double partial per CTA).
 int64_t tb200_ct_forward_rays_workspace_len(int n_det, int n_ang) {
-  const int64_t nblk = (n_det + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
-  return 2 * ((nblk + 1) * (int64_t)n_ang * FW_WARPS + 8);
+  const int64_t nblk2 = (n_det + 63) / 64;  // 2-warp CTAs: the larger count of warps
+  return 2 * ((nblk2 + 1) * (int64_t)n_ang * 2 + 8);
 }
 
 // Tuning knobs of the ray-driven forward projector (results never depend on them): run_tan = |s/c| above which an angle
 // takes the run form (0 < run_tan <= 7.9); min_ctas = 4 or 8 resident CTAs per SM to compile for (<= 128 / 64 registers).
 int tb200_ct_forward_set_tuning(double run_tan, int min_ctas) {
   TB200_REQUIRE(run_tan > 0.0 && run_tan <= FW_RUN_TAN_MAX, "run_tan out of range");
-  TB200_REQUIRE(min_ctas == 4 || min_ctas == 8, "min_ctas must be 4 or 8");
+  TB200_REQUIRE(min_ctas == 4 || min_ctas == 8 || min_ctas == 42 || min_ctas == 44 || min_ctas == 82 || min_ctas == 84,
+                "min_ctas must be 4 or 8 (optionally followed by the digit 2 or 4: warps per CTA forced)");
   g_fw_run_tan = run_tan;
-  g_fw_minb = min_ctas;
+  g_fw_warps_override = min_ctas > 9 ? min_ctas % 10 : 0;
+  g_fw_minb = min_ctas > 9 ? min_ctas / 10 : min_ctas;
   return 0;
 }
 
@@ -331,35 +334,51 @@ static int forward_rays_launch(int nx, int ny, int n_det, int n_ang, const doubl
   nparts = 0;
   if (n_ang == 0) return 0;
   TB200_REQUIRE(geom && x && y, "null pointer");
-  const int nblk = (n_det + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
+  // rays per CTA: 128, or 64 when 128 would leave fewer than ~6 waves of CTAs (an angle shard of a multi-GPU run: the
+  // long central CTAs then finish together and the SMs idle behind them; measured 0.83 -> see profiles/)
+  int warps = FW_WARPS;
+  {
+    const int nb4 = (n_det + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
+    if ((int64_t)nb4 * n_ang < (int64_t)6 * sm_count() * g_fw_minb) warps = 2;
+    if (g_fw_warps_override) warps = g_fw_warps_override;
+  }
+  const int nblk = (n_det + warps * 32 - 1) / (warps * 32);
   const int ranks = nblk + ((nblk & 1) ? 0 : 1);  // centre-out sequence mid, mid+1, mid-1, ...: covers [0, nblk) in `ranks` steps
   const int64_t nctas = (int64_t)ranks * n_ang;
   TB200_REQUIRE(nctas < ((int64_t)1 << 31), "too many CTAs");
   const int vec4 = ((uintptr_t)x % 32) == 0;
   const size_t qbytes = (size_t)ny * sizeof(double);
   const double run_tan = g_fw_run_tan;
-#define FW_LAUNCH(QT, MB, SMEM)                                                                                          \
-  ct_forward_rays_kernel<QT, MB><<<(unsigned)nctas, FW_WARPS * 32, SMEM, st>>>(nx, ny, n_det, n_ang, nblk, geom, x, y, coef_host, \
-                                                                               coef_dev, z, part, vec4, run_tan, po)
+#define FW_LAUNCH(QT, MB, WW, SMEM)                                                                                   \
+  ct_forward_rays_kernel<QT, MB, WW><<<(unsigned)nctas, WW * 32, SMEM, st>>>(nx, ny, n_det, n_ang, nblk, geom, x, y, coef_host, \
+                                                                             coef_dev, z, part, vec4, run_tan, po)
+#define FW_LAUNCH_W(QT, MB, SMEM)        \
+  do {                                   \
+    if (warps == 2) FW_LAUNCH(QT, MB, 2, SMEM); \
+    else FW_LAUNCH(QT, MB, 4, SMEM);     \
+  } while (0)
   if (qbytes <= 96 * 1024) {
     if (qbytes > 48 * 1024) {
       static thread_local int configured_dev = -1;
       int dev = 0;
       cudaGetDevice(&dev);
       if (dev != configured_dev) {
-        cudaFuncSetAttribute(ct_forward_rays_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        cudaFuncSetAttribute(ct_forward_rays_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(ct_forward_rays_kernel<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(ct_forward_rays_kernel<true, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(ct_forward_rays_kernel<true, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(ct_forward_rays_kernel<true, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         configured_dev = dev;
       }
     }
-    if (g_fw_minb == 8) FW_LAUNCH(true, 8, qbytes);
-    else FW_LAUNCH(true, 4, qbytes);
+    if (g_fw_minb == 8) FW_LAUNCH_W(true, 8, qbytes);
+    else FW_LAUNCH_W(true, 4, qbytes);
   } else {
-    if (g_fw_minb == 8) FW_LAUNCH(false, 8, 0);
-    else FW_LAUNCH(false, 4, 0);
+    if (g_fw_minb == 8) FW_LAUNCH_W(false, 8, 0);
+    else FW_LAUNCH_W(false, 4, 0);
   }
+#undef FW_LAUNCH_W
 #undef FW_LAUNCH
-  nparts = nctas * FW_WARPS;
+  nparts = nctas * warps;
   return check_launch("ct_forward_rays");
 }
 
