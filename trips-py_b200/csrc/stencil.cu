@@ -78,35 +78,50 @@ correlate2d_kernel(int nrow, int ncol, const double* __restrict__ x, const doubl
 // Space-time operator on nt frames of nrow x ncol (nt = 1 and no temporal part => plain 2-D operator).
 // Output layout: [ nt * p2 spatial rows | ntr * N temporal rows ],  p2 = nrow*(ncol-1) + (nrow-1)*ncol, N = nrow*ncol,
 // ntr = nt - 1, or nt when x_next (the first frame owned by the next rank) is given.
+// (row, col) of a flat index that advances by a fixed stride: one 32-bit division per thread, none per element.
+struct RowCol {
+  unsigned r, c, step_r, step_c, width;
+  __device__ __forceinline__ RowCol(unsigned idx, unsigned stride, unsigned w) : width(w) {
+    r = idx / w, c = idx - r * w;
+    step_r = stride / w, step_c = stride - step_r * w;
+  }
+  __device__ __forceinline__ void next() {
+    c += step_c, r += step_r;
+    if (c >= width) c -= width, ++r;
+  }
+};
+
+// blockIdx.y = section: frames 0 .. nt-1 are the spatial rows of that frame, nt .. nt+ntr-1 the temporal rows between
+// frame (y - nt) and its successor.  All index arithmetic is 32-bit inside a section (nrow*ncol < 2^31).
 __global__ void __launch_bounds__(256)
 fd_apply_kernel(int nt, int nrow, int ncol, int ntr, const double* __restrict__ x, const double* __restrict__ x_next,
                 double* __restrict__ u, double* __restrict__ wout, double eps2, double expo) {
-  const int64_t N = (int64_t)nrow * ncol;
-  const int64_t p1 = (int64_t)nrow * (ncol - 1), p2 = p1 + (int64_t)(nrow - 1) * ncol;
-  const int64_t total = (int64_t)nt * p2 + (int64_t)ntr * N;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
-    double a, b;
-    if (q < (int64_t)nt * p2) {
-      const int64_t t = q / p2, rq = q % p2;
-      const double* xf = x + t * N;
-      if (rq < p1) {
-        const int64_t r = rq / (ncol - 1), c = rq % (ncol - 1);
-        a = xf[r * ncol + c];
-        b = xf[r * ncol + c + 1];
-      } else {
-        const int64_t e = rq - p1;
-        a = xf[e];
-        b = xf[e + ncol];
-      }
-    } else {
-      const int64_t e = q - (int64_t)nt * p2;
-      const int64_t t = e / N, p = e % N;
-      a = x[t * N + p];
-      b = (t + 1 < nt) ? x[(t + 1) * N + p] : x_next[p];
-    }
+  const unsigned N = (unsigned)nrow * ncol;
+  const unsigned p1 = (unsigned)nrow * (ncol - 1), p2 = p1 + (unsigned)(nrow - 1) * ncol;
+  const unsigned stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned sec = blockIdx.y;
+  auto emit = [&](int64_t q, double a, double b) {
     const double d = __dsub_rn(a, b);
     u[q] = d;
     if (wout != nullptr) wout[q] = pow(__dadd_rn(__dmul_rn(d, d), eps2), expo);
+  };
+  if (sec < (unsigned)nt) {
+    const double* xf = x + (int64_t)sec * N;
+    const int64_t qb = (int64_t)sec * p2;
+    if (ncol > 1) {  // differences along the row: entry (r, c) of nrow x (ncol-1) = x[r, c] - x[r, c+1]
+      RowCol rc(first, stride, (unsigned)(ncol - 1));
+      for (unsigned rq = first; rq < p1; rq += stride, rc.next()) {
+        const unsigned e = rc.r * (unsigned)ncol + rc.c;
+        emit(qb + rq, xf[e], xf[e + 1]);
+      }
+    }
+    for (unsigned e = first; e < p2 - p1; e += stride) emit(qb + p1 + e, xf[e], xf[e + ncol]);  // between rows
+  } else {
+    const unsigned t = sec - nt;
+    const int64_t qb = (int64_t)nt * p2 + (int64_t)t * N;
+    const double* xa = x + (int64_t)t * N;
+    const double* xb = (t + 1 < (unsigned)nt) ? x + (int64_t)(t + 1) * N : x_next;
+    for (unsigned p = first; p < N; p += stride) emit(qb + p, xa[p], xb[p]);
   }
 }
 
@@ -115,26 +130,29 @@ __device__ __forceinline__ double wr_at(const double* __restrict__ r, const doub
 }
 
 // out = L^T (w . r).  rt_prev: the temporal rows of the last frame owned by the previous rank (or NULL).
+// blockIdx.y = frame.
 __global__ void __launch_bounds__(256)
 fd_adjoint_kernel(int nt, int nrow, int ncol, int ntr, const double* __restrict__ r, const double* __restrict__ w,
                   const double* __restrict__ rt_prev, const double* __restrict__ wt_prev, double* __restrict__ out) {
-  const int64_t N = (int64_t)nrow * ncol;
-  const int64_t p1 = (int64_t)nrow * (ncol - 1), p2 = p1 + (int64_t)(nrow - 1) * ncol;
+  const unsigned N = (unsigned)nrow * ncol;
+  const unsigned p1 = (unsigned)nrow * (ncol - 1), p2 = p1 + (unsigned)(nrow - 1) * ncol;
   const int64_t tbase = (int64_t)nt * p2;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < (int64_t)nt * N; q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t t = q / N, p = q % N;
-    const int64_t row = p / ncol, c = p % ncol;
-    const int64_t sb = t * p2;
+  const unsigned stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  const int64_t sb = (int64_t)t * p2;
+  RowCol rc(first, stride, (unsigned)ncol);
+  for (unsigned p = first; p < N; p += stride, rc.next()) {
+    const unsigned row = rc.r, c = rc.c;
     double acc = 0.0;
     // same order as scipy's csc scatter: ascending row index of L
-    if (c > 0) acc = __dsub_rn(acc, wr_at(r, w, sb + row * (ncol - 1) + c - 1));
-    if (c < ncol - 1) acc = __dadd_rn(acc, wr_at(r, w, sb + row * (ncol - 1) + c));
-    if (row > 0) acc = __dsub_rn(acc, wr_at(r, w, sb + p1 + (row - 1) * ncol + c));
-    if (row < nrow - 1) acc = __dadd_rn(acc, wr_at(r, w, sb + p1 + row * ncol + c));
-    if (t > 0) acc = __dsub_rn(acc, wr_at(r, w, tbase + (t - 1) * N + p));
+    if (c > 0) acc = __dsub_rn(acc, wr_at(r, w, sb + row * (unsigned)(ncol - 1) + c - 1));
+    if (c < (unsigned)ncol - 1) acc = __dadd_rn(acc, wr_at(r, w, sb + row * (unsigned)(ncol - 1) + c));
+    if (row > 0) acc = __dsub_rn(acc, wr_at(r, w, sb + p1 + (row - 1) * (unsigned)ncol + c));
+    if (row < (unsigned)nrow - 1) acc = __dadd_rn(acc, wr_at(r, w, sb + p1 + row * (unsigned)ncol + c));
+    if (t > 0) acc = __dsub_rn(acc, wr_at(r, w, tbase + (int64_t)(t - 1) * N + p));
     else if (rt_prev != nullptr) acc = __dsub_rn(acc, wt_prev ? __dmul_rn(wt_prev[p], rt_prev[p]) : rt_prev[p]);
-    if (t < ntr) acc = __dadd_rn(acc, wr_at(r, w, tbase + t * N + p));
-    out[q] = acc;
+    if (t < ntr) acc = __dadd_rn(acc, wr_at(r, w, tbase + (int64_t)t * N + p));
+    out[(int64_t)t * N + p] = acc;
   }
 }
 
@@ -148,8 +166,10 @@ __global__ void __launch_bounds__(256)
 cd2d_apply_kernel(int nrow, int ncol, const double* __restrict__ x, double* __restrict__ u, double* __restrict__ wout,
                   double eps2, double expo) {
   const int64_t N = (int64_t)nrow * ncol;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = q / ncol, c = q % ncol;
+  const unsigned stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+  RowCol rc(first, stride, (unsigned)ncol);
+  for (unsigned q = first; q < (unsigned)N; q += stride, rc.next()) {
+    const int r = (int)rc.r, c = (int)rc.c;
     double u1 = 0.0, u2 = 0.0;
     if (c >= 1 && c <= ncol - 2) u1 = __dsub_rn(__dmul_rn(0.5, x[q + 1]), __dmul_rn(0.5, x[q - 1]));
     if (r >= 1 && r <= nrow - 2) u2 = __dsub_rn(__dmul_rn(0.5, x[q + ncol]), __dmul_rn(0.5, x[q - ncol]));
@@ -171,8 +191,10 @@ __global__ void __launch_bounds__(256)
 cd2d_adjoint_kernel(int nrow, int ncol, const double* __restrict__ r, const double* __restrict__ w,
                     double* __restrict__ out) {
   const int64_t N = (int64_t)nrow * ncol;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < N; q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = q / ncol, c = q % ncol;
+  const unsigned stride = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+  RowCol rc(first, stride, (unsigned)ncol);
+  for (unsigned q = first; q < (unsigned)N; q += stride, rc.next()) {
+    const int row = (int)rc.r, c = (int)rc.c;
     double acc = 0.0;
     // within-row part: L-row (row, c') is non-zero for 1 <= c' <= ncol-2 with -0.5 at c'-1 and +0.5 at c'+1
     if (c - 1 >= 1 && c - 1 <= ncol - 2) acc = __dadd_rn(acc, __dmul_rn(0.5, wr_at(r, w, q - 1)));
@@ -235,11 +257,14 @@ int64_t tb200_fd_rows(int nt, int nrow, int ncol, int has_next) {
 int tb200_fd_apply(int nt, int nrow, int ncol, const double* x, const double* x_next, double* u, double* wout, double eps,
                    double expo, void* stream) {
   TB200_REQUIRE(nt >= 1 && nrow >= 1 && ncol >= 1 && x && u, "bad argument");
+  TB200_REQUIRE((int64_t)nrow * ncol < ((int64_t)1 << 31), "frame too large for 32-bit indexing");
   const int ntr = x_next ? nt : nt - 1;
   const int64_t total = tb200_fd_rows(nt, nrow, ncol, x_next != nullptr);
   if (total == 0) return 0;
-  fd_apply_kernel<<<grid_for(total, 256 * 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(nt, nrow, ncol, ntr, x, x_next, u,
-                                                                                      wout, eps * eps, expo);
+  TB200_REQUIRE(nt + ntr <= 65535, "too many frames for this launch shape");
+  const int secs = nt + ntr;
+  const dim3 grid((unsigned)grid_for((int64_t)nrow * ncol, 256 * 4, secs >= 8 ? 148 * 2 : 148 * 16), (unsigned)secs);
+  fd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(nt, nrow, ncol, ntr, x, x_next, u, wout, eps * eps, expo);
   return check_launch("fd_apply");
 }
 
@@ -248,10 +273,10 @@ int tb200_fd_apply(int nt, int nrow, int ncol, const double* x, const double* x_
 int tb200_fd_adjoint(int nt, int nrow, int ncol, int has_next, const double* r, const double* w, const double* rt_prev,
                      const double* wt_prev, double* out, void* stream) {
   TB200_REQUIRE(nt >= 1 && nrow >= 1 && ncol >= 1 && r && out, "bad argument");
+  TB200_REQUIRE((int64_t)nrow * ncol < ((int64_t)1 << 31) && nt <= 65535, "frame too large / too many frames");
   const int ntr = has_next ? nt : nt - 1;
-  const int64_t total = (int64_t)nt * nrow * ncol;
-  fd_adjoint_kernel<<<grid_for(total, 256 * 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(nt, nrow, ncol, ntr, r, w, rt_prev,
-                                                                                        wt_prev, out);
+  const dim3 grid((unsigned)grid_for((int64_t)nrow * ncol, 256 * 4, nt >= 8 ? 148 * 2 : 148 * 16), (unsigned)nt);
+  fd_adjoint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(nt, nrow, ncol, ntr, r, w, rt_prev, wt_prev, out);
   return check_launch("fd_adjoint");
 }
 
@@ -259,6 +284,7 @@ int tb200_fd_adjoint(int nt, int nrow, int ncol, int has_next, const double* r, 
 // weights wout = (u1^2 + u2^2 + eps^2)^expo written to both halves (MMGKS.py:64-78 with nt = 1).
 int tb200_cd2d_apply(int nrow, int ncol, const double* x, double* u, double* wout, double eps, double expo, void* stream) {
   TB200_REQUIRE(nrow >= 1 && ncol >= 1 && x && (u || wout), "bad argument");
+  TB200_REQUIRE((int64_t)nrow * ncol < ((int64_t)1 << 31), "image too large for 32-bit indexing");
   const int64_t N = (int64_t)nrow * ncol;
   cd2d_apply_kernel<<<grid_for(N, 256 * 4, 148 * 16), 256, 0, (cudaStream_t)stream>>>(nrow, ncol, x, u, wout, eps * eps, expo);
   return check_launch("cd2d_apply");
