@@ -68,68 +68,30 @@ __device__ __forceinline__ void fw_rows(double& acc, double& e1, int r0, int r1,
                                         double biasy, const double* __restrict__ qtab, const double* __restrict__ x, int nx,
                                         uint64_t pol) {
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-  if (r0 >= r1) return;
   const double* xr = x + (int64_t)r0 * nx;
-  if (CHECKED) {
 #pragma unroll 2
-    for (int iy = r0; iy < r1; ++iy, xr += nx) {
-      const double Q = QTAB ? qtab[iy] : __dmul_rn(centred_coord(iy, biasy), s);
-      const int i0 = __double2loint(__dadd_rn(e1, MAGIC)) + 1;  // first integer above the bracket's left end (or one below)
-      e1 = __dadd_rn(e1, slope);
+  for (int iy = r0; iy < r1; ++iy, xr += nx) {
+    const double Q = QTAB ? qtab[iy] : __dmul_rn(centred_coord(iy, biasy), s);
+    const int i0 = __double2loint(__dadd_rn(e1, MAGIC)) + 1;  // first integer above the bracket's left end (or one below)
+    e1 = __dadd_rn(e1, slope);
+    if (CHECKED) {
 #pragma unroll
       for (int k = 0; k < LMAX; ++k) {
         const int ix = i0 + k;
         if ((unsigned)ix < (unsigned)nx) acc = fw_candidate(acc, r, Q, ix, ld_gather_f64(xr + ix, pol));
       }
-    }
-    return;
-  }
-  if (LMAX > 4) {  // wide brackets: 2 * LMAX values in flight would not fit the 64-register budget
-#pragma unroll 2
-    for (int iy = r0; iy < r1; ++iy, xr += nx) {
-      const double Q = QTAB ? qtab[iy] : __dmul_rn(centred_coord(iy, biasy), s);
-      const int i0 = __double2loint(__dadd_rn(e1, MAGIC)) + 1;
-      e1 = __dadd_rn(e1, slope);
+    } else {
       double xv[LMAX];
 #pragma unroll
       for (int k = 0; k < LMAX; ++k) xv[k] = ld_gather_f64(xr + (i0 + k), pol);
+      // coordinates of consecutive pixels differ by exactly 1 (half-integers far below 2^52: the additions are exact),
+      // so cx of candidate k is the same double as centred_coord(i0 + k)
       double cx = centred_coord(i0, r.biasx);
 #pragma unroll
       for (int k = 0; k < LMAX; ++k) {
         acc = fw_candidate_cx(acc, r, Q, cx, xv[k]);
         if (k + 1 < LMAX) cx = __dadd_rn(cx, 1.0);
       }
-    }
-    return;
-  }
-  // interior rows, software pipelined: the gathers of row iy + 1 are in flight while row iy is evaluated, so even a
-  // lone warp (the tail of a small launch, e.g. one rank's angles of a multi-GPU run) hides their latency
-  double xn[LMAX];
-  int i0 = __double2loint(__dadd_rn(e1, MAGIC)) + 1;
-  e1 = __dadd_rn(e1, slope);
-#pragma unroll
-  for (int k = 0; k < LMAX; ++k) xn[k] = ld_gather_f64(xr + (i0 + k), pol);
-#pragma unroll 2
-  for (int iy = r0; iy < r1; ++iy) {
-    double xv[LMAX];
-#pragma unroll
-    for (int k = 0; k < LMAX; ++k) xv[k] = xn[k];
-    const int i0c = i0;
-    const double Q = QTAB ? qtab[iy] : __dmul_rn(centred_coord(iy, biasy), s);
-    if (iy + 1 < r1) {
-      xr += nx;
-      i0 = __double2loint(__dadd_rn(e1, MAGIC)) + 1;
-      e1 = __dadd_rn(e1, slope);
-#pragma unroll
-      for (int k = 0; k < LMAX; ++k) xn[k] = ld_gather_f64(xr + (i0 + k), pol);
-    }
-    // coordinates of consecutive pixels differ by exactly 1 (half-integers far below 2^52: the additions are exact),
-    // so cx of candidate k is the same double as centred_coord(i0 + k)
-    double cx = centred_coord(i0c, r.biasx);
-#pragma unroll
-    for (int k = 0; k < LMAX; ++k) {
-      acc = fw_candidate_cx(acc, r, Q, cx, xv[k]);
-      if (k + 1 < LMAX) cx = __dadd_rn(cx, 1.0);
     }
   }
 }
