@@ -185,9 +185,12 @@ int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geo
  * ws: tb200_ct_forward_rays_workspace_len(n_det, n_ang) doubles iff norm_out != NULL. */
 int64_t tb200_ct_forward_rays_workspace_len(int n_det, int n_ang);
 int tb200_ct_forward_set_tuning(double run_tan, int min_ctas); /* tuning knobs; results never depend on them */
+int tb200_ct_forward_rays_plan(int n_det, int n_ang, int* rays_per_cta, int* blocks_per_angle);
+/* cta_order (nullable): n_ang * blocks_per_angle int32 (tb200_ct_forward_rays_plan), entry b = angle * blocks_per_angle +
+ * block of the CTA to run b-th - heaviest first keeps the SMs evenly loaded to the end; the result does not depend on it. */
 int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
                               double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
-                              void* stream);
+                              const int32_t* cta_order, void* stream);
 int64_t tb200_ct_backproject_workspace_len(int nx, int ny);
 int tb200_ct_backproject_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* u, double* y,
                              double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
@@ -212,7 +215,8 @@ int tb200_ct_backproject_sharded_f64(int nx, int ny, int iy_begin, int iy_end, i
                                      void* stream);
 int tb200_ct_forward_rays_sharded_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
                                       double* const* peers_host, int n_peers, double coef_host, const double* coef_dev,
-                                      const double* z, double* partials, int64_t* n_partials_out, void* stream);
+                                      const double* z, double* partials, int64_t* n_partials_out, const int32_t* cta_order,
+                                      void* stream);
 /* One Golub-Kahan step (trips/utilities/decompositions.py:230-255) on the matrix-free operator, as
  * tb200_gk_step_sell_f64; ws: max(tb200_spmv_workspace_len(m), tb200_ct_backproject_workspace_len(nx, ny),
  * tb200_ct_forward_rays_workspace_len(n_det, n_ang)).  colidx == NULL: fully matrix-free (ray-driven forward

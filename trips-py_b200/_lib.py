@@ -61,14 +61,15 @@ SIGNATURES = {
     "tb200_ct_forward_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_forward_rays_workspace_len": (c_i64, [c_int, c_int]),
     "tb200_ct_forward_set_tuning": (c_int, [c_dbl, c_int]),
-    "tb200_ct_forward_rays_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_ct_forward_rays_plan": (c_int, [c_int, c_int, c_ptr, c_ptr]),
+    "tb200_ct_forward_rays_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_backproject_workspace_len": (c_i64, [c_int, c_int]),
     "tb200_ct_backproject_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_backproject_rows_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_backproject_sharded_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_dbl,
                                                  c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_forward_rays_sharded_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_dbl, c_ptr, c_ptr,
-                                                  c_ptr, c_ptr, c_ptr]),
+                                                  c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_comm_mailbox_bytes": (c_i64, []),
     "tb200_comm_handle_bytes": (c_int, []),
     "tb200_comm_max_ranks": (c_int, []),

@@ -69,7 +69,7 @@ __device__ __forceinline__ void fw_rows(double& acc, double& e1, int r0, int r1,
                                         uint64_t pol) {
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
   const double* xr = x + (int64_t)r0 * nx;
-#pragma unroll 2
+#pragma unroll(LMAX <= 2 ? 4 : 2)
   for (int iy = r0; iy < r1; ++iy, xr += nx) {
     const double Q = QTAB ? qtab[iy] : __dmul_rn(centred_coord(iy, biasy), s);
     const int i0 = __double2loint(__dadd_rn(e1, MAGIC)) + 1;  // first integer above the bracket's left end (or one below)
@@ -234,16 +234,24 @@ __global__ void __launch_bounds__(W * 32, MINB * 4 / W)
 ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const double* __restrict__ geom,
                        const double* __restrict__ x, double* __restrict__ y, double coef_host,
                        const double* __restrict__ coef_dev, const double* __restrict__ z, double* __restrict__ partials,
-                       int vec4, double run_tan, PeerOut po) {
+                       int vec4, double run_tan, PeerOut po, const int32_t* __restrict__ cta_order) {
   extern __shared__ __align__(16) double qtab[];  // QTAB: cy*s for every image row of this CTA's angle
   const int lane = threadIdx.x & 31;
-  // CTA -> (angle, block of 128 detectors), blocks from the detector centre outwards: the long central rays of every
-  // angle are scheduled first, the short peripheral ones fill the tail
-  const int a = blockIdx.x % n_ang;
-  const int rank = blockIdx.x / n_ang;
-  const int mid = nblk >> 1;
-  const int blk = (rank & 1) ? mid + ((rank + 1) >> 1) : mid - (rank >> 1);
-  const bool blk_ok = blk >= 0 && blk < nblk;  // (nblk even: one rank of the sequence falls outside)
+  // CTA -> (angle, block of W*32 detectors).  With cta_order: entry b = angle * nblk + block of the b-th heaviest CTA
+  // (longest-processing-time-first: the SMs drain evenly).  Without: blocks from the detector centre outwards, the long
+  // central rays of every angle first, the short peripheral ones in the tail.
+  int a, blk;
+  bool blk_ok = true;
+  if (cta_order != nullptr) {
+    const int p = cta_order[blockIdx.x];
+    a = p / nblk, blk = p - a * nblk;
+  } else {
+    a = blockIdx.x % n_ang;
+    const int rank = blockIdx.x / n_ang;
+    const int mid = nblk >> 1;
+    blk = (rank & 1) ? mid + ((rank + 1) >> 1) : mid - (rank >> 1);
+    blk_ok = blk >= 0 && blk < nblk;  // (nblk even: one rank of the sequence falls outside)
+  }
   const int d = blk * (W * 32) + threadIdx.x;
   const bool live = blk_ok && d < n_det;
   const double* gp = geom + 6 * (int64_t)a;
@@ -298,6 +306,15 @@ ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const dou
   }
 }
 
+// warps per CTA the launcher uses for a problem of this size
+static int fw_warps_for(int n_det, int n_ang) {
+  int warps = FW_WARPS;
+  const int nb4 = (n_det + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
+  if ((int64_t)nb4 * n_ang < (int64_t)6 * sm_count() * g_fw_minb) warps = 2;
+  if (g_fw_warps_override) warps = g_fw_warps_override;
+  return warps;
+}
+
 }  // namespace tb200
 
 using namespace tb200;
@@ -328,7 +345,7 @@ int tb200_ct_forward_set_tuning(double run_tan, int min_ctas) {
 // tb200_ct_fill_rows' matrix.  ws: tb200_ct_forward_rays_workspace_len(n_det, n_ang) doubles iff norm_out != NULL.
 static int forward_rays_launch(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
                                double coef_host, const double* coef_dev, const double* z, double* part, const PeerOut& po,
-                               cudaStream_t st, int64_t& nparts) {
+                               const int32_t* cta_order, cudaStream_t st, int64_t& nparts) {
   TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0, "bad geometry");
   TB200_REQUIRE((int64_t)nx * ny < ((int64_t)1 << 31) && (int64_t)n_ang * n_det < ((int64_t)1 << 31), "index space exceeds int32");
   nparts = 0;
@@ -336,22 +353,17 @@ static int forward_rays_launch(int nx, int ny, int n_det, int n_ang, const doubl
   TB200_REQUIRE(geom && x && y, "null pointer");
   // rays per CTA: 128, or 64 when 128 would leave fewer than ~6 waves of CTAs (an angle shard of a multi-GPU run: the
   // long central CTAs then finish together and the SMs idle behind them; measured 0.83 -> see profiles/)
-  int warps = FW_WARPS;
-  {
-    const int nb4 = (n_det + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
-    if ((int64_t)nb4 * n_ang < (int64_t)6 * sm_count() * g_fw_minb) warps = 2;
-    if (g_fw_warps_override) warps = g_fw_warps_override;
-  }
+  const int warps = fw_warps_for(n_det, n_ang);
   const int nblk = (n_det + warps * 32 - 1) / (warps * 32);
   const int ranks = nblk + ((nblk & 1) ? 0 : 1);  // centre-out sequence mid, mid+1, mid-1, ...: covers [0, nblk) in `ranks` steps
-  const int64_t nctas = (int64_t)ranks * n_ang;
+  const int64_t nctas = (int64_t)(cta_order ? nblk : ranks) * n_ang;
   TB200_REQUIRE(nctas < ((int64_t)1 << 31), "too many CTAs");
   const int vec4 = ((uintptr_t)x % 32) == 0;
   const size_t qbytes = (size_t)ny * sizeof(double);
   const double run_tan = g_fw_run_tan;
 #define FW_LAUNCH(QT, MB, WW, SMEM)                                                                                   \
   ct_forward_rays_kernel<QT, MB, WW><<<(unsigned)nctas, WW * 32, SMEM, st>>>(nx, ny, n_det, n_ang, nblk, geom, x, y, coef_host, \
-                                                                             coef_dev, z, part, vec4, run_tan, po)
+                                                                             coef_dev, z, part, vec4, run_tan, po, cta_order)
 #define FW_LAUNCH_W(QT, MB, SMEM)        \
   do {                                   \
     if (warps == 2) FW_LAUNCH(QT, MB, 2, SMEM); \
@@ -382,15 +394,26 @@ static int forward_rays_launch(int nx, int ny, int n_det, int n_ang, const doubl
   return check_launch("ct_forward_rays");
 }
 
+// CTA shape of the launch for this problem size: *rays_per_cta (64 or 128) and *blocks_per_angle.  A caller that wants the
+// CTAs scheduled heaviest first passes cta_order: n_ang * blocks_per_angle int32, entry b = angle * blocks_per_angle + block.
+int tb200_ct_forward_rays_plan(int n_det, int n_ang, int* rays_per_cta, int* blocks_per_angle) {
+  TB200_REQUIRE(n_det > 0 && n_ang >= 0 && rays_per_cta && blocks_per_angle, "bad argument");
+  const int warps = fw_warps_for(n_det, n_ang);
+  *rays_per_cta = warps * 32;
+  *blocks_per_angle = (n_det + warps * 32 - 1) / (warps * 32);
+  return 0;
+}
+
 int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
                               double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
-                              void* stream) {
+                              const int32_t* cta_order, void* stream) {
   TB200_REQUIRE(norm_out == nullptr || ws != nullptr, "norm_out requires a workspace");
   cudaStream_t st = (cudaStream_t)stream;
   PeerOut po;
   po.n = 0;
   int64_t nparts = 0;
-  int rc = forward_rays_launch(nx, ny, n_det, n_ang, geom, x, y, coef_host, coef_dev, z, norm_out ? ws : nullptr, po, st, nparts);
+  int rc = forward_rays_launch(nx, ny, n_det, n_ang, geom, x, y, coef_host, coef_dev, z, norm_out ? ws : nullptr, po, cta_order, st,
+                               nparts);
   if (rc) return rc;
   if (norm_out && nparts > 0) {
     finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, nparts, norm_out);
@@ -405,14 +428,15 @@ int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double
 // partials: tb200_ct_forward_rays_workspace_len doubles, to be summed over the ranks by tb200_comm_allreduce_dd.
 int tb200_ct_forward_rays_sharded_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
                                       double* const* peers_host, int n_peers, double coef_host, const double* coef_dev,
-                                      const double* z, double* partials, int64_t* n_partials_out, void* stream) {
+                                      const double* z, double* partials, int64_t* n_partials_out, const int32_t* cta_order,
+                                      void* stream) {
   TB200_REQUIRE(partials && n_partials_out, "null pointer");
   TB200_REQUIRE(n_peers >= 0 && n_peers <= 15 && (n_peers == 0 || peers_host), "bad peer list");
   PeerOut po;
   po.n = n_peers;
   for (int i = 0; i < n_peers; ++i) po.p[i] = peers_host[i];
-  return forward_rays_launch(nx, ny, n_det, n_ang, geom, x, y, coef_host, coef_dev, z, partials, po, (cudaStream_t)stream,
-                             *n_partials_out);
+  return forward_rays_launch(nx, ny, n_det, n_ang, geom, x, y, coef_host, coef_dev, z, partials, po, cta_order,
+                             (cudaStream_t)stream, *n_partials_out);
 }
 
 }  // extern "C"

@@ -267,7 +267,8 @@ int tb200_ct_backproject_sharded_f64(int nx, int ny, int iy_begin, int iy_end, i
 // matrix-free CT operator, enqueued as 6 kernels (7 with the image transpose) on `stream`, every scalar on the device:
 //   v = A^T u_k - beta_prev * v_prev ; alpha = ||v|| ; v /= alpha ; u = A v - alpha * u_k ; beta = ||u|| ; u /= beta
 // Arguments as tb200_gk_step_sell_f64, the operator as tb200_ct_forward_f64 / tb200_ct_backproject_f64.
-// colidx == NULL selects the ray-driven forward projector (tb200_ct_forward_rays_f64): sliceptr .. xT_scratch unused.
+// colidx == NULL selects the ray-driven forward projector (tb200_ct_forward_rays_f64): sliceptr, rowlen, rowskip, xT_scratch
+// unused; cta_order then is that projector's (nullable) heaviest-first CTA list.
 // ws: max(tb200_spmv_workspace_len(n_ang*n_det), tb200_ct_backproject_workspace_len(nx, ny),
 //         tb200_ct_forward_rays_workspace_len(n_det, n_ang)) doubles.
 int tb200_vec_div(int64_t n, const double* x, double d_host, const double* d_dev, double* out, void* stream);
@@ -278,7 +279,7 @@ int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geo
 
 int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
                               double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
-                              void* stream);
+                              const int32_t* cta_order, void* stream);
 
 int tb200_gk_step_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
                          const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
@@ -300,7 +301,7 @@ int tb200_gk_step_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geo
   if (rc) return rc;
   mark(2);
   if (colidx == nullptr)  // fully matrix-free: the ray-driven forward projector (ct_forward.cu), no index arrays
-    rc = tb200_ct_forward_rays_f64(nx, ny, n_det, n_ang, geom, v_out, u_out, 0.0, alpha_pair + 1, u_k, beta_pair, ws, stream);
+    rc = tb200_ct_forward_rays_f64(nx, ny, n_det, n_ang, geom, v_out, u_out, 0.0, alpha_pair + 1, u_k, beta_pair, ws, cta_order, stream);
   else
     rc = tb200_ct_forward_f64(nx, ny, n_det, n_ang, geom, sliceptr, rowlen, rowskip, colidx, cta_order, xT_scratch, v_out, u_out, 0.0,
                               alpha_pair + 1, u_k, beta_pair, ws, stream);

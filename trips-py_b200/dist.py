@@ -484,6 +484,9 @@ class BandShardedCT(LinearOperator):
         cm, sm = cos_t[idx].contiguous(), sin_t[idx].contiguous()
         check(lib().tb200_ct_geometry(self.n_loc_ang, K._p(cm), K._p(sm), K._p(self.geom_loc), K._stream()), "ct_geometry")
         _lib.count(2)
+        self.cta_order = None  # heaviest-first CTA list of the forward projector for this rank's angles
+        if os.environ.get("TB200_CT_FORWARD_ORDER", "lpt") == "lpt":
+            self.cta_order = K.forward_cta_order(self.nx, self.ny, self.n_det, cm, sm, dev)
         # every rank's copies of a gathered image ("vt") and a gathered sinogram ("ut") live in the peer-mapped arena
         self.comm = PeerComm({"vt": self.n, "ut": self.m_pad}, group=group, device=dev)
         self.vt, self.ut = self.comm.local("vt"), self.comm.local("ut")
@@ -528,8 +531,8 @@ class BandShardedCT(LinearOperator):
         ptrs, n = peers if peers is not None else (None, 0)
         check(lib().tb200_ct_forward_rays_sharded_f64(
             self.nx, self.ny, self.n_det, self.n_loc_ang, K._p(self.geom_loc), K._p(x_full), K._p(out_rows), ptrs, n,
-            float(coef_host), K._p(coef_dev), K._p(z_rows), K._p(self.ws), ctypes.byref(self.npart), K._stream()),
-            "ct_forward_rays_sharded")
+            float(coef_host), K._p(coef_dev), K._p(z_rows), K._p(self.ws), ctypes.byref(self.npart), K._p(self.cta_order),
+            K._stream()), "ct_forward_rays_sharded")
         _lib.count(1)
 
     def _finish(self, norm_out):

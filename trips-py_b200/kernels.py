@@ -511,6 +511,41 @@ def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False, layout="csr", fan=Non
     return CSRDevice(shape, rowptr, colidx, vals)
 
 
+def forward_cta_order(nx, ny, n_det, cos_t, sin_t, device):
+    """Heaviest-first CTA list of the ray-driven forward projector (tb200_ct_forward_rays_f64, cta_order): entry b =
+    angle * blocks_per_angle + block.  The work of a CTA is estimated from the geometry - per ray the image rows it can
+    meet times the candidates per row (lockstep form), or the rows of the run form times their aligned groups - and the
+    CTAs are sorted by it (longest processing time first), so the SMs drain evenly at the end of the launch: on one
+    rank's angles of an 8-GPU run the kernel's SMs were busy between 57 % and 98 % of the time in centre-out order
+    (profiles/r2_forward_one_of_8_ranks_ncu_full.txt).  Scheduling only: the product never depends on it."""
+    n_ang = int(cos_t.numel())
+    rays, nblk = ctypes.c_int(0), ctypes.c_int(0)
+    check(lib().tb200_ct_forward_rays_plan(int(n_det), n_ang, ctypes.byref(rays), ctypes.byref(nblk)), "ct_forward_rays_plan")
+    rays, nblk = rays.value, nblk.value
+    if n_ang == 0:
+        return None
+    c = cos_t.detach().cpu().numpy().astype(np.float64)[:, None]
+    s = sin_t.detach().cpu().numpy().astype(np.float64)[:, None]
+    ac, as_ = np.abs(c), np.abs(s)
+    sd = (np.arange(nblk * rays) - 0.5 * (n_det - 1))[None, :]
+    live = (np.arange(nblk * rays) < n_det)[None, :]
+    x0, y0 = 0.5 * (nx - 1), 0.5 * (ny - 1)
+    d2 = 0.5 * (ac + as_)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        # rows met: |cy - (sd - cx c)/s| < d2/|s| for some |cx| <= x0 + 1/2  (every row when the ray is parallel to the y axis)
+        reach = (ac * (x0 + 0.5) + d2) / np.maximum(as_, 1e-300)
+        lo = np.clip(sd / np.where(as_ > 0, s, 1.0) - reach, -y0 - 0.5, y0 + 0.5)
+        hi = np.clip(sd / np.where(as_ > 0, s, 1.0) + reach, -y0 - 0.5, y0 + 0.5)
+        rows = np.where(as_ * (y0 + 0.5) + d2 > np.abs(sd) - ac * (x0 + 0.5), np.maximum(hi - lo, 0.0), 0.0)
+        rows = np.where(as_ < 1e-12, np.where(np.abs(sd) < ac * (x0 + 0.5) + d2, float(ny), 0.0), rows)
+        width = (ac + as_) / np.maximum(ac, 1e-300)
+    run_form = as_ > 7.9 * ac
+    per_row = np.where(run_form, 4.0 * (np.minimum(np.ceil(width), nx) + 2) // 4 * 1.0 + 5.0, np.ceil(np.minimum(width, 10.0)) + 0.3)
+    work = np.where(live, rows * per_row, 0.0).reshape(n_ang, nblk, rays).sum(axis=2).reshape(-1)
+    order = np.argsort(-work, kind="stable").astype(np.int32)
+    return torch.from_numpy(order).to(device)
+
+
 class CTProjector:
     """Matrix-free parallel-beam CT operator (csrc/ct_forward.cu, ct_project.cu): neither values nor indices are stored.
     forward='rays' (default): the ray-driven forward projector enumerates each ray's pixels on the fly; back-projection
@@ -536,6 +571,8 @@ class CTProjector:
         self.stored = 0
         if self.forward_mode == "index":
             self._build_index(align)
+        elif os.environ.get("TB200_CT_FORWARD_ORDER", "lpt") == "lpt":
+            self.cta_order = forward_cta_order(self.nx, self.ny, self.n_det, cos_t, sin_t, dev)
 
     @property
     def nnz(self):
@@ -670,7 +707,8 @@ class CTProjector:
             if norm_out is not None:
                 ws = Workspace.get(self.device).buf("ct_fw", int(lib().tb200_ct_forward_rays_workspace_len(self.n_det, self.n_ang)))
             check(lib().tb200_ct_forward_rays_f64(self.nx, self.ny, self.n_det, self.n_ang, _p(self.geom), _p(x), _p(out), ch,
-                                                  _p(cd), _p(z), _p(norm_out), _p(ws), _stream()), "ct_forward_rays")
+                                                  _p(cd), _p(z), _p(norm_out), _p(ws), _p(self.cta_order), _stream()),
+                  "ct_forward_rays")
             _lib.count(2 if norm_out is not None else 1)
             return out
         ws = Workspace.get(self.device).spmv(m) if norm_out is not None else None
