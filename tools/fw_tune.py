@@ -43,6 +43,10 @@ def main():
     for minb in (8, 82, 84, 4):  # 82 / 84: 64 registers with 2 / 4 warps per CTA forced
         for run_tan in ((5.0, 7.9) if minb != 8 else (3.0, 5.0, 7.9)):
             _lib.check(_lib.lib().tb200_ct_forward_set_tuning(run_tan, minb))
+            pr = op.projector  # the CTA list is tied to the launch plan: rebuild it after changing the knobs
+            if pr.cta_order is not None or os.environ.get("TB200_CT_FORWARD_ORDER", "lpt") == "lpt":
+                from trips_b200.kernels import forward_cta_order
+                pr.cta_order = forward_cta_order(pr.nx, pr.ny, pr.n_det, pr.cos_t, pr.sin_t, pr.device)
             t = timeit(lambda: op.apply_dev(x, out=y, norm_out=pair))
             if ref is None:
                 ref = y.clone()

@@ -511,18 +511,21 @@ def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False, layout="csr", fan=Non
     return CSRDevice(shape, rowptr, colidx, vals)
 
 
-def forward_cta_order(nx, ny, n_det, cos_t, sin_t, device):
+def forward_cta_order(nx, ny, n_det, cos_t, sin_t, device, force=False):
     """Heaviest-first CTA list of the ray-driven forward projector (tb200_ct_forward_rays_f64, cta_order): entry b =
     angle * blocks_per_angle + block.  The work of a CTA is estimated from the geometry - per ray the image rows it can
     meet times the candidates per row (lockstep form), or the rows of the run form times their aligned groups - and the
     CTAs are sorted by it (longest processing time first), so the SMs drain evenly at the end of the launch: on one
     rank's angles of an 8-GPU run the kernel's SMs were busy between 57 % and 98 % of the time in centre-out order
-    (profiles/r2_forward_one_of_8_ranks_ncu_full.txt).  Scheduling only: the product never depends on it."""
+    (profiles/r2_forward_one_of_8_ranks_ncu_full.txt); heaviest first: 0.88 -> 0.77 ms.  Scheduling only: the product
+    never depends on it.  The list is tied to the launch plan (tb200_ct_forward_rays_plan) at the time of the call."""
     n_ang = int(cos_t.numel())
     rays, nblk = ctypes.c_int(0), ctypes.c_int(0)
     check(lib().tb200_ct_forward_rays_plan(int(n_det), n_ang, ctypes.byref(rays), ctypes.byref(nblk)), "ct_forward_rays_plan")
     rays, nblk = rays.value, nblk.value
-    if n_ang == 0:
+    # large launches (128-ray CTAs: many waves) drain evenly in the built-in centre-out order, which also keeps the
+    # co-resident CTAs in similar image rows (measured at 2048^2 x 720: 4.43 ms against 4.55 ms heaviest-first)
+    if n_ang == 0 or (rays == 128 and not force):
         return None
     c = cos_t.detach().cpu().numpy().astype(np.float64)[:, None]
     s = sin_t.detach().cpu().numpy().astype(np.float64)[:, None]
