@@ -18,10 +18,9 @@
 
 namespace tb200 {
 
-constexpr int kGRows = 32;      // rows per shared-memory tile
 constexpr int kGThreads = 256;
 constexpr int kGMaxExtra = 4;
-constexpr int kGBlocksX = 148;  // fixed => deterministic reduction tree
+constexpr int kGBlocksX = 296;  // 2 CTAs per SM; fixed => deterministic reduction tree
 
 struct GramExtras {
   const double* ptr[kGMaxExtra];
@@ -59,11 +58,15 @@ __host__ __device__ __forceinline__ void pair_to_tiles(int p, int nt, int& ti, i
   tj = i + p;
 }
 
+// A CTA streams tiles of `rows` consecutive rows through shared memory; thread (pair, rg) accumulates the 4 x 4 block
+// `pair` of the Gram matrix over the rows of group rg of every tile (rows / RG rows per tile).  For the small K of the
+// Krylov solvers (k <= ~20) a handful of 4 x 4 blocks exists, so the rows of a tile are split over up to 64 groups to
+// keep all 256 threads busy (round 1 used 32-row tiles and left 90 % of the threads idle: 617 us for 1M x 8, now tens).
 // partials layout: [blockIdx.x][pair][rg][16 entries][hi, lo]
-__global__ void __launch_bounds__(kGThreads)
+__global__ void __launch_bounds__(kGThreads, 2)
 gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const double* __restrict__ w, GramExtras ex,
-               int K, int Kpad, int npairs, int RG, double* __restrict__ partials) {
-  extern __shared__ double T[];  // kGRows x Kpad
+               int K, int Kpad, int npairs, int RG, int rows, double* __restrict__ partials) {
+  extern __shared__ double T[];  // rows x Kpad
   const int nt = (K + 3) / 4;
   const int slot = blockIdx.y * kGThreads + threadIdx.x;  // (pair, rg) assignment
   const bool active = slot < npairs * RG;
@@ -75,15 +78,15 @@ gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const
   double hi[16], lo[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) hi[q] = lo[q] = 0.0;
-  const int rows_per_group = kGRows / RG;
-  const int64_t nblk = (m + kGRows - 1) / kGRows;
+  const int rows_per_group = rows / RG;
+  const int64_t nblk = (m + rows - 1) / rows;
 
   for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const int64_t row0 = blk * kGRows;
+    const int64_t row0 = blk * rows;
     __syncthreads();
     // stage the tile: lanes run along rows (contiguous in memory), warps over columns
-    for (int idx = threadIdx.x; idx < kGRows * Kpad; idx += kGThreads) {
-      const int r = idx % kGRows, j = idx / kGRows;
+    for (int idx = threadIdx.x; idx < rows * Kpad; idx += kGThreads) {
+      const int r = idx % rows, j = idx / rows;
       const int64_t row = row0 + r;
       double v = 0.0;
       if (row < m && j < K) {
@@ -125,41 +128,59 @@ gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const
   }
 }
 
-// One thread per (pair, entry): fixed-order double-double sum over CTAs and row groups; writes both triangles.
-__global__ void __launch_bounds__(256)
+// One CTA per (pair, entry): double-double sum over CTAs and row groups - every thread a fixed strided subset in order,
+// then a fixed tree; writes both triangles.
+__global__ void __launch_bounds__(128)
 gram_finalize_kernel(int nbx, int npairs, int RG, int nt, int K, const double* __restrict__ partials,
                      double* __restrict__ Ghi, double* __restrict__ Glo) {
-  const int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= npairs * 16) return;
+  __shared__ double sh[128], sl[128];
+  const int id = blockIdx.x;
   const int pair = id / 16, q = id % 16;
   int ti, tj;
   pair_to_tiles(pair, nt, ti, tj);
   const int i = 4 * ti + q / 4, j = 4 * tj + q % 4;
-  if (i >= K || j >= K) return;
+  if (i >= K || j >= K) return;  // (uniform over the CTA)
   double shi = 0.0, slo = 0.0;
-  for (int bx = 0; bx < nbx; ++bx)
-    for (int rg = 0; rg < RG; ++rg) {
-      const double* p = partials + ((((int64_t)bx * npairs + pair) * RG + rg) * 16 + q) * 2;
+  const int terms = nbx * RG;
+  for (int t = threadIdx.x; t < terms; t += 128) {
+    const int bx = t / RG, rg = t % RG;
+    const double* p = partials + ((((int64_t)bx * npairs + pair) * RG + rg) * 16 + q) * 2;
+    double s, e;
+    two_sum(shi, p[0], s, e);
+    slo += e + p[1];
+    shi = s;
+  }
+  sh[threadIdx.x] = shi, sl[threadIdx.x] = slo;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
       double s, e;
-      two_sum(shi, p[0], s, e);
-      slo += e + p[1];
-      shi = s;
+      two_sum(sh[threadIdx.x], sh[threadIdx.x + o], s, e);
+      sl[threadIdx.x] = sl[threadIdx.x] + sl[threadIdx.x + o] + e;
+      sh[threadIdx.x] = s;
     }
-  double s, e;
-  two_sum(shi, slo, s, e);
-  Ghi[i * K + j] = s;
-  Glo[i * K + j] = e;
-  Ghi[j * K + i] = s;
-  Glo[j * K + i] = e;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double s, e;
+    two_sum(sh[0], sl[0], s, e);
+    Ghi[i * K + j] = s;
+    Glo[i * K + j] = e;
+    Ghi[j * K + i] = s;
+    Glo[j * K + i] = e;
+  }
 }
 
-static void gram_shape(int K, int& Kpad, int& npairs, int& RG, int& gy) {
+static void gram_shape(int K, int& Kpad, int& npairs, int& RG, int& gy, int& rows) {
   const int nt = (K + 3) / 4;
   Kpad = 4 * nt + 1;  // odd stride: conflict-free column staging
   npairs = nt * (nt + 1) / 2;
   RG = 1;
-  while (RG < 8 && npairs * RG * 2 <= kGThreads) RG *= 2;
+  while (RG < 64 && npairs * RG * 2 <= kGThreads) RG *= 2;
   gy = (npairs * RG + kGThreads - 1) / kGThreads;
+  rows = 4 * RG < 32 ? 32 : 4 * RG;  // at least four rows per group and tile
+  while (rows > 32 && (size_t)rows * Kpad * sizeof(double) > 96 * 1024) rows >>= 1;
+  if (rows < RG) rows = RG;
 }
 
 // ---- host double-double arithmetic for the k x k factorisation ------------------------------------------
@@ -209,8 +230,8 @@ extern "C" {
 
 // Workspace (doubles) for a Gram pass over K = k + n_extra columns.
 int64_t tb200_gram_workspace_len(int64_t K) {
-  int Kpad, npairs, RG, gy;
-  gram_shape((int)K, Kpad, npairs, RG, gy);
+  int Kpad, npairs, RG, gy, rows;
+  gram_shape((int)K, Kpad, npairs, RG, gy, rows);
   return (int64_t)kGBlocksX * npairs * RG * 32;
 }
 
@@ -231,9 +252,9 @@ int tb200_weighted_gram(int64_t m, int64_t k, const double* B, int64_t ld, const
     ex.weighted[i] = (i < n_extra && extra_weighted) ? extra_weighted[i] : 0;
     TB200_REQUIRE(i >= n_extra || ex.ptr[i], "null extra column");
   }
-  int Kpad, npairs, RG, gy;
-  gram_shape(K, Kpad, npairs, RG, gy);
-  const size_t smem = (size_t)kGRows * Kpad * sizeof(double);
+  int Kpad, npairs, RG, gy, rows;
+  gram_shape(K, Kpad, npairs, RG, gy, rows);
+  const size_t smem = (size_t)rows * Kpad * sizeof(double);
   cudaStream_t st = (cudaStream_t)stream;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(gram_dd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -243,10 +264,10 @@ int tb200_weighted_gram(int64_t m, int64_t k, const double* B, int64_t ld, const
     }
   }
   dim3 grid(kGBlocksX, gy);
-  gram_dd_kernel<<<grid, kGThreads, smem, st>>>(m, (int)k, B, ld, w, ex, K, Kpad, npairs, RG, ws);
+  gram_dd_kernel<<<grid, kGThreads, smem, st>>>(m, (int)k, B, ld, w, ex, K, Kpad, npairs, RG, rows, ws);
   int rc = check_launch("weighted_gram");
   if (rc) return rc;
-  gram_finalize_kernel<<<(npairs * 16 + 255) / 256, 256, 0, st>>>(kGBlocksX, npairs, RG, (K + 3) / 4, K, ws, Ghi, Glo);
+  gram_finalize_kernel<<<npairs * 16, 128, 0, st>>>(kGBlocksX, npairs, RG, (K + 3) / 4, K, ws, Ghi, Glo);
   return check_launch("weighted_gram finalize");
 }
 

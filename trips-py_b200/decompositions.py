@@ -135,7 +135,9 @@ class ArnoldiState:
     (decompositions.py:216-218); reorth='cgs2' is the north-star design: two block projections
     h = V^T w, w -= V h, each a single stream of the basis (h accumulates both passes)."""
 
-    def __init__(self, A, b_dev, kmax, reorth="mgs"):
+    def __init__(self, A, b_dev, kmax, reorth="mgs", comm=None):
+        # comm: model space split over the ranks (dist.BandComm / FrameComm) - dot products and norms are summed across them
+        self.comm = comm if (comm is not None and comm.is_sharded("model")) else None
         if A.shape[0] != A.shape[1]:
             raise Exception("Please check the size of the matrx A: it should be square in order to apply hybrid GMRES")
         if reorth not in ("mgs", "cgs2"):
@@ -151,8 +153,17 @@ class ArnoldiState:
         self._h2 = torch.zeros(kmax + 2, dtype=F64, device=dev)
         self._dot = torch.zeros(2, dtype=F64, device=dev)
         K.vec_norm2(b_dev, out=self.beta0)
+        self._sync_norm(self.beta0)
         K.vec_div(b_dev, self.beta0[1:2], out=self.V.next_col())
         self.V.push()
+
+    def _sync_norm(self, pair):
+        if self.comm is not None:
+            self.comm.sync_norm_(pair, "model")
+
+    def _sum(self, t):
+        if self.comm is not None:
+            self.comm.sum_(t, "model")
 
     @property
     def k(self):
@@ -168,15 +179,19 @@ class ArnoldiState:
         if self.reorth == "mgs":
             for j in range(k):  # h_j = v_j . w ; w -= h_j v_j                        (decompositions.py:216-218)
                 K.vec_dot(self.V.col(j), w, out=self._dot)
+                self._sum(self._dot[0:1])
                 hcol[j:j + 1].copy_(self._dot[0:1])
                 K.vec_axpy(self._dot[0:1], self.V.col(j), w, out=w, sign=-1.0,
                            norm_out=self.nrm[k - 1] if j == k - 1 else None)
         else:
             K.basis_dots(self.V, k, w, out=hcol)
+            self._sum(hcol[:k])
             K.basis_combine(self.V, k, hcol, w=w, sign=-1.0, out=w)
             K.basis_dots(self.V, k, w, out=self._h2)
+            self._sum(self._h2[:k])
             K.basis_combine(self.V, k, self._h2, w=w, sign=-1.0, out=w, norm_out=self.nrm[k - 1])
             hcol[:k].add_(self._h2[:k])
+        self._sync_norm(self.nrm[k - 1])
         hcol[k:k + 1].copy_(self.nrm[k - 1, 1:2])  # h_{k+1,k} = ||w||              (decompositions.py:224-226)
         K.vec_div(w, self.nrm[k - 1, 1:2], out=self.V.next_col())
         self.V.push()

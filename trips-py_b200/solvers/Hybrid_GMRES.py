@@ -34,11 +34,12 @@ def Hybrid_GMRES(A, b, n_iter, regparam="gcv", x_true=None, **kwargs):
         raise Exception("Please check the size of the matrx A: it should be square in order to apply hybrid GMRES")
     dev = A.device
     bd = to_device_vector(b, dev)
-    st = ArnoldiState(A, bd, n_iter, reorth=kwargs.get("b200_reorth", "mgs"))
+    comm = kwargs.get("b200_comm")  # dist.BandComm / FrameComm: model space split over the ranks
+    st = ArnoldiState(A, bd, n_iter, reorth=kwargs.get("b200_reorth", "mgs"), comm=comm)
     beta0 = float(st.beta0.cpu()[1])
     x_history = LazyHistory()
     lambda_history, residual_history = [], []
-    err = ErrorTracker(x_true, dev)
+    err = ErrorTracker(x_true, dev, comm=comm if (comm is not None and comm.is_sharded("model")) else None)
     keep = kwargs.get("b200_history", "lazy")
     rp_kwargs = {k: v for k, v in kwargs.items() if not k.startswith("b200_")}
     xd = None
@@ -58,11 +59,13 @@ def Hybrid_GMRES(A, b, n_iter, regparam="gcv", x_true=None, **kwargs):
             lambdah = generalized_crossvalidation(Q_A, np.diag(s), eye, bhat, **rp_kwargs)
         elif isinstance(regparam, str) and regparam == "dp":
             h = K.basis_dots(st.V, k + 1, bd)  # V^T b                              (discrepancy_principle.py:34)
+            st._sum(h)
             explicit = rp_kwargs.get("explicitProj", False)
             resid = 0.0
             if explicit:
                 res = K.new_pair(dev)
                 K.basis_combine(st.V, k + 1, h, w=bd, sign=-1.0, norm_out=res)
+                st._sync_norm(res)
                 resid = float(res.cpu()[1])
             lambdah = discrepancy_principle_projected(H, None, h.cpu().numpy()[:k + 1], resid, delta,
                                                       rp_kwargs.get("eta", 1.01), explicit)

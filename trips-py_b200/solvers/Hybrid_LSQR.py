@@ -10,6 +10,7 @@ variant='modified', fullsize=m (:84) while its numerator stays 'standard' (gcv.p
 loop index.  Refused: dp_stop=True (the reference path at :88-94 raises a shape error before it can stop).
 """
 import numpy as np
+import torch
 from scipy import linalg as la
 
 from .. import kernels as K
@@ -42,13 +43,46 @@ def Hybrid_LSQR(A, b, n_iter=100, regparam="gcv", x_true=None, **kwargs):
     xd = None
     lambdah = 0
     ii = -1
-    for ii in range(n_iter):
-        st.step()  # (U, B, V) = golub_kahan_update(A, U, B, V)                          (Hybrid_LSQR.py:74)
-        if ii == 0:
-            lambdah = 0
-            continue
-        beta0, al, be = st.scalars_host()
-        k = al.size
+    use_dp = isinstance(regparam, str) and regparam == "dp"
+    explicit = rp_kwargs.get("explicitProj", False)
+    # Pipelined by one iteration: the projected problem of iteration ii (host: SVD / root finding / least squares on
+    # (k+1) x k matrices, as in the reference) is solved WHILE the device runs Golub-Kahan step ii + 1, which does not
+    # depend on it.  What the host needs from iteration ii - the bidiagonal entries and, for 'dp', U^T b - is reduced on the
+    # device right after step ii and copied to pinned memory asynchronously; the lift x = V y follows step ii + 1 on the stream
+    # (it only reads columns < k of V).  Same values as the sequential loop, in the same order.
+    pending = None
+    pinned = torch.empty((2, 3 * n_iter + 8), dtype=torch.float64).pin_memory()  # double buffer of the per-iteration D2H
+    flip = [0]
+
+    def snapshot(k):
+        """Enqueue the device-side reductions of the current iterate and their async D2H; returns what finish() needs."""
+        parts = [st.beta0[1:2], st.alpha[:k, 1], st.beta[:k, 1]]
+        resid_pair = None
+        if use_dp:
+            h = K.basis_dots(st.U, k + 1, bd)  # U^T b                                   (discrepancy_principle.py:34)
+            if comm is not None:
+                comm.sum_(h, "data")
+            parts.append(h[:k + 1])
+            if explicit:  # ||b - U U^T b|| is only consulted by the explicitProj variant (discrepancy_principle.py:69,82)
+                resid_pair = K.new_pair(dev)
+                K.basis_combine(st.U, k + 1, h, w=bd, sign=-1.0, norm_out=resid_pair)
+                if comm is not None:
+                    comm.sync_norm_(resid_pair, "data")
+                parts.append(resid_pair[1:2])
+        packed = torch.cat(parts)
+        host = pinned[flip[0]][:packed.numel()]
+        flip[0] ^= 1
+        host.copy_(packed, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return k, host, ev
+
+    def finish(snap):
+        nonlocal xd, lambdah
+        k, host, ev = snap
+        ev.synchronize()
+        v = host.numpy()
+        beta0, al, be = v[0], v[1:1 + k], v[1 + k:1 + 2 * k]
         B = np.zeros((k + 1, k))
         B[np.arange(k), np.arange(k)] = al
         B[np.arange(1, k + 1), np.arange(k)] = be
@@ -58,21 +92,11 @@ def Hybrid_LSQR(A, b, n_iter=100, regparam="gcv", x_true=None, **kwargs):
         if isinstance(regparam, str) and regparam == "gcv":
             Q_A, s, _ = la.svd(B, full_matrices=False)
             lambdah = generalized_crossvalidation(Q_A, np.diag(s), eye, bhat, variant="modified", fullsize=m_total, **rp_kwargs)
-        elif isinstance(regparam, str) and regparam == "dp":
+        elif use_dp:
             # discrepancy_principle(U, B, L, b): U^T b and ||b - U U^T b|| come from the device basis
-            h = K.basis_dots(st.U, k + 1, bd)
-            if comm is not None:
-                comm.sum_(h, "data")
-            explicit = rp_kwargs.get("explicitProj", False)
-            resid = 0.0
-            if explicit:  # ||b - U U^T b|| is only consulted by the explicitProj variant (discrepancy_principle.py:69,82)
-                res = K.new_pair(dev)
-                K.basis_combine(st.U, k + 1, h, w=bd, sign=-1.0, norm_out=res)
-                if comm is not None:
-                    comm.sync_norm_(res, "data")
-                resid = float(res.cpu()[1])
-            lambdah = discrepancy_principle_projected(B, None, h.cpu().numpy()[:k + 1], resid, delta,
-                                                      rp_kwargs.get("eta", 1.01), explicit)
+            h = v[1 + 2 * k:2 + 3 * k]
+            resid = float(v[2 + 3 * k]) if explicit else 0.0
+            lambdah = discrepancy_principle_projected(B, None, h, resid, delta, rp_kwargs.get("eta", 1.01), explicit)
         elif isinstance(regparam, str) and regparam == "l_curve":
             Q_A, s, _ = la.svd(B, full_matrices=False)  #                                       (Hybrid_LSQR.py:94-98)
             lambdah = l_curve(np.diag(s), eye, Q_A.T @ bhat.reshape((-1, 1)))
@@ -86,6 +110,19 @@ def Hybrid_LSQR(A, b, n_iter=100, regparam="gcv", x_true=None, **kwargs):
         if keep != "none":
             x_history.append_lift(st.V, k, y)
         err.add(xd)
+
+    if isinstance(regparam, str) and regparam not in ("gcv", "dp", "l_curve"):
+        raise NotImplementedError(f"regparam={regparam!r}: 'gcv', 'dp', 'l_curve' or a number")
+    for ii in range(n_iter):
+        st.step()  # (U, B, V) = golub_kahan_update(A, U, B, V)                          (Hybrid_LSQR.py:74)
+        snap = snapshot(st.k) if ii > 0 else None  # ii == 0: lambda = 0 and no iterate   (Hybrid_LSQR.py:77-78)
+        if pending is not None:
+            finish(pending)  # host work of iteration ii - 1, overlapped with step ii on the device
+        pending = snap
+        if ii == 0:
+            lambdah = 0
+    if pending is not None:
+        finish(pending)
     if xd is None:
         raise ValueError("Hybrid_LSQR forms no iterate when n_iter < 2 (the reference raises UnboundLocalError)")
     info = {"xHistory": x_history, "regParam": lambdah, "regParam_history": lambda_history,
