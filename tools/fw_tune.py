@@ -46,7 +46,7 @@ def main():
             pr = op.projector  # the CTA list is tied to the launch plan: rebuild it after changing the knobs
             if pr.cta_order is not None or os.environ.get("TB200_CT_FORWARD_ORDER", "lpt") == "lpt":
                 from trips_b200.kernels import forward_cta_order
-                pr.cta_order = forward_cta_order(pr.nx, pr.ny, pr.n_det, pr.cos_t, pr.sin_t, pr.device)
+                pr.cta_order = forward_cta_order(pr.nx, pr.ny, pr.n_det, pr.cos_t, pr.sin_t, pr.device, force=minb > 9)
             t = timeit(lambda: op.apply_dev(x, out=y, norm_out=pair))
             if ref is None:
                 ref = y.clone()
@@ -55,6 +55,11 @@ def main():
     u = torch.randn(m, dtype=torch.float64, device="cuda")
     z = torch.empty(n, dtype=torch.float64, device="cuda")
     print(f"back-projection {timeit(lambda: op.adjoint_dev(u, out=z, norm_out=pair)):7.3f} ms")
+    if a.every == 1:  # one rank's image band of an 8 / 4-GPU run: rows [0, ny / G) from all angles
+        pr = op.projector
+        for G in (8, 4, 2):
+            lo, hi = pr.ny // 2 - pr.ny // (2 * G), pr.ny // 2 + pr.ny // (2 * G)
+            print(f"back-projection of a 1/{G} band (all angles) {timeit(lambda: pr.backproject_rows(u, z, lo, hi)):7.3f} ms")
 
 
 if __name__ == "__main__":

@@ -97,9 +97,12 @@ __device__ __forceinline__ void bp_tile(double (&acc)[2], const double* __restri
 // CTA = 4 warps side by side, each warp two 8 x 4 pixel tiles one above the other (32 x 8 pixels per CTA, two pixels per
 // thread): a compact tile keeps the two gather requests of an angle within 2-3 sectors whatever the angle.
 constexpr int BP_ROWS = 8;  // image rows per CTA
+#ifndef BP_MIN_CTAS
+#define BP_MIN_CTAS 6  // measured: 7 CTAs per SM (72 registers) is 2 % slower, 8 spills
+#endif
 
 template <int UNROLL, bool OFFS, bool FOLD>
-__global__ void __launch_bounds__(128, 6)
+__global__ void __launch_bounds__(128, BP_MIN_CTAS)
 ct_backproject_kernel(int nx, int ny, int iy_begin, int iy_end, int n_det, int n_ang, const double* __restrict__ geom,
                       const double* __restrict__ u, double* __restrict__ y, double coef_host,
                       const double* __restrict__ coef_dev, const double* __restrict__ z, int64_t z_offset,
