@@ -274,6 +274,9 @@ void* tb200_comm_arena(void* comm, int peer);
 int tb200_comm_destroy(void* comm);
 int tb200_comm_allreduce_dd(void* comm, int box, int64_t epoch, const double* partials, int64_t npart, int nval, double* out,
                             void* stream);
+int tb200_comm_allreduce_scale(void* comm, int box, int64_t epoch, const double* partials, int64_t npart, int64_t n,
+                               const double* x, double* out, int64_t keep_begin, int64_t keep_n, double* keep, double* pair_out,
+                               void* stream); /* allreduce_dd of one value + scale by its square root, one launch */
 int tb200_comm_push(void* comm, unsigned rank_mask, int64_t offset_bytes, const double* src, int64_t n, void* stream);
 int tb200_halo_exchange(void* comm, int box, int64_t epoch, int64_t offset_bytes, const double* send_prev, const double* send_next,
                         int64_t n, double* recv_prev, double* recv_next, double* scratch_pair, void* stream);

@@ -78,6 +78,7 @@ SIGNATURES = {
     "tb200_comm_arena": (c_ptr, [c_ptr, c_int]),
     "tb200_comm_destroy": (c_int, [c_ptr]),
     "tb200_comm_allreduce_dd": (c_int, [c_ptr, c_int, c_i64, c_ptr, c_i64, c_int, c_ptr, c_ptr]),
+    "tb200_comm_allreduce_scale": (c_int, [c_ptr, c_int, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),
     "tb200_comm_push": (c_int, [c_ptr, ctypes.c_uint, c_i64, c_ptr, c_i64, c_ptr]),
     "tb200_halo_exchange": (c_int, [c_ptr, c_int, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_comm_scale": (c_int, [c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),

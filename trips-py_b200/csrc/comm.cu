@@ -143,6 +143,66 @@ comm_scale_kernel(int64_t n, const double* __restrict__ x, const double* __restr
   }
 }
 
+// tb200_comm_allreduce_dd and tb200_comm_scale in ONE launch (nval = 1): CTA 0 reduces the launch partials and posts the
+// rank's total to every mailbox; every CTA waits (one polling thread per rank) until all ranks' totals have arrived,
+// adds them in rank order - the same double-double sum in every CTA of every rank - and divides its share of x by the
+// square root.  Saves a launch and the serial 1-CTA kernel between a projector and the normalisation of its result.
+__global__ void __launch_bounds__(256)
+comm_allreduce_scale_kernel(PeerTable pt, int rank, int nranks, int box, unsigned long long epoch,
+                            const double* __restrict__ partials, int64_t npart, int64_t n, const double* __restrict__ x,
+                            double* __restrict__ out, int64_t keep_begin, int64_t keep_n, double* __restrict__ keep,
+                            double* __restrict__ pair_out) {
+  __shared__ double red[64];
+  __shared__ double tot_s[2];
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  if (blockIdx.x == 0) {
+    dd_t acc = dd_zero();
+    for (int64_t i = threadIdx.x; i < npart; i += blockDim.x) acc = dd_add(acc, dd_t{partials[2 * i], partials[2 * i + 1]});
+    const dd_t tot = dd_block_sum(acc, red);
+    if (threadIdx.x == 0) red[0] = tot.hi, red[1] = tot.lo;
+    __syncthreads();
+    if ((int)threadIdx.x < nranks) {
+      MailSlot* dst = mail(pt.base[threadIdx.x], box, rank);
+      dst->hilo[0] = red[0];
+      dst->hilo[1] = red[1];
+      __threadfence_system();
+      st_release_sys(&dst->epoch, epoch);
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nranks) {
+    const MailSlot* src = mail(pt.base[rank], box, threadIdx.x);
+    const long long t0 = clock64();
+    while (ld_acquire_sys(&src->epoch) < epoch) {
+      if (clock64() - t0 > 8000000000LL) {
+        timed_out = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    dd_t tot = dd_zero();
+    for (int r = 0; r < nranks; ++r) {
+      const volatile double* v = mail(pt.base[rank], box, r)->hilo;
+      tot = dd_add(tot, dd_t{v[0], v[1]});
+    }
+    if (timed_out) tot.hi = __longlong_as_double(0x7ff8000000000000LL);
+    tot_s[0] = tot.hi;
+    tot_s[1] = sqrt(tot.hi);
+    if (blockIdx.x == 0) pair_out[0] = tot_s[0], pair_out[1] = tot_s[1];
+  }
+  __syncthreads();
+  const double d = tot_s[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = __ddiv_rn(x[i], d);
+    out[i] = v;
+    const int64_t k = i - keep_begin;
+    if (keep != nullptr && k >= 0 && k < keep_n) keep[k] = v;
+  }
+}
+
 static PeerTable table_of(const Comm* c) {
   PeerTable pt;
   for (int r = 0; r < TB200_COMM_MAX_RANKS; ++r) pt.base[r] = (r < c->nranks) ? c->base[r] : nullptr;
@@ -253,6 +313,24 @@ int tb200_comm_allreduce_dd(void* comm, int box, int64_t epoch, const double* pa
   comm_allreduce_dd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(table_of(c), c->rank, c->nranks, box, (unsigned long long)epoch,
                                                                  partials, npart, nval, out);
   return check_launch("comm_allreduce_dd");
+}
+
+// tb200_comm_allreduce_dd (one value) followed by tb200_comm_scale with its square root, in one launch:
+// pair_out = (total, sqrt(total)), out = x / sqrt(total), keep[0:keep_n) = out[keep_begin : keep_begin + keep_n).
+// Every CTA waits for the mailboxes itself, so the grid is limited to what is resident at once.
+int tb200_comm_allreduce_scale(void* comm, int box, int64_t epoch, const double* partials, int64_t npart, int64_t n,
+                               const double* x, double* out, int64_t keep_begin, int64_t keep_n, double* keep, double* pair_out,
+                               void* stream) {
+  Comm* c = (Comm*)comm;
+  TB200_REQUIRE(c && pair_out && n >= 0 && (n == 0 || (x && out)), "null pointer");
+  TB200_REQUIRE(box >= 0 && box < TB200_COMM_BOXES && epoch > 0, "bad mailbox / epoch");
+  TB200_REQUIRE(npart >= 0 && (npart == 0 || partials), "bad partials");
+  TB200_REQUIRE(keep == nullptr || (keep_begin >= 0 && keep_n >= 0 && keep_begin + keep_n <= n), "bad keep slice");
+  const int grid = grid_for(n > 0 ? n : 1, 256 * 8, sm_count() * 4);  // <= 4 CTAs of 256 threads per SM: all resident
+  comm_allreduce_scale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table_of(c), c->rank, c->nranks, box,
+                                                                      (unsigned long long)epoch, partials, npart, n, x, out,
+                                                                      keep_begin, keep_n, keep, pair_out);
+  return check_launch("comm_allreduce_scale");
 }
 
 // Copies src[0:n) to offset_bytes of the arena of every rank in rank_mask (bit r = rank r; the own arena included if

@@ -566,7 +566,7 @@ struct CtRays {
 };
 
 template <typename VT, int WARPS, bool GEOM, int CH>
-__global__ void __launch_bounds__(WARPS * 32, GEOM ? 512 / (WARPS * 32) : 1)
+__global__ void __launch_bounds__(WARPS * 32, GEOM ? 512 / (WARPS * 32) : (CH == 8 ? 512 / (WARPS * 32) : 1))
 spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t* __restrict__ rowlen,
                  const int32_t* __restrict__ col, const VT* __restrict__ val, const double* __restrict__ x,
                  double* __restrict__ y, double coef_host, const double* __restrict__ coef_dev,
@@ -1000,6 +1000,7 @@ static int spmv_launch(int order, int64_t m, int64_t nnz, const int64_t* rowptr,
 }
 
 static int g_sell_warps = 4;  // tuning knob (tb200_spmv_set_variant, bits 8-9: 0/2 -> 4, 1 -> 2, 3 -> 1 warps per CTA)
+static int g_sell_ch8 = 0;    // tuning knob (bit 10): stored values with 8 entries per pipeline stage and 16 warps per SM
 
 template <typename VT, bool GEOM = false, int CH = 16>
 static int sell_launch(int64_t m, const int64_t* sliceptr, const int32_t* rowlen, const int32_t* col, const VT* val,
@@ -1041,11 +1042,12 @@ int tb200_spmv_launches(int with_norm) { return with_norm ? 2 : 1; }
 // plus 8 * gather mode of the tile kernel (0 = per row group, 1 = lane-per-row, 2 = row-major, 3 = no gathers:
 // measurement only).  Results are bit-identical across variants (except gather mode 3).
 int tb200_spmv_set_variant(int v) {
-  TB200_REQUIRE(v >= 0 && (v & 7) <= 6 && ((v >> 3) & 3) <= 3 && (v >> 8) <= 3,
-                "variant = CSR kernel (0..6) + 8 * gather mode (0..3) + 256 * log2(SELL warps per CTA) (0..3)");
+  TB200_REQUIRE(v >= 0 && (v & 7) <= 6 && ((v >> 3) & 3) <= 3 && (v >> 8) <= 7,
+                "variant = CSR kernel (0..6) + 8 * gather mode (0..3) + 256 * log2(SELL warps per CTA) (0..3) + 1024 * (SELL 8-entry stages)");
   g_seq_variant = v & 7;
   g_seq_gather_mode = (v >> 3) & 3;
-  g_sell_warps = ((v >> 8) == 1) ? 2 : ((v >> 8) == 3) ? 1 : 4;
+  g_sell_warps = (((v >> 8) & 3) == 1) ? 2 : (((v >> 8) & 3) == 3) ? 1 : 4;
+  g_sell_ch8 = (v >> 10) & 1;
   return 0;
 }
 
@@ -1099,6 +1101,9 @@ int tb200_spmv_sell_f64(int64_t m, int64_t n, const int64_t* sliceptr, const int
   int rc = check_sell_args(m, n, sliceptr, rowlen, colidx, vals, x, y, norm_out, ws);
   if (rc) return rc;
   if (m == 0) return 0;
+  if (g_sell_ch8)
+    return sell_launch<double, false, 8>(m, sliceptr, rowlen, colidx, vals, x, y, coef_host, coef_dev, z, norm_out, ws,
+                                         (cudaStream_t)stream);
   return sell_launch<double>(m, sliceptr, rowlen, colidx, vals, x, y, coef_host, coef_dev, z, norm_out, ws,
                              (cudaStream_t)stream);
 }

@@ -404,6 +404,14 @@ class PeerComm:
         _lib.count(1)
         return out
 
+    def allreduce_scale(self, box, partials, npart, x, out, keep_begin, keep, pair_out):
+        """pair_out = (sum over ranks and partials, its square root); out = x / sqrt; keep = out[keep_begin : +len(keep)].
+        tb200_comm_allreduce_dd + tb200_comm_scale in one launch."""
+        check(lib().tb200_comm_allreduce_scale(self._comm, int(box), self._next_epoch(box), K._p(partials), int(npart),
+                                               x.numel(), K._p(x), K._p(out), int(keep_begin), keep.numel(), K._p(keep),
+                                               K._p(pair_out), K._stream()), "comm_allreduce_scale")
+        _lib.count(1)
+
     def barrier(self):
         self.allreduce_dd(self.BOX_MISC, None, 0, self._scratch)
 
@@ -412,6 +420,24 @@ class PeerComm:
         check(lib().tb200_comm_push(self._comm, mask, self.offsets[name] + 8 * int(offset_doubles), K._p(src), src.numel(),
                                     K._stream()), "comm_push")
         _lib.count(1)
+
+    def halo_exchange(self, name, send_prev, send_next, box=None):
+        """One-block halo exchange with the neighbouring ranks through the arena region `name` (>= 2 * n doubles):
+        send_prev goes to rank - 1, send_next to rank + 1 (either may be None at the ends); returns (recv_prev, recv_next) =
+        what rank - 1 sent as its send_next and what rank + 1 sent as its send_prev (None at the ends).
+        tb200_halo_exchange: peer stores + one mailbox epoch, no NCCL."""
+        ref = send_prev if send_prev is not None else send_next
+        n = ref.numel()
+        if 2 * n > self.counts[name]:
+            raise ValueError(f"arena region {name!r} holds {self.counts[name]} doubles, the halo needs {2 * n}")
+        box = self.BOX_HALO if box is None else box
+        recv_prev = torch.empty(n, dtype=F64, device=self.device) if self.rank > 0 else None
+        recv_next = torch.empty(n, dtype=F64, device=self.device) if self.rank + 1 < self.world else None
+        check(lib().tb200_halo_exchange(self._comm, int(box), self._next_epoch(box), self.offsets[name], K._p(send_prev),
+                                        K._p(send_next), n, K._p(recv_prev), K._p(recv_next), K._p(self._scratch), K._stream()),
+              "halo_exchange")
+        _lib.count(2)
+        return recv_prev, recv_next
 
     def destroy(self):
         if self._comm is not None:
@@ -424,6 +450,9 @@ class PeerComm:
             self.destroy()
         except Exception:  # noqa: BLE001
             pass
+
+
+FUSE_ALLREDUCE_SCALE = os.environ.get("TB200_FUSE_ALLREDUCE_SCALE", "1") != "0"
 
 
 def band_rows(ny, world, rank):
@@ -648,6 +677,15 @@ class ShardedGKState:
         if k + 1 >= self.alpha.shape[0]:
             raise RuntimeError("ShardedGKState capacity exceeded")
         self.backproject(k)
+        if FUSE_ALLREDUCE_SCALE:  # K2 + K3 and K5 + K6 as one launch each
+            self.comm.allreduce_scale(PeerComm.BOX_ALPHA, self.ws, self._npart.value, self.vt, self.v_full, self.row_lo * self.nx,
+                                      self.V.next_col(), self.alpha[k])
+            self.V.push()
+            self.forward(k)
+            self.comm.allreduce_scale(PeerComm.BOX_BETA, self.ws, self._npart.value, self.ut, self.u_full, self.my_chunk,
+                                      self.U.next_col(), self.beta[k])
+            self.U.push()
+            return
         self.comm.allreduce_dd(PeerComm.BOX_ALPHA, self.ws, self._npart.value, self.alpha[k])
         check(lib().tb200_comm_scale(self.n, K._p(self.vt), K._p(self.alpha[k, 1:2]), K._p(self.v_full), self.row_lo * self.nx,
                                      self.n_band, K._p(self.V.next_col()), K._stream()), "comm_scale")
