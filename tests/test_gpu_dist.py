@@ -202,6 +202,10 @@ def _p2p_worker(rank, world, port, out_dir):
         xt = O.shepp_logan(max(PNX, PNY))[:PNY, :PNX].reshape(-1, 1)
         x_l, i_l = tb.Hybrid_LSQR(op, b[rows], n_iter=10, regparam=1e-2, x_true=xt[lo * PNX:hi * PNX], b200_comm=comm)
         x_c, i_c = tb.CGLS(op, b[rows], np.zeros((op.shape[1], 1)), 8, 0.0, b200_comm=comm)
+        M = op.T @ op  # the normal operator on the band-sharded model space (configs[3]: Hybrid_GMRES on A^T A)
+        rhs = op.adjoint_dev(torch.from_numpy(b[rows]).cuda())
+        x_g, i_g = tb.Hybrid_GMRES(M, rhs, 8, regparam=1e-2, b200_comm=comm)
+        x_g2, _ = tb.Hybrid_GMRES(M, rhs, 8, regparam=1e-2, b200_comm=comm, b200_reorth="cgs2")
         st = op.gk_state(torch.from_numpy(b[rows]).cuda(), PSTEPS)
         for _ in range(PSTEPS):
             st.step()
@@ -227,7 +231,7 @@ def _p2p_worker(rank, world, port, out_dir):
         pc.destroy()
         np.savez(os.path.join(out_dir, f"p{rank}.npz"), U=U, V=V, B=B, rows=rows, band=np.array([lo, hi]),
                  host=np.array([al, be]), hu1=hu[1].numpy(), hv0=hv[0].numpy(), y_rows=y_rows, z_band=z_band,
-                 x_lsqr=x_l, rre_lsqr=np.array(i_l["relError"]), x_cgls=x_c)
+                 x_lsqr=x_l, rre_lsqr=np.array(i_l["relError"]), x_cgls=x_c, x_gmres=x_g, x_gmres2=x_g2)
         st.close()
     finally:
         dist.destroy_process_group()
@@ -260,6 +264,9 @@ def test_band_sharded_matrix_free_golub_kahan_is_bit_identical_to_one_gpu(tmp_pa
     xt = O.shepp_logan(max(PNX, PNY))[:PNY, :PNX].reshape(-1, 1)
     xl1, il1 = tb.Hybrid_LSQR(A1, b, n_iter=10, regparam=1e-2, x_true=xt)
     xc1, _ = tb.CGLS(A1, b, np.zeros((PNX * PNY, 1)), 8, 0.0)
+    M1, rhs1 = A1.T @ A1, A1.T @ b
+    xg1, _ = tb.Hybrid_GMRES(M1, rhs1, 8, regparam=1e-2)
+    xg12, _ = tb.Hybrid_GMRES(M1, rhs1, 8, regparam=1e-2, b200_reorth="cgs2")
     rel = lambda a, c: np.linalg.norm(a - c) / np.linalg.norm(c)  # noqa: E731
     for p in parts:
         lo, hi = p["band"]
@@ -268,6 +275,7 @@ def test_band_sharded_matrix_free_golub_kahan_is_bit_identical_to_one_gpu(tmp_pa
         assert np.array_equal(p["x_lsqr"], xl1[lo * PNX:hi * PNX])
         assert np.allclose(p["rre_lsqr"], il1["relError"], rtol=1e-12)
         assert rel(p["x_cgls"], xc1[lo * PNX:hi * PNX]) < 1e-9
+        assert rel(p["x_gmres"], xg1[lo * PNX:hi * PNX]) < 1e-9 and rel(p["x_gmres2"], xg12[lo * PNX:hi * PNX]) < 1e-9
         assert np.array_equal(p["B"], B1)
         assert np.array_equal(p["U"], U1[p["rows"]])
         lo, hi = p["band"]
