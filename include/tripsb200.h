@@ -191,6 +191,11 @@ int tb200_ct_forward_rays_plan(int n_det, int n_ang, int* rays_per_cta, int* blo
 int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* x, double* y,
                               double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
                               const int32_t* cta_order, void* stream);
+/* The same ray-driven forward projection for the flat-detector fan beam of tb200_ctfan_* (per-ray geometry): replaces the
+ * forward product of astra's 'line_fanflat' projector (trips/test_problems/Tomography.py:57-67, 73-83). */
+int tb200_ctfan_forward_rays_f64(double so, double dd, double dps, int nx, int ny, int n_det, int n_ang, const double* cosv,
+                                 const double* sinv, const double* x, double* y, double coef_host, const double* coef_dev,
+                                 const double* z, double* norm_out, double* ws, void* stream);
 int64_t tb200_ct_backproject_workspace_len(int nx, int ny);
 int tb200_ct_backproject_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const double* u, double* y,
                              double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,

@@ -460,3 +460,31 @@ def test_difference_operator_frame_sharding_with_halos(tb):
     g0 = host(lo.adjoint_dev(r0))
     g1 = host(hi.adjoint_dev(r1, rt_prev=dev(rt[2])))
     assert np.array_equal(np.r_[g0, g1], g_glob)
+
+
+@pytest.mark.parametrize("nx,ny,views,n_det,geom", [(24, None, 16, None, None), (64, None, 45, None, None),
+                                                    (33, 20, 7, None, None), (40, 40, 9, 70, (90.0, 25.0, 1.1)),
+                                                    (48, None, 5, None, (60.0, 0.0, 1.0)), (256, None, 24, None, None)])
+def test_fan_beam_matrix_free_forward_is_bit_identical_to_the_stored_matrix(tb, nx, ny, views, n_det, geom):
+    """FanBeamCT(layout='implicit'): the ray-driven forward projector with per-ray geometry (the reference's own ASTRA
+    geometry, Tomography.py:57-67) gives the bits of the stored product; A^T stays a stored SpMV; Golub-Kahan on it equals
+    Golub-Kahan on the stored pair."""
+    import torch
+
+    kw = {} if geom is None else dict(source_origin=geom[0], detector_origin=geom[1], detector_pixel_size=geom[2])
+    st = tb.FanBeamCT(nx, views, ny=ny, n_det=n_det, layout="sell", **kw)
+    mf = tb.FanBeamCT(nx, views, ny=ny, n_det=n_det, layout="implicit", **kw)
+    assert mf.shape == st.shape and mf.nnz == st.nnz and mf.A_sell is None and mf.A is None
+    rng = np.random.default_rng(9)
+    x, u, z = rng.standard_normal(st.shape[1]), rng.standard_normal(st.shape[0]), rng.standard_normal(st.shape[0])
+    assert torch.equal(mf.apply_dev(dev(x)), st.apply_dev(dev(x)))
+    assert torch.equal(mf.adjoint_dev(dev(u)), st.adjoint_dev(dev(u)))
+    pair_a = torch.zeros(2, dtype=torch.float64, device="cuda")
+    pair_b = torch.zeros(2, dtype=torch.float64, device="cuda")
+    ya = mf.apply_dev(dev(x), coef=0.25, z=dev(z), norm_out=pair_a)
+    yb = st.apply_dev(dev(x), coef=0.25, z=dev(z), norm_out=pair_b)
+    assert torch.equal(ya, yb) and torch.equal(pair_a, pair_b)
+    b = rng.standard_normal(st.shape[0])
+    ga, gb = tb.golub_kahan_device(mf, b, 6), tb.golub_kahan_device(st, b, 6)
+    assert np.array_equal(ga.B_host(), gb.B_host()) and np.array_equal(ga.V.to_numpy(), gb.V.to_numpy())
+    assert (mf.to_scipy() != st.to_scipy()).nnz == 0

@@ -338,3 +338,103 @@ def test_ray_driven_forward_projection_awkward_angles():
     y, hits, _ = forward_rays_spec(nx, ny, n_det, theta, x)
     assert hits == A.nnz
     assert np.array_equal(y, A @ x)
+
+
+# ---- fan beam: the same walk with per-ray geometry (ct_forward_rays_fan_kernel) ------------------------------------------
+
+def forward_rays_fan_spec(nx, ny, n_det, theta, x, fan, run_tan=7.9):
+    """NumPy transcription of ct_forward_rays_fan_kernel: per-ray (c, s, rho) from the builder's ray tables, the form chosen
+    per warp of 32 neighbouring rays (run form for the shallow rays of a warp in which some ray has |s/c| > run_tan, lockstep
+    with the widest bracket of the warp otherwise)."""
+    x0, y0 = 0.5 * (nx - 1), 0.5 * (ny - 1)
+    X = x.reshape(ny, nx)
+    y = np.zeros(len(theta) * n_det)
+    hits = 0
+    warp = np.arange(n_det) // 32
+    nw = warp.max() + 1
+    for a, th in enumerate(theta):
+        c, s, rho, d2, inv_hi, inv_hilo = O._ray_tables(np.cos(th), np.sin(th), n_det, fan)
+        ac, as_ = np.abs(c), np.abs(s)
+        acc = np.zeros(n_det)
+
+        def candidate(ix, Q, ok):
+            cx = np.clip(ix, 0, nx - 1) - x0
+            t = rho - (cx * c + Q)
+            e = d2 - np.abs(t)
+            with np.errstate(invalid="ignore", over="ignore"):
+                sl = e * inv_hilo
+                w = np.where(sl < inv_hi, sl, inv_hi)
+            return ok & (e > 0), w
+
+        need = np.zeros(nw, dtype=bool)
+        np.logical_or.at(need, warp, as_ > run_tan * ac)
+        in_runs = need[warp] & (as_ > ac)
+        in_lock = ~in_runs
+        with np.errstate(divide="ignore", invalid="ignore"):
+            width = (ac + as_) / ac + 2.0 * FW_ETA + 1e-7
+            inv_c = np.where(c != 0, 1.0 / c, 0.0)
+        lm = np.where(in_lock, np.ceil(np.minimum(width, 64.0)), 2).astype(np.int64)
+        lmax_w = np.full(nw, 2, dtype=np.int64)
+        np.maximum.at(lmax_w, warp, lm)
+        lmax = lmax_w[warp]
+        h = d2 * np.abs(inv_c)
+        slope = -s * inv_c
+        E0 = (rho + y0 * s) * inv_c + x0 - h - FW_ETA - 0.5
+        # lockstep lanes
+        if in_lock.any():
+            e1 = E0.copy()
+            for iy in range(ny):
+                Q = (iy - y0) * s
+                with np.errstate(invalid="ignore"):
+                    i0 = ((np.where(in_lock, e1, 0.0) + MAGIC) - MAGIC).astype(np.int64) + 1
+                e1 = e1 + slope
+                for k in range(int(lmax[in_lock].max())):
+                    ix = i0 + k
+                    ok = in_lock & (k < lmax) & (ix >= 0) & (ix < nx)
+                    hit, w = candidate(ix, Q, ok)
+                    acc = np.where(hit, acc + w * X[iy, np.clip(ix, 0, nx - 1)], acc)
+                    hits += int(hit.sum())
+        # run-form lanes
+        if in_runs.any():
+            flat = (ac + as_) >= 0.5 * nx * ac
+            wlen = np.where(flat, float(nx), np.ceil(2.0 * h + 2.0 * FW_ETA + 1e-7))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                reach = (ac * (x0 + 1.0) + d2) / as_ + 1e-6
+                yc = rho / s
+            ra = np.where(in_runs, np.maximum(np.ceil(yc - reach + y0), 0), 0).astype(np.int64)
+            rb = np.where(in_runs, np.minimum(np.floor(yc + reach + y0) + 1, ny), 0).astype(np.int64)
+            for iy in range(ny):
+                rowok = in_runs & (iy >= ra) & (iy < rb)
+                if not rowok.any():
+                    continue
+                Q = (iy - y0) * s
+                e1 = np.clip(np.where(flat, 0.0, E0 + iy * slope), -1073741824.0, 1073741824.0)
+                i0 = ((e1 + MAGIC) - MAGIC).astype(np.int64) + 1
+                lo_i = np.where(flat, 0, np.maximum(i0, 0))
+                hi_i = np.where(flat, nx - 1, np.minimum(i0 + wlen - 1.0, nx - 1.0)).astype(np.int64)
+                hi_i = np.where(rowok, hi_i, -1)
+                live_rows = hi_i >= lo_i
+                if not live_rows.any():
+                    continue
+                for ix in range(int(lo_i[live_rows].min()), int(hi_i.max()) + 1):
+                    ok = (ix >= lo_i) & (ix <= hi_i)
+                    hit, w = candidate(np.full(n_det, ix), Q, ok)
+                    acc = np.where(hit, acc + w * X[iy, ix], acc)
+                    hits += int(hit.sum())
+        y[a * n_det:(a + 1) * n_det] = acc
+    return y, hits
+
+
+@pytest.mark.parametrize("nx,ny,views,n_det,fan", [(16, 16, 12, None, None), (24, 24, 9, 40, (60.0, 20.0, 1.1)),
+                                                   (21, 13, 8, 33, (40.0, 0.0, 1.0)), (32, 32, 10, 70, (70.0, 30.0, 1.3)),
+                                                   (20, 36, 16, 45, None)])
+def test_ray_driven_fan_beam_forward_projection_equals_the_stored_product_bitwise(nx, ny, views, n_det, fan):
+    n_det = O.ct_num_detectors(nx) if n_det is None else n_det
+    fan = O.fan_geometry(nx) if fan is None else fan
+    theta = O.ct_angles(views)
+    A = O.ct_matrix(nx, theta, ny=ny, n_det=n_det, fan=fan)
+    x = np.random.default_rng(nx + 7 * ny).standard_normal(nx * ny)
+    for run_tan in (7.9, 0.7):
+        y, hits = forward_rays_fan_spec(nx, ny, n_det, theta, x, fan, run_tan)
+        assert hits == A.nnz
+        assert np.array_equal(y, A @ x)

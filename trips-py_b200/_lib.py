@@ -63,6 +63,8 @@ SIGNATURES = {
     "tb200_ct_forward_set_tuning": (c_int, [c_dbl, c_int]),
     "tb200_ct_forward_rays_plan": (c_int, [c_int, c_int, c_ptr, c_ptr]),
     "tb200_ct_forward_rays_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_ctfan_forward_rays_f64": (c_int, [c_dbl, c_dbl, c_dbl, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr,
+                                             c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_backproject_workspace_len": (c_i64, [c_int, c_int]),
     "tb200_ct_backproject_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_backproject_rows_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

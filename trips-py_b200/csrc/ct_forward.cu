@@ -306,6 +306,76 @@ ct_forward_rays_kernel(int nx, int ny, int n_det, int n_ang, int nblk, const dou
   }
 }
 
+// Fan beam (flat detector, tb200_ctgeom.cuh Beam): the same walk with PER-RAY geometry - every ray of a fan has its own
+// normal (c, s) and offset rho, computed once per lane by the builder's ray_geometry(), so cy*s is formed per lane and the
+// form (lockstep with LMAX candidates / run form) is chosen per WARP from the widest bracket among its 32 rays (a wider
+// bracket is still a superset).  Replaces the forward product of astra's 'line_fanflat' projector
+// (trips/test_problems/Tomography.py:57-67, 73-83).
+__global__ void __launch_bounds__(FW_WARPS * 32, 5)
+ct_forward_rays_fan_kernel(Beam bm, int nx, int ny, int n_det, int n_ang, int nblk, const double* __restrict__ cosv,
+                           const double* __restrict__ sinv, const double* __restrict__ x, double* __restrict__ y,
+                           double coef_host, const double* __restrict__ coef_dev, const double* __restrict__ z,
+                           double* __restrict__ partials, int vec4, double run_tan) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int a = blockIdx.x % n_ang;
+  const int rank = blockIdx.x / n_ang;
+  const int mid = nblk >> 1;
+  const int blk = (rank & 1) ? mid + ((rank + 1) >> 1) : mid - (rank >> 1);
+  const bool blk_ok = blk >= 0 && blk < nblk;
+  const int d = blk * (FW_WARPS * 32) + threadIdx.x;
+  const bool live = blk_ok && d < n_det;
+  RayGeom g;
+  double rho;
+  ray_geometry(bm, cosv[a], sinv[a], live ? d : 0, n_det, g, rho);
+  FwRay r;
+  r.c = g.c, r.d2 = g.d2, r.inv_hi = g.inv_hi, r.inv_hilo = g.inv_hilo, r.sd = rho;
+  r.biasx = centred_bias(nx);
+  const double s = g.s;
+  const double biasy = centred_bias(ny);
+  const uint64_t pol = policy_evict_last();
+  const double ac = fabs(r.c), as = fabs(s);
+  // If some ray of the warp needs the run form, all its shallow rays (|s| > |c|) take it; the others - and every ray of a
+  // warp without such a ray - walk in lockstep with the widest bracket among them.  (The 32 rays of a warp are nearly
+  // parallel, so in practice a warp is all of one kind; the split only keeps degenerate fans correct.)
+  const bool need_runs = __any_sync(FULL, live && as > run_tan * ac);
+  const bool in_runs = need_runs && live && as > ac;
+  const bool in_lock = live && !in_runs;
+  const double width = (ac + as) / ac + 2.0 * FW_ETA + 1e-7;
+  int lmax = in_lock ? (int)ceil(fmin(width, 64.0)) : 2;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(FULL, lmax, o));
+  double acc_r = 0.0, acc_l = 0.0;
+  if (need_runs) acc_r = fw_runs(r, s, in_runs, nx, ny, biasy, x, (int64_t)nx * ny, vec4 != 0, pol);
+  if (__any_sync(FULL, in_lock)) {
+    if (lmax <= 2) acc_l = fw_lockstep<2, false>(r, s, in_lock, nx, ny, biasy, nullptr, x, pol);
+    else if (lmax == 3) acc_l = fw_lockstep<3, false>(r, s, in_lock, nx, ny, biasy, nullptr, x, pol);
+    else if (lmax == 4) acc_l = fw_lockstep<4, false>(r, s, in_lock, nx, ny, biasy, nullptr, x, pol);
+    else if (lmax == 5) acc_l = fw_lockstep<5, false>(r, s, in_lock, nx, ny, biasy, nullptr, x, pol);
+    else if (lmax == 6) acc_l = fw_lockstep<6, false>(r, s, in_lock, nx, ny, biasy, nullptr, x, pol);
+    else if (lmax == 7) acc_l = fw_lockstep<7, false>(r, s, in_lock, nx, ny, biasy, nullptr, x, pol);
+    else if (lmax == 8) acc_l = fw_lockstep<8, false>(r, s, in_lock, nx, ny, biasy, nullptr, x, pol);
+    else acc_l = fw_lockstep<9, false>(r, s, in_lock, nx, ny, biasy, nullptr, x, pol);  // (lmax <= 9: |s/c| <= run_tan <= 7.9)
+  }
+  double acc = in_runs ? acc_r : acc_l;
+  const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
+  dd_t nrm = dd_zero();
+  if (live) {
+    const int64_t row = (int64_t)a * n_det + d;
+    if (z != nullptr) acc = __dsub_rn(acc, __dmul_rn(coef, z[row]));
+    y[row] = acc;
+    nrm = dd_fma(nrm, acc, acc);
+  }
+  if (partials != nullptr) {
+    const dd_t tot2 = dd_warp_sum(nrm);
+    if (lane == 0) {
+      const int64_t w = (int64_t)blockIdx.x * FW_WARPS + (threadIdx.x >> 5);
+      partials[2 * w] = tot2.hi;
+      partials[2 * w + 1] = tot2.lo;
+    }
+  }
+}
+
 // warps per CTA the launcher uses for a problem of this size
 static int fw_warps_for(int n_det, int n_ang) {
   int warps = FW_WARPS;
@@ -418,6 +488,37 @@ int tb200_ct_forward_rays_f64(int nx, int ny, int n_det, int n_ang, const double
   if (norm_out && nparts > 0) {
     finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, nparts, norm_out);
     rc = check_launch("ct_forward_rays finalize");
+  }
+  return rc;
+}
+
+// Fan-beam form: y = A x - coef*z for the flat-detector fan-beam matrix of tb200_ctfan_fill_rows (source at distance so,
+// detector at dd, bins of width dps; cosv / sinv: the n_ang angles), matrix-free and bit-identical to the stored product.
+// ws as tb200_ct_forward_rays_f64.
+int tb200_ctfan_forward_rays_f64(double so, double dd, double dps, int nx, int ny, int n_det, int n_ang, const double* cosv,
+                                 const double* sinv, const double* x, double* y, double coef_host, const double* coef_dev,
+                                 const double* z, double* norm_out, double* ws, void* stream) {
+  TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0, "bad geometry");
+  TB200_REQUIRE((int64_t)nx * ny < ((int64_t)1 << 31) && (int64_t)n_ang * n_det < ((int64_t)1 << 31), "index space exceeds int32");
+  TB200_REQUIRE(so > 0.0 && dd >= 0.0 && dps > 0.0 && so * so > 0.25 * ((double)nx * nx + (double)ny * ny),
+                "fan beam: the source must lie outside the image");
+  TB200_REQUIRE(norm_out == nullptr || ws != nullptr, "norm_out requires a workspace");
+  if (n_ang == 0) return 0;
+  TB200_REQUIRE(cosv && sinv && x && y, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Beam bm = {1, so, dd, dps};
+  const int nblk = (n_det + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
+  const int ranks = nblk + ((nblk & 1) ? 0 : 1);
+  const int64_t nctas = (int64_t)ranks * n_ang;
+  TB200_REQUIRE(nctas < ((int64_t)1 << 31), "too many CTAs");
+  ct_forward_rays_fan_kernel<<<(unsigned)nctas, FW_WARPS * 32, 0, st>>>(bm, nx, ny, n_det, n_ang, nblk, cosv, sinv, x, y, coef_host,
+                                                                        coef_dev, z, norm_out ? ws : nullptr,
+                                                                        ((uintptr_t)x % 32) == 0, g_fw_run_tan);
+  int rc = check_launch("ctfan_forward_rays");
+  if (rc) return rc;
+  if (norm_out) {
+    finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, nctas * FW_WARPS, norm_out);
+    rc = check_launch("ctfan_forward_rays finalize");
   }
   return rc;
 }

@@ -452,8 +452,11 @@ class FanBeamCT(CSROperator):
     """Flat-detector fan-beam tomography matrix, line (chord-length) model - the geometry the reference's Tomography
     class requests from ASTRA (`astra.create_proj_geom('fanflat', ...)` + `'line_fanflat'`, Tomography.py:57-67):
     `views` angles in [0, pi), int(sqrt(2)*nx) bins of width (so+dd)/so, source at 3*nx, detector at nx.
-    A and the exact transpose are built on the device and stored (CSR and/or SELL-32-4); every ray of a fan has its own
-    direction, so the values are not re-evaluated on the fly here (layout 'implicit' is parallel-beam only).
+    A and the exact transpose are built on the device and stored (CSR and/or SELL-32-4).  layout='implicit' keeps only
+    the stored transpose: the forward product is the ray-driven matrix-free projector with per-ray geometry
+    (tb200_ctfan_forward_rays_f64, bit-identical to the stored product); the pixel-driven back-projector does not carry
+    over to a fan (every candidate bin has its own normal), so A^T u stays a stored SpMV - half the memory, and the
+    forward product no longer streams 12 bytes per entry.
     ASTRA itself is not part of the reference tree: rotation sense and image-axis orientation follow ASTRA's documented
     conventions but cannot be pinned against it."""
 
@@ -473,10 +476,18 @@ class FanBeamCT(CSROperator):
         cos_t = torch.from_numpy(np.cos(theta)).to(device)
         sin_t = torch.from_numpy(np.sin(theta)).to(device)
         K._lib.require_device()
+        self._fan_forward = None
         if layout == "auto":
             layout = "both" if 1.5 * len(theta) * self.nx * self.ny <= 2e8 else "sell"
+        if layout == "implicit":
+            at = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=True, layout="sell", fan=self.fan)
+            LinearOperator.__init__(self, (at.shape[1], at.shape[0]), device)
+            self.A = self.AT = self.A_sell = None
+            self.AT_sell, self.order = at, "sequential"
+            self._fan_forward = (cos_t, sin_t)
+            return
         if layout not in ("csr", "sell", "both"):
-            raise ValueError("layout must be 'auto', 'csr', 'sell' or 'both'")
+            raise ValueError("layout must be 'auto', 'csr', 'sell', 'both' or 'implicit'")
         mats = {}
         for lay in (("csr", "sell") if layout == "both" else (layout,)):
             a = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=False, layout=lay, fan=self.fan)
@@ -486,6 +497,39 @@ class FanBeamCT(CSROperator):
             mats[lay] = (a, at)
         csr, sell = mats.get("csr", (None, None)), mats.get("sell", (None, None))
         super().__init__(csr[0], csr[1], "sequential", sell[0], sell[1])
+
+
+    # -- layout='implicit': matrix-free forward product, stored transpose ----------------------------------------------------
+    @property
+    def nnz(self):
+        return self.AT_sell.nnz if self._fan_forward is not None else super().nnz
+
+    def _csr(self, transposed):
+        if self._fan_forward is not None and not transposed and self.A is None:
+            # the forward matrix on demand (export / cross-checks): built, not stored with the operator
+            return K.ct_build(self.nx, self.ny, self.n_det, *self._fan_forward, transpose=False, layout="csr", fan=self.fan)
+        return super()._csr(transposed)
+
+    def apply_dev(self, x, out=None, coef=None, z=None, norm_out=None):
+        if self._fan_forward is None:
+            return super().apply_dev(x, out=out, coef=coef, z=z, norm_out=norm_out)
+        m, n = self.shape
+        K._vec(x, n, "x")
+        out = torch.empty(m, dtype=F64, device=self.device) if out is None else K._vec(out, m, "out")
+        ch, cd = 0.0, None
+        if z is not None:
+            K._vec(z, m, "z")
+            ch, cd = (0.0, coef) if isinstance(coef, torch.Tensor) else (float(coef), None)
+        cos_t, sin_t = self._fan_forward
+        L = K.lib()
+        ws = None
+        if norm_out is not None:
+            ws = K.Workspace.get(self.device).buf("ct_fw", int(L.tb200_ct_forward_rays_workspace_len(self.n_det, len(self.theta))))
+        K.check(L.tb200_ctfan_forward_rays_f64(*self.fan, self.nx, self.ny, self.n_det, len(self.theta), K._p(cos_t), K._p(sin_t),
+                                               K._p(x), K._p(out), ch, K._p(cd), K._p(z), K._p(norm_out), K._p(ws), K._stream()),
+                "ctfan_forward_rays")
+        K._lib.count(2 if norm_out is not None else 1)
+        return out
 
 
 class BlockDiagCT(CSROperator):
