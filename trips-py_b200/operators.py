@@ -477,8 +477,8 @@ class FanBeamCT(CSROperator):
         sin_t = torch.from_numpy(np.sin(theta)).to(device)
         K._lib.require_device()
         self._fan_forward = None
-        if layout == "auto":
-            layout = "both" if 1.5 * len(theta) * self.nx * self.ny <= 2e8 else "sell"
+        if layout == "auto":  # small: both stored layouts (export, tests); large: matrix-free forward + stored transpose
+            layout = "both" if 1.5 * len(theta) * self.nx * self.ny <= 2e8 else "implicit"
         if layout == "implicit":
             at = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=True, layout="sell", fan=self.fan)
             LinearOperator.__init__(self, (at.shape[1], at.shape[0]), device)
