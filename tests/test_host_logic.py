@@ -236,3 +236,31 @@ def test_host_basis_appends_in_place_only_behind_the_newest_view():
     release_host_buffers()
     assert not _HostBasis.registry
     assert np.array_equal(U2[:, 2], np.full(6, 20.0))  # returned arrays stay valid
+
+
+def test_forward_cta_order_is_a_permutation_heaviest_first():
+    """kernels.forward_cta_order (scheduling list of the ray-driven forward projector for small launches): a permutation of
+    all (angle, block) pairs, central blocks of near-diagonal angles first, empty edge blocks last."""
+    import torch
+    from trips_b200 import kernels as K
+
+    nx, views, n_det = 512, 24, 724
+    th = np.linspace(0, np.pi, views, endpoint=False)
+    order = K.forward_cta_order(nx, nx, n_det, torch.from_numpy(np.cos(th)), torch.from_numpy(np.sin(th)), "cpu", force=True)
+    o = order.numpy()
+    nblk = o.size // views
+    assert o.size == views * nblk and sorted(o.tolist()) == list(range(o.size))
+    first_blocks, last_blocks = o[:views] % nblk, o[-views:] % nblk
+    assert np.all(np.abs(first_blocks - (nblk - 1) / 2) <= nblk / 4 + 1)   # heavy = near the detector centre
+    assert np.all(np.minimum(last_blocks, nblk - 1 - last_blocks) <= 1)    # light = the detector's ends
+
+
+def test_band_rows_partition_the_image():
+    from trips_b200.dist import band_rows, shard_angles
+
+    for ny, world in ((2048, 8), (52, 2), (30, 4), (7, 3), (4096, 16)):
+        edges = [band_rows(ny, world, r) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == ny
+        assert all(edges[r][1] == edges[r + 1][0] for r in range(world - 1))
+        assert all(lo % 4 == 0 for lo, _ in edges)
+    assert sorted(np.concatenate([shard_angles(45, 4, r) for r in range(4)]).tolist()) == list(range(45))

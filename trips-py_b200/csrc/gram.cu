@@ -175,12 +175,16 @@ static void gram_shape(int K, int& Kpad, int& npairs, int& RG, int& gy, int& row
   const int nt = (K + 3) / 4;
   Kpad = 4 * nt + 1;  // odd stride: conflict-free column staging
   npairs = nt * (nt + 1) / 2;
-  RG = 1;
-  while (RG < 64 && npairs * RG * 2 <= kGThreads) RG *= 2;
+  // as many row groups as fit one CTA next to the 4 x 4 blocks (K <= 4: one block, 256 groups), so that (nearly) every
+  // thread accumulates; several CTAs in y only when there are more blocks than threads
+  RG = npairs <= kGThreads ? kGThreads / npairs : 1;
   gy = (npairs * RG + kGThreads - 1) / kGThreads;
-  rows = 4 * RG < 32 ? 32 : 4 * RG;  // at least four rows per group and tile
-  while (rows > 32 && (size_t)rows * Kpad * sizeof(double) > 96 * 1024) rows >>= 1;
-  if (rows < RG) rows = RG;
+  // rows per group and tile: ~256 rows per tile (two barriers and one staging pass per tile), within 64 KB of shared
+  // memory so that two CTAs stay resident per SM
+  int rpg = (256 + RG - 1) / RG;
+  if (rpg < 4) rpg = 4;
+  while (rpg > 1 && (size_t)RG * rpg * Kpad * sizeof(double) > 64 * 1024) --rpg;
+  rows = RG * rpg;
 }
 
 // ---- host double-double arithmetic for the k x k factorisation ------------------------------------------
