@@ -218,8 +218,8 @@ def _p2p_worker(rank, world, port, out_dir):
         # halo exchange through peer memory (tb200_halo_exchange): what FrameComm does with isend / irecv
         from trips_b200.dist import PeerComm
 
-        pc = PeerComm({"halo": 2 * 96})
-        for rep in range(3):  # repeated: epochs advance, the areas are reused
+        pc = PeerComm({"halo": 4 * 96})
+        for rep in range(5):  # repeated without a barrier in between: epochs advance, the two halo buffers alternate
             sp = torch.full((96,), -float(10 * rep + rank + 1), dtype=torch.float64, device="cuda") if rank > 0 else None
             sn = torch.full((96,), float(10 * rep + rank + 1), dtype=torch.float64, device="cuda") if rank + 1 < world else None
             rp, rn = pc.halo_exchange("halo", sp, sn)
@@ -227,7 +227,6 @@ def _p2p_worker(rank, world, port, out_dir):
                 assert torch.equal(rp, torch.full_like(rp, float(10 * rep + rank)))        # rank - 1 sent +(its rank + 1)
             if rank + 1 < world:
                 assert torch.equal(rn, torch.full_like(rn, -float(10 * rep + rank + 2)))   # rank + 1 sent -(its rank + 1)
-            pc.barrier()  # the areas are rewritten by the next repetition
         pc.destroy()
         np.savez(os.path.join(out_dir, f"p{rank}.npz"), U=U, V=V, B=B, rows=rows, band=np.array([lo, hi]),
                  host=np.array([al, be]), hu1=hu[1].numpy(), hv0=hv[0].numpy(), y_rows=y_rows, z_band=z_band,

@@ -347,15 +347,18 @@ int tb200_comm_push(void* comm, unsigned rank_mask, int64_t offset_bytes, const 
 }
 
 // One-frame halo exchange for a frame-sharded operator (dynamic CT): send_next / send_prev (nullable,
-// n doubles each) are stored into the halo areas of rank+1 / rank-1 at offset_bytes (+ 8n for the block coming from the
-// next rank); after the call's epoch has been exchanged through mailbox `box`, recv_prev / recv_next (nullable outputs)
-// hold what the neighbours sent.  Replaces the torch.distributed isend/irecv pair of dist.FrameComm.
+// n doubles each) are stored into the halo area (4n doubles at offset_bytes of every arena: two alternating buffers) of
+// rank+1 / rank-1; after the call's epoch has been exchanged through mailbox `box`, recv_prev / recv_next (nullable
+// outputs) hold what the neighbours sent.  Replaces the torch.distributed isend/irecv pair of dist.FrameComm.
 int tb200_halo_exchange(void* comm, int box, int64_t epoch, int64_t offset_bytes, const double* send_prev, const double* send_next,
                         int64_t n, double* recv_prev, double* recv_next, double* scratch_pair, void* stream) {
   Comm* c = (Comm*)comm;
   TB200_REQUIRE(c && scratch_pair, "null pointer");
   int rc;
-  // area layout at offset_bytes: [0, n) = block received from the previous rank, [n, 2n) = block received from the next
+  // area layout at offset_bytes: two buffers of 2n doubles, used alternately (epoch parity) so that a neighbour's stores
+  // of the NEXT exchange never land on data this rank has not copied out yet; in a buffer [0, n) = block received from
+  // the previous rank, [n, 2n) = block received from the next
+  offset_bytes += (epoch & 1) ? 16 * n : 0;
   if (send_next && c->rank + 1 < c->nranks) {
     rc = tb200_comm_push(comm, 1u << (c->rank + 1), offset_bytes, send_next, n, stream);
     if (rc) return rc;

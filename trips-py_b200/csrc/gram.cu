@@ -85,20 +85,22 @@ gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const
     const int64_t row0 = blk * rows;
     __syncthreads();
     // stage the tile: lanes run along rows (contiguous in memory), warps over columns
-    for (int idx = threadIdx.x; idx < rows * Kpad; idx += kGThreads) {
-      const int r = idx % rows, j = idx / rows;
+    for (int r = threadIdx.x; r < rows; r += kGThreads) {  // (no index division: column loop outside, rows strided)
       const int64_t row = row0 + r;
-      double v = 0.0;
-      if (row < m && j < K) {
-        if (j < k) {
-          v = B[(int64_t)j * ld + row];
-          if (w) v = __dmul_rn(v, w[row]);
-        } else {
-          v = ex.ptr[j - k][row];
-          if (w && ex.weighted[j - k]) v = __dmul_rn(v, w[row]);
-        }
+      const bool in = row < m;
+      const double wr = (in && w) ? w[row] : 1.0;
+      double* Tr = T + r * Kpad;
+      for (int j = 0; j < k; ++j) {
+        double v = in ? B[(int64_t)j * ld + row] : 0.0;
+        if (w) v = __dmul_rn(v, wr);
+        Tr[j] = v;
       }
-      T[r * Kpad + j] = v;
+      for (int j = k; j < K; ++j) {
+        double v = in ? ex.ptr[j - k][row] : 0.0;
+        if (w && ex.weighted[j - k]) v = __dmul_rn(v, wr);
+        Tr[j] = v;
+      }
+      for (int j = K; j < Kpad; ++j) Tr[j] = 0.0;
     }
     __syncthreads();
     if (active) {

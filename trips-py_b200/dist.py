@@ -114,6 +114,21 @@ class FrameComm(_Comm):
     SHARDED = ("data", "model", "reg")
     frames = True
 
+    def __init__(self, group=None, peer=None):
+        """peer=True: halos travel through NVLink peer memory (tb200_halo_exchange) instead of NCCL send / recv; default:
+        peer memory on the NCCL backend (env TB200_FRAME_HALO=nccl switches back), torch.distributed elsewhere."""
+        super().__init__(group)
+        if peer is None:
+            peer = dist.get_backend(group) == "nccl" and os.environ.get("TB200_FRAME_HALO", "peer") != "nccl"
+        self.peer, self._pc, self._pc_n = bool(peer), None, 0
+
+    def _peer_exchange(self, send_prev, send_next, n):
+        if self._pc is None or self._pc_n < n:  # (collective: every rank gets here in the same exchange)
+            if self._pc is not None:
+                self._pc.destroy()
+            self._pc, self._pc_n = PeerComm({"halo": 4 * n}, group=self.group), n
+        return self._pc.halo_exchange("halo", send_prev, send_next, n=n)
+
     @property
     def first(self):
         return self.rank == 0
@@ -142,11 +157,15 @@ class FrameComm(_Comm):
 
     def halo_from_next(self, my_first_frame):
         """Every rank hands its first frame to the previous rank; returns the next rank's first frame (None on the last)."""
+        if self.peer:
+            return self._peer_exchange(None if self.first else my_first_frame.contiguous(), None, my_first_frame.numel())[1]
         return self._exchange(my_first_frame, None if self.first else self.rank - 1,
                               None if self.last else self.rank + 1, "next")
 
     def halo_from_prev(self, my_last_block):
         """Every rank hands a block to the next rank; returns the previous rank's block (None on the first)."""
+        if self.peer:
+            return self._peer_exchange(None, None if self.last else my_last_block.contiguous(), my_last_block.numel())[0]
         return self._exchange(my_last_block, None if self.last else self.rank + 1,
                               None if self.first else self.rank - 1, "prev")
 
@@ -421,15 +440,16 @@ class PeerComm:
                                     K._stream()), "comm_push")
         _lib.count(1)
 
-    def halo_exchange(self, name, send_prev, send_next, box=None):
-        """One-block halo exchange with the neighbouring ranks through the arena region `name` (>= 2 * n doubles):
+    def halo_exchange(self, name, send_prev, send_next, box=None, n=None):
+        """One-block halo exchange with the neighbouring ranks through the arena region `name` (>= 4 * n doubles):
         send_prev goes to rank - 1, send_next to rank + 1 (either may be None at the ends); returns (recv_prev, recv_next) =
         what rank - 1 sent as its send_next and what rank + 1 sent as its send_prev (None at the ends).
         tb200_halo_exchange: peer stores + one mailbox epoch, no NCCL."""
-        ref = send_prev if send_prev is not None else send_next
-        n = ref.numel()
-        if 2 * n > self.counts[name]:
-            raise ValueError(f"arena region {name!r} holds {self.counts[name]} doubles, the halo needs {2 * n}")
+        if n is None:
+            n = (send_prev if send_prev is not None else send_next).numel()
+        n = int(n)
+        if 4 * n > self.counts[name]:
+            raise ValueError(f"arena region {name!r} holds {self.counts[name]} doubles, the halo needs {4 * n}")
         box = self.BOX_HALO if box is None else box
         recv_prev = torch.empty(n, dtype=F64, device=self.device) if self.rank > 0 else None
         recv_next = torch.empty(n, dtype=F64, device=self.device) if self.rank + 1 < self.world else None
