@@ -14,10 +14,11 @@ import torch
 
 from .. import kernels as K
 from ..operators import as_operator, to_device_vector
-from ._common import ErrorTracker, LazyHistory, dev_scalar, host_column, need_delta, tikhonov_projected
+from ._common import ErrorTracker, LazyHistory, dev_scalar, host_column, need_delta, tikhonov_projected, single_threaded_host_blas
 from ._gks_core import GKSBases, adjoint_L_weighted, choose_lambda, expand, factor_pair
 
 
+@single_threaded_host_blas
 def GKS(A, b, L, projection_dim=3, n_iter=50, regparam="gcv", x_true=None, **kwargs):
     delta, dp_stop = need_delta(regparam, kwargs, "gcv or a different stopping criterion.")
     if "dp_stop" in kwargs:  # the reference forwards it twice: golub_kahan(A, b, projection_dim, dp_stop, **kwargs) (:36)

@@ -21,9 +21,10 @@ from ..operators import as_operator, to_device_vector
 from ..reg_param.discrepancy_principle import discrepancy_principle_projected
 from ..reg_param.gcv import generalized_crossvalidation
 from ..reg_param.l_curve import l_curve
-from ._common import ErrorTracker, LazyHistory, dev_scalar, host_column, need_delta, tikhonov_projected
+from ._common import ErrorTracker, LazyHistory, dev_scalar, host_column, need_delta, tikhonov_projected, single_threaded_host_blas
 
 
+@single_threaded_host_blas
 def Hybrid_GMRES(A, b, n_iter, regparam="gcv", x_true=None, **kwargs):
     delta, dp_stop = need_delta(regparam, kwargs, "gcv or a different stopping criterion.")
     if dp_stop is not False:

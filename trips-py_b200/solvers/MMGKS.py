@@ -26,7 +26,7 @@ from scipy import sparse
 
 from .. import kernels as K
 from ..operators import as_operator, to_device_vector
-from ._common import ErrorTracker, LazyHistory, dev_scalar, host_column, tikhonov_projected
+from ._common import ErrorTracker, LazyHistory, dev_scalar, host_column, tikhonov_projected, single_threaded_host_blas
 from ._gks_core import GKSBases, adjoint_L_weighted, apply_L_with_weights, choose_lambda, expand, factor_pair
 
 
@@ -57,6 +57,7 @@ def _group_sparsity_weights(Ls, xd, n_space, qnorm):
     return wr if nt == 1 else wr.repeat(nt)
 
 
+@single_threaded_host_blas
 def MMGKS(A, b, L, pnorm=2, qnorm=1, projection_dim=3, n_iter=5, regparam="gcv", x_true=None, **kwargs):
     # unlike the other drivers the reference does not validate delta up front (:30-36); the discrepancy-principle
     # routine raises the same Exception when it is missing (discrepancy_principle.py:21-23)

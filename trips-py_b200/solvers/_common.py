@@ -5,6 +5,26 @@ import torch
 from .. import kernels as K
 
 
+def single_threaded_host_blas(fn):
+    """Decorator of the solver drivers: the host side of these solvers is LAPACK on (k+1) x k matrices with k <= ~100
+    (SVD, QR, least squares - NumPy / SciPy, as in the reference).  A multi-threaded OpenBLAS is slower on such sizes and
+    has pathological cases (measured: the discrepancy-principle solve at k = 50 takes 54 ms with 8 threads, 1.0 ms with
+    one), so the BLAS pool is limited to one thread for the duration of the call (threadpoolctl; no-op if unavailable).
+    The long vectors never touch the host BLAS."""
+    import functools
+
+    @functools.wraps(fn)
+    def run(*args, **kwargs):
+        try:
+            from threadpoolctl import threadpool_limits
+        except Exception:  # noqa: BLE001
+            return fn(*args, **kwargs)
+        with threadpool_limits(limits=1, user_api="blas"):
+            return fn(*args, **kwargs)
+
+    return run
+
+
 class LazyHistory:
     """List-like `info['xHistory']`.
 
