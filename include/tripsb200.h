@@ -110,14 +110,23 @@ int tb200_basis_dots(int64_t n, int64_t k, const double* V, int64_t ld, const do
 /* out = w + sign * V h (w NULL => out = sign * V h); optional fused norm of out */
 int tb200_basis_combine(int64_t n, int64_t k, const double* V, int64_t ld, const double* h, const double* w, double sign,
                         double* out, double* norm_out, double* ws, void* stream);
+/* A/B switch: 1 (default) = two rows per 16-byte access where n, ld and the pointers allow it; same results. */
+void tb200_basis_set_vec2(int on);
 
 /* ---- weighted Gram + k x k factorisation (replaces the per-iteration host QRs) ----------------------------
  * la.qr(AV*wf), la.qr(LV*wr), Q_A.T@b: MMGKS.py:57-59,94-106 ; la.qr(AV), la.qr(LV): GKS.py:54-58.
  * Double-double accumulation; tb200_gram_factor_dd runs on the HOST (all pointers host). */
 int64_t tb200_gram_workspace_len(int64_t K);
+/* A/B switch: 1 (default) = tiles arrive by double-buffered cp.async.bulk, 0 = ordinary loads, single buffer. */
+void tb200_gram_set_bulk(int on);
 int tb200_weighted_gram(int64_t m, int64_t k, const double* B, int64_t ld, const double* w, int n_extra,
                         const double* const* extras_host, const int* extra_weighted_host, double* Ghi, double* Glo,
                         double* ws, void* stream);
+/* Only the columns c >= c0 of G (and their mirror rows) are computed and written: for a basis whose first c0 columns have
+ * not changed since their Gram matrix was formed (GKS.py:54-58 re-factors the whole of AV, LV every iteration). */
+int tb200_weighted_gram_panel(int64_t m, int64_t k, const double* B, int64_t ld, const double* w, int n_extra,
+                              const double* const* extras_host, const int* extra_weighted_host, int64_t c0, double* Ghi,
+                              double* Glo, double* ws, void* stream);
 int tb200_gram_factor_dd(int k, int ne, const double* Ghi_host, const double* Glo_host, double* R_host, double* C_host,
                          double* resid2_host);
 

@@ -192,6 +192,34 @@ def test_basis_kernels(tb, n, k):
     assert np.array_equal(basis.to_numpy()[:, :k], V)
 
 
+@pytest.mark.parametrize("n,k", [(100_000, 11), (65_538, 4), (4098, 21), (1000, 1)])
+def test_basis_kernels_two_rows_per_access_equal_one_row(tb, n, k):
+    """basis_combine accumulates every row in the same order whether a thread takes one row or two per access: same
+    bits (incl. the fused norm); basis_dots only regroups its partial sums."""
+    K = tb.kernels
+    rng = np.random.default_rng(8)
+    V = rng.standard_normal((n, k))
+    basis = K.Basis(n, k, "cuda")
+    for j in range(k):
+        basis.next_col().copy_(dev(V[:, j]))
+        basis.push()
+    w, h = dev(rng.standard_normal(n)), dev(rng.standard_normal(k))
+    got = []
+    try:
+        for v in (1, 0):
+            tb._lib.lib().tb200_basis_set_vec2(v)
+            pair = K.new_pair("cuda")
+            o1 = host(K.basis_combine(basis, k, h, w=w, sign=-1.0, norm_out=pair))
+            o2 = host(K.basis_combine(basis, k, h))
+            got.append((o1, o2, host(pair), host(K.basis_dots(basis, k, w))))
+    finally:
+        tb._lib.lib().tb200_basis_set_vec2(1)
+    assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+    assert np.array_equal(got[0][2], got[1][2])
+    assert rel(got[0][3], got[1][3]) < 1e-13 and rel(got[0][3], V.T @ host(w)) < 1e-13
+    assert rel(got[0][0], host(w) - V @ host(h)) < 1e-13
+
+
 @pytest.mark.parametrize("m,k,weighted", [(5000, 3, False), (20_001, 10, True), (3000, 37, True)])
 def test_weighted_gram_and_factor_match_householder(tb, m, k, weighted):
     K = tb.kernels
@@ -225,6 +253,72 @@ def test_weighted_gram_and_factor_match_householder(tb, m, k, weighted):
     y1 = np.linalg.lstsq(np.vstack((R, np.sqrt(lam) * np.eye(k))), np.r_[C[:, 0], np.zeros(k)], rcond=None)[0]
     y2 = np.linalg.lstsq(np.vstack((Rr, np.sqrt(lam) * np.eye(k))), np.r_[Q.T @ b, np.zeros(k)], rcond=None)[0]
     assert rel(y1, y2) < 1e-9
+
+
+@pytest.mark.parametrize("m,k,weighted", [(100_002, 7, True), (100_002, 29, False), (77_778, 55, True), (100_003, 12, True),
+                                          (513, 5, True), (40, 3, False)])
+def test_weighted_gram_bulk_copy_pipeline_equals_plain_staging(tb, m, k, weighted):
+    """The double-buffered cp.async.bulk staging and the ordinary-load staging feed the same accumulation: same bits; and
+    both are the Gram matrix to double-double accuracy (checked against a long-double product).  Odd m (odd leading
+    dimension) cannot be bulk-copied and takes the plain path by itself; m % tile != 0 exercises the partial tile."""
+    K = tb.kernels
+    rng = np.random.default_rng(11)
+    B = rng.standard_normal((m, k)) * np.logspace(0, -5, k)[None, :]
+    b = rng.standard_normal(m)
+    w = rng.uniform(1e-3, 30, m) if weighted else None
+    basis = K.Basis(m, k + 2, "cuda")
+    for j in range(k):
+        basis.next_col().copy_(dev(B[:, j]))
+        basis.push()
+    bd, wd = dev(b), (dev(w) if weighted else None)
+    out = []
+    try:
+        for bulk in (1, 0):
+            tb._lib.lib().tb200_gram_set_bulk(bulk)
+            out.append(K.weighted_gram(basis, k, wd, extras=(bd, bd), extra_weighted=(0, 1)))
+    finally:
+        tb._lib.lib().tb200_gram_set_bulk(1)
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    M = np.column_stack((B * w[:, None] if weighted else B, b, b * w if weighted else b)).astype(np.longdouble)
+    G = M.T @ M
+    scale = np.sqrt(np.outer(np.diag(G), np.diag(G))).astype(np.float64)
+    got = out[0][0].astype(np.longdouble) + out[0][1].astype(np.longdouble)
+    assert np.max(np.abs((got - G).astype(np.float64)) / scale) < 1e-15
+
+
+@pytest.mark.parametrize("m", [60_000, 4099])
+def test_incremental_gram_panel_equals_the_full_pass(tb, m):
+    """An append-only, unweighted basis: the panel pass (new columns of G only) merged into the cached matrix equals the
+    full double-double pass to double-double accuracy at every size, including panels that straddle 4-column blocks,
+    several new columns at once, and a stale cache (another extra vector) that must fall back to the full pass."""
+    K = tb.kernels
+    rng = np.random.default_rng(5)
+    kmax = 23
+    B = rng.standard_normal((m, kmax)) * np.logspace(0, -4, kmax)[None, :]
+    b = dev(rng.standard_normal(m))
+    basis = K.Basis(m, kmax, "cuda")
+    inc = K.IncrementalGram()
+    k = 0
+    for grow in (3, 1, 1, 1, 2, 1, 1, 5, 1, 1, 1, 1, 1, 1, 1, 1):
+        for _ in range(grow):
+            basis.next_col().copy_(dev(B[:, k]))
+            basis.push()
+            k += 1
+        hi, lo = inc.update(basis, k, extras=(b,), extra_weighted=(0,))
+        fhi, flo = K.weighted_gram(basis, k, None, extras=(b,), extra_weighted=(0,))
+        got = hi.astype(np.longdouble) + lo.astype(np.longdouble)
+        want = fhi.astype(np.longdouble) + flo.astype(np.longdouble)
+        scale = np.sqrt(np.outer(np.diag(fhi), np.diag(fhi)))
+        assert np.max(np.abs((got - want).astype(np.float64)) / scale) < 1e-17, k   # (long double carries 64 bits)
+        assert np.array_equal(hi, hi.T) and np.array_equal(lo, lo.T)
+        R1, C1, r1 = K.gram_factor(hi, lo, k)
+        R2, C2, r2 = K.gram_factor(fhi, flo, k)
+        assert np.allclose(R1, R2, rtol=1e-13, atol=0) and np.allclose(C1, C2, rtol=1e-12, atol=1e-300)
+    assert k == kmax
+    b2 = dev(rng.standard_normal(m))
+    hi, lo = inc.update(basis, k, extras=(b2,), extra_weighted=(0,))  # different extra: cache key changes -> full pass
+    fhi, flo = K.weighted_gram(basis, k, None, extras=(b2,), extra_weighted=(0,))
+    assert np.array_equal(hi, fhi) and np.array_equal(lo, flo)
 
 
 @pytest.mark.parametrize("nx,views", [(24, 16), (64, 90), (33, 7)])

@@ -18,7 +18,9 @@ import trips_oracle as O  # noqa: E402
 from trips_b200 import _lib  # noqa: E402
 
 
-def run(name, fn, iters):
+def run(name, fn, iters, warm=True):
+    if warm:  # the first call of a configuration pays allocator growth and kernel attribute set-up
+        fn()
     torch.cuda.synchronize()
     l0 = _lib.launch_count
     t0 = time.perf_counter()

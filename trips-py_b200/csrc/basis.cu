@@ -29,32 +29,63 @@ __device__ __forceinline__ double ld_stream_f64(const double* p) {
 
 static inline int basis_grid(int64_t n) { return grid_for(n, kBThreads * 4, kBMaxBlocks); }
 
-// partials[j * gridDim.x + blockIdx.x] = sum over this CTA's segment of V[:, j] * w
+template <int VEC>
+struct RowVec;
+template <>
+struct RowVec<1> {
+  double v[1];
+  __device__ __forceinline__ void load_stream(const double* p) { v[0] = ld_stream_f64(p); }
+  __device__ __forceinline__ void load(const double* p) { v[0] = __ldg(p); }
+};
+template <>
+struct RowVec<2> {  // two consecutive rows, one 16-byte access (the column must be 16-byte aligned)
+  double v[2];
+  __device__ __forceinline__ void load_stream(const double* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+  }
+  __device__ __forceinline__ void load(const double* p) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+    v[0] = t.x, v[1] = t.y;
+  }
+};
+
+// partials[j * gridDim.x + blockIdx.x] = sum over this CTA's segment of V[:, j] * w.
+// VEC rows per thread and step: with VEC = 2 a thread has 8 x 16 bytes of V in flight per step, which is what it takes
+// to cover the HBM latency at the 4-8 steps per thread these launches have (VEC = 1 measured 25-45 % of the HBM peak).
+template <int VEC>
 __global__ void __launch_bounds__(kBThreads)
 basis_dots_kernel(int64_t n, int k, const double* __restrict__ V, int64_t ld, const double* __restrict__ w,
                   double* __restrict__ partials) {
   __shared__ double red[kJT][kBThreads / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   // contiguous segment per CTA so the w re-reads (once per column tile) stay in this SM's L1
-  const int64_t seg = ((n + gridDim.x - 1) / gridDim.x + kBThreads - 1) / kBThreads * kBThreads;
+  const int64_t seg = ((n + gridDim.x - 1) / gridDim.x + kBThreads * VEC - 1) / (kBThreads * VEC) * (kBThreads * VEC);
   const int64_t lo = (int64_t)blockIdx.x * seg;
   int64_t hi = lo + seg;
-  if (hi > n) hi = n;
+  if (hi > n) hi = n;  // (VEC = 2: n is even, so is hi)
   for (int j0 = 0; j0 < k; j0 += kJT) {
     const int jn = (k - j0 < kJT) ? (k - j0) : kJT;
     double acc[kJT];
 #pragma unroll
     for (int t = 0; t < kJT; ++t) acc[t] = 0.0;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += kBThreads) {
-      const double wi = __ldg(w + i);
+    for (int64_t i = lo + (int64_t)threadIdx.x * VEC; i < hi; i += kBThreads * VEC) {
+      RowVec<VEC> wi;
+      wi.load(w + i);
       if (jn == kJT) {
-        double v[kJT];
+        RowVec<VEC> v[kJT];
 #pragma unroll
-        for (int t = 0; t < kJT; ++t) v[t] = ld_stream_f64(V + (int64_t)(j0 + t) * ld + i);
+        for (int t = 0; t < kJT; ++t) v[t].load_stream(V + (int64_t)(j0 + t) * ld + i);
 #pragma unroll
-        for (int t = 0; t < kJT; ++t) acc[t] = fma(v[t], wi, acc[t]);
+        for (int t = 0; t < kJT; ++t)
+#pragma unroll
+          for (int r = 0; r < VEC; ++r) acc[t] = fma(v[t].v[r], wi.v[r], acc[t]);
       } else {
-        for (int t = 0; t < jn; ++t) acc[t] = fma(ld_stream_f64(V + (int64_t)(j0 + t) * ld + i), wi, acc[t]);
+        for (int t = 0; t < jn; ++t) {
+          RowVec<VEC> v;
+          v.load_stream(V + (int64_t)(j0 + t) * ld + i);
+#pragma unroll
+          for (int r = 0; r < VEC; ++r) acc[t] = fma(v.v[r], wi.v[r], acc[t]);
+        }
       }
     }
     __syncthreads();
@@ -85,7 +116,9 @@ __global__ void __launch_bounds__(256) basis_dots_finalize_kernel(int nb, const 
 }
 
 // out = (w ? w : 0) + sign * sum_j h[j] V[:, j]; optional partial ||out||^2 per CTA.
-// k <= kmax columns of coefficients are staged in shared memory.
+// k <= kmax columns of coefficients are staged in shared memory.  Every row is accumulated in the same order whatever
+// VEC is (four interleaved partial sums over the columns, then (a0 + a1) + (a2 + a3)), so the result does not depend on it.
+template <int VEC>
 __global__ void __launch_bounds__(kBThreads)
 basis_combine_kernel(int64_t n, int k, const double* __restrict__ V, int64_t ld, const double* __restrict__ h,
                      const double* __restrict__ w, double sign, double* __restrict__ out, double* __restrict__ partials) {
@@ -94,25 +127,51 @@ basis_combine_kernel(int64_t n, int k, const double* __restrict__ V, int64_t ld,
   for (int j = threadIdx.x; j < k; j += kBThreads) hs[j] = h[j];
   __syncthreads();
   dd_t nrm = dd_zero();
-  for (int64_t i = (int64_t)blockIdx.x * kBThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBThreads) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  for (int64_t i = ((int64_t)blockIdx.x * kBThreads + threadIdx.x) * VEC; i < n; i += (int64_t)gridDim.x * kBThreads * VEC) {
+    double a[4][VEC];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int r = 0; r < VEC; ++r) a[t][r] = 0.0;
     int j = 0;
-    for (; j + 4 <= k; j += 4) {
-      const double v0 = ld_stream_f64(V + (int64_t)(j + 0) * ld + i);
-      const double v1 = ld_stream_f64(V + (int64_t)(j + 1) * ld + i);
-      const double v2 = ld_stream_f64(V + (int64_t)(j + 2) * ld + i);
-      const double v3 = ld_stream_f64(V + (int64_t)(j + 3) * ld + i);
-      a0 = fma(v0, hs[j + 0], a0);
-      a1 = fma(v1, hs[j + 1], a1);
-      a2 = fma(v2, hs[j + 2], a2);
-      a3 = fma(v3, hs[j + 3], a3);
+    for (; j + 8 <= k; j += 8) {
+      RowVec<VEC> v[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[t].load_stream(V + (int64_t)(j + t) * ld + i);
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int r = 0; r < VEC; ++r) a[t & 3][r] = fma(v[t].v[r], hs[j + t], a[t & 3][r]);
     }
-    for (; j < k; ++j) a0 = fma(ld_stream_f64(V + (int64_t)j * ld + i), hs[j], a0);
-    const double vh = (a0 + a1) + (a2 + a3);
-    double r = (sign < 0.0) ? -vh : vh;
-    if (w != nullptr) r = (sign < 0.0) ? __dsub_rn(w[i], vh) : __dadd_rn(w[i], vh);
-    out[i] = r;
-    if (partials != nullptr) nrm = dd_fma(nrm, r, r);
+    for (; j + 4 <= k; j += 4) {
+      RowVec<VEC> v[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) v[t].load_stream(V + (int64_t)(j + t) * ld + i);
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int r = 0; r < VEC; ++r) a[t][r] = fma(v[t].v[r], hs[j + t], a[t][r]);
+    }
+    for (; j < k; ++j) {
+      RowVec<VEC> v;
+      v.load_stream(V + (int64_t)j * ld + i);
+#pragma unroll
+      for (int r = 0; r < VEC; ++r) a[0][r] = fma(v.v[r], hs[j], a[0][r]);
+    }
+    RowVec<VEC> wv, res;
+    if (w != nullptr) wv.load(w + i);
+#pragma unroll
+    for (int r = 0; r < VEC; ++r) {
+      const double vh = (a[0][r] + a[1][r]) + (a[2][r] + a[3][r]);
+      double x = (sign < 0.0) ? -vh : vh;
+      if (w != nullptr) x = (sign < 0.0) ? __dsub_rn(wv.v[r], vh) : __dadd_rn(wv.v[r], vh);
+      res.v[r] = x;
+      if (partials != nullptr) nrm = dd_fma(nrm, x, x);
+    }
+    if (VEC == 2)
+      *reinterpret_cast<double2*>(out + i) = make_double2(res.v[0], res.v[VEC - 1]);
+    else
+      out[i] = res.v[0];
   }
   if (partials != nullptr) {
     const dd_t tot = dd_block_sum(nrm, red);
@@ -123,11 +182,20 @@ basis_combine_kernel(int64_t n, int k, const double* __restrict__ V, int64_t ld,
   }
 }
 
+static bool g_basis_vec2 = true;
+// two rows per access need even n and ld and 16-byte aligned bases
+static inline bool vec2_ok(int64_t n, int64_t ld, const void* a, const void* b, const void* c) {
+  return g_basis_vec2 && n % 2 == 0 && ld % 2 == 0 && (uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0 && (uintptr_t)c % 16 == 0;
+}
+
 }  // namespace tb200
 
 using namespace tb200;
 
 extern "C" {
+
+// A/B switch (tests, tuning): 1 (default) = two rows per 16-byte access where the alignment allows, 0 = one row.
+void tb200_basis_set_vec2(int on) { g_basis_vec2 = on != 0; }
 
 // Doubles of workspace needed by tb200_basis_dots for k columns (and by basis_combine's fused norm).
 int64_t tb200_basis_workspace_len(int64_t k) { return (int64_t)kBMaxBlocks * (k > 2 ? k : 2); }
@@ -140,7 +208,10 @@ int tb200_basis_dots(int64_t n, int64_t k, const double* V, int64_t ld, const do
   TB200_REQUIRE(V && w && h && ws, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int g = basis_grid(n);
-  basis_dots_kernel<<<g, kBThreads, 0, st>>>(n, (int)k, V, ld, w, ws);
+  if (vec2_ok(n, ld, V, w, nullptr))
+    basis_dots_kernel<2><<<g, kBThreads, 0, st>>>(n, (int)k, V, ld, w, ws);
+  else
+    basis_dots_kernel<1><<<g, kBThreads, 0, st>>>(n, (int)k, V, ld, w, ws);
   int rc = check_launch("basis_dots");
   if (rc) return rc;
   basis_dots_finalize_kernel<<<(unsigned)k, 256, 0, st>>>(g, ws, h);
@@ -157,8 +228,12 @@ int tb200_basis_combine(int64_t n, int64_t k, const double* V, int64_t ld, const
   TB200_REQUIRE(k * 8 <= 48 * 1024, "k too large for the coefficient stage");
   cudaStream_t st = (cudaStream_t)stream;
   const int g = basis_grid(n);
-  basis_combine_kernel<<<g, kBThreads, (size_t)k * sizeof(double), st>>>(n, (int)k, V, ld, h, w, sign, out,
-                                                                         norm_out ? ws : nullptr);
+  if (vec2_ok(n, ld, V, w, out))
+    basis_combine_kernel<2><<<g, kBThreads, (size_t)k * sizeof(double), st>>>(n, (int)k, V, ld, h, w, sign, out,
+                                                                              norm_out ? ws : nullptr);
+  else
+    basis_combine_kernel<1><<<g, kBThreads, (size_t)k * sizeof(double), st>>>(n, (int)k, V, ld, h, w, sign, out,
+                                                                              norm_out ? ws : nullptr);
   int rc = check_launch("basis_combine");
   if (rc || !norm_out) return rc;
   finalize_dd_kernel<<<1, 1024, 0, st>>>(ws, g, norm_out);

@@ -58,95 +58,245 @@ __host__ __device__ __forceinline__ void pair_to_tiles(int p, int nt, int& ti, i
   tj = i + p;
 }
 
-// A CTA streams tiles of `rows` consecutive rows through shared memory; thread (pair, rg) accumulates the 4 x 4 block
-// `pair` of the Gram matrix over the rows of group rg of every tile (rows / RG rows per tile).  For the small K of the
-// Krylov solvers (k <= ~20) a handful of 4 x 4 blocks exists, so the rows of a tile are split over up to 64 groups to
-// keep all 256 threads busy (round 1 used 32-row tiles and left 90 % of the threads idle: 617 us for 1M x 8, now tens).
-// partials layout: [blockIdx.x][pair][rg][16 entries][hi, lo]
+// ---- mbarrier / bulk-copy (TMA, 1-D) primitives ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared bulk copy (bytes a multiple of 16, both addresses 16-byte aligned), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// A CTA streams tiles of `rows` = RG * rpg consecutive rows through shared memory, column-major (T[column][row], the
+// layout the basis has in HBM, so a tile is one contiguous segment per column).  Thread (pair, rg) accumulates the
+// 4 x 4 block `pair` of the Gram matrix over rows rg, rg + RG, rg + 2 RG, ... of every tile: the lanes of a warp read
+// consecutive rows of the same columns (broadcast / conflict-free).  For the small K of the Krylov solvers a handful of
+// 4 x 4 blocks exists, so a tile is split over up to 256 row groups to keep all threads busy.
+//
+// BULK = true (every column 16-byte aligned): full tiles arrive by cp.async.bulk (one per column, issued by warp 0,
+// completion on an mbarrier) into one of two buffers, so tile t + 1 is in flight while tile t is accumulated - the
+// round-2 profile of the single-buffered kernel showed the fp64 pipe idle 70 % of the time waiting on the staging
+// loads.  The row weights travel as one more column and are applied in shared memory before the accumulation.
+// BULK = false and the last, partial tile: staged by ordinary loads (zero-filled past m).
+//
+// BW = 4: an item is a 4 x 4 block (ti, tj), ti <= tj, of the full Gram matrix.  BW = 1 ("panel"): only the columns
+// c >= c0 of G are wanted (a basis that gained columns since its Gram matrix was last formed, unweighted: everything
+// left of c0 is unchanged) - an item is the 4 x 1 block (rows 4 ti .. 4 ti + 3, column c0 + pj), O(K) items instead of
+// O(K^2 / 32), and the pass is HBM-bound (it still reads every column once).
+// partials layout: [blockIdx.x][item][4 * BW entries][hi, lo]
+template <bool BULK, int BW>
 __global__ void __launch_bounds__(kGThreads, 2)
-gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const double* __restrict__ w, GramExtras ex,
-               int K, int Kpad, int npairs, int RG, int rows, double* __restrict__ partials) {
-  extern __shared__ double T[];  // rows x Kpad
+gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const double* __restrict__ w,
+               const __grid_constant__ GramExtras ex, int K, int c0, int npairs, int RG, int rpg, int KC,
+               double* __restrict__ partials) {
+  constexpr int NE = 4 * BW;
+  extern __shared__ __align__(16) double T[];  // [2][KC][rows]  (one buffer when !BULK)
+  __shared__ uint64_t bars[2];
   const int nt = (K + 3) / 4;
+  const int rows = RG * rpg;
+  const int S = rows;
+  const size_t bufsz = (size_t)KC * S;
+  const int Kw = K + (w ? 1 : 0);
   const int slot = blockIdx.y * kGThreads + threadIdx.x;  // (pair, rg) assignment
   const bool active = slot < npairs * RG;
-  int ti = 0, tj = 0, rg = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int ti = 0, cb = 0, rg = 0;  // cb: first column of the item's b operand
   if (active) {
-    pair_to_tiles(slot % npairs, nt, ti, tj);
-    rg = slot / npairs;
+    if (BW == 4) {
+      int tj;
+      pair_to_tiles(slot / RG, nt, ti, tj);
+      cb = 4 * tj;
+    } else {
+      ti = (slot / RG) % nt;
+      cb = c0 + (slot / RG) / nt;
+    }
+    rg = slot % RG;
   }
-  double hi[16], lo[16];
+  double hi[NE], lo[NE];
 #pragma unroll
-  for (int q = 0; q < 16; ++q) hi[q] = lo[q] = 0.0;
-  const int rows_per_group = rows / RG;
-  const int64_t nblk = (m + rows - 1) / rows;
+  for (int q = 0; q < NE; ++q) hi[q] = lo[q] = 0.0;
 
-  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+  auto colptr = [&](int j) -> const double* { return j < k ? B + (int64_t)j * ld : (j < K ? ex.ptr[j - k] : w); };
+  auto weighted = [&](int j) -> bool { return w && (j < k || ex.weighted[j - k]); };
+  auto accumulate = [&](const double* Tb_) {
+    if (!active) return;
+    const double* pa = Tb_ + (size_t)(4 * ti) * S + rg;
+    const double* pb = Tb_ + (size_t)cb * S + rg;
+    for (int i = 0; i < rpg; ++i) {
+      double a[4], b[BW];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = pa[q * S];
+#pragma unroll
+      for (int q = 0; q < BW; ++q) b[q] = pb[q * S];
+#pragma unroll
+      for (int qi = 0; qi < 4; ++qi)
+#pragma unroll
+        for (int qj = 0; qj < BW; ++qj) dd_mac(a[qi], b[qj], hi[qi * BW + qj], lo[qi * BW + qj]);
+      pa += RG;
+      pb += RG;
+    }
+  };
+  // the pad columns K .. 4 nt - 1 of the last 4-wide block are read (their products are discarded): keep them zero
+  for (int j = Kw + warp; j < KC; j += kGThreads / 32)
+    for (int r = lane; r < rows; r += 32) {
+      T[(size_t)j * S + r] = 0.0;
+      if (BULK) T[bufsz + (size_t)j * S + r] = 0.0;
+    }
+
+  const int64_t nfull = m / rows;
+  if (BULK) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t blk, int buf) {  // warp 0: one bulk copy per column
+      if (warp != 0) return;
+      if (lane == 0) mbar_arrive_expect_tx(&bars[buf], (uint32_t)Kw * (uint32_t)rows * 8u);
+      __syncwarp();
+      double* dst = T + buf * bufsz;
+      for (int j = lane; j < Kw; j += 32) bulk_g2s(dst + (size_t)j * S, colptr(j) + blk * rows, (uint32_t)rows * 8u, &bars[buf]);
+    };
+    if ((int64_t)blockIdx.x < nfull) issue(blockIdx.x, 0);
+    int t = 0;
+    for (int64_t blk = blockIdx.x; blk < nfull; blk += gridDim.x, ++t) {
+      const int buf = t & 1;
+      if (blk + gridDim.x < nfull) issue(blk + gridDim.x, buf ^ 1);  // (buf^1 was last read before the barrier ending t-1)
+      mbar_wait(&bars[buf], (t >> 1) & 1);
+      double* Tc = T + buf * bufsz;
+      if (w) {
+        const double* Tw = Tc + (size_t)K * S;
+        for (int j = warp; j < K; j += kGThreads / 32)
+          if (weighted(j))
+            for (int r = lane; r < rows; r += 32) Tc[(size_t)j * S + r] = __dmul_rn(Tc[(size_t)j * S + r], Tw[r]);
+        __syncthreads();
+      }
+      accumulate(Tc);
+      if (w) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my generic writes before the next bulk write
+      __syncthreads();
+    }
+  }
+  // tiles staged by ordinary loads: all of them when !BULK, else the partial last tile (owned by the next CTA in turn)
+  const int64_t nblk = (m + rows - 1) / rows;
+  for (int64_t blk = BULK ? nfull + ((blockIdx.x - nfull % gridDim.x + gridDim.x) % gridDim.x) : (int64_t)blockIdx.x; blk < nblk;
+       blk += gridDim.x) {
     const int64_t row0 = blk * rows;
     __syncthreads();
-    // stage the tile: lanes run along rows (contiguous in memory), warps over columns
-    for (int r = threadIdx.x; r < rows; r += kGThreads) {  // (no index division: column loop outside, rows strided)
-      const int64_t row = row0 + r;
-      const bool in = row < m;
-      const double wr = (in && w) ? w[row] : 1.0;
-      double* Tr = T + r * Kpad;
-      for (int j = 0; j < k; ++j) {
-        double v = in ? B[(int64_t)j * ld + row] : 0.0;
-        if (w) v = __dmul_rn(v, wr);
-        Tr[j] = v;
+    for (int j = warp; j < K; j += kGThreads / 32) {
+      const double* src = colptr(j);
+      const bool wt = weighted(j);
+      for (int r = lane; r < rows; r += 32) {
+        const int64_t row = row0 + r;
+        double v = row < m ? src[row] : 0.0;
+        if (wt && row < m) v = __dmul_rn(v, w[row]);
+        T[(size_t)j * S + r] = v;
       }
-      for (int j = k; j < K; ++j) {
-        double v = in ? ex.ptr[j - k][row] : 0.0;
-        if (w && ex.weighted[j - k]) v = __dmul_rn(v, wr);
-        Tr[j] = v;
-      }
-      for (int j = K; j < Kpad; ++j) Tr[j] = 0.0;
     }
     __syncthreads();
+    accumulate(T);
+  }
+  if (RG == 1) {
     if (active) {
-      const double* Ta = T + 4 * ti;
-      const double* Tb = T + 4 * tj;
-      for (int r = rg * rows_per_group; r < (rg + 1) * rows_per_group; ++r) {
-        double a[4], b[4];
+      double* out = partials + (((int64_t)blockIdx.x * npairs + slot) * NE) * 2;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          a[q] = Ta[r * Kpad + q];
-          b[q] = Tb[r * Kpad + q];
-        }
-#pragma unroll
-        for (int qi = 0; qi < 4; ++qi)
-#pragma unroll
-          for (int qj = 0; qj < 4; ++qj) dd_mac(a[qi], b[qj], hi[qi * 4 + qj], lo[qi * 4 + qj]);
+      for (int q = 0; q < NE; ++q) {
+        out[2 * q] = hi[q];
+        out[2 * q + 1] = lo[q];
       }
     }
+    return;
   }
-  if (active) {
-    double* out = partials + ((((int64_t)blockIdx.x * npairs + (slot % npairs)) * RG + rg) * 16) * 2;
+  // RG > 1 (one CTA in y): the row groups of a block are summed inside the CTA, in double-double and in a fixed order
+  // (C threads per entry, strided, then those C in order), so one partial per (CTA, entry) is left for the finalize
+  // kernel - with up to 256 groups that kernel used to dominate the small-K launches.
+  __syncthreads();
+  double* red = T;  // [2 NE][256]: entry component major, slot minor
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      out[2 * q] = hi[q];
-      out[2 * q + 1] = lo[q];
+  for (int q = 0; q < NE; ++q) {
+    red[(2 * q) * kGThreads + threadIdx.x] = hi[q];
+    red[(2 * q + 1) * kGThreads + threadIdx.x] = lo[q];
+  }
+  __syncthreads();
+  const int E = npairs * NE;
+  const int C = E >= kGThreads ? 1 : kGThreads / E;
+  double* red2 = T + 2 * NE * kGThreads;  // [E * C][2]
+  double* outb = partials + (int64_t)blockIdx.x * npairs * NE * 2;
+  for (int id = threadIdx.x; id < E * C; id += kGThreads) {
+    const int e = id / C, c = id % C, pair = e / NE, q = e % NE;
+    const double* ph = red + (2 * q) * kGThreads + pair * RG;
+    const double* pl = ph + kGThreads;
+    double shi = 0.0, slo = 0.0;
+    for (int g = c; g < RG; g += C) {
+      double s_, e_;
+      two_sum(shi, ph[g], s_, e_);
+      slo += e_ + pl[g];
+      shi = s_;
+    }
+    if (C == 1) {
+      outb[2 * e] = shi;
+      outb[2 * e + 1] = slo;
+    } else {
+      red2[2 * id] = shi;
+      red2[2 * id + 1] = slo;
+    }
+  }
+  if (C > 1) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += kGThreads) {
+      double shi = 0.0, slo = 0.0;
+      for (int c = 0; c < C; ++c) {
+        double s_, e_;
+        two_sum(shi, red2[2 * (e * C + c)], s_, e_);
+        slo += e_ + red2[2 * (e * C + c) + 1];
+        shi = s_;
+      }
+      outb[2 * e] = shi;
+      outb[2 * e + 1] = slo;
     }
   }
 }
 
-// One CTA per (pair, entry): double-double sum over CTAs and row groups - every thread a fixed strided subset in order,
+// One CTA per (pair, entry): double-double sum over the CTAs of the pass - every thread a fixed strided subset in order,
 // then a fixed tree; writes both triangles.
 __global__ void __launch_bounds__(128)
-gram_finalize_kernel(int nbx, int npairs, int RG, int nt, int K, const double* __restrict__ partials,
+gram_finalize_kernel(int nbx, int npairs, int nt, int K, int c0, const double* __restrict__ partials,
                      double* __restrict__ Ghi, double* __restrict__ Glo) {
   __shared__ double sh[128], sl[128];
   const int id = blockIdx.x;
-  const int pair = id / 16, q = id % 16;
-  int ti, tj;
-  pair_to_tiles(pair, nt, ti, tj);
-  const int i = 4 * ti + q / 4, j = 4 * tj + q % 4;
+  const int NE = c0 < 0 ? 16 : 4;
+  const int pair = id / NE, q = id % NE;
+  int i, j;
+  if (c0 < 0) {
+    int ti, tj;
+    pair_to_tiles(pair, nt, ti, tj);
+    i = 4 * ti + q / 4, j = 4 * tj + q % 4;
+  } else {  // panel: item = (ti, pj); the entries below the diagonal belong to the item of the mirrored position
+    i = 4 * (pair % nt) + q, j = c0 + pair / nt;
+    if (i > j) return;
+  }
   if (i >= K || j >= K) return;  // (uniform over the CTA)
   double shi = 0.0, slo = 0.0;
-  const int terms = nbx * RG;
-  for (int t = threadIdx.x; t < terms; t += 128) {
-    const int bx = t / RG, rg = t % RG;
-    const double* p = partials + ((((int64_t)bx * npairs + pair) * RG + rg) * 16 + q) * 2;
+  for (int bx = threadIdx.x; bx < nbx; bx += 128) {
+    const double* p = partials + (((int64_t)bx * npairs + pair) * NE + q) * 2;
     double s, e;
     two_sum(shi, p[0], s, e);
     slo += e + p[1];
@@ -173,20 +323,24 @@ gram_finalize_kernel(int nbx, int npairs, int RG, int nt, int K, const double* _
   }
 }
 
-static void gram_shape(int K, int& Kpad, int& npairs, int& RG, int& gy, int& rows) {
+constexpr size_t kGReduceBytes = (32 + 2) * kGThreads * sizeof(double);
+constexpr size_t kGBufBytes = 54 * 1024;  // one staging buffer; two buffers per CTA, two CTAs per SM
+
+static void gram_shape(int K, bool has_w, int c0, int& KC, int& npairs, int& RG, int& gy, int& rpg) {
   const int nt = (K + 3) / 4;
-  Kpad = 4 * nt + 1;  // odd stride: conflict-free column staging
-  npairs = nt * (nt + 1) / 2;
+  const int Kw = K + (has_w ? 1 : 0);
+  KC = 4 * nt > Kw ? 4 * nt : Kw;
+  npairs = c0 < 0 ? nt * (nt + 1) / 2 : nt * (K - c0);  // items: 4 x 4 blocks, or 4 x 1 blocks of the panel
   // as many row groups as fit one CTA next to the 4 x 4 blocks (K <= 4: one block, 256 groups), so that (nearly) every
   // thread accumulates; several CTAs in y only when there are more blocks than threads
   RG = npairs <= kGThreads ? kGThreads / npairs : 1;
   gy = (npairs * RG + kGThreads - 1) / kGThreads;
-  // rows per group and tile: ~256 rows per tile (two barriers and one staging pass per tile), within 64 KB of shared
-  // memory so that two CTAs stay resident per SM
-  int rpg = (256 + RG - 1) / RG;
+  // ~256 rows per tile (one barrier pair per tile), an even number of rows (16-byte columns), within one buffer
+  const int step = (RG & 1) ? 2 : 1;
+  rpg = (256 + RG - 1) / RG;
   if (rpg < 4) rpg = 4;
-  while (rpg > 1 && (size_t)RG * rpg * Kpad * sizeof(double) > 64 * 1024) --rpg;
-  rows = RG * rpg;
+  rpg = (rpg + step - 1) / step * step;
+  while (rpg > step && (size_t)RG * rpg * KC * sizeof(double) > kGBufBytes) rpg -= step;
 }
 
 // ---- host double-double arithmetic for the k x k factorisation ------------------------------------------
@@ -232,25 +386,31 @@ static inline hdd h_sqrt(hdd a) {
 
 using namespace tb200;
 
+static bool g_gram_bulk = true;
+
 extern "C" {
+
+// A/B switch for tests and tuning: 0 = stage every tile with ordinary loads (single buffer), 1 = bulk copies (default).
+void tb200_gram_set_bulk(int on) { g_gram_bulk = on != 0; }
 
 // Workspace (doubles) for a Gram pass over K = k + n_extra columns.
 int64_t tb200_gram_workspace_len(int64_t K) {
-  int Kpad, npairs, RG, gy, rows;
-  gram_shape((int)K, Kpad, npairs, RG, gy, rows);
-  return (int64_t)kGBlocksX * npairs * RG * 32;
+  const int64_t nt = (K + 3) / 4;
+  return (int64_t)kGBlocksX * (nt * (nt + 1) / 2) * 32;  // one (hi, lo) per CTA and entry of every 4 x 4 block
 }
 
-// G = M^T M for M = [diag(w) B[:, 0..k) | extras], K = k + n_extra, accumulated in double-double.
-// B column j is contiguous at B + j*ld; w (length m) may be NULL; extras: up to 4 column pointers, each with a
-// flag saying whether the row weights apply to it.  Ghi/Glo: K x K row-major device outputs (G = Ghi + Glo).
-int tb200_weighted_gram(int64_t m, int64_t k, const double* B, int64_t ld, const double* w, int n_extra,
-                        const double* const* extras, const int* extra_weighted, double* Ghi, double* Glo, double* ws,
-                        void* stream) {
+}  // extern "C"
+
+static int gram_launch(int64_t m, int64_t k, const double* B, int64_t ld, const double* w, int n_extra,
+                       const double* const* extras, const int* extra_weighted, int c0, double* Ghi, double* Glo, double* ws,
+                       void* stream) {
   TB200_REQUIRE(m >= 0 && k >= 0 && ld >= m && n_extra >= 0 && n_extra <= kGMaxExtra, "bad size");
   const int K = (int)k + n_extra;
   TB200_REQUIRE(K >= 1 && K <= 512, "need 1 <= k + n_extra <= 512");
   TB200_REQUIRE((k == 0 || B) && Ghi && Glo && ws, "null pointer");
+  TB200_REQUIRE(c0 < K, "panel starts past the last column");
+  const int nt = (K + 3) / 4;
+  if (c0 <= 0 || K - c0 > 2 * (nt + 1)) c0 = -1;  // a wide panel: the full pass is a superset and fits the workspace
   GramExtras ex;
   ex.n = n_extra;
   for (int i = 0; i < kGMaxExtra; ++i) {
@@ -258,24 +418,57 @@ int tb200_weighted_gram(int64_t m, int64_t k, const double* B, int64_t ld, const
     ex.weighted[i] = (i < n_extra && extra_weighted) ? extra_weighted[i] : 0;
     TB200_REQUIRE(i >= n_extra || ex.ptr[i], "null extra column");
   }
-  int Kpad, npairs, RG, gy, rows;
-  gram_shape(K, Kpad, npairs, RG, gy, rows);
-  const size_t smem = (size_t)rows * Kpad * sizeof(double);
+  int KC, npairs, RG, gy, rpg;
+  gram_shape(K, w != nullptr, c0, KC, npairs, RG, gy, rpg);
+  const int rows = RG * rpg;
+  TB200_REQUIRE((size_t)rows * KC * sizeof(double) <= kGBufBytes, "k + n_extra too large for one shared-memory tile");
+  // bulk copies need every column segment 16-byte aligned (rows is even): B, ld, the extras and w
+  bool bulk = g_gram_bulk && ((uintptr_t)B % 16 == 0) && (ld % 2 == 0) && (!w || (uintptr_t)w % 16 == 0);
+  for (int i = 0; i < n_extra; ++i) bulk = bulk && ((uintptr_t)ex.ptr[i] % 16 == 0);
+  size_t smem = (size_t)rows * KC * sizeof(double) * (bulk ? 2 : 1);
+  if (RG > 1 && smem < kGReduceBytes) smem = kGReduceBytes;  // the in-CTA reduction over row groups reuses the tiles
   cudaStream_t st = (cudaStream_t)stream;
+  auto kern = c0 < 0 ? (bulk ? gram_dd_kernel<true, 4> : gram_dd_kernel<false, 4>)
+                     : (bulk ? gram_dd_kernel<true, 1> : gram_dd_kernel<false, 1>);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(gram_dd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("weighted_gram: %s", cudaGetErrorString(e));
       return (int)e;
     }
   }
   dim3 grid(kGBlocksX, gy);
-  gram_dd_kernel<<<grid, kGThreads, smem, st>>>(m, (int)k, B, ld, w, ex, K, Kpad, npairs, RG, rows, ws);
+  kern<<<grid, kGThreads, smem, st>>>(m, (int)k, B, ld, w, ex, K, c0, npairs, RG, rpg, KC, ws);
   int rc = check_launch("weighted_gram");
   if (rc) return rc;
-  gram_finalize_kernel<<<npairs * 16, 128, 0, st>>>(kGBlocksX, npairs, RG, (K + 3) / 4, K, ws, Ghi, Glo);
+  gram_finalize_kernel<<<npairs * (c0 < 0 ? 16 : 4), 128, 0, st>>>(kGBlocksX, npairs, nt, K, c0, ws, Ghi, Glo);
   return check_launch("weighted_gram finalize");
 }
+
+extern "C" {
+
+// G = M^T M for M = [diag(w) B[:, 0..k) | extras], K = k + n_extra, accumulated in double-double.
+// B column j is contiguous at B + j*ld; w (length m) may be NULL; extras: up to 4 column pointers, each with a
+// flag saying whether the row weights apply to it.  Ghi/Glo: K x K row-major device outputs (G = Ghi + Glo).
+int tb200_weighted_gram(int64_t m, int64_t k, const double* B, int64_t ld, const double* w, int n_extra,
+                        const double* const* extras, const int* extra_weighted, double* Ghi, double* Glo, double* ws,
+                        void* stream) {
+  return gram_launch(m, k, B, ld, w, n_extra, extras, extra_weighted, -1, Ghi, Glo, ws, stream);
+}
+
+// The same, but only the columns c >= c0 of G (entries (i, c) and (c, i), i <= c) are computed and written; the rest of
+// Ghi/Glo is left untouched.  For a basis whose first c0 columns (and weights) have not changed since their Gram matrix
+// was formed: O(K) block products instead of O(K^2) (GKS: AV, LV; MMGKS with pnorm = 2: AV).
+int tb200_weighted_gram_panel(int64_t m, int64_t k, const double* B, int64_t ld, const double* w, int n_extra,
+                              const double* const* extras, const int* extra_weighted, int64_t c0, double* Ghi, double* Glo,
+                              double* ws, void* stream) {
+  TB200_REQUIRE(c0 >= 0, "bad panel start");
+  return gram_launch(m, k, B, ld, w, n_extra, extras, extra_weighted, (int)c0, Ghi, Glo, ws, stream);
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // Host-side, double-double: from the K x K Gram matrix of [B | z_1..z_ne] (K = k + ne, row-major hi/lo parts)
 // compute   R (k x k upper triangular, row-major, B = Q R with positive diagonal),

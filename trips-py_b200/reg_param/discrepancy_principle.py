@@ -66,26 +66,32 @@ def discrepancy_principle_projected(A, L, b_proj, resid_norm, delta, eta=1.01, e
             testzero += out_of_range2
     else:
         testzero = out_of_range2 - target
-    sv2 = sv2.reshape(-1, 1)
     if not testzero < 0:
         return 0
+    # Newton on beta = 1/lambda (:77-97), the same arithmetic on 1-D arrays and Python scalars: at k ~ 30 the reference's
+    # (k, 1)-array form spends its time in NumPy call overhead (30 steps x a dozen calls), which is host time the
+    # device waits for in every iteration of the hybrid solvers
+    sv2 = np.ascontiguousarray(sv2, dtype=np.float64).ravel()
+    bh = np.ascontiguousarray(bhat, dtype=np.float64).ravel()
+    nrm2 = la.blas.dnrm2
     beta = 1e-8
     alpha = None
     iterations = 0
-    while (iterations < 30) or ((iterations <= 100) and (np.abs(alpha) < 10 ** (-16))):
-        zbeta = ((sv2 * beta + 1) ** (-1)) * bhat
-        f = la.norm(zbeta) ** 2 - target
+    while (iterations < 30) or ((iterations <= 100) and (abs(alpha) < 10 ** (-16))):
+        d = 1.0 / (sv2 * beta + 1)
+        zbeta = d * bh
+        f = nrm2(zbeta) ** 2 - target
         if explicitProj:
             f += out_of_range2
-        wbeta = ((sv2 * beta + 1) ** (-1)) * zbeta
-        f_prime = 2 / beta * zbeta.T @ (wbeta - zbeta)
+        wbeta = d * zbeta
+        f_prime = 2 / beta * float(zbeta @ (wbeta - zbeta))
         beta_new = beta - f / f_prime
         if abs(beta_new - beta) < 10 ** (-12) * beta:
             if alpha is None:
-                alpha = 1 / beta_new[0, 0]
+                alpha = 1 / beta_new
             break
         beta = beta_new
-        alpha = 1 / beta_new[0, 0]
+        alpha = 1 / beta_new
         iterations += 1
     return alpha
 

@@ -33,6 +33,7 @@ class GKSBases:
         self.V = Basis(A.shape[1], kmax, dev)
         self.AV = Basis(A.shape[0], kmax, dev)
         self.LV = Basis(L.shape[0], kmax, dev)
+        self.gram_AV, self.gram_LV = K.IncrementalGram(), K.IncrementalGram()  # for the passes without row weights
         for j in range(projection_dim):  # AV = A@V ; LV = L@V                            (GKS.py:37-38)
             self.V.next_col().copy_(st.V.col(j))
             self.V.push()
@@ -107,7 +108,7 @@ def factor_pair(bases, bd, wf=None, wr=None):
     k = bases.k
     comm = bases.comm
     if wf is None:
-        Ghi, Glo = K.weighted_gram(bases.AV, k, None, extras=(bd,), extra_weighted=(0,), comm=_gram_comm(comm, "data"))
+        Ghi, Glo = bases.gram_AV.update(bases.AV, k, extras=(bd,), extra_weighted=(0,), comm=_gram_comm(comm, "data"))
         R_A, C, res2 = K.gram_factor(Ghi, Glo, k)
         c_plain = c_w = C[:, 0:1]
         resid_w = float(np.sqrt(res2[0]))
@@ -116,7 +117,10 @@ def factor_pair(bases, bd, wf=None, wr=None):
         R_A, C, res2 = K.gram_factor(Ghi, Glo, k)
         c_plain, c_w = C[:, 0:1], C[:, 1:2]
         resid_w = float(np.sqrt(res2[1]))
-    Ghi, Glo = K.weighted_gram(bases.LV, k, wr, comm=_gram_comm(comm, "reg"))
+    if wr is None:
+        Ghi, Glo = bases.gram_LV.update(bases.LV, k, comm=_gram_comm(comm, "reg"))
+    else:
+        Ghi, Glo = K.weighted_gram(bases.LV, k, wr, comm=_gram_comm(comm, "reg"))
     R_L, _, _ = K.gram_factor(Ghi, Glo, k)
     return R_A, R_L, c_plain, c_w, resid_w
 
