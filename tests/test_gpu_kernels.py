@@ -273,12 +273,18 @@ def test_weighted_gram_bulk_copy_pipeline_equals_plain_staging(tb, m, k, weighte
     bd, wd = dev(b), (dev(w) if weighted else None)
     out = []
     try:
-        for bulk in (1, 0):
-            tb._lib.lib().tb200_gram_set_bulk(bulk)
-            out.append(K.weighted_gram(basis, k, wd, extras=(bd, bd), extra_weighted=(0, 1)))
+        for block in (2, 4):
+            tb._lib.lib().tb200_gram_set_block(block)
+            for bulk in (1, 0):
+                tb._lib.lib().tb200_gram_set_bulk(bulk)
+                out.append(K.weighted_gram(basis, k, wd, extras=(bd, bd), extra_weighted=(0, 1)))
     finally:
         tb._lib.lib().tb200_gram_set_bulk(1)
-    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+        tb._lib.lib().tb200_gram_set_block(2)
+    for a in (0, 2):  # same block shape: same accumulation order whatever the staging
+        assert np.array_equal(out[a][0], out[a + 1][0]) and np.array_equal(out[a][1], out[a + 1][1])
+    d = (out[0][0].astype(np.longdouble) + out[0][1]) - (out[2][0].astype(np.longdouble) + out[2][1])
+    assert np.max(np.abs(d.astype(np.float64)) / np.sqrt(np.outer(np.diag(out[0][0]), np.diag(out[0][0])))) < 1e-17
     M = np.column_stack((B * w[:, None] if weighted else B, b, b * w if weighted else b)).astype(np.longdouble)
     G = M.T @ M
     scale = np.sqrt(np.outer(np.diag(G), np.diag(G))).astype(np.float64)

@@ -32,7 +32,8 @@ def main():
     lib = _lib.lib()
     peak = float(os.environ.get("FP64_PEAK", 18.3e12))
     hbm = float(os.environ.get("HBM_PEAK", 6550e9))
-    print("m | k | weighted | plain us | bulk us | fp64-bound us | hbm-bound us | frac of max(bound), bulk")
+    print("m | k | weighted | 4x4 plain us | 4x4 bulk us | 2x2 bulk us | fp64-bound us (useful entries) | hbm-bound us | "
+          "frac of max(bound), 2x2 bulk")
     for m in (1 << 20, 1 << 21):
         g = torch.Generator(device="cuda").manual_seed(1)
         kmax = 56
@@ -60,10 +61,13 @@ def main():
                     assert rc == 0
 
                 res = []
+                lib.tb200_gram_set_block(4)
                 for bulk in (0, 1):
                     lib.tb200_gram_set_bulk(bulk)
                     res.append(timed(launch))
                 lib.tb200_gram_set_bulk(1)
+                lib.tb200_gram_set_block(2)
+                res.append(timed(launch))
                 if wt is None:  # panel pass: the last basis column + the extra
                     def panel():
                         Kt = k + len(ext)
@@ -80,11 +84,10 @@ def main():
                     print(f"{m} | {k} | panel (last column + extra) | - | {tp:.1f} | - | "
                           f"{8 * m * (k + 1) / hbm * 1e6:.1f} | {8 * m * (k + 1) / hbm * 1e6 / tp:.2f}", flush=True)
                 Kt = k + len(ext)
-                nt = (Kt + 3) // 4
-                t_fp = nt * (nt + 1) / 2 * 160 * m / peak * 1e6
+                t_fp = Kt * (Kt + 1) / 2 * 10 * m / peak * 1e6  # 10 fp64 instructions per needed entry and row
                 t_hbm = 8 * m * (Kt + (wt is not None)) / hbm * 1e6
-                print(f"{m} | {k} | {wt is not None} | {res[0]:.1f} | {res[1]:.1f} | {t_fp:.1f} | {t_hbm:.1f} | "
-                      f"{max(t_fp, t_hbm) / res[1]:.2f}", flush=True)
+                print(f"{m} | {k} | {wt is not None} | {res[0]:.1f} | {res[1]:.1f} | {res[2]:.1f} | {t_fp:.1f} | {t_hbm:.1f} | "
+                      f"{max(t_fp, t_hbm) / res[2]:.2f}", flush=True)
         del basis
 
 

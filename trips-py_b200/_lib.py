@@ -46,6 +46,7 @@ SIGNATURES = {
     "tb200_basis_combine": (c_int, [c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_gram_workspace_len": (c_i64, [c_i64]),
     "tb200_gram_set_bulk": (None, [c_int]),
+    "tb200_gram_set_block": (None, [c_int]),
     "tb200_basis_set_vec2": (None, [c_int]),
     "tb200_weighted_gram": (c_int, [c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_weighted_gram_panel": (c_int, [c_i64, c_i64, c_ptr, c_i64, c_ptr, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),

@@ -102,17 +102,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // left of c0 is unchanged) - an item is the 4 x 1 block (rows 4 ti .. 4 ti + 3, column c0 + pj), O(K) items instead of
 // O(K^2 / 32), and the pass is HBM-bound (it still reads every column once).
 // partials layout: [blockIdx.x][item][4 * BW entries][hi, lo]
-template <bool BULK, int BW>
-__global__ void __launch_bounds__(kGThreads, 2)
+template <bool BULK, int BH, int BW, int NT>
+__global__ void __launch_bounds__(NT, 2)
 gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const double* __restrict__ w,
-               const __grid_constant__ GramExtras ex, int K, int c0, int npairs, int RG, int rpg, int KC,
+               const __grid_constant__ GramExtras ex, int K, int c0, int npairs, int RG, int rpg, int S, int KC,
                double* __restrict__ partials) {
-  constexpr int NE = 4 * BW;
+  constexpr int NE = BH * BW;
+  constexpr int kGThreads = NT;  // (shadows the default: this instance's CTA size)
   extern __shared__ __align__(16) double T[];  // [2][KC][rows]  (one buffer when !BULK)
   __shared__ uint64_t bars[2];
-  const int nt = (K + 3) / 4;
-  const int rows = RG * rpg;
-  const int S = rows;
+  const int nt = (K + BH - 1) / BH;  // row tiles (= column tiles of the square blocks)
+  const int rows = RG * rpg;  // S >= rows: column stride in shared memory (see gram_shape)
   const size_t bufsz = (size_t)KC * S;
   const int Kw = K + (w ? 1 : 0);
   const int slot = blockIdx.y * kGThreads + threadIdx.x;  // (pair, rg) assignment
@@ -120,10 +120,10 @@ gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int ti = 0, cb = 0, rg = 0;  // cb: first column of the item's b operand
   if (active) {
-    if (BW == 4) {
+    if (BW == BH) {
       int tj;
       pair_to_tiles(slot / RG, nt, ti, tj);
-      cb = 4 * tj;
+      cb = BW * tj;
     } else {
       ti = (slot / RG) % nt;
       cb = c0 + (slot / RG) / nt;
@@ -138,16 +138,16 @@ gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const
   auto weighted = [&](int j) -> bool { return w && (j < k || ex.weighted[j - k]); };
   auto accumulate = [&](const double* Tb_) {
     if (!active) return;
-    const double* pa = Tb_ + (size_t)(4 * ti) * S + rg;
+    const double* pa = Tb_ + (size_t)(BH * ti) * S + rg;
     const double* pb = Tb_ + (size_t)cb * S + rg;
     for (int i = 0; i < rpg; ++i) {
-      double a[4], b[BW];
+      double a[BH], b[BW];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) a[q] = pa[q * S];
+      for (int q = 0; q < BH; ++q) a[q] = pa[q * S];
 #pragma unroll
       for (int q = 0; q < BW; ++q) b[q] = pb[q * S];
 #pragma unroll
-      for (int qi = 0; qi < 4; ++qi)
+      for (int qi = 0; qi < BH; ++qi)
 #pragma unroll
         for (int qj = 0; qj < BW; ++qj) dd_mac(a[qi], b[qj], hi[qi * BW + qj], lo[qi * BW + qj]);
       pa += RG;
@@ -278,17 +278,17 @@ gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const
 // One CTA per (pair, entry): double-double sum over the CTAs of the pass - every thread a fixed strided subset in order,
 // then a fixed tree; writes both triangles.
 __global__ void __launch_bounds__(128)
-gram_finalize_kernel(int nbx, int npairs, int nt, int K, int c0, const double* __restrict__ partials,
+gram_finalize_kernel(int nbx, int npairs, int bs, int nt, int K, int c0, const double* __restrict__ partials,
                      double* __restrict__ Ghi, double* __restrict__ Glo) {
   __shared__ double sh[128], sl[128];
   const int id = blockIdx.x;
-  const int NE = c0 < 0 ? 16 : 4;
+  const int NE = c0 < 0 ? bs * bs : 4;
   const int pair = id / NE, q = id % NE;
   int i, j;
   if (c0 < 0) {
     int ti, tj;
     pair_to_tiles(pair, nt, ti, tj);
-    i = 4 * ti + q / 4, j = 4 * tj + q % 4;
+    i = bs * ti + q / bs, j = bs * tj + q % bs;
   } else {  // panel: item = (ti, pj); the entries below the diagonal belong to the item of the mirrored position
     i = 4 * (pair % nt) + q, j = c0 + pair / nt;
     if (i > j) return;
@@ -323,14 +323,18 @@ gram_finalize_kernel(int nbx, int npairs, int nt, int K, int c0, const double* _
   }
 }
 
-constexpr size_t kGReduceBytes = (32 + 2) * kGThreads * sizeof(double);
+static inline size_t gram_reduce_bytes(int ne, int threads) { return (size_t)(2 * ne + 2) * threads * sizeof(double); }
 constexpr size_t kGBufBytes = 54 * 1024;  // one staging buffer; two buffers per CTA, two CTAs per SM
 
-static void gram_shape(int K, bool has_w, int c0, int& KC, int& npairs, int& RG, int& gy, int& rpg) {
-  const int nt = (K + 3) / 4;
+// bs: side of the square blocks of the full pass (4 or 2); the panel pass uses 4 x 1 blocks.  threads: CTA size.
+static void gram_shape(int K, bool has_w, int c0, int bs, int threads, int& KC, int& npairs, int& RG, int& gy, int& rpg,
+                       int& S) {
+  const int kGThreads = threads;
+  if (c0 >= 0) bs = 4;
+  const int nt = (K + bs - 1) / bs;
   const int Kw = K + (has_w ? 1 : 0);
-  KC = 4 * nt > Kw ? 4 * nt : Kw;
-  npairs = c0 < 0 ? nt * (nt + 1) / 2 : nt * (K - c0);  // items: 4 x 4 blocks, or 4 x 1 blocks of the panel
+  KC = bs * nt > Kw ? bs * nt : Kw;
+  npairs = c0 < 0 ? nt * (nt + 1) / 2 : nt * (K - c0);  // items: bs x bs blocks, or 4 x 1 blocks of the panel
   // as many row groups as fit one CTA next to the 4 x 4 blocks (K <= 4: one block, 256 groups), so that (nearly) every
   // thread accumulates; several CTAs in y only when there are more blocks than threads
   RG = npairs <= kGThreads ? kGThreads / npairs : 1;
@@ -340,7 +344,12 @@ static void gram_shape(int K, bool has_w, int c0, int& KC, int& npairs, int& RG,
   rpg = (256 + RG - 1) / RG;
   if (rpg < 4) rpg = 4;
   rpg = (rpg + step - 1) / step * step;
-  while (rpg > step && (size_t)RG * rpg * KC * sizeof(double) > kGBufBytes) rpg -= step;
+  while (rpg > step && (size_t)(RG * rpg + 2) * KC * sizeof(double) > kGBufBytes) rpg -= step;
+  // column stride: even (16-byte columns for the bulk copies) with S / 2 odd - the threads of a half-warp that hold
+  // different blocks read the same row of different columns, and a stride that is a multiple of 4 doubles would put
+  // every second (S = 8j: every) column on the same bank (measured 2x on the whole pass at K = 56)
+  const int rows = RG * rpg;
+  S = (rows / 2) % 2 == 1 ? rows : rows + 2;
 }
 
 // ---- host double-double arithmetic for the k x k factorisation ------------------------------------------
@@ -387,11 +396,14 @@ static inline hdd h_sqrt(hdd a) {
 using namespace tb200;
 
 static bool g_gram_bulk = true;
+static int g_gram_block = 2;
 
 extern "C" {
 
 // A/B switch for tests and tuning: 0 = stage every tile with ordinary loads (single buffer), 1 = bulk copies (default).
 void tb200_gram_set_bulk(int on) { g_gram_bulk = on != 0; }
+// Block shape of the full pass: 2 (default; 2 x 2 blocks, 512 threads) or 4 (4 x 4 blocks, 256 threads).
+void tb200_gram_set_block(int bs) { g_gram_block = bs == 4 ? 4 : 2; }
 
 // Workspace (doubles) for a Gram pass over K = k + n_extra columns.
 int64_t tb200_gram_workspace_len(int64_t K) {
@@ -418,18 +430,23 @@ static int gram_launch(int64_t m, int64_t k, const double* B, int64_t ld, const 
     ex.weighted[i] = (i < n_extra && extra_weighted) ? extra_weighted[i] : 0;
     TB200_REQUIRE(i >= n_extra || ex.ptr[i], "null extra column");
   }
-  int KC, npairs, RG, gy, rpg;
-  gram_shape(K, w != nullptr, c0, KC, npairs, RG, gy, rpg);
-  const int rows = RG * rpg;
-  TB200_REQUIRE((size_t)rows * KC * sizeof(double) <= kGBufBytes, "k + n_extra too large for one shared-memory tile");
+  // full pass: 2 x 2 blocks on 512 threads by default (finer items: fewer idle threads and padded entries than 4 x 4 on
+  // 256), 4 x 4 for K > 128 where the items outnumber the threads anyway; panel: 4 x 1 on 256
+  const int bs = c0 >= 0 ? 4 : ((g_gram_block == 2 && K <= 128) ? 2 : 4);
+  const int threads = (c0 < 0 && bs == 2) ? 512 : 256;
+  int KC, npairs, RG, gy, rpg, S;
+  gram_shape(K, w != nullptr, c0, bs, threads, KC, npairs, RG, gy, rpg, S);
+  TB200_REQUIRE((size_t)S * KC * sizeof(double) <= kGBufBytes, "k + n_extra too large for one shared-memory tile");
   // bulk copies need every column segment 16-byte aligned (rows is even): B, ld, the extras and w
   bool bulk = g_gram_bulk && ((uintptr_t)B % 16 == 0) && (ld % 2 == 0) && (!w || (uintptr_t)w % 16 == 0);
   for (int i = 0; i < n_extra; ++i) bulk = bulk && ((uintptr_t)ex.ptr[i] % 16 == 0);
-  size_t smem = (size_t)rows * KC * sizeof(double) * (bulk ? 2 : 1);
-  if (RG > 1 && smem < kGReduceBytes) smem = kGReduceBytes;  // the in-CTA reduction over row groups reuses the tiles
+  size_t smem = (size_t)S * KC * sizeof(double) * (bulk ? 2 : 1);
+  const size_t red_bytes = gram_reduce_bytes(c0 < 0 ? bs * bs : 4, threads);
+  if (RG > 1 && smem < red_bytes) smem = red_bytes;  // the in-CTA reduction over row groups reuses the tiles
   cudaStream_t st = (cudaStream_t)stream;
-  auto kern = c0 < 0 ? (bulk ? gram_dd_kernel<true, 4> : gram_dd_kernel<false, 4>)
-                     : (bulk ? gram_dd_kernel<true, 1> : gram_dd_kernel<false, 1>);
+  auto kern = c0 >= 0 ? (bulk ? gram_dd_kernel<true, 4, 1, 256> : gram_dd_kernel<false, 4, 1, 256>)
+              : bs == 2 ? (bulk ? gram_dd_kernel<true, 2, 2, 512> : gram_dd_kernel<false, 2, 2, 512>)
+                        : (bulk ? gram_dd_kernel<true, 4, 4, 256> : gram_dd_kernel<false, 4, 4, 256>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -438,10 +455,11 @@ static int gram_launch(int64_t m, int64_t k, const double* B, int64_t ld, const 
     }
   }
   dim3 grid(kGBlocksX, gy);
-  kern<<<grid, kGThreads, smem, st>>>(m, (int)k, B, ld, w, ex, K, c0, npairs, RG, rpg, KC, ws);
+  kern<<<grid, threads, smem, st>>>(m, (int)k, B, ld, w, ex, K, c0, npairs, RG, rpg, S, KC, ws);
   int rc = check_launch("weighted_gram");
   if (rc) return rc;
-  gram_finalize_kernel<<<npairs * (c0 < 0 ? 16 : 4), 128, 0, st>>>(kGBlocksX, npairs, nt, K, c0, ws, Ghi, Glo);
+  gram_finalize_kernel<<<npairs * (c0 < 0 ? bs * bs : 4), 128, 0, st>>>(kGBlocksX, npairs, bs, (K + bs - 1) / bs, K, c0, ws,
+                                                                       Ghi, Glo);
   return check_launch("weighted_gram finalize");
 }
 
