@@ -119,7 +119,7 @@ void tb200_basis_set_vec2(int on);
 int64_t tb200_gram_workspace_len(int64_t K);
 /* A/B switch: 1 (default) = tiles arrive by double-buffered cp.async.bulk, 0 = ordinary loads, single buffer. */
 void tb200_gram_set_bulk(int on);
-/* Block shape of the full pass: 2 (default: 2 x 2 blocks on 512 threads) or 4 (4 x 4 blocks on 256 threads). */
+/* Block shape of the full pass: 0 (default) = chosen per K, 2 = 2 x 2 blocks (<= 512 threads), 4 = 4 x 4 (<= 256). */
 void tb200_gram_set_block(int bs);
 int tb200_weighted_gram(int64_t m, int64_t k, const double* B, int64_t ld, const double* w, int n_extra,
                         const double* const* extras_host, const int* extra_weighted_host, double* Ghi, double* Glo,

@@ -280,7 +280,7 @@ def test_weighted_gram_bulk_copy_pipeline_equals_plain_staging(tb, m, k, weighte
                 out.append(K.weighted_gram(basis, k, wd, extras=(bd, bd), extra_weighted=(0, 1)))
     finally:
         tb._lib.lib().tb200_gram_set_bulk(1)
-        tb._lib.lib().tb200_gram_set_block(2)
+        tb._lib.lib().tb200_gram_set_block(0)
     for a in (0, 2):  # same block shape: same accumulation order whatever the staging
         assert np.array_equal(out[a][0], out[a + 1][0]) and np.array_equal(out[a][1], out[a + 1][1])
     d = (out[0][0].astype(np.longdouble) + out[0][1]) - (out[2][0].astype(np.longdouble) + out[2][1])

@@ -32,8 +32,8 @@ def main():
     lib = _lib.lib()
     peak = float(os.environ.get("FP64_PEAK", 18.3e12))
     hbm = float(os.environ.get("HBM_PEAK", 6550e9))
-    print("m | k | weighted | 4x4 plain us | 4x4 bulk us | 2x2 bulk us | fp64-bound us (useful entries) | hbm-bound us | "
-          "frac of max(bound), 2x2 bulk")
+    print("m | k | weighted | 4x4 plain us | 4x4 bulk us | 2x2 bulk us | default us | fp64-bound us (useful entries) | "
+          "hbm-bound us | frac of max(bound), default")
     for m in (1 << 20, 1 << 21):
         g = torch.Generator(device="cuda").manual_seed(1)
         kmax = 56
@@ -43,7 +43,7 @@ def main():
             basis.push()
         b = torch.randn(m, dtype=torch.float64, device="cuda", generator=g)
         w = torch.rand(m, dtype=torch.float64, device="cuda", generator=g) + 0.5
-        for k in (4, 8, 16, 28, 40, 54):
+        for k in (4, 8, 16, 20, 28, 32, 36, 40, 44, 48, 54):
             for wt in (None, w):
                 ext, ew = ((b,), (0,)) if wt is None else ((b, b), (0, 1))
 
@@ -68,6 +68,8 @@ def main():
                 lib.tb200_gram_set_bulk(1)
                 lib.tb200_gram_set_block(2)
                 res.append(timed(launch))
+                lib.tb200_gram_set_block(0)
+                res.append(timed(launch))
                 if wt is None:  # panel pass: the last basis column + the extra
                     def panel():
                         Kt = k + len(ext)
@@ -86,8 +88,8 @@ def main():
                 Kt = k + len(ext)
                 t_fp = Kt * (Kt + 1) / 2 * 10 * m / peak * 1e6  # 10 fp64 instructions per needed entry and row
                 t_hbm = 8 * m * (Kt + (wt is not None)) / hbm * 1e6
-                print(f"{m} | {k} | {wt is not None} | {res[0]:.1f} | {res[1]:.1f} | {res[2]:.1f} | {t_fp:.1f} | {t_hbm:.1f} | "
-                      f"{max(t_fp, t_hbm) / res[2]:.2f}", flush=True)
+                print(f"{m} | {k} | {wt is not None} | {res[0]:.1f} | {res[1]:.1f} | {res[2]:.1f} | {res[3]:.1f} | {t_fp:.1f} | {t_hbm:.1f} | "
+                      f"{max(t_fp, t_hbm) / res[3]:.2f}", flush=True)
         del basis
 
 

@@ -18,7 +18,8 @@ PSF = tb.gauss_psf((9, 9), (3, 3))
 Ab = tb.PSFBlur2D(PSF, n, n)
 xt = O.shepp_logan(n).reshape(-1, 1)
 b, delta = O.add_noise(O.blur_data(xt, PSF, n, n), 0.01, rng)
-tb.MMGKS(Ab, b, tb.FirstDerivative2D(n, n), pnorm=2, qnorm=1, projection_dim=3, n_iter=12, regparam="dp", delta=float(delta))
+tb.MMGKS(Ab, b, tb.FirstDerivative2D(n, n), pnorm=2, qnorm=1, projection_dim=3, n_iter=int(os.environ.get("N_ITER", 12)), regparam="dp",
+         delta=float(delta))
 if "--cfg5" in sys.argv:
     nx, nt, per = 256, 64, 12
     th = O.ct_angles(nt * per)

@@ -18,7 +18,6 @@
 
 namespace tb200 {
 
-constexpr int kGThreads = 256;
 constexpr int kGMaxExtra = 4;
 constexpr int kGBlocksX = 296;  // 2 CTAs per SM; fixed => deterministic reduction tree
 
@@ -108,7 +107,7 @@ gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const
                const __grid_constant__ GramExtras ex, int K, int c0, int npairs, int RG, int rpg, int S, int KC,
                double* __restrict__ partials) {
   constexpr int NE = BH * BW;
-  constexpr int kGThreads = NT;  // (shadows the default: this instance's CTA size)
+  const int kGThreads = blockDim.x;  // (shadows the default) this launch's CTA size: a multiple of 32, <= NT
   extern __shared__ __align__(16) double T[];  // [2][KC][rows]  (one buffer when !BULK)
   __shared__ uint64_t bars[2];
   const int nt = (K + BH - 1) / BH;  // row tiles (= column tiles of the square blocks)
@@ -140,6 +139,7 @@ gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const
     if (!active) return;
     const double* pa = Tb_ + (size_t)(BH * ti) * S + rg;
     const double* pb = Tb_ + (size_t)cb * S + rg;
+#pragma unroll 2
     for (int i = 0; i < rpg; ++i) {
       double a[BH], b[BW];
 #pragma unroll
@@ -327,18 +327,32 @@ static inline size_t gram_reduce_bytes(int ne, int threads) { return (size_t)(2 
 constexpr size_t kGBufBytes = 54 * 1024;  // one staging buffer; two buffers per CTA, two CTAs per SM
 
 // bs: side of the square blocks of the full pass (4 or 2); the panel pass uses 4 x 1 blocks.  threads: CTA size.
-static void gram_shape(int K, bool has_w, int c0, int bs, int threads, int& KC, int& npairs, int& RG, int& gy, int& rpg,
-                       int& S) {
-  const int kGThreads = threads;
+static void gram_shape(int K, bool has_w, int c0, int bs, int max_threads, int& KC, int& npairs, int& RG, int& gy, int& rpg,
+                       int& S, int& threads) {
   if (c0 >= 0) bs = 4;
   const int nt = (K + bs - 1) / bs;
   const int Kw = K + (has_w ? 1 : 0);
   KC = bs * nt > Kw ? bs * nt : Kw;
   npairs = c0 < 0 ? nt * (nt + 1) / 2 : nt * (K - c0);  // items: bs x bs blocks, or 4 x 1 blocks of the panel
-  // as many row groups as fit one CTA next to the 4 x 4 blocks (K <= 4: one block, 256 groups), so that (nearly) every
-  // thread accumulates; several CTAs in y only when there are more blocks than threads
-  RG = npairs <= kGThreads ? kGThreads / npairs : 1;
-  gy = (npairs * RG + kGThreads - 1) / kGThreads;
+  // Threads: one per (item, row group).  The CTA size is what the items need, not a fixed 256 / 512: with 276 items a
+  // 512-thread CTA would leave 46 % of its threads idle (measured: fp64 pipe 63 % busy at K = 46).  Among the row-group
+  // counts that fit, take the one with the best product of (useful lanes / launched lanes) and (balance of the two
+  // resident CTAs' warps over the four schedulers of an SM); ties go to the larger CTA.
+  RG = 1, threads = 32;
+  if (npairs > max_threads) {
+    gy = (npairs + max_threads - 1) / max_threads;
+    threads = ((npairs + gy - 1) / gy + 31) / 32 * 32;
+  } else {
+    gy = 1;
+    double best = -1.0;
+    for (int rg = 1; rg * npairs <= max_threads; ++rg) {
+      const int t = (rg * npairs + 31) / 32 * 32;
+      const int wps = 2 * t / 32;  // warps of two resident CTAs
+      // (a larger CTA also hides more latency: measured at K = 17, 512 threads at 0.97 beat 320 at 0.98)
+      const double score = (double)(rg * npairs) / t * (wps / 4.0) / ((wps + 3) / 4) * (0.85 + 0.15 * t / max_threads);
+      if (score >= best) best = score, RG = rg, threads = t;
+    }
+  }
   // ~256 rows per tile (one barrier pair per tile), an even number of rows (16-byte columns), within one buffer
   const int step = (RG & 1) ? 2 : 1;
   rpg = (256 + RG - 1) / RG;
@@ -396,14 +410,14 @@ static inline hdd h_sqrt(hdd a) {
 using namespace tb200;
 
 static bool g_gram_bulk = true;
-static int g_gram_block = 2;
+static int g_gram_block = 0;
 
 extern "C" {
 
 // A/B switch for tests and tuning: 0 = stage every tile with ordinary loads (single buffer), 1 = bulk copies (default).
 void tb200_gram_set_bulk(int on) { g_gram_bulk = on != 0; }
-// Block shape of the full pass: 2 (default; 2 x 2 blocks, 512 threads) or 4 (4 x 4 blocks, 256 threads).
-void tb200_gram_set_block(int bs) { g_gram_block = bs == 4 ? 4 : 2; }
+// Block shape of the full pass: 0 (default) = chosen per K, 2 = 2 x 2 blocks (<= 512 threads), 4 = 4 x 4 blocks (<= 256).
+void tb200_gram_set_block(int bs) { g_gram_block = (bs == 4 || bs == 2) ? bs : 0; }
 
 // Workspace (doubles) for a Gram pass over K = k + n_extra columns.
 int64_t tb200_gram_workspace_len(int64_t K) {
@@ -430,12 +444,17 @@ static int gram_launch(int64_t m, int64_t k, const double* B, int64_t ld, const 
     ex.weighted[i] = (i < n_extra && extra_weighted) ? extra_weighted[i] : 0;
     TB200_REQUIRE(i >= n_extra || ex.ptr[i], "null extra column");
   }
-  // full pass: 2 x 2 blocks on 512 threads by default (finer items: fewer idle threads and padded entries than 4 x 4 on
-  // 256), 4 x 4 for K > 128 where the items outnumber the threads anyway; panel: 4 x 1 on 256
-  const int bs = c0 >= 0 ? 4 : ((g_gram_block == 2 && K <= 128) ? 2 : 4);
-  const int threads = (c0 < 0 && bs == 2) ? 512 : 256;
-  int KC, npairs, RG, gy, rpg, S;
-  gram_shape(K, w != nullptr, c0, bs, threads, KC, npairs, RG, gy, rpg, S);
+  // full pass: 2 x 2 blocks on up to 512 threads (finer items: fewer idle threads and padded entries; measured 10-40 %
+  // faster than 4 x 4 blocks on 256 threads for K <= 56) - except where its items fill only ~300 threads of a CTA
+  // (K = 45..48: 276 / 300 items, one row group), where four independent accumulations per thread on 9 warps do not keep
+  // the pipe busy and the 4 x 4 shape (16 per thread) is 12 % faster.  K > 128: 4 x 4.  Panel: 4 x 1 blocks on 256.
+  int bs = 4, max_threads = 256;
+  int KC, npairs, RG, gy, rpg, S, threads;
+  if (c0 < 0 && K <= 128 && g_gram_block != 4) {
+    gram_shape(K, w != nullptr, c0, 2, 512, KC, npairs, RG, gy, rpg, S, threads);
+    if (g_gram_block == 2 || threads >= 320) bs = 2, max_threads = 512;
+  }
+  gram_shape(K, w != nullptr, c0, bs, max_threads, KC, npairs, RG, gy, rpg, S, threads);
   TB200_REQUIRE((size_t)S * KC * sizeof(double) <= kGBufBytes, "k + n_extra too large for one shared-memory tile");
   // bulk copies need every column segment 16-byte aligned (rows is even): B, ld, the extras and w
   bool bulk = g_gram_bulk && ((uintptr_t)B % 16 == 0) && (ld % 2 == 0) && (!w || (uintptr_t)w % 16 == 0);
