@@ -7,6 +7,31 @@ import trips_oracle as O
 from conftest import GOLDEN
 
 
+def test_spectral_gcv_objective_equals_the_solve_based_form():
+    """generalized_crossvalidation evaluates the objective from one SVD of R_A R_L^-1; gcv_value is the reference's
+    two-solves-per-evaluation form (gcv.py:25-78).  Same function of lambda, square and (k+1) x k, L = I and triangular
+    L, 'modified' trace size; a singular R_L falls back to the solve-based form."""
+    from trips_b200.reg_param import gcv as G
+
+    rng = np.random.default_rng(12)
+    for k, rect, ident in ((6, False, False), (17, True, True), (40, False, False), (40, True, True), (9, True, False)):
+        RA = np.triu(rng.standard_normal((k, k))) + np.diag(np.logspace(0.5, -2, k))
+        if rect:
+            RA = np.vstack((RA, np.zeros((1, k))))
+            RA[k, k - 1] = 0.3
+        RL = np.eye(k) if ident else np.triu(rng.standard_normal((k, k))) + 2 * np.eye(k)
+        c = rng.standard_normal((RA.shape[0], 1))
+        s2, ch2 = G._spectral_form(RA, RL, c)
+        for trace_size in (RA.shape[0], 500):
+            for lam in (1e-6, 1e-3, 0.2, 30.0):
+                d = s2 + lam
+                got = float(np.dot((lam / d) ** 2, ch2)) / (trace_size - float(np.sum(s2 / d))) ** 2
+                assert got == pytest.approx(G.gcv_value(lam, RA, RL, c, trace_size), rel=1e-9)
+    RL = np.triu(rng.standard_normal((5, 5)))
+    RL[2, 2] = 0.0
+    assert G._spectral_form(np.eye(5), RL, np.ones((5, 1))) is None
+
+
 def test_product_gcv_matches_reference_values():
     from trips_b200.reg_param import generalized_crossvalidation
     from trips_b200.reg_param.gcv import gcv_value
