@@ -189,6 +189,25 @@ int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geo
                          const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
                          double* xT_scratch, const double* x, double* y, double coef_host, const double* coef_dev,
                          const double* z, double* norm_out, double* ws, void* stream);
+/* The STORED parallel-beam CT matrix over the same row-aligned index layout: tb200_ct_fill_rows_aligned_vals writes the
+ * values next to the indices, tb200_ct_spmv_sell_f64 is the SELL-32-4 product y = A x - coef*z on it (vals double, or
+ * float with vals_f32 != 0), tb200_gk_step_sell_ct_f64 one golub_kahan_update (decompositions.py:230-255) with A in this
+ * layout and A^T plain SELL.  Same bits as tb200_spmv_sell_f64 / scipy on the plain layout; the x-gathers of the A launch
+ * share sectors (the north-star's stored CSR SpMV, trips/utilities/decompositions.py:240). */
+int tb200_ct_fill_rows_aligned_vals(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
+                                    const int64_t* sliceptr, const int32_t* rowskip, int transpose_shallow, int32_t* colidx,
+                                    double* vals, void* stream);
+int tb200_ct_spmv_sell_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
+                           const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const void* vals,
+                           int vals_f32, const int32_t* cta_order, double* xT_scratch, const double* x, double* y,
+                           double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
+                           void* stream);
+int tb200_gk_step_sell_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* a_sliceptr,
+                              const int32_t* a_rowlen, const int32_t* a_rowskip, const int32_t* a_col, const double* a_val,
+                              const int32_t* a_cta_order, double* xT_scratch, const int64_t* at_sliceptr,
+                              const int32_t* at_rowlen, const int32_t* at_col, const double* at_val, const double* u_k,
+                              const double* v_prev, const double* beta_prev_dev, double* v_out, double* u_out,
+                              double* alpha_pair, double* beta_pair, double* ws, void* const* events_host, void* stream);
 /* Ray-driven forward projection with NO index array (csrc/ct_forward.cu): the pixels of a ray are enumerated row by row
  * from the ray equation (candidate bracket + the builder's exact predicate), summed in ascending column index: same
  * bits as tb200_ct_forward_f64 / tb200_spmv_sell_f64 on the stored matrix and as scipy's A @ x.  Replaces `A @ v`

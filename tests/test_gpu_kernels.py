@@ -402,6 +402,42 @@ def test_matrix_free_projectors_are_bit_identical_to_the_stored_matrix(tb, nx, n
     assert (mf.to_scipy() != A0).nnz == 0  # explicit() materialises the same matrix on demand
 
 
+@pytest.mark.parametrize("nx,ny,views,n_det,angles", [
+    (24, None, 16, None, None), (64, None, 90, None, None), (33, 20, 7, None, None), (40, 56, 9, 70, None),
+    (48, None, 5, None, [0.0, np.pi / 2, np.pi / 4, 3 * np.pi / 4, 3.0]), (128, None, 13, None, None),
+    (20, None, len(AWKWARD), 29, AWKWARD), (130, 70, 40, None, None), (96, 200, 24, 333, None)])
+def test_row_aligned_stored_sell_layout_is_bit_identical_to_the_plain_one(tb, nx, ny, views, n_det, angles, monkeypatch):
+    """ParallelBeamCT(layout='sell') stores A in the row-aligned layout of the index-only projector with the values next
+    to the indices (leading padding per ray, shallow rays addressing the transposed image): the same matrix (to_scipy),
+    the same bits of A x with and without the fused epilogue, in fp32 storage too, and the same Golub-Kahan factors as
+    the plain SELL layout (TB200_SELL_ALIGNED=0)."""
+    import torch
+
+    kw = dict(ny=ny, n_det=n_det, angles=None if angles is None else np.array(angles))
+    op = tb.ParallelBeamCT(nx, views, layout="sell", **kw)
+    assert isinstance(op.A_sell, tb.kernels.CtSellDevice)
+    monkeypatch.setenv("TB200_SELL_ALIGNED", "0")
+    plain = tb.ParallelBeamCT(nx, views, layout="sell", **kw)
+    monkeypatch.delenv("TB200_SELL_ALIGNED")
+    assert not isinstance(plain.A_sell, tb.kernels.CtSellDevice)
+    A0 = tb.ParallelBeamCT(nx, views, layout="csr", **kw).to_scipy()
+    As = op.to_scipy()
+    assert np.array_equal(As.indptr, A0.indptr) and np.array_equal(As.indices, A0.indices) and np.array_equal(As.data, A0.data)
+    rng = np.random.default_rng(9)
+    x, z = rng.standard_normal(A0.shape[1]), rng.standard_normal(A0.shape[0])
+    assert np.array_equal(host(op.apply_dev(dev(x))), A0 @ x)
+    coef = torch.tensor([0.37], dtype=torch.float64, device="cuda")
+    pair = torch.zeros(2, dtype=torch.float64, device="cuda")
+    y = host(op.apply_dev(dev(x), coef=coef, z=dev(z), norm_out=pair))
+    want = A0 @ x - 0.37 * z
+    assert np.array_equal(y, want) and float(pair[1]) == float(np.sqrt(O.exact_dot(want, want)))
+    assert np.array_equal(host(op.with_f32_storage().apply_dev(dev(x))), host(plain.with_f32_storage().apply_dev(dev(x))))
+    b = rng.standard_normal(A0.shape[0])
+    got, ref = tb.golub_kahan_device(op, b, 6), tb.golub_kahan_device(plain, b, 6)
+    assert np.array_equal(got.B_host(), ref.B_host())
+    assert np.array_equal(got.U.to_numpy(), ref.U.to_numpy()) and np.array_equal(got.V.to_numpy(), ref.V.to_numpy())
+
+
 @pytest.mark.parametrize("forward", ["rays", "index"])
 def test_matrix_free_golub_kahan_equals_stored_matrix_golub_kahan(tb, forward):
     nx, views, steps = 48, 36, 12

@@ -62,6 +62,10 @@ SIGNATURES = {
     "tb200_ct_geometry": (c_int, [c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_count_rows_first": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_fill_rows_aligned": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr]),
+    "tb200_ct_fill_rows_aligned_vals": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
+    "tb200_ct_spmv_sell_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr,
+                                       c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "tb200_gk_step_sell_ct_f64": (c_int, [c_int, c_int, c_int, c_int] + [c_ptr] * 22),
     "tb200_ct_forward_f64": (c_int, [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "tb200_ct_forward_rays_workspace_len": (c_i64, [c_int, c_int]),
     "tb200_ct_forward_set_tuning": (c_int, [c_dbl, c_int]),

@@ -324,6 +324,14 @@ int tb200_ct_count_rows_first(int nx, int ny, int n_det, int n_ang, const double
   TB200_REQUIRE(first_row != nullptr || (int64_t)n_ang * n_det == 0, "null first_row");
   return count_rows(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, counts, stream, first_row, first_run);
 }
+// the same fill with the VALUES written next to the indices (the stored row-aligned layout of tb200_ct_spmv_sell_f64)
+int tb200_ct_fill_rows_aligned_vals(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
+                                    const int64_t* sliceptr, const int32_t* rowskip, int transpose_shallow, int32_t* colidx,
+                                    double* vals, void* stream) {
+  TB200_REQUIRE(vals != nullptr || (int64_t)n_ang * n_det == 0, "null vals");
+  return fill_rows(PARALLEL, nx, ny, n_det, n_ang, cosv, sinv, sliceptr, 1, colidx, vals, stream, rowskip,
+                   transpose_shallow);
+}
 int tb200_ct_fill_rows_aligned(int nx, int ny, int n_det, int n_ang, const double* cosv, const double* sinv,
                                const int64_t* sliceptr, const int32_t* rowskip, int transpose_shallow, int32_t* colidx,
                                void* stream) {

@@ -581,7 +581,7 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
   const uint64_t pol_keep = policy_evict_last();
   const uint64_t pol_stream = policy_evict_first();
   const double coef = (z != nullptr) ? (coef_dev ? *coef_dev : coef_host) : 0.0;
-  const int64_t group = (GEOM && ct.cta_order != nullptr) ? (int64_t)ct.cta_order[blockIdx.x] : (int64_t)blockIdx.x;
+  const int64_t group = (ct.cta_order != nullptr) ? (int64_t)ct.cta_order[blockIdx.x] : (int64_t)blockIdx.x;
   const int64_t slice = group * WARPS + warp;
   const int64_t nslices = (m + 31) >> 5;
   const int64_t row = slice * 32 + lane;
@@ -592,7 +592,7 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
     w = (int)((sliceptr[slice + 1] - base) >> 5);
     if (row < m) {
       len = rowlen[row];
-      if (GEOM && ct.rowskip != nullptr) skip = ct.rowskip[row];
+      if (ct.rowskip != nullptr) skip = ct.rowskip[row];
     }
   }
   const int nit = (w + CH - 1) / CH;
@@ -619,6 +619,13 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
     } else {
       bias_q = centred_bias(ct.ny), coef_q = g.s, bias_r = centred_bias(ct.nx), coef_r = g.c;
     }
+  }
+  if (!GEOM && ct.xT != nullptr) {
+    // stored values over the row-aligned CT index layout (tb200_ct_spmv_sell_f64): the indices of a shallow ray address
+    // the transposed image, exactly as in the GEOM case - only the gather base depends on the ray
+    const int64_t r = (row < m) ? row : 0;
+    const double* gp = ct.geom + 6 * (r / ct.n_det);
+    if (fabs(gp[1]) > fabs(gp[0])) xb = ct.xT;
   }
   auto entry_values = [&](const int32_t (&c)[CH], double (&v)[CH]) {
 #pragma unroll
@@ -704,7 +711,7 @@ spmv_sell_kernel(int64_t m, const int64_t* __restrict__ sliceptr, const int32_t*
       const unsigned along = __ballot_sync(0xffffffffu, ok && (c1[PB + 1] - c1[PB]) <= 2 && (c1[PB] - c1[PB - 1]) <= 2);
       const unsigned across = __ballot_sync(0xffffffffu, ok && okn && abs(c1[PB] - cn) <= 6);
       row_major = __popc(along) > __popc(across) + 8;
-      if (gather_mode == 1 || (GEOM && ct.xT != nullptr)) row_major = false;  // shallow rays read the transposed image
+      if (gather_mode == 1 || ct.xT != nullptr) row_major = false;  // shallow rays read the transposed image
       if (gather_mode == 2) row_major = true;
     }
     if (row_major) gather_row_major(c1, x0);
@@ -1125,17 +1132,8 @@ int tb200_spmv_sell_f32s(int64_t m, int64_t n, const int64_t* sliceptr, const in
 // long central rays are scheduled before the short peripheral ones.  rowskip (nullable): leading padding of each row
 // inside its lane (tb200_ct_fill_rows_aligned).  xT_scratch: nx*ny doubles, REQUIRED iff the indices were filled with
 // transpose_shallow != 0 (the image is transposed into it first), NULL otherwise.
-int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
-                         const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
-                         double* xT_scratch, const double* x, double* y, double coef_host, const double* coef_dev,
-                         const double* z, double* norm_out, double* ws, void* stream) {
-  TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0 && (int64_t)nx * ny < ((int64_t)1 << 31), "bad geometry");
-  const int64_t m = (int64_t)n_ang * n_det;
-  int rc = check_sell_args(m, (int64_t)nx * ny, sliceptr, rowlen, colidx, nullptr, x, y, norm_out, ws);
-  if (rc) return rc;
-  TB200_REQUIRE(geom != nullptr || m == 0, "null geometry table");
-  if (m == 0) return 0;
-  CtRays ct;
+static int ct_rays_setup(int nx, int ny, int n_det, const double* geom, const int32_t* rowskip, const int32_t* cta_order,
+                         double* xT_scratch, const double* x, void* stream, CtRays& ct) {
   ct.geom = geom;
   ct.cta_order = (g_sell_warps == 4) ? cta_order : nullptr;  // the order is a permutation of groups of FOUR slices
   ct.rowskip = rowskip;
@@ -1148,7 +1146,7 @@ int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geo
   if (xT_scratch != nullptr) {  // xT[ix*ny + iy] = x[iy*nx + ix]
     const dim3 tg((unsigned)((nx + 31) / 32), (unsigned)((ny + 31) / 32));
     transpose_f64_kernel<<<tg, dim3(32, 8), 0, (cudaStream_t)stream>>>(ny, nx, x, xT_scratch);
-    rc = check_launch("ct_forward transpose");
+    int rc = check_launch("ct_forward transpose");
     if (rc) return rc;
   }
   ct.nx = nx, ct.ny = ny, ct.n_det = n_det;
@@ -1157,8 +1155,51 @@ int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geo
   const uint64_t mg = (((uint64_t)1) << (32 + sh)) / (uint64_t)nx;
   ct.nx_magic = (uint32_t)(mg > 0xffffffffull ? 0xffffffffull : mg);
   ct.nx_shift = sh;
+  return 0;
+}
+
+int tb200_ct_forward_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
+                         const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const int32_t* cta_order,
+                         double* xT_scratch, const double* x, double* y, double coef_host, const double* coef_dev,
+                         const double* z, double* norm_out, double* ws, void* stream) {
+  TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0 && (int64_t)nx * ny < ((int64_t)1 << 31), "bad geometry");
+  const int64_t m = (int64_t)n_ang * n_det;
+  int rc = check_sell_args(m, (int64_t)nx * ny, sliceptr, rowlen, colidx, nullptr, x, y, norm_out, ws);
+  if (rc) return rc;
+  TB200_REQUIRE(geom != nullptr || m == 0, "null geometry table");
+  if (m == 0) return 0;
+  CtRays ct;
+  rc = ct_rays_setup(nx, ny, n_det, geom, rowskip, cta_order, xT_scratch, x, stream, ct);
+  if (rc) return rc;
   return sell_launch<double, true, 8>(m, sliceptr, rowlen, colidx, (const double*)nullptr, x, y, coef_host, coef_dev, z,
                                    norm_out, ws, (cudaStream_t)stream, ct);
+}
+
+// y = A x - coef*z with the STORED values of the parallel-beam CT matrix over the same row-aligned index layout
+// (tb200_ct_fill_rows_aligned_vals): the stored SELL-32-4 product whose x-gathers share sectors the way the index-only
+// projector's do - rowskip aligns the rays of a slice on the image rows, shallow rays address the transposed image formed
+// in xT_scratch (REQUIRED iff filled with transpose_shallow != 0), cta_order schedules the long slices first.
+// vals: double, or float when vals_f32 != 0 (fp32 storage, fp64 accumulation).  Same bits as tb200_spmv_sell_f64 on the
+// plain layout: the order in which a row's entries are added is the same.
+int tb200_ct_spmv_sell_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* sliceptr,
+                           const int32_t* rowlen, const int32_t* rowskip, const int32_t* colidx, const void* vals,
+                           int vals_f32, const int32_t* cta_order, double* xT_scratch, const double* x, double* y,
+                           double coef_host, const double* coef_dev, const double* z, double* norm_out, double* ws,
+                           void* stream) {
+  TB200_REQUIRE(nx > 0 && ny > 0 && n_det > 0 && n_ang >= 0 && (int64_t)nx * ny < ((int64_t)1 << 31), "bad geometry");
+  const int64_t m = (int64_t)n_ang * n_det;
+  int rc = check_sell_args(m, (int64_t)nx * ny, sliceptr, rowlen, colidx, vals, x, y, norm_out, ws);
+  if (rc) return rc;
+  TB200_REQUIRE(geom != nullptr || m == 0, "null geometry table");
+  if (m == 0) return 0;
+  CtRays ct;
+  rc = ct_rays_setup(nx, ny, n_det, geom, rowskip, cta_order, xT_scratch, x, stream, ct);
+  if (rc) return rc;
+  if (vals_f32)
+    return sell_launch<float>(m, sliceptr, rowlen, colidx, (const float*)vals, x, y, coef_host, coef_dev, z, norm_out, ws,
+                              (cudaStream_t)stream, ct);
+  return sell_launch<double>(m, sliceptr, rowlen, colidx, (const double*)vals, x, y, coef_host, coef_dev, z, norm_out, ws,
+                             (cudaStream_t)stream, ct);
 }
 
 // One Golub-Kahan step (the reference's golub_kahan_update, trips/utilities/decompositions.py:230-255) on SELL-32-4
@@ -1190,6 +1231,35 @@ int tb200_gk_step_sell_f64(int64_t m, int64_t n, const int64_t* a_sliceptr, cons
   mark(2);
   rc = tb200_spmv_sell_f64(m, n, a_sliceptr, a_rowlen, a_col, a_val, v_out, u_out, 0.0, alpha_pair + 1, u_k, beta_pair, ws,
                            stream);
+  mark(3);
+  if (rc) return rc;
+  return tb200_vec_div(m, u_out, 0.0, beta_pair + 1, u_out, stream);
+}
+
+// The same Golub-Kahan step with A in the row-aligned CT layout (tb200_ct_spmv_sell_f64) and A^T as a plain SELL matrix.
+int tb200_gk_step_sell_ct_f64(int nx, int ny, int n_det, int n_ang, const double* geom, const int64_t* a_sliceptr,
+                              const int32_t* a_rowlen, const int32_t* a_rowskip, const int32_t* a_col, const double* a_val,
+                              const int32_t* a_cta_order, double* xT_scratch, const int64_t* at_sliceptr,
+                              const int32_t* at_rowlen, const int32_t* at_col, const double* at_val, const double* u_k,
+                              const double* v_prev, const double* beta_prev_dev, double* v_out, double* u_out,
+                              double* alpha_pair, double* beta_pair, double* ws, void* const* events_host, void* stream) {
+  TB200_REQUIRE(u_k && v_out && u_out && alpha_pair && beta_pair && ws, "null pointer");
+  TB200_REQUIRE((v_prev == nullptr) == (beta_prev_dev == nullptr), "v_prev and beta_prev_dev go together");
+  const int64_t m = (int64_t)n_ang * n_det, n = (int64_t)nx * ny;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto mark = [&](int i) {
+    if (events_host != nullptr && events_host[i] != nullptr) cudaEventRecord((cudaEvent_t)events_host[i], st);
+  };
+  mark(0);
+  int rc = tb200_spmv_sell_f64(n, m, at_sliceptr, at_rowlen, at_col, at_val, u_k, v_out, 0.0, beta_prev_dev, v_prev,
+                               alpha_pair, ws, stream);
+  mark(1);
+  if (rc) return rc;
+  rc = tb200_vec_div(n, v_out, 0.0, alpha_pair + 1, v_out, stream);
+  if (rc) return rc;
+  mark(2);
+  rc = tb200_ct_spmv_sell_f64(nx, ny, n_det, n_ang, geom, a_sliceptr, a_rowlen, a_rowskip, a_col, a_val, 0, a_cta_order,
+                              xT_scratch, v_out, u_out, 0.0, alpha_pair + 1, u_k, beta_pair, ws, stream);
   mark(3);
   if (rc) return rc;
   return tb200_vec_div(m, u_out, 0.0, beta_pair + 1, u_out, stream);

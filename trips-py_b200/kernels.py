@@ -144,13 +144,16 @@ class CSRDevice:
 ORDERS = {"sequential": 0, "tree": 1}
 
 
-def _sell_addresses(sliceptr, rowlen):
-    """Device tensors (row, addr) for every stored entry of a SELL-32-4 matrix, in CSR (row-major) order."""
+def _sell_addresses(sliceptr, rowlen, skip=None):
+    """Device tensors (row, addr) for every stored entry of a SELL-32-4 matrix, in CSR (row-major) order; skip: leading
+    padding of each row inside its lane (row-aligned CT layout)."""
     m = rowlen.numel()
     rows = torch.repeat_interleave(torch.arange(m, device=rowlen.device, dtype=torch.int64), rowlen.to(torch.int64))
     start = torch.zeros(m + 1, dtype=torch.int64, device=rowlen.device)
     torch.cumsum(rowlen.to(torch.int64), 0, out=start[1:])
     j = torch.arange(rows.numel(), device=rowlen.device, dtype=torch.int64) - start[rows]
+    if skip is not None:
+        j = j + skip.to(torch.int64)[rows]
     addr = sliceptr[rows >> 5] + (j >> 2) * 128 + (rows & 31) * 4 + (j & 3)
     return rows, addr, start
 
@@ -205,6 +208,43 @@ class SellDevice:
         return SellDevice(self.shape, self.sliceptr, self.rowlen, self.colidx, self.vals.to(torch.float32))
 
 
+class CtSellDevice(SellDevice):
+    """The stored parallel-beam CT matrix A (rows = rays) in the ROW-ALIGNED SELL-32-4 layout of the index-only projector
+    (CTProjector(forward='index')), values next to the indices: entry j of ray r sits at position rowskip[r] + j of its
+    lane, so that the 32 rays of a slice cross the same image rows at the same positions and their x-gathers share
+    32-byte sectors; the indices of shallow rays (|sin| > |cos|) address the transposed image, formed per product in
+    `xT`.  The order in which a row's entries are added is CSR order: same bits as the plain layout and as scipy."""
+
+    def __init__(self, proj, vals):
+        SellDevice.__init__(self, proj.shape, proj.sliceptr, proj.rowlen, proj.colidx, vals)
+        self.proj = proj  # geometry table, rowskip, xT scratch, cta_order, nx / ny / n_det / n_ang
+
+    def to_csr(self):
+        p = self.proj
+        skip = p.rowskip if p.rowskip is not None else torch.zeros_like(self.rowlen)
+        rows, addr, start = _sell_addresses(self.sliceptr, self.rowlen, skip)
+        col = self.colidx[addr].to(torch.int64)
+        if p.tshallow:  # ix*ny + iy -> iy*nx + ix for the rows whose indices address the transposed image
+            ang = rows // p.n_det
+            shallow = (p.sin_t.abs() > p.cos_t.abs())[ang]
+            col = torch.where(shallow, (col % p.ny) * p.nx + col // p.ny, col)
+        return CSRDevice(self.shape, start, col.to(torch.int32).contiguous(), self.vals[addr].contiguous())
+
+    def to_f32_storage(self):
+        return CtSellDevice(self.proj, self.vals.to(torch.float32))
+
+    @property
+    def nbytes(self):
+        p = self.proj
+        return (SellDevice.nbytes.fget(self) + (4 * p.rowskip.numel() if p.rowskip is not None else 0)
+                + (8 * p.xT.numel() if p.xT is not None else 0) + 8 * p.geom.numel())
+
+
+def _ct_sell_args(A):
+    p = A.proj
+    return (p.nx, p.ny, p.n_det, p.n_ang, _p(p.geom), _p(A.sliceptr), _p(A.rowlen), _p(p.rowskip), _p(A.colidx), _p(A.vals))
+
+
 def _spmv_sell(A, x, out, coef, z, norm_out):
     m, n = A.shape
     coef_host, coef_dev = 0.0, None
@@ -214,6 +254,13 @@ def _spmv_sell(A, x, out, coef, z, norm_out):
         else:
             coef_host = float(coef)
     ws = Workspace.get(A.device).spmv(m) if norm_out is not None else None
+    if isinstance(A, CtSellDevice):
+        p = A.proj
+        check(lib().tb200_ct_spmv_sell_f64(*_ct_sell_args(A), int(A.vals.dtype != F64), _p(p.cta_order), _p(p.xT), _p(x),
+                                           _p(out), coef_host, _p(coef_dev), _p(z), _p(norm_out), _p(ws), _stream()),
+              "ct_spmv_sell")
+        _lib.count((2 if norm_out is not None else 1) + (1 if p.xT is not None else 0))
+        return out
     fn = lib().tb200_spmv_sell_f64 if A.vals.dtype == F64 else lib().tb200_spmv_sell_f32s
     check(fn(m, n, _p(A.sliceptr), _p(A.rowlen), _p(A.colidx), _p(A.vals), _p(x), _p(out), coef_host, _p(coef_dev), _p(z),
              _p(norm_out), _p(ws), _stream()), "spmv_sell")
@@ -231,6 +278,13 @@ def gk_step_sell(A, AT, u_k, v_prev, beta_prev, v_out, u_out, alpha_pair, beta_p
     ev = None
     if GK_STEP_EVENTS is not None:
         ev = (ctypes.c_void_p * 4)(*[e.cuda_event for e in GK_STEP_EVENTS()])
+    if isinstance(A, CtSellDevice) and A.vals.dtype == F64:
+        p = A.proj
+        check(lib().tb200_gk_step_sell_ct_f64(*_ct_sell_args(A), _p(p.cta_order), _p(p.xT), _p(AT.sliceptr), _p(AT.rowlen),
+                                              _p(AT.colidx), _p(AT.vals), _p(u_k), _p(v_prev), _p(beta_prev), _p(v_out),
+                                              _p(u_out), _p(alpha_pair), _p(beta_pair), _p(ws), ev, _stream()), "gk_step")
+        _lib.count(6 + (1 if p.xT is not None else 0))
+        return
     check(lib().tb200_gk_step_sell_f64(m, n, _p(A.sliceptr), _p(A.rowlen), _p(A.colidx), _p(A.vals), _p(AT.sliceptr),
                                        _p(AT.rowlen), _p(AT.colidx), _p(AT.vals), _p(u_k), _p(v_prev), _p(beta_prev),
                                        _p(v_out), _p(u_out), _p(alpha_pair), _p(beta_pair), _p(ws), ev, _stream()), "gk_step")
@@ -551,6 +605,13 @@ def ct_build(nx, ny, n_det, cos_t, sin_t, transpose=False, layout="csr", fan=Non
     return CSRDevice(shape, rowptr, colidx, vals)
 
 
+def ct_build_aligned(nx, ny, n_det, cos_t, sin_t):
+    """The stored parallel-beam A in the row-aligned SELL-32-4 layout (CtSellDevice)."""
+    proj = CTProjector(nx, ny, n_det, cos_t, sin_t, forward="stored")
+    vals, proj.vals = proj.vals, None
+    return CtSellDevice(proj, vals)
+
+
 def forward_cta_order(nx, ny, n_det, cos_t, sin_t, device, force=False):
     """Heaviest-first CTA list of the ray-driven forward projector (tb200_ct_forward_rays_f64, cta_order): entry b =
     angle * blocks_per_angle + block.  The work of a CTA is estimated from the geometry - per ray the image rows it can
@@ -593,8 +654,9 @@ class CTProjector:
     """Matrix-free parallel-beam CT operator (csrc/ct_forward.cu, ct_project.cu): neither values nor indices are stored.
     forward='rays' (default): the ray-driven forward projector enumerates each ray's pixels on the fly; back-projection
     is pixel-driven.  forward='index' is round 1's projector, which streams A's SELL-32-4 column indices (4 B per entry)
-    and re-evaluates only the values - kept for A/B measurements (TB200_CT_FORWARD=index).  All bit-identical to the
-    stored-matrix SpMVs."""
+    and re-evaluates only the values - kept for A/B measurements (TB200_CT_FORWARD=index).  forward='stored' builds the
+    same row-aligned index layout WITH the values (the A side of ParallelBeamCT(layout='sell'), see CtSellDevice).  All
+    bit-identical to the stored-matrix SpMVs."""
 
     def __init__(self, nx, ny, n_det, cos_t, sin_t, align=True, forward=None):
         dev = cos_t.device
@@ -607,13 +669,14 @@ class CTProjector:
         check(lib().tb200_ct_geometry(self.n_ang, _p(cos_t), _p(sin_t), _p(self.geom), _stream()), "ct_geometry")
         _lib.count(1)
         self.forward_mode = forward or os.environ.get("TB200_CT_FORWARD", "rays")
-        if self.forward_mode not in ("rays", "index"):
-            raise ValueError("forward must be 'rays' or 'index'")
+        if self.forward_mode not in ("rays", "index", "stored"):
+            raise ValueError("forward must be 'rays', 'index' or 'stored'")
         self._nnz = None
-        self.sliceptr = self.rowlen = self.rowskip = self.colidx = self.cta_order = self.xT = None
+        self.sliceptr = self.rowlen = self.rowskip = self.colidx = self.cta_order = self.xT = self.vals = None
         self.stored = 0
-        if self.forward_mode == "index":
-            self._build_index(align)
+        self.tshallow = False
+        if self.forward_mode in ("index", "stored"):
+            self._build_index(align, with_vals=self.forward_mode == "stored")
         elif os.environ.get("TB200_CT_FORWARD_ORDER", "lpt") == "lpt":
             self.cta_order = forward_cta_order(self.nx, self.ny, self.n_det, cos_t, sin_t, dev)
 
@@ -628,7 +691,7 @@ class CTProjector:
             self._nnz = int(counts.to(torch.int64).sum().item())
         return self._nnz
 
-    def _build_index(self, align):
+    def _build_index(self, align, with_vals=False):
         dev, m = self.device, self.shape[0]
         cos_t, sin_t = self.cos_t, self.sin_t
         self.rowlen = torch.zeros(m, dtype=torch.int32, device=dev)
@@ -679,9 +742,15 @@ class CTProjector:
         self.sliceptr = sell_slice_pointers(span)
         total = int(self.sliceptr[-1].item())
         self.colidx = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)[:total]
-        check(lib().tb200_ct_fill_rows_aligned(self.nx, self.ny, self.n_det, self.n_ang, _p(cos_t), _p(sin_t),
-                                               _p(self.sliceptr), _p(self.rowskip), int(self.tshallow), _p(self.colidx),
-                                               _stream()), "ct_fill")
+        if with_vals:
+            self.vals = torch.zeros(max(total, 1), dtype=F64, device=dev)[:total]
+            check(lib().tb200_ct_fill_rows_aligned_vals(self.nx, self.ny, self.n_det, self.n_ang, _p(cos_t), _p(sin_t),
+                                                        _p(self.sliceptr), _p(self.rowskip), int(self.tshallow),
+                                                        _p(self.colidx), _p(self.vals), _stream()), "ct_fill")
+        else:
+            check(lib().tb200_ct_fill_rows_aligned(self.nx, self.ny, self.n_det, self.n_ang, _p(cos_t), _p(sin_t),
+                                                   _p(self.sliceptr), _p(self.rowskip), int(self.tshallow), _p(self.colidx),
+                                                   _stream()), "ct_fill")
         _lib.count(3)
         self.stored = total
         self._nnz = int(self.rowlen.sum().item())

@@ -394,8 +394,14 @@ class ParallelBeamCT(CSROperator):
         if layout not in ("csr", "sell", "both"):
             raise ValueError("layout must be 'auto', 'csr', 'sell', 'both' or 'implicit'")
         mats = {}
+        # the SELL copy of A uses the row-aligned layout of the index-only projector with the values stored next to the
+        # indices (K.CtSellDevice): the x-gathers of neighbouring rays then share sectors.  TB200_SELL_ALIGNED=0: plain SELL
+        aligned = os.environ.get("TB200_SELL_ALIGNED", "1") != "0"
         for lay in (("csr", "sell") if layout == "both" else (layout,)):
-            a = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=False, layout=lay)
+            if lay == "sell" and aligned:
+                a = K.ct_build_aligned(self.nx, self.ny, n_det, cos_t, sin_t)
+            else:
+                a = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=False, layout=lay)
             at = K.ct_build(self.nx, self.ny, n_det, cos_t, sin_t, transpose=True, layout=lay)
             if a.nnz != at.nnz:
                 raise RuntimeError(f"CT builder: nnz(A)={a.nnz} differs from nnz(A^T)={at.nnz}")
