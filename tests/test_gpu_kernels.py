@@ -327,6 +327,44 @@ def test_incremental_gram_panel_equals_the_full_pass(tb, m):
     assert np.array_equal(hi, fhi) and np.array_equal(lo, flo)
 
 
+def test_gram_route_falls_back_to_householder_when_not_positive_definite(tb):
+    """A basis vector in the null space of L (a zero column of LV) makes the Gram matrix singular: the double-double
+    Cholesky refuses it and GKS / MMGKS factor that iteration the reference's way (Householder QR on the host) instead
+    of stopping - the reference's la.qr walks through the same situation (GKS.py:54-58, MMGKS.py:94-95)."""
+    import sys
+
+    K = tb.kernels
+    core = sys.modules[sys.modules[tb.GKS.__module__].GKSBases.__module__]
+    rng = np.random.default_rng(21)
+    m, k = 5000, 5
+    B = rng.standard_normal((m, k))
+    B[:, 2] = 0.0
+    basis = K.Basis(m, k, "cuda")
+    for j in range(k):
+        basis.next_col().copy_(dev(B[:, j]))
+        basis.push()
+    b, w = rng.standard_normal(m), rng.uniform(0.5, 2.0, m)
+    with pytest.warns(RuntimeWarning, match="Householder"):
+        R, C, r2 = core._factor(basis, k, dev(w), (dev(b), dev(b)), (0, 1), None, None)
+    Rw, Cw, rw = core.householder_factor(B * w[:, None], np.stack((b, b * w), axis=1))
+    assert R.shape == (k, k) and C.shape == (k, 2) and R[2, 2] == 0.0
+    assert np.allclose(R, Rw, rtol=0, atol=1e-12 * np.abs(Rw).max()) and np.allclose(C, Cw, atol=1e-10) and np.allclose(r2, rw)
+    with pytest.warns(RuntimeWarning, match="Householder"):
+        R, C, r2 = core._factor(basis, k, None, (dev(b),), (0,), K.IncrementalGram(), None)
+    Ru, Cu, ru = core.householder_factor(B, b[:, None])
+    assert np.allclose(R, Ru, rtol=0, atol=1e-12 * np.abs(Ru).max()) and np.allclose(C, Cu, atol=1e-10) and np.allclose(r2, ru)
+    # a healthy basis does not take the fallback
+    B[:, 2] = rng.standard_normal(m)
+    basis.col(2).copy_(dev(B[:, 2]))
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", RuntimeWarning)
+        R, C, r2 = core._factor(basis, k, dev(w), (dev(b), dev(b)), (0, 1), None, None)
+    Rw, Cw, rw = core.householder_factor(B * w[:, None], np.stack((b, b * w), axis=1))
+    assert np.allclose(R, Rw, rtol=1e-11, atol=1e-12 * np.abs(Rw).max()) and np.allclose(C, Cw, atol=1e-10)
+
+
 @pytest.mark.parametrize("nx,views", [(24, 16), (64, 90), (33, 7)])
 def test_ct_builder_is_bit_identical_to_the_numpy_statement(tb, nx, views):
     op = tb.ParallelBeamCT(nx, views)

@@ -7,6 +7,28 @@ import trips_oracle as O
 from conftest import GOLDEN
 
 
+def test_householder_factor_matches_the_gram_route_conventions():
+    """solvers/_gks_core.householder_factor (the fallback of the Gram / Cholesky route): R upper triangular with a
+    non-negative diagonal, R^T R = M^T M, C = Q^T Z, residuals; a zero column gives a zero diagonal entry, not an error."""
+    import trips_b200  # noqa: F401
+    from trips_b200.solvers._gks_core import householder_factor
+
+    rng = np.random.default_rng(4)
+    M = rng.standard_normal((300, 7))
+    M[:, 4] = 0.0
+    Z = rng.standard_normal((300, 2))
+    R, C, r2 = householder_factor(M, Z)
+    assert np.array_equal(R, np.triu(R)) and np.all(np.diag(R) >= 0) and R[4, 4] == 0.0
+    assert np.allclose(R.T @ R, M.T @ M)
+    # (for a rank-deficient M, Householder's Q carries an arbitrary unit column for the zero pivot - as the reference's
+    # Q_A does: the projection is onto k orthonormal columns either way)
+    import scipy.linalg as la
+
+    Q = la.qr(M, mode="economic")[0]
+    assert np.allclose(r2, np.sum((Z - Q @ (Q.T @ Z)) ** 2, axis=0))
+    assert np.allclose(np.sum(C ** 2, axis=0) + r2, np.sum(Z ** 2, axis=0))
+
+
 def test_spectral_gcv_objective_equals_the_solve_based_form():
     """generalized_crossvalidation evaluates the objective from one SVD of R_A R_L^-1; gcv_value is the reference's
     two-solves-per-evaluation form (gcv.py:25-78).  Same function of lambda, square and (k+1) x k, L = I and triangular

@@ -103,25 +103,61 @@ def _gram_comm(comm, space):
     return comm if (comm is not None and comm.is_sharded(space)) else None
 
 
+def householder_factor(M, Z):
+    """The reference's route, on the host: (R, C, resid2) of la.qr(M) with the rows of R signed so that its diagonal is
+    non-negative (the convention of the Gram / Cholesky route), C = Q^T Z, resid2[e] = ||Z[:, e] - Q Q^T Z[:, e]||^2.
+    M: m x k, Z: m x ne NumPy arrays (already weighted).  MMGKS.py:58-59,94-95; GKS.py:54-58."""
+    import scipy.linalg as la
+
+    Q, R = la.qr(M, mode="economic")
+    sg = np.where(np.diag(R) < 0, -1.0, 1.0)
+    Q, R = Q * sg[None, :], R * sg[:, None]
+    C = Q.T @ Z
+    resid2 = np.sum((Z - Q @ C) ** 2, axis=0)
+    return np.triu(R), C, resid2
+
+
+def _factor(B, k, w, extras, flags, inc, comm):
+    """R, Q^T extras, residuals of [diag(w) B[:, :k] | extras]: double-double Gram pass + Cholesky; if the Gram matrix is
+    not numerically positive definite (a basis vector in the null space of L, extreme weights - situations the
+    reference's Householder QR walks through), the columns are brought to the host and factored the reference's way."""
+    if w is None and inc is not None:
+        Ghi, Glo = inc.update(B, k, extras=extras, extra_weighted=flags, comm=comm)
+    else:
+        Ghi, Glo = K.weighted_gram(B, k, w, extras=extras, extra_weighted=flags, comm=comm)
+    try:
+        return K.gram_factor(Ghi, Glo, k)
+    except np.linalg.LinAlgError:
+        if comm is not None:  # row-sharded basis: no rank holds the columns
+            raise
+        import warnings
+
+        warnings.warn("Gram matrix of the Krylov basis is not positive definite: falling back to a Householder QR on "
+                      "the host for this iteration", RuntimeWarning, stacklevel=3)
+        wh = None if w is None else w.cpu().numpy()[:, None]
+        M = B.to_numpy(k)
+        Z = np.stack([e.cpu().numpy() for e in extras], axis=1) if extras else np.zeros((M.shape[0], 0))
+        if wh is not None:
+            M = M * wh
+            for e, f in enumerate(flags):
+                if f:
+                    Z[:, e] = Z[:, e] * wh[:, 0]
+        return householder_factor(M, Z)
+
+
 def factor_pair(bases, bd, wf=None, wr=None):
     """R_A, R_L, c_plain = Q_A^T b, c_w = Q_A^T (wf*b), resid_w = ||wf*b - Q_A Q_A^T wf*b||."""
     k = bases.k
     comm = bases.comm
     if wf is None:
-        Ghi, Glo = bases.gram_AV.update(bases.AV, k, extras=(bd,), extra_weighted=(0,), comm=_gram_comm(comm, "data"))
-        R_A, C, res2 = K.gram_factor(Ghi, Glo, k)
+        R_A, C, res2 = _factor(bases.AV, k, None, (bd,), (0,), bases.gram_AV, _gram_comm(comm, "data"))
         c_plain = c_w = C[:, 0:1]
         resid_w = float(np.sqrt(res2[0]))
     else:
-        Ghi, Glo = K.weighted_gram(bases.AV, k, wf, extras=(bd, bd), extra_weighted=(0, 1), comm=_gram_comm(comm, "data"))
-        R_A, C, res2 = K.gram_factor(Ghi, Glo, k)
+        R_A, C, res2 = _factor(bases.AV, k, wf, (bd, bd), (0, 1), None, _gram_comm(comm, "data"))
         c_plain, c_w = C[:, 0:1], C[:, 1:2]
         resid_w = float(np.sqrt(res2[1]))
-    if wr is None:
-        Ghi, Glo = bases.gram_LV.update(bases.LV, k, comm=_gram_comm(comm, "reg"))
-    else:
-        Ghi, Glo = K.weighted_gram(bases.LV, k, wr, comm=_gram_comm(comm, "reg"))
-    R_L, _, _ = K.gram_factor(Ghi, Glo, k)
+    R_L, _, _ = _factor(bases.LV, k, wr, (), (), bases.gram_LV, _gram_comm(comm, "reg"))
     return R_A, R_L, c_plain, c_w, resid_w
 
 
