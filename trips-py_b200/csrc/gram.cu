@@ -11,7 +11,8 @@
 // "Dot2"), the partials are combined in double-double in a fixed order, and the k x k Cholesky / triangular
 // solves run in double-double on the host.  The factors are then accurate to working precision for
 // kappa up to ~1e15, i.e. as good as Householder, while the basis is read exactly once (8*m*k bytes).
-// The accumulation is ~10 flops per multiply-add: this pass is FP64-pipe-bound for k >~ 24, not HBM-bound.
+// The accumulation is 10 fp64 instructions per multiply-add: this pass is bound by the fp64 issue rate, not by HBM
+// (DESIGN.md section 4b has the measurements).
 #include "tb200_common.cuh"
 #include <cmath>
 #include <vector>
@@ -85,10 +86,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // A CTA streams tiles of `rows` = RG * rpg consecutive rows through shared memory, column-major (T[column][row], the
-// layout the basis has in HBM, so a tile is one contiguous segment per column).  Thread (pair, rg) accumulates the
-// 4 x 4 block `pair` of the Gram matrix over rows rg, rg + RG, rg + 2 RG, ... of every tile: the lanes of a warp read
-// consecutive rows of the same columns (broadcast / conflict-free).  For the small K of the Krylov solvers a handful of
-// 4 x 4 blocks exists, so a tile is split over up to 256 row groups to keep all threads busy.
+// layout the basis has in HBM, so a tile is one contiguous segment per column).  Thread (item, rg) accumulates the
+// BH x BW block `item` of the Gram matrix over rows rg, rg + RG, rg + 2 RG, ... of every tile: the lanes of a warp read
+// consecutive rows of the same columns (broadcast / conflict-free) as long as they share the item.  For the small K of
+// the Krylov solvers only a handful of blocks exists, so a tile is split over up to 512 row groups to keep all threads
+// busy; their partial sums are combined inside the CTA before anything is written.
 //
 // BULK = true (every column 16-byte aligned): full tiles arrive by cp.async.bulk (one per column, issued by warp 0,
 // completion on an mbarrier) into one of two buffers, so tile t + 1 is in flight while tile t is accumulated - the
@@ -96,11 +98,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // loads.  The row weights travel as one more column and are applied in shared memory before the accumulation.
 // BULK = false and the last, partial tile: staged by ordinary loads (zero-filled past m).
 //
-// BW = 4: an item is a 4 x 4 block (ti, tj), ti <= tj, of the full Gram matrix.  BW = 1 ("panel"): only the columns
-// c >= c0 of G are wanted (a basis that gained columns since its Gram matrix was last formed, unweighted: everything
-// left of c0 is unchanged) - an item is the 4 x 1 block (rows 4 ti .. 4 ti + 3, column c0 + pj), O(K) items instead of
-// O(K^2 / 32), and the pass is HBM-bound (it still reads every column once).
-// partials layout: [blockIdx.x][item][4 * BW entries][hi, lo]
+// BH = BW (2 or 4): an item is a square block (ti, tj), ti <= tj, of the full Gram matrix; 2 x 2 on up to 512 threads is
+// the default (gram_launch).  BH = 4, BW = 1 ("panel"): only the columns c >= c0 of G are wanted (a basis that gained
+// columns since its Gram matrix was last formed, unweighted: everything left of c0 is unchanged) - an item is the 4 x 1
+// block (rows 4 ti .. 4 ti + 3, column c0 + pj), O(K) items instead of O(K^2), and the pass is HBM-bound (it still
+// reads every column once).
+// NT: upper bound of the CTA size (launch bounds); the launch uses the multiple of 32 that fits the items.
+// partials layout: [blockIdx.x][item][BH * BW entries][hi, lo]
 template <bool BULK, int BH, int BW, int NT>
 __global__ void __launch_bounds__(NT, 2)
 gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const double* __restrict__ w,
@@ -154,7 +158,7 @@ gram_dd_kernel(int64_t m, int k, const double* __restrict__ B, int64_t ld, const
       pb += RG;
     }
   };
-  // the pad columns K .. 4 nt - 1 of the last 4-wide block are read (their products are discarded): keep them zero
+  // the pad columns K .. BH nt - 1 of the last block are read (their products are discarded): keep them zero
   for (int j = Kw + warp; j < KC; j += kGThreads / 32)
     for (int r = lane; r < rows; r += 32) {
       T[(size_t)j * S + r] = 0.0;
