@@ -7,6 +7,55 @@ import trips_oracle as O
 from conftest import GOLDEN
 
 
+def test_incremental_gram_cache_semantics(monkeypatch):
+    """kernels.IncrementalGram on the host side (the device pass replaced by NumPy): the panel pass is requested exactly
+    when the same basis buffer has only gained columns and the extras are the same vectors; a shrunken k, another
+    buffer or another extra vector fall back to the full pass; the merged matrix is always the full Gram matrix."""
+    import torch
+    import trips_b200  # noqa: F401
+    from trips_b200 import kernels as K
+
+    rng = np.random.default_rng(6)
+    m, kmax = 50, 9
+    data = torch.from_numpy(rng.standard_normal((kmax, m)))  # (kmax, m): column j of the basis is row j
+    b1, b2 = torch.from_numpy(rng.standard_normal(m)), torch.from_numpy(rng.standard_normal(m))
+    calls = []
+
+    def fake_weighted_gram(B, k, w=None, extras=(), extra_weighted=(), comm=None, first_col=0):
+        assert w is None
+        calls.append(first_col)
+        M = np.column_stack([B[:k].numpy().T] + [e.numpy() for e in extras])
+        G = M.T @ M
+        if first_col > 0:  # what the panel kernel leaves: only the columns >= first_col and their mirror rows
+            P = np.zeros_like(G)
+            P[:, first_col:] = G[:, first_col:]
+            P[first_col:, :] = G[first_col:, :]
+            G = P
+        return G, np.zeros_like(G)
+
+    monkeypatch.setattr(K, "weighted_gram", fake_weighted_gram)
+    inc = K.IncrementalGram()
+
+    def full(B, k, extras):
+        M = np.column_stack([B[:k].numpy().T] + [e.numpy() for e in extras])
+        return M.T @ M
+
+    for k in (3, 4, 5, 7):
+        hi, _ = inc.update(data, k, extras=(b1,), extra_weighted=(0,))
+        assert np.array_equal(hi, full(data, k, (b1,)))
+    assert calls == [0, 3, 4, 5]
+    hi, _ = inc.update(data, 7, extras=(b1,), extra_weighted=(0,))  # nothing new: full pass (k did not grow)
+    hi, _ = inc.update(data, 5, extras=(b1,), extra_weighted=(0,))  # truncated basis
+    assert calls[-2:] == [0, 0] and np.array_equal(hi, full(data, 5, (b1,)))
+    hi, _ = inc.update(data, 6, extras=(b2,), extra_weighted=(0,))  # another right-hand side
+    assert calls[-1] == 0 and np.array_equal(hi, full(data, 6, (b2,)))
+    hi, _ = inc.update(data, 8, extras=(b2,), extra_weighted=(0,))
+    assert calls[-1] == 6 and np.array_equal(hi, full(data, 8, (b2,)))
+    other = data.clone()
+    hi, _ = inc.update(other, 9, extras=(b2,), extra_weighted=(0,))  # another buffer (a grown / re-allocated basis)
+    assert calls[-1] == 0 and np.array_equal(hi, full(other, 9, (b2,)))
+
+
 def test_householder_factor_matches_the_gram_route_conventions():
     """solvers/_gks_core.householder_factor (the fallback of the Gram / Cholesky route): R upper triangular with a
     non-negative diagonal, R^T R = M^T M, C = Q^T Z, residuals; a zero column gives a zero diagonal entry, not an error."""
