@@ -7,6 +7,36 @@ import trips_oracle as O
 from conftest import GOLDEN
 
 
+def test_solver_drivers_limit_the_host_blas_pool_only_for_the_call():
+    """solvers/_common.single_threaded_host_blas: one BLAS thread inside the call (k x k LAPACK is slower, at some sizes
+    pathologically, on a multi-threaded OpenBLAS), the caller's pool size restored afterwards, signature and name kept."""
+    import inspect
+
+    threadpoolctl = pytest.importorskip("threadpoolctl")
+    import trips_b200 as tb
+    from trips_b200.solvers._common import single_threaded_host_blas
+
+    def blas_threads():
+        return [p["num_threads"] for p in threadpoolctl.threadpool_info() if p["user_api"] == "blas"]
+
+    before = blas_threads()
+    seen = []
+
+    @single_threaded_host_blas
+    def probe(a, b=2):
+        """doc"""
+        seen.append(blas_threads())
+        return a + b
+
+    assert probe(1, b=3) == 4 and probe.__name__ == "probe" and probe.__doc__ == "doc"
+    assert all(t == 1 for t in seen[0]) and blas_threads() == before
+    with pytest.raises(ZeroDivisionError):  # restored after an exception too
+        single_threaded_host_blas(lambda: 1 / 0)()
+    assert blas_threads() == before
+    for fn in (tb.Hybrid_LSQR, tb.Hybrid_GMRES, tb.GKS, tb.MMGKS):  # the reference signatures survive the decorator
+        assert list(inspect.signature(fn).parameters)[:2] == ["A", "b"]
+
+
 def test_incremental_gram_cache_semantics(monkeypatch):
     """kernels.IncrementalGram on the host side (the device pass replaced by NumPy): the panel pass is requested exactly
     when the same basis buffer has only gained columns and the extras are the same vectors; a shrunken k, another
